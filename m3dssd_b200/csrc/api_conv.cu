@@ -1,0 +1,230 @@
+// m3d_conv2d_nhwc: validate the descriptor, pick tile shapes, encode the TMA
+// tensor maps and launch the tcgen05 implicit-GEMM kernel.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "igemm.cuh"
+
+namespace m3d {
+
+static thread_local char g_last_error[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+  }
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// 2-D bf16 matrix [rows][cols] (cols contiguous), box {box_cols, box_rows}.
+int make_tmap_2d(CUtensorMap* map, const void* base, long rows, long cols, int box_cols, int box_rows) {
+  auto enc = get_encode();
+  M3D_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(box_cols * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  M3D_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d rows=%ld cols=%ld box=%dx%d) failed: %d", rows, cols,
+              box_cols, box_rows, static_cast<int>(r));
+  return M3D_OK;
+}
+
+// NHWC bf16 activation [N][H][W][C] as (C, W, H, N); box {bk, tw*stride, th*stride, 1}
+// traversed with element strides {1, stride, stride, 1}.
+int make_tmap_nhwc(CUtensorMap* map, const void* base, int N, int H, int W, int C, int bk, int tw, int th, int stride) {
+  auto enc = get_encode();
+  M3D_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
+                           static_cast<cuuint64_t>(H) * W * C * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(tw * stride),
+                       static_cast<cuuint32_t>(th * stride), 1};
+  cuuint32_t es[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  M3D_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(nhwc N=%d H=%d W=%d C=%d box=%dx%dx%d) failed: %d", N, H, W, C,
+              bk, tw * stride, th * stride, static_cast<int>(r));
+  return M3D_OK;
+}
+
+// Output tile = TH x TW pixels with TH * TW = 128: pick the shape wasting the
+// fewest padded pixels (ties go to the squarest, which shares the most halo).
+void pick_tile(int P, int Q, int max_tw, int* TW, int* TH) {
+  const int cands[5] = {16, 8, 32, 64, 128};
+  long best = -1;
+  for (int i = 0; i < 5; ++i) {
+    const int tw = cands[i], th = kTileM / tw;
+    if (tw > max_tw) continue;
+    const long tiles = static_cast<long>((Q + tw - 1) / tw) * ((P + th - 1) / th);
+    if (best < 0 || tiles < best) {
+      best = tiles;
+      *TW = tw;
+      *TH = th;
+    }
+  }
+}
+
+static int sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sms;
+}
+
+static int pick_bn(int cout, int bk, long m_tiles, bool gather) {
+  if (bk == 16) return cout <= 16 ? 16 : 32;
+  if (bk == 32) return cout <= 32 ? 32 : 64;
+  if (cout <= 16 && gather) return 16;
+  if (cout <= 32) return 32;
+  if (cout <= 48) return 48;
+  if (cout <= 64) return 64;
+  if (cout <= 128) return 128;
+  // A deformable gather is paid once per N tile: always take the widest tile.
+  if (gather) return 256;
+  // Plain conv: 256-wide tiles halve the A traffic, but only when there are
+  // enough tiles left to occupy every SM.
+  return (m_tiles * ((cout + 255) / 256) >= sm_count()) ? 256 : 128;
+}
+
+}  // namespace m3d
+
+using namespace m3d;
+
+extern "C" const char* m3d_last_error(void) { return g_last_error; }
+extern "C" int m3d_version(void) { return 100; }
+
+extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3D_REQUIRE(d != nullptr, "desc is NULL");
+  M3D_REQUIRE(d->num_inputs >= 1 && d->num_inputs <= M3D_MAX_CONCAT, "num_inputs=%d out of range", d->num_inputs);
+  M3D_REQUIRE(d->R >= 1 && d->S >= 1 && d->stride >= 1 && d->dil >= 1 && d->pad >= 0, "bad kernel geometry");
+  M3D_REQUIRE(d->N >= 1 && d->H >= 1 && d->W >= 1 && d->Cout >= 1, "bad tensor geometry");
+  M3D_REQUIRE(d->weight != nullptr && d->out != nullptr, "weight/out is NULL");
+  const int groups = d->groups < 1 ? 1 : d->groups;
+  const int P = (d->H + 2 * d->pad - (d->dil * (d->R - 1) + 1)) / d->stride + 1;  // dcn_v2_cuda.c:40-41
+  const int Q = (d->W + 2 * d->pad - (d->dil * (d->S - 1) + 1)) / d->stride + 1;
+  M3D_REQUIRE(P >= 1 && Q >= 1, "empty output %dx%d", P, Q);
+  const bool split = d->act_dtype == M3D_F32;
+  const bool gather = split || d->om != nullptr || d->force_gather;
+  if (split) {
+    M3D_REQUIRE(d->out_dtype == M3D_F32, "fp32 activations need fp32 output");
+    M3D_REQUIRE(d->weight_lo != nullptr, "fp32 mode needs weight_lo");
+  }
+  long ktot = 0;
+  int bk = 64;
+  for (int i = 0; i < d->num_inputs; ++i) {
+    M3D_REQUIRE(d->in[i] != nullptr, "input %d is NULL", i);
+    M3D_REQUIRE(d->in_c[i] % 16 == 0 && d->in_c[i] > 0, "input %d: %d channels (need a multiple of 16)", i, d->in_c[i]);
+    if (d->in_c[i] % 64 != 0) {
+      const int need = d->in_c[i] % 32 == 0 ? 32 : 16;
+      if (need < bk) bk = need;
+    }
+    ktot += static_cast<long>(d->R) * d->S * d->in_c[i];
+  }
+  if (gather) {
+    M3D_REQUIRE(bk == 64, "gather/DCN path needs input channels in multiples of 64");
+    M3D_REQUIRE(groups == 1, "gather/DCN path does not batch groups");
+    M3D_REQUIRE(d->R * d->S <= 9 || d->om == nullptr, "deformable kernels above 3x3 unsupported");
+  }
+  int TW = 16, TH = 8;
+  pick_tile(P, Q, 256 / d->stride, &TW, &TH);
+  const int tiles_w = (Q + TW - 1) / TW, tiles_h = (P + TH - 1) / TH;
+  const long m_tiles = static_cast<long>(tiles_w) * tiles_h * d->N;
+  const int BN = pick_bn(d->Cout, bk, m_tiles * groups, gather);
+  const int n_tiles = (d->Cout + BN - 1) / BN;
+  const long total_tiles = m_tiles * n_tiles * groups;
+  M3D_REQUIRE(total_tiles < (1L << 30), "too many tiles");
+
+  if (!gather) {
+    ConvTmaParams p;
+    memset(&p, 0, sizeof(p));
+    for (int i = 0; i < d->num_inputs; ++i) {
+      M3D_REQUIRE(d->in_cstride[i] % 8 == 0, "input %d: channel stride %d not a multiple of 8", i, d->in_cstride[i]);
+      int rc = make_tmap_nhwc(&p.tmap_a[i], d->in[i], d->N, d->H, d->W, d->in_cstride[i], bk, TW, TH, d->stride);
+      if (rc != M3D_OK) return rc;
+      p.chunks[i] = d->in_c[i] / bk;
+      p.a_coff[i] = d->in_coff[i];
+      p.a_goff[i] = d->in_goff[i];
+    }
+    int rc = make_tmap_2d(&p.tmap_b, d->weight, d->weight_rows, ktot, bk, BN);
+    if (rc != M3D_OK) return rc;
+    p.num_inputs = d->num_inputs;
+    p.R = d->R, p.S = d->S, p.stride = d->stride, p.pad = d->pad, p.dil = d->dil;
+    p.N = d->N, p.P = P, p.Q = Q;
+    p.TW = TW, p.TH = TH, p.tiles_w = tiles_w, p.tiles_h = tiles_h;
+    p.Cout = d->Cout, p.n_tiles = n_tiles, p.groups = groups, p.b_goff = d->weight_goff;
+    p.out = d->out, p.out_cstride = d->out_cstride, p.out_coff = d->out_coff, p.out_goff = d->out_goff;
+    p.bias = d->bias, p.bias_goff = d->bias_goff;
+    p.res = d->res, p.res_cstride = d->res_cstride, p.res_coff = d->res_coff, p.res_goff = d->res_goff;
+    p.slope = d->slope;
+    p.total_tiles = static_cast<int>(total_tiles);
+    rc = launch_conv_tma(p, BN, bk, d->out_dtype, stream);
+    if (rc == M3D_ERR_UNSUPPORTED) set_last_error("no TMA conv kernel for BN=%d BK=%d", BN, bk);
+    return rc;
+  }
+
+  ConvGatherParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = make_tmap_2d(&p.tmap_b, d->weight, d->weight_rows, ktot, 64, BN);
+  if (rc != M3D_OK) return rc;
+  if (split) {
+    rc = make_tmap_2d(&p.tmap_b_lo, d->weight_lo, d->weight_rows, ktot, 64, BN);
+    if (rc != M3D_OK) return rc;
+  }
+  p.num_inputs = d->num_inputs;
+  for (int i = 0; i < d->num_inputs; ++i) {
+    p.in[i] = d->in[i];
+    p.in_cstride[i] = d->in_cstride[i];
+    p.in_coff[i] = d->in_coff[i];
+    p.chunks[i] = d->in_c[i] / 64;
+    M3D_REQUIRE((d->in_cstride[i] % (split ? 4 : 8)) == 0 && (d->in_coff[i] % (split ? 4 : 8)) == 0,
+                "input %d: channel stride/offset must keep 16-byte alignment", i);
+  }
+  p.H = d->H, p.W = d->W;
+  p.R = d->R, p.S = d->S, p.stride = d->stride, p.pad = d->pad, p.dil = d->dil;
+  p.N = d->N, p.P = P, p.Q = Q;
+  p.TW = TW, p.TH = TH, p.tiles_w = tiles_w, p.tiles_h = tiles_h;
+  p.Cout = d->Cout, p.n_tiles = n_tiles;
+  p.om = d->om, p.om_cstride = d->om_cstride, p.sigmoid_mask = d->sigmoid_mask;
+  if (d->om != nullptr) M3D_REQUIRE(d->om_cstride >= 3 * d->R * d->S, "om_cstride %d < 3*R*S", d->om_cstride);
+  p.out = d->out, p.out_cstride = d->out_cstride, p.out_coff = d->out_coff;
+  p.bias = d->bias;
+  p.res = d->res, p.res_cstride = d->res_cstride, p.res_coff = d->res_coff;
+  p.slope = d->slope;
+  p.total_tiles = static_cast<int>(total_tiles);
+  rc = launch_conv_gather(p, BN, d->act_dtype == M3D_F32 ? DT_F32 : DT_BF16, d->out_dtype == M3D_F32 ? DT_F32 : DT_BF16,
+                          stream);
+  if (rc == M3D_ERR_UNSUPPORTED) set_last_error("no gather conv kernel for BN=%d", BN);
+  return rc;
+}
