@@ -89,6 +89,82 @@ typedef struct m3d_conv_desc {
 
 int m3d_conv2d_nhwc(const m3d_conv_desc* desc, m3d_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * DCNv2 operator, reference FFI shape (replaces dcn_v2_cuda_forward,
+ * model/DCNv2/src/dcn_v2_cuda.h:9-17): NCHW fp32 device tensors,
+ * offset [B, 2*kh*kw, Ho, Wo] (dh, dw interleaved per tap), mask [B, kh*kw, Ho, Wo].
+ * Differences: `ones`/`columns` scratch tensors are gone (the caller passes one
+ * opaque workspace of m3d_dcn_v2_forward_workspace() bytes), shape errors are
+ * returned (reference: THError, dcn_v2_cuda.c:33-38), the batch is handled in
+ * one launch.  precision: M3D_F32 = fp32-accurate (bf16x3 split products),
+ * M3D_BF16 = bf16 operands / fp32 accumulate.  deformable_group must be 1.
+ * ---------------------------------------------------------------------- */
+size_t m3d_dcn_v2_forward_workspace(int B, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil,
+                                    int precision);
+int m3d_dcn_v2_forward(const float* input, const float* weight, const float* bias, const float* offset,
+                       const float* mask, float* output, int B, int C, int H, int W, int Cout, int kh, int kw,
+                       int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int deformable_group,
+                       int precision, void* workspace, size_t workspace_bytes, m3d_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * gpu_nms.  m3d_nms is the drop-in for `_nms` (lib/nms/gpu_nms.hpp:1-2): HOST
+ * pointers, boxes [n, boxes_dim] already sorted by score, keep_out receives the
+ * kept row indices; synchronous.  The +1 pixel IoU convention and the strict
+ * `IoU > thresh` test follow lib/nms/nms_kernel.cu:24-32,71 in the reference's
+ * compiled operation order.  m3d_nms_batched is the device-resident, batched
+ * form used by the detection tail: boxes [batch, max_n, box_stride] (x1,y1,x2,y2
+ * first), num[b] valid rows (NULL = max_n), keep [batch, max_n], num_keep [batch].
+ * ---------------------------------------------------------------------- */
+int m3d_nms(int* keep_out, int* num_out, const float* boxes_host, int boxes_num, int boxes_dim,
+            float nms_overlap_thresh, int device_id);
+size_t m3d_nms_workspace_bytes(int batch, int max_n);
+int m3d_nms_batched(const float* boxes, int box_stride, const int* num, int batch, int max_n, float thresh,
+                    void* workspace, size_t workspace_bytes, int* keep, int* num_keep, m3d_stream_t stream);
+
+/* Detection decode (lib/rpn_util.py:1444-1521): per image, exact top-`topk` of
+ * score (descending, ties by lower index), anchor decode of the selected rows
+ * into dets [batch, topk, 14] = x1,y1,x2,y2,score,cls,x3d,y3d,z3d,w3d,h3d,l3d,ry3d,anchor. */
+int m3d_decode_topk(const float* score, const unsigned char* cls_pred, const float* bbox_2d, const float* bbox_3d,
+                    const float* anchors /*[A,9]*/, const float* means11, const float* stds11, int batch, int A, int H,
+                    int W, float feat_stride, float scale_factor, int topk, float* dets, int* det_idx, int* det_num,
+                    m3d_stream_t stream);
+int m3d_gather_kept(const float* dets, int row_len, int batch, int max_n, const int* keep, const int* num_keep,
+                    int max_out, float* out, m3d_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Bandwidth-bound layers around the GEMMs (NHWC activations).
+ * ---------------------------------------------------------------------- */
+/* DLA.base_layer (model/pose_dla_dcn.py:336-340): 7x7 conv on the NCHW fp32 image, BN folded, LeakyReLU. */
+int m3d_stem_conv7x7(const float* image_nchw, const float* weight /*[16,3,7,7]*/, const float* bias, void* out,
+                     int out_dtype, int out_cstride, int N, int H, int W, float slope, m3d_stream_t stream);
+/* nn.MaxPool2d(2) (model/pose_dla_dcn.py:306). */
+int m3d_maxpool2x2_nhwc(const void* in, void* out, int dtype, int N, int H, int W, int C, int in_cstride,
+                        int out_cstride, m3d_stream_t stream);
+/* IDAUp up_i + skip add (model/pose_dla_dcn.py:536-552): depthwise ConvTranspose2d(2f, stride f, pad f/2). */
+int m3d_upsample_add_nhwc(const void* x, const float* weight /*[C,2f,2f]*/, const void* skip, void* out, int dtype,
+                          int N, int H, int W, int C, int f, int x_cstride, int skip_cstride, int out_cstride,
+                          m3d_stream_t stream);
+/* softmax over classes + fg prob + top-1 anchor + score/class (model/M3d_inference_align.py:229-234). */
+int m3d_cls_softmax(const float* logits, int logits_cstride, int N, int H, int W, int A, int K, float* cls_out,
+                    float* prob_out, float* fg_max, int* fg_arg, float* score, unsigned char* cls_pred,
+                    m3d_stream_t stream);
+/* shape_align / center_align offset builders (model/module/feturealign_mgpu.py:119-136,58-77). */
+int m3d_shape_align_om(const float* fg_max, const int* fg_arg, const float* anchors, int anchor_ld, float feat_stride,
+                       float thresh, float* om /*[npix,27]*/, long npix, m3d_stream_t stream);
+int m3d_center_align_om(const float* fg_max, const int* fg_arg, const float* heads, int heads_cstride, int x_coff,
+                        int y_coff, const float* anchors, int anchor_ld, float feat_stride, float mean_x, float mean_y,
+                        float std_x, float std_y, float thresh, float* om, int om_cstride, long npix,
+                        m3d_stream_t stream);
+/* flatten_tensor + cat of the 11 regression heads (model/M3d_inference_align.py:280-295). */
+int m3d_flatten_heads(const float* heads, int heads_cstride, int N, int H, int W, int A,
+                      const int* slot_of_output /*host, 11 ints: slot of x,y,w,h,x3d,y3d,z3d,w3d,h3d,l3d,rY3d*/,
+                      float* bbox_2d, float* bbox_3d, m3d_stream_t stream);
+/* layout conversion for the NCHW-facing operators */
+int m3d_nchw_to_nhwc(const void* in, int in_dtype, void* out, int out_dtype, int N, int C, int H, int W,
+                     int out_cstride, int out_coff, m3d_stream_t stream);
+int m3d_nhwc_to_nchw(const void* in, int in_dtype, void* out, int out_dtype, int N, int C, int H, int W,
+                     int in_cstride, int in_coff, m3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

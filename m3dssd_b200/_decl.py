@@ -1,13 +1,40 @@
 """argtypes/restype declarations for the C ABI beyond m3d_conv2d_nhwc."""
 import ctypes as C
 
+vp, i, f, sz, lg = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_long
+
+_SIGS = {
+    "m3d_dcn_v2_forward": [vp, vp, vp, vp, vp, vp] + [i] * 16 + [vp, sz, vp],
+    "m3d_nms": [vp, vp, vp, i, i, f, i],
+    "m3d_nms_batched": [vp, i, vp, i, i, f, vp, sz, vp, vp, vp],
+    "m3d_decode_topk": [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, f, f, i, vp, vp, vp, vp],
+    "m3d_gather_kept": [vp, i, i, i, vp, vp, i, vp, vp],
+    "m3d_stem_conv7x7": [vp, vp, vp, vp, i, i, i, i, i, f, vp],
+    "m3d_maxpool2x2_nhwc": [vp, vp, i, i, i, i, i, i, i, vp],
+    "m3d_upsample_add_nhwc": [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp],
+    "m3d_cls_softmax": [vp, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp],
+    "m3d_shape_align_om": [vp, vp, vp, i, f, f, vp, lg, vp],
+    "m3d_center_align_om": [vp, vp, vp, i, i, i, vp, i, f, f, f, f, f, f, vp, i, lg, vp],
+    "m3d_flatten_heads": [vp, i, i, i, i, i, vp, vp, vp, vp],
+    "m3d_nchw_to_nhwc": [vp, i, vp, i, i, i, i, i, i, i, vp],
+    "m3d_nhwc_to_nchw": [vp, i, vp, i, i, i, i, i, i, i, vp],
+}
+_SIZE_FNS = {
+    "m3d_dcn_v2_forward_workspace": [i] * 11,
+    "m3d_nms_workspace_bytes": [i, i],
+}
+
 
 def declare(L):
-    vp, i, f = C.c_void_p, C.c_int, C.c_float
     for name, args in _SIGS.items():
         fn = getattr(L, name)
         fn.restype = C.c_int
         fn.argtypes = args
+    for name, args in _SIZE_FNS.items():
+        fn = getattr(L, name)
+        fn.restype = C.c_size_t
+        fn.argtypes = args
 
 
-_SIGS = {}
+def exported_names():
+    return ["m3d_last_error", "m3d_version", "m3d_conv2d_nhwc"] + list(_SIGS) + list(_SIZE_FNS)

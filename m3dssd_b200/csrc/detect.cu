@@ -1,0 +1,443 @@
+// Detection tail on the device: score top-K selection + sort, anchor decode,
+// bitmask NMS (warp-ballot) with an on-device greedy sweep.
+//
+// Reference: lib/rpn_util.py:1444-1555 (im_detect_3d: de-normalise, decode,
+// argsort(-score), top nms_topN_pre, gpu_nms, gather), lib/nms/nms_kernel.cu
+// (devIoU :24-32, bitmask kernel :34-78, host sweep :124-139) and
+// lib/nms/gpu_nms.pyx:16-31.  The reference handles one image per call with a
+// host round trip (D2H of 3000 boxes, cudaMalloc/cudaFree, 1.1 MB mask D2H, CPU
+// sweep); here everything stays on the device and is batched over images.
+#include <algorithm>
+#include <cstdint>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace m3d {
+
+constexpr int kSelThreads = 1024;
+constexpr int kMaxTopK = 4096;
+
+// ------------------------------------------------------------------ top-K
+// Exact top-K of `score` (descending; ties -> lower index first) for one image
+// per block: 3-pass radix select on the fp32 bit pattern (scores are >= 0, so
+// the unsigned pattern is order-preserving), ordered compaction, bitonic sort.
+__device__ __forceinline__ uint32_t score_key(float s) {
+  uint32_t u = __float_as_uint(s);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // total order for any sign
+}
+
+template <int BITS>
+__device__ void radix_pass(const float* __restrict__ score, int M, uint32_t prefix, uint32_t prefix_mask, int shift,
+                           uint32_t* hist /*smem [1<<BITS]*/, int need, uint32_t* out_digit, int* out_need) {
+  constexpr int NB = 1 << BITS;
+  for (int i = threadIdx.x; i < NB; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    const uint32_t k = score_key(score[i]);
+    if ((k & prefix_mask) == prefix) atomicAdd(&hist[(k >> shift) & (NB - 1)], 1u);
+  }
+  __syncthreads();
+  // two-level descending scan: 32 warp partial sums, then inside the crossing group
+  {
+    constexpr int PER = NB / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t v = 0;
+    for (int i = lane; i < PER; i += 32) v += hist[warp * PER + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __shared__ uint32_t s_part[32];
+    if (lane == 0) s_part[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int acc = 0;
+      int g = 31;
+      for (; g > 0; --g) {
+        if (acc + static_cast<int>(s_part[g]) >= need) break;
+        acc += s_part[g];
+      }
+      int d = g * PER + PER - 1;
+      for (; d > g * PER; --d) {
+        if (acc + static_cast<int>(hist[d]) >= need) break;
+        acc += hist[d];
+      }
+      *out_digit = static_cast<uint32_t>(d);
+      *out_need = need - acc;  // how many still to take from inside digit d
+    }
+  }
+  __syncthreads();
+}
+
+struct DecodeParams {
+  const float* score;         // [N, M]
+  const unsigned char* cls;   // [N, M]
+  const float* bbox_2d;       // [N, M, 4]
+  const float* bbox_3d;       // [N, M, 7]
+  const float* anchors;       // [A, 9]
+  float means[11], stds[11];
+  int M, A, H, W;
+  float feat_stride, scale_factor;
+  int topk;
+  float* dets;   // [N, topk, 14]
+  int* det_idx;  // [N, topk] flattened anchor index of each row (or -1)
+  int* det_num;  // [N]
+};
+
+__global__ void __launch_bounds__(kSelThreads) topk_decode_kernel(const DecodeParams p) {
+  __shared__ uint32_t hist[2048];
+  __shared__ unsigned long long keys[kMaxTopK];
+  __shared__ uint32_t s_digit;
+  __shared__ int s_need, s_cnt_gt, s_cnt_eq;
+  __shared__ int s_warp_gt[32], s_warp_eq[32];
+  const int n = blockIdx.x;
+  const float* score = p.score + static_cast<long>(n) * p.M;
+  const int K = min(p.topk, p.M);
+
+  // ---- threshold key T: the K-th largest
+  uint32_t prefix = 0, mask = 0;
+  int need = K;
+  radix_pass<11>(score, p.M, prefix, mask, 21, hist, need, &s_digit, &s_need);
+  prefix |= s_digit << 21, mask |= 0x7FFu << 21, need = s_need;
+  radix_pass<11>(score, p.M, prefix, mask, 10, hist, need, &s_digit, &s_need);
+  prefix |= s_digit << 10, mask |= 0x7FFu << 10, need = s_need;
+  radix_pass<10>(score, p.M, prefix, mask, 0, hist, need, &s_digit, &s_need);
+  const uint32_t T = prefix | s_digit;
+  const int need_eq = s_need;  // number of elements equal to T to take (lowest indices)
+
+  // ---- ordered compaction: keys > T (all) and == T (first need_eq by index)
+  if (threadIdx.x == 0) s_cnt_gt = 0, s_cnt_eq = 0;
+  for (int i = threadIdx.x; i < kMaxTopK; i += blockDim.x) keys[i] = 0ull;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < p.M; base += kSelThreads) {
+    const int i = base + threadIdx.x;
+    uint32_t k = 0;
+    bool gt = false, eq = false;
+    if (i < p.M) {
+      k = score_key(score[i]);
+      gt = k > T;
+      eq = k == T;
+    }
+    const uint32_t bgt = __ballot_sync(0xffffffffu, gt), beq = __ballot_sync(0xffffffffu, eq);
+    if (lane == 0) s_warp_gt[warp] = __popc(bgt), s_warp_eq[warp] = __popc(beq);
+    __syncthreads();
+    int off_gt = s_cnt_gt, off_eq = s_cnt_eq;
+    for (int w = 0; w < warp; ++w) off_gt += s_warp_gt[w], off_eq += s_warp_eq[w];
+    const uint32_t lt = (1u << lane) - 1;
+    const unsigned long long packed = (static_cast<unsigned long long>(k) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(i));
+    if (gt) {
+      const int pos = off_gt + __popc(bgt & lt);
+      keys[pos] = packed;  // pos < K - need_eq by construction
+    }
+    if (eq) {
+      const int r = off_eq + __popc(beq & lt);
+      if (r < need_eq) keys[(K - need_eq) + r] = packed;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tg = 0, te = 0;
+      for (int w = 0; w < kSelThreads / 32; ++w) tg += s_warp_gt[w], te += s_warp_eq[w];
+      s_cnt_gt += tg, s_cnt_eq += te;
+    }
+    __syncthreads();
+  }
+
+  // ---- bitonic sort, descending on (key, ~index): higher score first, lower index first on ties
+  for (int size = 2; size <= kMaxTopK; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < kMaxTopK / 2; t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const unsigned long long a = keys[lo], b = keys[hi];
+        if ((a < b) == desc) {
+          keys[lo] = b;
+          keys[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- decode the K selected boxes (lib/rpn_util.py:1462-1521, 1137-1186)
+  if (threadIdx.x == 0) p.det_num[n] = K;
+  const int HW = p.H * p.W;
+  for (int r = threadIdx.x; r < p.topk; r += blockDim.x) {
+    float* d = p.dets + (static_cast<long>(n) * p.topk + r) * 14;
+    if (r >= K) {
+      for (int j = 0; j < 14; ++j) d[j] = 0.f;
+      p.det_idx[static_cast<long>(n) * p.topk + r] = -1;
+      continue;
+    }
+    const int idx = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(keys[r] & 0xFFFFFFFFull));
+    p.det_idx[static_cast<long>(n) * p.topk + r] = idx;
+    const int a = idx / HW, h = (idx / p.W) % p.H, w = idx % p.W;
+    const float* an = p.anchors + a * 9;
+    // rois (locate_anchors, lib/rpn_util.py:1345-1386): float64 shift + float32 anchor, rounded to float32
+    const float rx1 = static_cast<float>(static_cast<double>(w) * p.feat_stride + static_cast<double>(an[0]));
+    const float ry1 = static_cast<float>(static_cast<double>(h) * p.feat_stride + static_cast<double>(an[1]));
+    const float rx2 = static_cast<float>(static_cast<double>(w) * p.feat_stride + static_cast<double>(an[2]));
+    const float ry2 = static_cast<float>(static_cast<double>(h) * p.feat_stride + static_cast<double>(an[3]));
+    const float widths = rx2 - rx1 + 1.0f, heights = ry2 - ry1 + 1.0f;
+    const float ctr_x = rx1 + 0.5f * widths, ctr_y = ry1 + 0.5f * heights;
+    const float* b2 = p.bbox_2d + (static_cast<long>(n) * p.M + idx) * 4;
+    const float* b3 = p.bbox_3d + (static_cast<long>(n) * p.M + idx) * 7;
+    float t3[7];
+    for (int j = 0; j < 7; ++j) t3[j] = b3[j] * p.stds[4 + j] + p.means[4 + j];
+    const float x3d = t3[0] * widths + ctr_x;
+    const float y3d = t3[1] * heights + ctr_y;
+    const float z3d = an[4] + t3[2];
+    const float w3d = expf(t3[3]) * an[5];
+    const float h3d = expf(t3[4]) * an[6];
+    const float l3d = expf(t3[5]) * an[7];
+    const float ry3d = an[8] + t3[6];
+    const float dx = b2[0] * p.stds[0] + p.means[0];
+    const float dy = b2[1] * p.stds[1] + p.means[1];
+    const float dw = b2[2] * p.stds[2] + p.means[2];
+    const float dh = b2[3] * p.stds[3] + p.means[3];
+    const float pcx = dx * widths + ctr_x, pcy = dy * heights + ctr_y;
+    const float pw = expf(dw) * widths, ph = expf(dh) * heights;
+    d[0] = (pcx - 0.5f * pw) / p.scale_factor;
+    d[1] = (pcy - 0.5f * ph) / p.scale_factor;
+    d[2] = (pcx + 0.5f * pw) / p.scale_factor;
+    d[3] = (pcy + 0.5f * ph) / p.scale_factor;
+    d[4] = score[idx];
+    d[5] = static_cast<float>(p.cls[static_cast<long>(n) * p.M + idx]);
+    d[6] = x3d / p.scale_factor;
+    d[7] = y3d / p.scale_factor;
+    d[8] = z3d, d[9] = w3d, d[10] = h3d, d[11] = l3d, d[12] = ry3d;
+    d[13] = static_cast<float>(a);
+  }
+}
+
+// -------------------------------------------------------------------- NMS
+// IoU with the +1 pixel convention, in the exact operation order the
+// reference's kernel has when built with nvcc's default -fmad=true
+// (FMUL, FFMA(wb, hb, Sa), FMUL, FADD, IEEE divide) so `> thresh` never flips.
+__device__ __forceinline__ float dev_iou(const float4 a, const float4 b) {
+  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+  const float width = fmaxf(__fadd_rn(__fsub_rn(right, left), 1.f), 0.f);
+  const float height = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.f), 0.f);
+  const float interS = __fmul_rn(width, height);
+  const float Sa = __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.f), __fadd_rn(__fsub_rn(a.w, a.y), 1.f));
+  const float SaSb = __fmaf_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f), Sa);
+  return __fdiv_rn(interS, __fsub_rn(SaSb, interS));
+}
+
+// mask[n][i][cb] bit k  <=>  j = cb*64 + k > i  and  IoU(box_i, box_j) > thresh.
+// Block = 4 warps; block (cb, rb, n) covers rows rb*64..+63 against columns
+// cb*64..+63 (upper triangle only).  Lanes own columns (2 per lane), rows are
+// broadcast from shared memory, one ballot yields 32 mask bits.
+__global__ void __launch_bounds__(128) nms_mask_kernel(const float* __restrict__ boxes, int box_stride,
+                                                       const int* __restrict__ num, int max_n, float thresh,
+                                                       unsigned long long* __restrict__ mask, int col_blocks) {
+  const int cb = blockIdx.x, rb = blockIdx.y, n = blockIdx.z;
+  if (cb < rb) return;
+  const int nb = num ? num[n] : max_n;
+  if (rb * 64 >= nb || cb * 64 >= nb) return;
+  __shared__ float4 rows[64];
+  const float* b = boxes + static_cast<long>(n) * max_n * box_stride;
+  if (threadIdx.x < 64) {
+    const int i = rb * 64 + threadIdx.x;
+    rows[threadIdx.x] = i < nb ? make_float4(b[i * box_stride], b[i * box_stride + 1], b[i * box_stride + 2], b[i * box_stride + 3])
+                               : make_float4(0, 0, 0, 0);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j0 = cb * 64 + lane, j1 = j0 + 32;
+  const float4 c0 = j0 < nb ? make_float4(b[j0 * box_stride], b[j0 * box_stride + 1], b[j0 * box_stride + 2], b[j0 * box_stride + 3])
+                            : make_float4(0, 0, 0, 0);
+  const float4 c1 = j1 < nb ? make_float4(b[j1 * box_stride], b[j1 * box_stride + 1], b[j1 * box_stride + 2], b[j1 * box_stride + 3])
+                            : make_float4(0, 0, 0, 0);
+  __syncthreads();
+  for (int r = warp; r < 64; r += 4) {
+    const int i = rb * 64 + r;
+    if (i >= nb) break;
+    const float4 a = rows[r];
+    const bool s0 = (j0 < nb) && (j0 > i) && (dev_iou(a, c0) > thresh);
+    const bool s1 = (j1 < nb) && (j1 > i) && (dev_iou(a, c1) > thresh);
+    const uint32_t lo = __ballot_sync(0xffffffffu, s0), hi = __ballot_sync(0xffffffffu, s1);
+    if (lane == 0)
+      mask[(static_cast<long>(n) * max_n + i) * col_blocks + cb] = (static_cast<unsigned long long>(hi) << 32) | lo;
+  }
+}
+
+// Greedy sweep (nms_kernel.cu:124-139), one warp per image.  Lane l keeps the
+// "removed" words l and l+32 in registers.  Each 64-box block is resolved
+// sequentially from its diagonal mask words (held one row per lane pair), then
+// the kept rows are OR-ed into the later words in parallel across lanes.
+__global__ void __launch_bounds__(32) nms_sweep_kernel(const unsigned long long* __restrict__ mask,
+                                                       const int* __restrict__ num, int max_n, int col_blocks,
+                                                       int* __restrict__ keep, int* __restrict__ num_keep) {
+  const int n = blockIdx.x, lane = threadIdx.x;
+  const int nb = num ? num[n] : max_n;
+  const unsigned long long* m = mask + static_cast<long>(n) * max_n * col_blocks;
+  int* kp = keep + static_cast<long>(n) * max_n;
+  const int nblocks = (nb + 63) / 64;
+  unsigned long long remv0 = 0, remv1 = 0;  // words lane and lane + 32
+  int kept = 0;
+  for (int blk = 0; blk < nblocks; ++blk) {
+    const int r0 = blk * 64 + lane, r1 = r0 + 32;
+    const unsigned long long d0 = r0 < nb ? m[static_cast<long>(r0) * col_blocks + blk] : 0ull;
+    const unsigned long long d1 = r1 < nb ? m[static_cast<long>(r1) * col_blocks + blk] : 0ull;
+    unsigned long long cur = __shfl_sync(0xffffffffu, blk < 32 ? remv0 : remv1, blk & 31);
+    unsigned long long keptbits = 0;
+    const int lim = min(64, nb - blk * 64);
+    for (int b = 0; b < lim; ++b) {
+      const unsigned long long drow = __shfl_sync(0xffffffffu, b < 32 ? d0 : d1, b & 31);
+      if (!((cur >> b) & 1ull)) {
+        keptbits |= 1ull << b;
+        cur |= drow;
+      }
+    }
+    // record kept indices (in order) and OR their rows into later words
+    unsigned long long kb = keptbits;
+    while (kb) {  // four kept rows per trip so their mask loads overlap
+      int rows4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        rows4[u] = -1;
+        if (kb) {
+          const int b = __ffsll(static_cast<long long>(kb)) - 1;
+          kb &= kb - 1;
+          rows4[u] = blk * 64 + b;
+          if (lane == 0) kp[kept] = rows4[u];
+          ++kept;
+        }
+      }
+      unsigned long long v0[4], v1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned long long* mr = m + static_cast<long>(rows4[u] < 0 ? 0 : rows4[u]) * col_blocks;
+        v0[u] = (rows4[u] >= 0 && lane > blk && lane < col_blocks) ? mr[lane] : 0ull;
+        v1[u] = (rows4[u] >= 0 && lane + 32 > blk && lane + 32 < col_blocks) ? mr[lane + 32] : 0ull;
+      }
+      remv0 |= v0[0] | v0[1] | v0[2] | v0[3];
+      remv1 |= v1[0] | v1[1] | v1[2] | v1[3];
+    }
+  }
+  if (lane == 0) num_keep[n] = kept;
+}
+
+// Gather the first `max_out` kept rows of every image (im_detect_3d's aboxes[keep]).
+__global__ void gather_kept_kernel(const float* __restrict__ dets, int row_len, int max_n, const int* __restrict__ keep,
+                                   const int* __restrict__ num_keep, int max_out, float* __restrict__ out) {
+  const int n = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= max_out * row_len) return;
+  const int r = i / row_len, c = i % row_len;
+  float v = 0.f;
+  if (r < num_keep[n]) v = dets[(static_cast<long>(n) * max_n + keep[static_cast<long>(n) * max_n + r]) * row_len + c];
+  out[(static_cast<long>(n) * max_out + r) * row_len + c] = v;
+}
+
+// persistent device workspace for the host-pointer gpu_nms entry
+struct NmsWorkspace {
+  std::mutex mu;
+  float* boxes = nullptr;
+  unsigned long long* mask = nullptr;
+  int* keep = nullptr;
+  int* num_keep = nullptr;
+  int cap = 0, device = -1;
+};
+static NmsWorkspace g_nms_ws;
+
+}  // namespace m3d
+
+using namespace m3d;
+
+static inline cudaStream_t S(m3d_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" size_t m3d_nms_workspace_bytes(int batch, int max_n) {
+  const size_t cb = (max_n + 63) / 64;
+  return static_cast<size_t>(batch) * max_n * cb * sizeof(unsigned long long);
+}
+
+extern "C" int m3d_nms_batched(const float* boxes, int box_stride, const int* num, int batch, int max_n, float thresh,
+                               void* workspace, size_t workspace_bytes, int* keep, int* num_keep, m3d_stream_t stream) {
+  M3D_REQUIRE(boxes && keep && num_keep && workspace, "NULL pointer");
+  M3D_REQUIRE(batch >= 1 && max_n >= 1 && box_stride >= 4, "bad geometry");
+  const int cb = (max_n + 63) / 64;
+  M3D_REQUIRE(cb <= 64, "at most 4096 boxes per image (got %d)", max_n);
+  if (workspace_bytes < m3d_nms_workspace_bytes(batch, max_n)) {
+    set_last_error("NMS workspace too small: %zu < %zu", workspace_bytes, m3d_nms_workspace_bytes(batch, max_n));
+    return M3D_ERR_WORKSPACE;
+  }
+  unsigned long long* mask = static_cast<unsigned long long*>(workspace);
+  dim3 grid(cb, cb, batch);
+  nms_mask_kernel<<<grid, 128, 0, S(stream)>>>(boxes, box_stride, num, max_n, thresh, mask, cb);
+  M3D_CUDA_OK(cudaGetLastError());
+  nms_sweep_kernel<<<batch, 32, 0, S(stream)>>>(mask, num, max_n, cb, keep, num_keep);
+  M3D_CUDA_OK(cudaGetLastError());
+  return M3D_OK;
+}
+
+// Drop-in for `_nms` (lib/nms/gpu_nms.hpp:1-2): HOST pointers in and out, boxes
+// already sorted by score, synchronous.  Device buffers persist between calls.
+extern "C" int m3d_nms(int* keep_out, int* num_out, const float* boxes_host, int boxes_num, int boxes_dim,
+                       float nms_overlap_thresh, int device_id) {
+  M3D_REQUIRE(keep_out && num_out, "NULL pointer");
+  if (boxes_num <= 0) {
+    *num_out = 0;
+    return M3D_OK;
+  }
+  M3D_REQUIRE(boxes_host != nullptr && boxes_dim >= 4, "bad boxes");
+  M3D_REQUIRE(boxes_num <= 4096, "at most 4096 boxes (got %d)", boxes_num);
+  int cur = 0;
+  M3D_CUDA_OK(cudaGetDevice(&cur));
+  if (cur != device_id) M3D_CUDA_OK(cudaSetDevice(device_id));
+  std::lock_guard<std::mutex> lock(g_nms_ws.mu);
+  NmsWorkspace& ws = g_nms_ws;
+  if (ws.device != device_id || ws.cap < boxes_num) {
+    if (ws.boxes) cudaFree(ws.boxes), cudaFree(ws.mask), cudaFree(ws.keep), cudaFree(ws.num_keep);
+    ws.cap = std::max(boxes_num, 3072);
+    ws.device = device_id;
+    const size_t cb = (ws.cap + 63) / 64;
+    M3D_CUDA_OK(cudaMalloc(&ws.boxes, sizeof(float) * ws.cap * 16));
+    M3D_CUDA_OK(cudaMalloc(&ws.mask, sizeof(unsigned long long) * ws.cap * cb));
+    M3D_CUDA_OK(cudaMalloc(&ws.keep, sizeof(int) * ws.cap));
+    M3D_CUDA_OK(cudaMalloc(&ws.num_keep, sizeof(int)));
+  }
+  M3D_REQUIRE(boxes_dim <= 16, "boxes_dim %d > 16", boxes_dim);
+  cudaStream_t st = cudaStreamPerThread;
+  M3D_CUDA_OK(cudaMemcpyAsync(ws.boxes, boxes_host, sizeof(float) * boxes_num * boxes_dim, cudaMemcpyHostToDevice, st));
+  const int cb = (boxes_num + 63) / 64;
+  dim3 grid(cb, cb, 1);
+  nms_mask_kernel<<<grid, 128, 0, st>>>(ws.boxes, boxes_dim, nullptr, boxes_num, nms_overlap_thresh, ws.mask, cb);
+  M3D_CUDA_OK(cudaGetLastError());
+  nms_sweep_kernel<<<1, 32, 0, st>>>(ws.mask, nullptr, boxes_num, cb, ws.keep, ws.num_keep);
+  M3D_CUDA_OK(cudaGetLastError());
+  M3D_CUDA_OK(cudaMemcpyAsync(num_out, ws.num_keep, sizeof(int), cudaMemcpyDeviceToHost, st));
+  M3D_CUDA_OK(cudaStreamSynchronize(st));
+  M3D_CUDA_OK(cudaMemcpyAsync(keep_out, ws.keep, sizeof(int) * (*num_out), cudaMemcpyDeviceToHost, st));
+  M3D_CUDA_OK(cudaStreamSynchronize(st));
+  if (cur != device_id) M3D_CUDA_OK(cudaSetDevice(cur));
+  return M3D_OK;
+}
+
+extern "C" int m3d_decode_topk(const float* score, const unsigned char* cls_pred, const float* bbox_2d,
+                               const float* bbox_3d, const float* anchors, const float* means11, const float* stds11,
+                               int batch, int A, int H, int W, float feat_stride, float scale_factor, int topk,
+                               float* dets, int* det_idx, int* det_num, m3d_stream_t stream) {
+  M3D_REQUIRE(score && cls_pred && bbox_2d && bbox_3d && anchors && means11 && stds11 && dets && det_idx && det_num,
+              "NULL pointer");
+  M3D_REQUIRE(topk >= 1 && topk <= kMaxTopK, "topk=%d out of range (1..%d)", topk, kMaxTopK);
+  DecodeParams p;
+  p.score = score, p.cls = cls_pred, p.bbox_2d = bbox_2d, p.bbox_3d = bbox_3d, p.anchors = anchors;
+  for (int i = 0; i < 11; ++i) p.means[i] = means11[i], p.stds[i] = stds11[i];
+  p.M = A * H * W, p.A = A, p.H = H, p.W = W;
+  p.feat_stride = feat_stride, p.scale_factor = scale_factor, p.topk = topk;
+  p.dets = dets, p.det_idx = det_idx, p.det_num = det_num;
+  topk_decode_kernel<<<batch, kSelThreads, 0, S(stream)>>>(p);
+  M3D_CUDA_OK(cudaGetLastError());
+  return M3D_OK;
+}
+
+extern "C" int m3d_gather_kept(const float* dets, int row_len, int batch, int max_n, const int* keep, const int* num_keep,
+                               int max_out, float* out, m3d_stream_t stream) {
+  M3D_REQUIRE(dets && keep && num_keep && out, "NULL pointer");
+  dim3 grid((max_out * row_len + 255) / 256, batch);
+  gather_kept_kernel<<<grid, 256, 0, S(stream)>>>(dets, row_len, max_n, keep, num_keep, max_out, out);
+  M3D_CUDA_OK(cudaGetLastError());
+  return M3D_OK;
+}

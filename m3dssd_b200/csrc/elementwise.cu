@@ -1,0 +1,554 @@
+// Bandwidth-bound kernels around the implicit-GEMM layers (NHWC activations):
+// stem 7x7 conv (C_in = 3), 2x2 max-pool, depthwise transposed-conv up-sample +
+// skip add, class softmax / fg-prob / top-1 anchor, alignment offset builders,
+// head flattening, and NCHW <-> NHWC conversion for the drop-in operators.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace m3d {
+
+template <typename T>
+__device__ __forceinline__ float to_f(T v) {
+  return static_cast<float>(v);
+}
+template <typename T>
+__device__ __forceinline__ T from_f(float v) {
+  return static_cast<T>(v);
+}
+
+static inline int cdiv(long a, long b) { return static_cast<int>((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------
+// Stem: 7x7 / pad 3 / stride 1 convolution of the NCHW fp32 image (3 channels)
+// with BN folded into (w, bias) and LeakyReLU, written as NHWC with 16 real
+// channels.  model/pose_dla_dcn.py:336-340 (DLA.base_layer).
+// Each thread produces 2 vertically adjacent pixels x 16 channels from a
+// shared-memory input tile; weights are broadcast from shared memory.
+// ---------------------------------------------------------------------------
+constexpr int STEM_TW = 32, STEM_TH = 16, STEM_CO = 16;
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) stem_conv7x7_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, OutT* __restrict__ out,
+                                                           int out_cstride, int N, int H, int W, float slope) {
+  __shared__ float s_in[3][STEM_TH + 6][STEM_TW + 6 + 2];
+  __shared__ __align__(16) float s_w[147][STEM_CO];  // [c*49 + r*7 + s][co]
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads; thread -> rows ty and ty + 8
+  const int w0 = blockIdx.x * STEM_TW, h0 = blockIdx.y * STEM_TH, n = blockIdx.z;
+  for (int i = threadIdx.x; i < 147 * STEM_CO; i += 256) {
+    const int co = i % STEM_CO, k = i / STEM_CO;
+    s_w[k][co] = w[co * 147 + k];
+  }
+  for (int i = threadIdx.x; i < 3 * (STEM_TH + 6) * (STEM_TW + 6); i += 256) {
+    const int x = i % (STEM_TW + 6);
+    const int y = (i / (STEM_TW + 6)) % (STEM_TH + 6);
+    const int c = i / ((STEM_TW + 6) * (STEM_TH + 6));
+    const int gy = h0 + y - 3, gx = w0 + x - 3;
+    float v = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(img + ((static_cast<long>(n) * 3 + c) * H + gy) * W + gx);
+    s_in[c][y][x] = v;
+  }
+  __syncthreads();
+  float acc0[STEM_CO], acc1[STEM_CO];
+#pragma unroll
+  for (int co = 0; co < STEM_CO; ++co) acc0[co] = acc1[co] = __ldg(bias + co);
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+#pragma unroll
+      for (int s = 0; s < 7; ++s) {
+        const float a0 = s_in[c][ty + r][tx + s];
+        const float a1 = s_in[c][ty + 8 + r][tx + s];
+        const float4* wp = reinterpret_cast<const float4*>(&s_w[c * 49 + r * 7 + s][0]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 wv = wp[q];
+          acc0[4 * q + 0] = fmaf(a0, wv.x, acc0[4 * q + 0]);
+          acc0[4 * q + 1] = fmaf(a0, wv.y, acc0[4 * q + 1]);
+          acc0[4 * q + 2] = fmaf(a0, wv.z, acc0[4 * q + 2]);
+          acc0[4 * q + 3] = fmaf(a0, wv.w, acc0[4 * q + 3]);
+          acc1[4 * q + 0] = fmaf(a1, wv.x, acc1[4 * q + 0]);
+          acc1[4 * q + 1] = fmaf(a1, wv.y, acc1[4 * q + 1]);
+          acc1[4 * q + 2] = fmaf(a1, wv.z, acc1[4 * q + 2]);
+          acc1[4 * q + 3] = fmaf(a1, wv.w, acc1[4 * q + 3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int gy = h0 + ty + 8 * half, gx = w0 + tx;
+    if (gy < H && gx < W) {
+      float* acc = half ? acc1 : acc0;
+      OutT* o = out + ((static_cast<long>(n) * H + gy) * W + gx) * out_cstride;
+      if constexpr (sizeof(OutT) == 2) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float a = acc[2 * i], b = acc[2 * i + 1];
+          a = a > 0.f ? a : a * slope;
+          b = b > 0.f ? b : b * slope;
+          __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+          pk[i] = *reinterpret_cast<uint32_t*>(&t);
+        }
+        reinterpret_cast<uint4*>(o)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        reinterpret_cast<uint4*>(o)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 v;
+          v.x = acc[4 * i], v.y = acc[4 * i + 1], v.z = acc[4 * i + 2], v.w = acc[4 * i + 3];
+          v.x = v.x > 0.f ? v.x : v.x * slope;
+          v.y = v.y > 0.f ? v.y : v.y * slope;
+          v.z = v.z > 0.f ? v.z : v.z * slope;
+          v.w = v.w > 0.f ? v.w : v.w * slope;
+          reinterpret_cast<float4*>(o)[i] = v;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// 2x2 / stride 2 max-pool (nn.MaxPool2d(2), model/pose_dla_dcn.py:306), NHWC.
+// One thread per 8 channels (bf16) / 4 channels (fp32): 16-byte vectors.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool2x2_kernel(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int C,
+                                  int in_cstride, int out_cstride) {
+  constexpr int V = 16 / sizeof(T);
+  const int Ho = H / 2, Wo = W / 2, cv = C / V;
+  const long total = static_cast<long>(N) * Ho * Wo * cv;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv) * V;
+    long r = i / cv;
+    const int x = static_cast<int>(r % Wo);
+    r /= Wo;
+    const int y = static_cast<int>(r % Ho);
+    const int n = static_cast<int>(r / Ho);
+    const T* p00 = in + ((static_cast<long>(n) * H + 2 * y) * W + 2 * x) * in_cstride + c;
+    const T* p10 = p00 + static_cast<long>(W) * in_cstride;
+    T a[V], b[V], cc[V], d[V], o[V];
+    *reinterpret_cast<uint4*>(a) = __ldg(reinterpret_cast<const uint4*>(p00));
+    *reinterpret_cast<uint4*>(b) = __ldg(reinterpret_cast<const uint4*>(p00 + in_cstride));
+    *reinterpret_cast<uint4*>(cc) = __ldg(reinterpret_cast<const uint4*>(p10));
+    *reinterpret_cast<uint4*>(d) = __ldg(reinterpret_cast<const uint4*>(p10 + in_cstride));
+#pragma unroll
+    for (int k = 0; k < V; ++k) o[k] = from_f<T>(fmaxf(fmaxf(to_f(a[k]), to_f(b[k])), fmaxf(to_f(cc[k]), to_f(d[k]))));
+    *reinterpret_cast<uint4*>(out + ((static_cast<long>(n) * Ho + y) * Wo + x) * out_cstride + c) =
+        *reinterpret_cast<uint4*>(o);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// IDAUp: depthwise ConvTranspose2d(k = 2f, stride f, pad f/2, groups = C, no
+// bias) followed by "+ skip" (model/pose_dla_dcn.py:536-552).  Output pixel
+// (oy, ox) gathers the <= ceil(k/f)^2 = 4 input pixels that reach it:
+//   oy = iy * f - pad + ky   <=>   iy = (oy + pad - ky) / f   when divisible.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void upsample_add_kernel(const T* __restrict__ x, const float* __restrict__ wt, const T* __restrict__ skip,
+                                    T* __restrict__ out, int N, int H, int W, int C, int f, int x_cstride,
+                                    int skip_cstride, int out_cstride) {
+  constexpr int V = 16 / sizeof(T);
+  const int k = 2 * f, pad = f / 2;
+  const int Ho = H * f, Wo = W * f, cv = C / V;
+  const long total = static_cast<long>(N) * Ho * Wo * cv;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv) * V;
+    long r = i / cv;
+    const int ox = static_cast<int>(r % Wo);
+    r /= Wo;
+    const int oy = static_cast<int>(r % Ho);
+    const int n = static_cast<int>(r / Ho);
+    float acc[V];
+    if (skip != nullptr) {
+      T s[V];
+      *reinterpret_cast<uint4*>(s) =
+          __ldg(reinterpret_cast<const uint4*>(skip + ((static_cast<long>(n) * Ho + oy) * Wo + ox) * skip_cstride + c));
+#pragma unroll
+      for (int q = 0; q < V; ++q) acc[q] = to_f(s[q]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < V; ++q) acc[q] = 0.f;
+    }
+    float up[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) up[q] = 0.f;
+    for (int ky = (oy + pad) % f; ky < k; ky += f) {
+      const int iy = (oy + pad - ky) / f;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = (ox + pad) % f; kx < k; kx += f) {
+        const int ix = (ox + pad - kx) / f;
+        if (ix < 0 || ix >= W) continue;
+        T v[V];
+        *reinterpret_cast<uint4*>(v) =
+            __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<long>(n) * H + iy) * W + ix) * x_cstride + c));
+#pragma unroll
+        for (int q = 0; q < V; ++q) up[q] = fmaf(to_f(v[q]), __ldg(wt + (c + q) * k * k + ky * k + kx), up[q]);
+      }
+    }
+    T o[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) o[q] = from_f<T>(up[q] + acc[q]);
+    *reinterpret_cast<uint4*>(out + ((static_cast<long>(n) * Ho + oy) * Wo + ox) * out_cstride + c) =
+        *reinterpret_cast<uint4*>(o);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Class softmax over the K classes of every (anchor, pixel), fg probability
+// 1 - p_bg, its top-1 anchor per pixel, detection score / class, and the
+// reference's flattened output layout (model/M3d_inference_align.py:229-234,
+// 300-301; lib/rpn_util.py:892-901, 1510-1511):
+//   logits NHWC fp32 [N,H,W,K*A], channel = class * A + anchor
+//   cls, prob  [N, (a*H + h)*W + w, K]
+// One block per (n, h, 32-pixel segment); tile staged in shared memory so both
+// the NHWC reads and the anchor-major writes are coalesced.
+// ---------------------------------------------------------------------------
+constexpr int SM_PIX = 32;
+
+__global__ void __launch_bounds__(256) cls_softmax_kernel(const float* __restrict__ logits, int lc_stride, int N, int H,
+                                                          int W, int A, int K, float* __restrict__ cls_out,
+                                                          float* __restrict__ prob_out, float* __restrict__ fg_max,
+                                                          int* __restrict__ fg_arg, float* __restrict__ score,
+                                                          unsigned char* __restrict__ cls_pred) {
+  extern __shared__ float s_tile[];  // [SM_PIX][K*A + 1]
+  const int KA = K * A, ld = KA + 1;
+  const int w0 = blockIdx.x * SM_PIX, h = blockIdx.y, n = blockIdx.z;
+  const int npix = min(SM_PIX, W - w0);
+  const float* src = logits + ((static_cast<long>(n) * H + h) * W + w0) * lc_stride;
+  for (int i = threadIdx.x; i < npix * KA; i += blockDim.x) {
+    const int px = i / KA, c = i - px * KA;
+    s_tile[px * ld + c] = __ldg(src + static_cast<long>(px) * lc_stride + c);
+  }
+  __syncthreads();
+  // softmax per (pixel, anchor): thread -> (a, px) with px fastest so writes are contiguous in w
+  for (int i = threadIdx.x; i < A * SM_PIX; i += blockDim.x) {
+    const int px = i % SM_PIX, a = i / SM_PIX;
+    if (px >= npix) continue;
+    float v[8];
+    float mx = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+      v[k] = s_tile[px * ld + k * A + a];
+      mx = fmaxf(mx, v[k]);
+    }
+    float sum = 0.f;
+    float e[8];
+    for (int k = 0; k < K; ++k) {
+      e[k] = expf(v[k] - mx);
+      sum += e[k];
+    }
+    const long row = (static_cast<long>(n) * A + a) * H * W + static_cast<long>(h) * W + (w0 + px);
+    float best = -1.f;
+    int bestk = 1;
+    for (int k = 0; k < K; ++k) {
+      const float p = e[k] / sum;
+      cls_out[row * K + k] = v[k];
+      prob_out[row * K + k] = p;
+      if (k >= 1 && p > best) {
+        best = p;
+        bestk = k;
+      }
+      if (k == 0) s_tile[px * ld + a] = 1.f - p;  // fg prob overwrites the class-0 logit slot
+    }
+    score[row] = best;
+    cls_pred[row] = static_cast<unsigned char>(bestk);
+  }
+  __syncthreads();
+  if (threadIdx.x < npix) {
+    const int px = threadIdx.x;
+    float best = -1.f;
+    int arg = 0;
+    for (int a = 0; a < A; ++a) {
+      const float f = s_tile[px * ld + a];
+      if (f > best) {  // first maximum wins, like torch.max / topk(k=1)
+        best = f;
+        arg = a;
+      }
+    }
+    const long pix = (static_cast<long>(n) * H + h) * W + w0 + px;
+    fg_max[pix] = best;
+    fg_arg[pix] = arg;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// shape_align offsets (model/module/feturealign_mgpu.py:119-136, 160-172):
+// tap (i, j) of the 3x3 DCNv2 moves by ((ah/stride/3 - 1)(i - 1), (aw/stride/3 - 1)(j - 1))
+// for the top-1 anchor, zeroed where fg <= thresh; modulation mask = fg.
+// om layout: [N,H,W,27] = 18 offsets (dh, dw per tap) + 9 masks.
+// ---------------------------------------------------------------------------
+__global__ void shape_align_om_kernel(const float* __restrict__ fg_max, const int* __restrict__ fg_arg,
+                                      const float* __restrict__ anchors, int anchor_ld, float feat_stride, float thresh,
+                                      float* __restrict__ om, long npix) {
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (i >= npix) return;
+  const float fg = fg_max[i];
+  const int a = fg_arg[i];
+  const float hard = fg > thresh ? 1.f : 0.f;
+  const float aw = anchors[a * anchor_ld + 2] - anchors[a * anchor_ld + 0];
+  const float ah = anchors[a * anchor_ld + 3] - anchors[a * anchor_ld + 1];
+  const float hstep = ah / feat_stride / 3.f - 1.f;
+  const float wstep = aw / feat_stride / 3.f - 1.f;
+  float* o = om + i * 27;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int ti = t / 3, tj = t % 3;
+    o[2 * t] = hstep * (static_cast<float>(ti) - 1.5f + 0.5f) * hard;
+    o[2 * t + 1] = wstep * (static_cast<float>(tj) - 1.5f + 0.5f) * hard;
+    o[18 + t] = fg;
+  }
+}
+
+// center_align offsets (feturealign_mgpu.py:58-77): the 1x1 DCNv2 samples at
+// (dy, dx) = ((by*std_y + mean_y) * ah/stride, (bx*std_x + mean_x) * aw/stride)
+// of the top-1 anchor, zeroed where fg <= thresh; mask = fg.  om: [N,H,W,3].
+__global__ void center_align_om_kernel(const float* __restrict__ fg_max, const int* __restrict__ fg_arg,
+                                       const float* __restrict__ heads, int heads_cstride, int x_coff, int y_coff,
+                                       const float* __restrict__ anchors, int anchor_ld, float feat_stride,
+                                       float mean_x, float mean_y, float std_x, float std_y, float thresh,
+                                       float* __restrict__ om, int om_cstride, long npix) {
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (i >= npix) return;
+  const float fg = fg_max[i];
+  const int a = fg_arg[i];
+  const float hard = fg > thresh ? 1.f : 0.f;
+  const float aw = (anchors[a * anchor_ld + 2] - anchors[a * anchor_ld + 0]) / feat_stride;
+  const float ah = (anchors[a * anchor_ld + 3] - anchors[a * anchor_ld + 1]) / feat_stride;
+  const float bx = heads[i * heads_cstride + x_coff + a];
+  const float by = heads[i * heads_cstride + y_coff + a];
+  om[i * om_cstride + 0] = (by * std_y + mean_y) * ah * hard;
+  om[i * om_cstride + 1] = (bx * std_x + mean_x) * aw * hard;
+  om[i * om_cstride + 2] = fg;
+}
+
+// ---------------------------------------------------------------------------
+// flatten_tensor + cat for the regression heads (M3d_inference_align.py:280-295):
+//   heads NHWC fp32 [N,H,W,11*A] (head-major: x,y,w,h,x3d,y3d,z3d,w3d,h3d,l3d,rY3d)
+//   bbox_2d [N, (a*H + h)*W + w, 4], bbox_3d [N, same, 7]
+// ---------------------------------------------------------------------------
+struct HeadSlots {
+  int s[11];  // buffer slot (36-channel group) of x,y,w,h,x3d,y3d,z3d,w3d,h3d,l3d,rY3d
+};
+
+__global__ void __launch_bounds__(256) flatten_heads_kernel(const float* __restrict__ heads, int hc_stride, int N, int H,
+                                                            int W, int A, const HeadSlots slots,
+                                                            float* __restrict__ bbox_2d, float* __restrict__ bbox_3d) {
+  extern __shared__ float s_tile[];  // [SM_PIX][11*A + 1]
+  const int C = 11 * A, ld = C + 1;
+  const int w0 = blockIdx.x * SM_PIX, h = blockIdx.y, n = blockIdx.z;
+  const int npix = min(SM_PIX, W - w0);
+  const float* src = heads + ((static_cast<long>(n) * H + h) * W + w0) * hc_stride;
+  for (int i = threadIdx.x; i < npix * C; i += blockDim.x) {
+    const int px = i / C, c = i - px * C;
+    s_tile[px * ld + c] = __ldg(src + static_cast<long>(px) * hc_stride + c);
+  }
+  __syncthreads();
+  // bbox_2d: 4 floats per row; thread -> (a, px, j) with (px, j) fastest
+  for (int i = threadIdx.x; i < A * SM_PIX * 4; i += blockDim.x) {
+    const int j = i & 3, px = (i >> 2) % SM_PIX, a = i / (4 * SM_PIX);
+    if (px >= npix) continue;
+    const long row = (static_cast<long>(n) * A + a) * H * W + static_cast<long>(h) * W + (w0 + px);
+    bbox_2d[row * 4 + j] = s_tile[px * ld + slots.s[j] * A + a];
+  }
+  for (int i = threadIdx.x; i < A * SM_PIX * 7; i += blockDim.x) {
+    const int j = i % 7, px = (i / 7) % SM_PIX, a = i / (7 * SM_PIX);
+    if (px >= npix) continue;
+    const long row = (static_cast<long>(n) * A + a) * H * W + static_cast<long>(h) * W + (w0 + px);
+    bbox_3d[row * 7 + j] = s_tile[px * ld + slots.s[4 + j] * A + a];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Layout conversion for the NCHW drop-in operators (DCNv2 / ANAB modules).
+// 32x32 shared-memory transpose between (C) and (H*W).
+// ---------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void nchw_to_nhwc_kernel(const TI* __restrict__ in, TO* __restrict__ out, int C, int HW, int out_cstride,
+                                    int out_coff) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < HW) tile[i][threadIdx.x] = to_f(in[(static_cast<long>(n) * C + c) * HW + p]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (c < C && p < HW) out[(static_cast<long>(n) * HW + p) * out_cstride + out_coff + c] = from_f<TO>(tile[threadIdx.x][i]);
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void nhwc_to_nchw_kernel(const TI* __restrict__ in, TO* __restrict__ out, int C, int HW, int in_cstride,
+                                    int in_coff) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (c < C && p < HW) tile[i][threadIdx.x] = to_f(in[(static_cast<long>(n) * HW + p) * in_cstride + in_coff + c]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < HW) out[(static_cast<long>(n) * C + c) * HW + p] = from_f<TO>(tile[threadIdx.x][i]);
+  }
+}
+
+}  // namespace m3d
+
+using namespace m3d;
+
+static inline cudaStream_t S(m3d_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" int m3d_stem_conv7x7(const float* image_nchw, const float* weight, const float* bias, void* out, int out_dtype,
+                                int out_cstride, int N, int H, int W, float slope, m3d_stream_t stream) {
+  M3D_REQUIRE(image_nchw && weight && bias && out, "NULL pointer");
+  M3D_REQUIRE(out_cstride >= 16 && out_cstride % 8 == 0, "out_cstride=%d", out_cstride);
+  dim3 grid(cdiv(W, STEM_TW), cdiv(H, STEM_TH), N);
+  if (out_dtype == M3D_BF16)
+    stem_conv7x7_kernel<__nv_bfloat16><<<grid, 256, 0, S(stream)>>>(image_nchw, weight, bias,
+                                                                    static_cast<__nv_bfloat16*>(out), out_cstride, N, H, W, slope);
+  else
+    stem_conv7x7_kernel<float><<<grid, 256, 0, S(stream)>>>(image_nchw, weight, bias, static_cast<float*>(out),
+                                                            out_cstride, N, H, W, slope);
+  M3D_CUDA_OK(cudaGetLastError());
+  return M3D_OK;
+}
+
+extern "C" int m3d_maxpool2x2_nhwc(const void* in, void* out, int dtype, int N, int H, int W, int C, int in_cstride,
+                                   int out_cstride, m3d_stream_t stream) {
+  M3D_REQUIRE(in && out, "NULL pointer");
+  M3D_REQUIRE(H % 2 == 0 && W % 2 == 0, "max-pool needs even H, W (got %dx%d)", H, W);
+  const int V = dtype == M3D_BF16 ? 8 : 4;
+  M3D_REQUIRE(C % V == 0 && in_cstride % V == 0 && out_cstride % V == 0, "channels must keep 16-byte vectors");
+  const long total = static_cast<long>(N) * (H / 2) * (W / 2) * (C / V);
+  const int grid = static_cast<int>(std::min<long>((total + 255) / 256, 148L * 16));
+  if (dtype == M3D_BF16)
+    maxpool2x2_kernel<__nv_bfloat16><<<grid, 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(in),
+                                                                  static_cast<__nv_bfloat16*>(out), N, H, W, C, in_cstride, out_cstride);
+  else
+    maxpool2x2_kernel<float><<<grid, 256, 0, S(stream)>>>(static_cast<const float*>(in), static_cast<float*>(out), N, H,
+                                                          W, C, in_cstride, out_cstride);
+  M3D_CUDA_OK(cudaGetLastError());
+  return M3D_OK;
+}
+
+extern "C" int m3d_upsample_add_nhwc(const void* x, const float* weight, const void* skip, void* out, int dtype, int N,
+                                     int H, int W, int C, int f, int x_cstride, int skip_cstride, int out_cstride,
+                                     m3d_stream_t stream) {
+  M3D_REQUIRE(x && weight && out, "NULL pointer");
+  M3D_REQUIRE(f >= 1 && f <= 8, "up-sampling factor %d", f);
+  const int V = dtype == M3D_BF16 ? 8 : 4;
+  M3D_REQUIRE(C % V == 0 && x_cstride % V == 0 && out_cstride % V == 0 && (skip == nullptr || skip_cstride % V == 0),
+              "channels must keep 16-byte vectors");
+  const long total = static_cast<long>(N) * H * f * W * f * (C / V);
+  const int grid = static_cast<int>(std::min<long>((total + 255) / 256, 148L * 16));
+  if (dtype == M3D_BF16)
+    upsample_add_kernel<__nv_bfloat16><<<grid, 256, 0, S(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), weight, static_cast<const __nv_bfloat16*>(skip),
+        static_cast<__nv_bfloat16*>(out), N, H, W, C, f, x_cstride, skip_cstride, out_cstride);
+  else
+    upsample_add_kernel<float><<<grid, 256, 0, S(stream)>>>(static_cast<const float*>(x), weight,
+                                                            static_cast<const float*>(skip), static_cast<float*>(out), N,
+                                                            H, W, C, f, x_cstride, skip_cstride, out_cstride);
+  M3D_CUDA_OK(cudaGetLastError());
+  return M3D_OK;
+}
+
+extern "C" int m3d_cls_softmax(const float* logits, int logits_cstride, int N, int H, int W, int A, int K, float* cls_out,
+                               float* prob_out, float* fg_max, int* fg_arg, float* score, unsigned char* cls_pred,
+                               m3d_stream_t stream) {
+  M3D_REQUIRE(logits && cls_out && prob_out && fg_max && fg_arg && score && cls_pred, "NULL pointer");
+  M3D_REQUIRE(K >= 2 && K <= 8 && A >= 1, "K=%d A=%d unsupported", K, A);
+  const size_t smem = static_cast<size_t>(SM_PIX) * (K * A + 1) * sizeof(float);
+  M3D_REQUIRE(smem <= 48 * 1024, "K*A too large");
+  dim3 grid(cdiv(W, SM_PIX), H, N);
+  cls_softmax_kernel<<<grid, 256, smem, S(stream)>>>(logits, logits_cstride, N, H, W, A, K, cls_out, prob_out, fg_max,
+                                                     fg_arg, score, cls_pred);
+  M3D_CUDA_OK(cudaGetLastError());
+  return M3D_OK;
+}
+
+extern "C" int m3d_shape_align_om(const float* fg_max, const int* fg_arg, const float* anchors, int anchor_ld,
+                                  float feat_stride, float thresh, float* om, long npix, m3d_stream_t stream) {
+  M3D_REQUIRE(fg_max && fg_arg && anchors && om, "NULL pointer");
+  shape_align_om_kernel<<<cdiv(npix, 256), 256, 0, S(stream)>>>(fg_max, fg_arg, anchors, anchor_ld, feat_stride, thresh,
+                                                                om, npix);
+  M3D_CUDA_OK(cudaGetLastError());
+  return M3D_OK;
+}
+
+extern "C" int m3d_center_align_om(const float* fg_max, const int* fg_arg, const float* heads, int heads_cstride,
+                                   int x_coff, int y_coff, const float* anchors, int anchor_ld, float feat_stride,
+                                   float mean_x, float mean_y, float std_x, float std_y, float thresh, float* om,
+                                   int om_cstride, long npix, m3d_stream_t stream) {
+  M3D_REQUIRE(fg_max && fg_arg && heads && anchors && om, "NULL pointer");
+  M3D_REQUIRE(om_cstride >= 3, "om_cstride=%d", om_cstride);
+  center_align_om_kernel<<<cdiv(npix, 256), 256, 0, S(stream)>>>(fg_max, fg_arg, heads, heads_cstride, x_coff, y_coff,
+                                                                 anchors, anchor_ld, feat_stride, mean_x, mean_y, std_x,
+                                                                 std_y, thresh, om, om_cstride, npix);
+  M3D_CUDA_OK(cudaGetLastError());
+  return M3D_OK;
+}
+
+extern "C" int m3d_flatten_heads(const float* heads, int heads_cstride, int N, int H, int W, int A,
+                                 const int* slot_of_output, float* bbox_2d, float* bbox_3d, m3d_stream_t stream) {
+  M3D_REQUIRE(heads && bbox_2d && bbox_3d && slot_of_output, "NULL pointer");
+  HeadSlots slots;
+  for (int i = 0; i < 11; ++i) {
+    M3D_REQUIRE(slot_of_output[i] >= 0 && slot_of_output[i] < 11, "bad head slot");
+    slots.s[i] = slot_of_output[i];
+  }
+  const size_t smem = static_cast<size_t>(SM_PIX) * (11 * A + 1) * sizeof(float);
+  M3D_REQUIRE(smem <= 96 * 1024, "A too large");
+  static bool configured = false;
+  if (!configured) {
+    M3D_CUDA_OK(cudaFuncSetAttribute(flatten_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    configured = true;
+  }
+  dim3 grid(cdiv(W, SM_PIX), H, N);
+  flatten_heads_kernel<<<grid, 256, smem, S(stream)>>>(heads, heads_cstride, N, H, W, A, slots, bbox_2d, bbox_3d);
+  M3D_CUDA_OK(cudaGetLastError());
+  return M3D_OK;
+}
+
+extern "C" int m3d_nchw_to_nhwc(const void* in, int in_dtype, void* out, int out_dtype, int N, int C, int H, int W,
+                                int out_cstride, int out_coff, m3d_stream_t stream) {
+  M3D_REQUIRE(in && out, "NULL pointer");
+  M3D_REQUIRE(in_dtype == M3D_F32, "NCHW side must be fp32");
+  const int HW = H * W;
+  dim3 grid(cdiv(HW, 32), cdiv(C, 32), N), block(32, 8);
+  if (out_dtype == M3D_BF16)
+    nchw_to_nhwc_kernel<float, __nv_bfloat16><<<grid, block, 0, S(stream)>>>(
+        static_cast<const float*>(in), static_cast<__nv_bfloat16*>(out), C, HW, out_cstride, out_coff);
+  else
+    nchw_to_nhwc_kernel<float, float><<<grid, block, 0, S(stream)>>>(static_cast<const float*>(in),
+                                                                     static_cast<float*>(out), C, HW, out_cstride, out_coff);
+  M3D_CUDA_OK(cudaGetLastError());
+  return M3D_OK;
+}
+
+extern "C" int m3d_nhwc_to_nchw(const void* in, int in_dtype, void* out, int out_dtype, int N, int C, int H, int W,
+                                int in_cstride, int in_coff, m3d_stream_t stream) {
+  M3D_REQUIRE(in && out, "NULL pointer");
+  M3D_REQUIRE(out_dtype == M3D_F32, "NCHW side must be fp32");
+  const int HW = H * W;
+  dim3 grid(cdiv(HW, 32), cdiv(C, 32), N), block(32, 8);
+  if (in_dtype == M3D_BF16)
+    nhwc_to_nchw_kernel<__nv_bfloat16, float><<<grid, block, 0, S(stream)>>>(
+        static_cast<const __nv_bfloat16*>(in), static_cast<float*>(out), C, HW, in_cstride, in_coff);
+  else
+    nhwc_to_nchw_kernel<float, float><<<grid, block, 0, S(stream)>>>(static_cast<const float*>(in),
+                                                                     static_cast<float*>(out), C, HW, in_cstride, in_coff);
+  M3D_CUDA_OK(cudaGetLastError());
+  return M3D_OK;
+}

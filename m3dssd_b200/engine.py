@@ -1,0 +1,395 @@
+"""Fused inference engine for the M3DSSD dense forward path.
+
+Reads the parameters of an RPN module (m3dssd_b200/model/M3d_inference_align.py,
+same state-dict layout as the reference), folds every eval-mode BatchNorm into
+the preceding convolution, packs weights for the tcgen05 kernels, pre-allocates
+all NHWC activations for a fixed (batch, H, W) and records the layer sequence
+as a list of C-ABI calls that is replayed per batch -- optionally as one CUDA
+graph.  Torch provides device memory and streams only.
+
+Forward path covered (reference file:line):
+  DLA trunk ............. model/pose_dla_dcn.py:330-397 (+ Tree :272-327, BasicBlock :93-121, Root :251-269)
+  DLAUp / IDAUp ......... model/pose_dla_dcn.py:519-578, 687-696; DeformConv :471-485; DCN model/DCNv2/dcn_v2.py:64-70
+  heads, softmax, align . model/M3d_inference_align.py:215-301; model/module/feturealign_mgpu.py
+  ANAB .................. model/module/attention.py:183-216
+  decode + NMS .......... lib/rpn_util.py:1444-1555; lib/nms/nms_kernel.cu
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+from .model import pose_dla_dcn as dla
+
+HEAD_ORDER = ["bbox_x", "bbox_y", "bbox_x3d", "bbox_y3d", "bbox_w", "bbox_h", "bbox_w3d", "bbox_h3d", "bbox_l3d",
+              "bbox_rY3d", "bbox_z3d"]  # slot order in the heads buffer (grouped by shared input)
+# output columns x,y,w,h | x3d,y3d,z3d,w3d,h3d,l3d,rY3d -> slot
+OUT_SLOTS = [0, 1, 4, 5, 2, 3, 10, 6, 7, 8, 9]
+
+
+class Act:
+    """An NHWC activation: `c` real channels inside a buffer with t.shape[-1] channels per pixel."""
+
+    def __init__(self, t, c, coff=0):
+        self.t, self.c, self.coff = t, c, coff
+
+
+def _fold(conv_w, conv_b, bn):
+    w = conv_w.detach().float()
+    b = conv_b.detach().float() if conv_b is not None else torch.zeros(w.shape[0], device=w.device)
+    if bn is not None:
+        scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+        w = w * scale.view(-1, 1, 1, 1)
+        b = (b - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+    return w, b
+
+
+class Engine:
+    def __init__(self, net, batch, height, width, precision="bf16", use_graph=True, topk=None, max_out=None):
+        assert precision in ("bf16", "fp32")
+        if not torch.cuda.is_available():
+            raise RuntimeError("m3dssd_b200.Engine needs a CUDA device: there is no CPU fallback")
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.net = net
+        self.conf = net.conf
+        self.B, self.H, self.W = batch, height, width
+        self.fp32 = precision == "fp32"
+        self.precision = precision
+        self.adt = torch.float32 if self.fp32 else torch.bfloat16
+        self.ops = []
+        self.bufs = {}
+        self.named = {}  # name -> Act of notable intermediate activations (parity checks)
+        self.n_launches = 0
+        self.use_graph = use_graph
+        self.graph = None
+        self.A = net.num_anchors
+        self.K = net.num_classes
+        self.topk = int(topk or self.conf.nms_topN_pre)
+        self.max_out = int(max_out or self.conf.nms_topN_post)
+        self.image = torch.zeros(batch, 3, height, width, dtype=torch.float32, device=self.dev)
+        with torch.no_grad():
+            self._build()
+
+    # ------------------------------------------------------------------ utils
+    def _cpad(self, c):
+        return (c + 63) // 64 * 64 if self.fp32 else c
+
+    def _new(self, name, n, h, w, c, dtype=None):
+        t = torch.zeros(n, h, w, c, dtype=dtype or self.adt, device=self.dev)
+        self.bufs[name] = t
+        return t
+
+    def _add(self, fn, launches=1):
+        self.ops.append(fn)
+        self.n_launches += launches
+
+    def _conv(self, name, inputs, w, b, bn, k, stride=1, pad=None, slope=0.01, res=None, out=None, out_dtype=None,
+              om=None, sigmoid_mask=False, out_coff=0):
+        """Register conv(+BN)(+res)(+LeakyReLU) over concatenated NHWC inputs; returns the output Act."""
+        pad = k // 2 if pad is None else pad
+        wf, bf = _fold(w, b, bn)
+        cout = wf.shape[0]
+        splits = [(a.c, self._cpad(a.c)) for a in inputs]
+        hi, lo = ops.pack_conv_weight(wf.cpu(), in_splits=splits, fp32_mode=self.fp32)
+        hi = hi.to(self.dev)
+        lo = lo.to(self.dev) if lo is not None else None
+        bias = bf.to(self.dev).contiguous()
+        x0 = inputs[0].t
+        N, H, W = x0.shape[:3]
+        P = (H + 2 * pad - k) // stride + 1
+        Q = (W + 2 * pad - k) // stride + 1
+        if out is None:
+            odt = out_dtype or self.adt
+            cbuf = self._cpad(cout) if odt == self.adt else cout
+            out = self._new(name, N, P, Q, cbuf, odt)
+        ins = [(a.t, a.coff, self._cpad(a.c)) for a in inputs]
+        res_t = res.t if res is not None else None
+        res_coff = res.coff if res is not None else 0
+        om_t = om
+
+        def run():
+            ops.conv2d_nhwc(ins, hi, out, R=k, S=k, stride=stride, pad=pad, Cout=cout, bias=bias, res=res_t,
+                            res_coff=res_coff, slope=slope, weight_lo=lo, om=om_t, sigmoid_mask=sigmoid_mask,
+                            out_coff=out_coff)
+
+        self._add(run)
+        return Act(out, cout, out_coff)
+
+    def _conv_module(self, name, inputs, conv, bn, slope=0.01, res=None, **kw):
+        return self._conv(name, inputs, conv.weight, conv.bias, bn, conv.kernel_size[0], conv.stride[0],
+                          conv.padding[0], slope, res, **kw)
+
+    def _maxpool(self, name, a):
+        N, H, W, cs = a.t.shape
+        out = self._new(name, N, H // 2, W // 2, cs)
+        x = a.t
+        self._add(lambda: ops.maxpool2x2(x, out))
+        return Act(out, a.c)
+
+    # ------------------------------------------------------------- DLA trunk
+    def _basic_block(self, name, blk, x, residual):
+        if not isinstance(blk, dla.BasicBlock):
+            raise NotImplementedError("fused engine implements BasicBlock trunks (dla34); got %s" % type(blk).__name__)
+        y = self._conv_module(name + ".conv1", [x], blk.conv1, blk.bn1)
+        return self._conv_module(name + ".conv2", [y], blk.conv2, blk.bn2, res=residual if residual is not None else x)
+
+    def _tree(self, name, tree, x, children=None):
+        children = [] if children is None else children
+        bottom = self._maxpool(name + ".down", x) if tree.downsample is not None else x
+        if tree.level_root:
+            children.append(bottom)
+        if tree.levels == 1:
+            residual = bottom
+            if tree.project is not None:
+                residual = self._conv_module(name + ".project", [bottom], tree.project[0], tree.project[1], slope=1.0)
+            x1 = self._basic_block(name + ".tree1", tree.tree1, x, residual)
+            x2 = self._basic_block(name + ".tree2", tree.tree2, x1, None)
+            root = tree.root
+            ins = [x2, x1] + children
+            return self._conv_module(name + ".root", ins, root.conv, root.bn, res=x2 if root.residual else None)
+        # levels > 1: the reference also evaluates self.project(bottom) here, but the nested
+        # tree1 recomputes its own residual and never reads it (model/pose_dla_dcn.py:314-320): skipped.
+        x1 = self._tree(name + ".tree1", tree.tree1, x)
+        children.append(x1)
+        return self._tree(name + ".tree2", tree.tree2, x1, children)
+
+    def _trunk(self):
+        base = self.net.base.base
+        B, H, W = self.B, self.H, self.W
+        w, b = _fold(base.base_layer[0].weight, None, base.base_layer[1])
+        w, b = w.to(self.dev).contiguous(), b.to(self.dev).contiguous()
+        c0 = w.shape[0]
+        assert c0 == 16, "stem kernel is specialised for 16 output channels"
+        s0 = self._new("stem", B, H, W, self._cpad(c0))
+        img = self.image
+        self._add(lambda: ops.stem_conv7x7(img, w, b, s0, 0.01))
+        x = Act(s0, c0)
+        x = self._conv_module("level0", [x], base.level0[0], base.level0[1])
+        levels = [x]
+        x = self._conv_module("level1", [x], base.level1[0], base.level1[1])
+        levels.append(x)
+        for i in range(2, 6):
+            x = self._tree("level%d" % i, getattr(base, "level%d" % i), x)
+            levels.append(x)
+        for i, a in enumerate(levels):
+            self.named["level%d" % i] = a
+        return levels
+
+    # ----------------------------------------------------------- aggregation
+    def _deform_conv(self, name, m, x):
+        """DeformConv = DCN 3x3 -> BN -> LeakyReLU (model/pose_dla_dcn.py:471-485), BN folded into the DCN."""
+        dcn = m.conv
+        N, H, W = x.t.shape[:3]
+        om = self._new(name + ".om", N, H, W, 32, torch.float32)
+        self._conv_module(name + ".offset", [x], dcn.conv_offset_mask, None, slope=1.0, out=om)
+        return self._conv(name, [x], dcn.weight, dcn.bias, m.actf[0], 3, 1, 1, 0.01, om=om, sigmoid_mask=True)
+
+    def _ida_up(self, name, ida, layers, startp, endp):
+        for i in range(startp + 1, endp):
+            k = i - startp
+            proj, up, node = (getattr(ida, "%s_%d" % (n, k)) for n in ("proj", "up", "node"))
+            p = self._deform_conv("%s.proj_%d" % (name, k), proj, layers[i])
+            f = up.stride[0]
+            N, H, W, cs = p.t.shape
+            skip = layers[i - 1]
+            u = self._new("%s.up_%d" % (name, k), N, H * f, W * f, cs)
+            wt = up.weight.detach().float().reshape(up.weight.shape[0], -1).contiguous().to(self.dev)
+            pt, st = p.t, skip.t
+            self._add(lambda pt=pt, wt=wt, st=st, u=u, f=f: ops.upsample_add(pt, wt, st, u, f))
+            layers[i] = self._deform_conv("%s.node_%d" % (name, k), node, Act(u, p.c))
+
+    def _dla_seg(self):
+        seg = self.net.base
+        layers = self._trunk()
+        first, last = seg.first_level, seg.last_level
+        out = [layers[-1]]
+        for i in range(len(layers) - first - 1):
+            self._ida_up("dla_up.ida_%d" % i, getattr(seg.dla_up, "ida_%d" % i), layers, len(layers) - i - 2,
+                         len(layers))
+            out.insert(0, layers[-1])
+        y = [out[i] for i in range(last - first)]  # the reference clones; nothing writes in place here
+        self._ida_up("ida_up", seg.ida_up, y, 0, len(y))
+        return y[-1]
+
+    # ------------------------------------------------------------------ heads
+    def _head_group(self, gname, names, x, heads_buf):
+        """Three-layer 1x1 heads that share input x; layer 1 is one wide GEMM, layers 2-3 are grouped GEMMs."""
+        net, A = self.net, self.A
+        mods = [getattr(net, n) for n in names]
+        slot0 = HEAD_ORDER.index(names[0])
+        assert [HEAD_ORDER.index(n) for n in names] == list(range(slot0, slot0 + len(names)))
+        N, H, W = x.t.shape[:3]
+        G = len(names)
+        mid = mods[0][0].out_channels
+        if self.fp32:
+            for g, m in enumerate(mods):
+                h1 = self._conv_module("%s.%d.l1" % (gname, g), [x], m[0], m[1])
+                h2 = self._conv_module("%s.%d.l2" % (gname, g), [h1], m[3], m[4])
+                self._conv_module("%s.%d.l3" % (gname, g), [h2], m[6], None, slope=1.0, out=heads_buf,
+                                  out_coff=(slot0 + g) * A)
+            return
+        # layer 1: concatenated output channels
+        w1 = torch.cat([_fold(m[0].weight, m[0].bias, m[1])[0] for m in mods])
+        b1 = torch.cat([_fold(m[0].weight, m[0].bias, m[1])[1] for m in mods])
+        h1 = self._conv("%s.l1" % gname, [x], w1, b1, None, 1, 1, 0, 0.01)
+        # layers 2 and 3: groups
+        h2 = self._new("%s.l2" % gname, N, H, W, G * mid)
+        w2 = torch.cat([ops.pack_conv_weight(_fold(m[3].weight, m[3].bias, m[4])[0].cpu())[0] for m in mods]).to(self.dev)
+        b2 = torch.cat([_fold(m[3].weight, m[3].bias, m[4])[1] for m in mods]).to(self.dev).contiguous()
+        rows3 = (A + 15) // 16 * 16
+        w3 = torch.zeros(G * rows3, mid, dtype=torch.bfloat16)
+        b3 = torch.zeros(G * rows3, dtype=torch.float32)
+        for g, m in enumerate(mods):
+            w3[g * rows3:g * rows3 + A] = ops.pack_conv_weight(m[6].weight.detach().float().cpu())[0]
+            b3[g * rows3:g * rows3 + A] = m[6].bias.detach().float().cpu()
+        w3, b3 = w3.to(self.dev), b3.to(self.dev)
+        h1t = h1.t
+
+        def run():
+            ops.conv2d_nhwc([(h1t, 0, mid)], w2, h2, R=1, S=1, Cout=mid, bias=b2, slope=0.01, groups=G, in_goff=[mid],
+                            weight_goff=mid, bias_goff=mid, out_goff=mid)
+            ops.conv2d_nhwc([(h2, 0, mid)], w3, heads_buf, R=1, S=1, Cout=A, bias=b3, slope=1.0, groups=G,
+                            in_goff=[mid], weight_goff=rows3, bias_goff=rows3, out_coff=slot0 * A, out_goff=A)
+
+        self._add(run, 2)
+
+    def _align(self, name, m, x, om):
+        return self._conv(name, [x], m.align.weight, m.align.bias, None, m.align.kernel_size[0], 1, m.align.padding,
+                          1.0, res=x, om=om)
+
+    def _anab(self, x):
+        raise NotImplementedError("ANAB fused path is built in engine_anab.py")
+
+    def _build(self):
+        net, conf = self.net, self.conf
+        A, K, B = self.A, self.K, self.B
+        feat = self._dla_seg()
+        self.named["feat"] = feat
+        N, Hf, Wf = feat.t.shape[:3]
+        self.Hf, self.Wf = Hf, Wf
+        M = A * Hf * Wf
+        self.M = M
+        # --- classification head
+        c = net.cls
+        h = self._conv_module("cls.l1", [feat], c[0], c[1])
+        h = self._conv_module("cls.l2", [h], c[3], c[4])
+        logits = self._new("cls.logits", N, Hf, Wf, K * A, torch.float32)
+        self._conv_module("cls.l3", [h], c[6], None, slope=1.0, out=logits)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.cls_out = torch.zeros(B, M, K, **f32)
+        self.prob_out = torch.zeros(B, M, K, **f32)
+        self.fg_max = torch.zeros(B, Hf, Wf, **f32)
+        self.fg_arg = torch.zeros(B, Hf, Wf, dtype=torch.int32, device=self.dev)
+        self.score = torch.zeros(B, M, **f32)
+        self.cls_pred = torch.zeros(B, M, dtype=torch.uint8, device=self.dev)
+        self._add(lambda: ops.cls_softmax(logits, A, K, self.cls_out, self.prob_out, self.fg_max, self.fg_arg,
+                                          self.score, self.cls_pred))
+        anchors = torch.tensor(np.asarray(conf.anchors), **f32).contiguous()
+        self.anchors = anchors
+        means = [float(v) for v in np.asarray(conf.bbox_means)[0]]
+        stds = [float(v) for v in np.asarray(conf.bbox_stds)[0]]
+        stride = float(conf.feat_stride)
+        # --- shape align
+        feats = feat
+        if net.shape_align is not None:
+            om_s = torch.zeros(B, Hf, Wf, 27, **f32)
+            thr = float(net.shape_align.thresh)
+            self._add(lambda: ops.shape_align_om(self.fg_max, self.fg_arg, anchors, stride, thr, om_s))
+            feats = self._align("shape_align", net.shape_align, feat, om_s)
+        # --- regression heads (slots follow HEAD_ORDER)
+        heads = self._new("heads", B, Hf, Wf, 11 * A, torch.float32)
+        self.heads = heads
+        self._head_group("headsA", ["bbox_x", "bbox_y", "bbox_x3d", "bbox_y3d"], feats, heads)
+        f2d = f3d = feats
+        if net.center_align2d is not None:
+            om2 = torch.zeros(B, Hf, Wf, 4, **f32)
+            om3 = torch.zeros(B, Hf, Wf, 4, **f32)
+            thr = float(net.center_align2d.thresh)
+            sx, sy, sx3, sy3 = (HEAD_ORDER.index(n) * A for n in ("bbox_x", "bbox_y", "bbox_x3d", "bbox_y3d"))
+            self._add(lambda: ops.center_align_om(self.fg_max, self.fg_arg, heads, sx, sy, anchors, stride, means[0:2],
+                                                  stds[0:2], thr, om2))
+            self._add(lambda: ops.center_align_om(self.fg_max, self.fg_arg, heads, sx3, sy3, anchors, stride,
+                                                  means[4:6], stds[4:6], thr, om3))
+            f2d = self._align("center_align2d", net.center_align2d, feats, om2)
+            f3d = self._align("center_align3d", net.center_align3d, feats, om3)
+        self.named["feats_shape"], self.named["feats_align2d"], self.named["feats_align3d"] = feats, f2d, f3d
+        self._head_group("headsB", ["bbox_w", "bbox_h"], f2d, heads)
+        self._head_group("headsC", ["bbox_w3d", "bbox_h3d", "bbox_l3d", "bbox_rY3d"], f3d, heads)
+        fz = f3d
+        if net.attention == "ANAB":
+            fz = self._anab(f3d)
+        self.named["feats_gl"] = fz
+        self._head_group("headsZ", ["bbox_z3d"], fz, heads)
+        self.bbox_2d = torch.zeros(B, M, 4, **f32)
+        self.bbox_3d = torch.zeros(B, M, 7, **f32)
+        self._add(lambda: ops.flatten_heads(heads, A, OUT_SLOTS, self.bbox_2d, self.bbox_3d))
+        self.n_forward_ops = len(self.ops)
+        # --- detection tail
+        self.means_t = torch.tensor(means, **f32)
+        self.stds_t = torch.tensor(stds, **f32)
+        self.dets = torch.zeros(B, self.topk, 14, **f32)
+        self.det_idx = torch.zeros(B, self.topk, dtype=torch.int32, device=self.dev)
+        self.det_num = torch.zeros(B, dtype=torch.int32, device=self.dev)
+        self.keep = torch.zeros(B, self.topk, dtype=torch.int32, device=self.dev)
+        self.num_keep = torch.zeros(B, dtype=torch.int32, device=self.dev)
+        self.nms_ws = torch.zeros(ops.nms_workspace_bytes(B, self.topk), dtype=torch.uint8, device=self.dev)
+        self.kept = torch.zeros(B, self.max_out, 14, **f32)
+        self.scale_factor = 1.0
+        self.feat_size = torch.tensor([Hf, Wf], dtype=torch.float32, device=self.dev)
+
+    # ------------------------------------------------------------------- run
+    def _run_forward(self):
+        for op in self.ops:
+            op()
+
+    def _run_detect(self):
+        ops.decode_topk(self.score, self.cls_pred, self.bbox_2d, self.bbox_3d, self.anchors, self.means_t, self.stds_t,
+                        self.A, self.Hf, self.Wf, float(self.conf.feat_stride), self.scale_factor, self.topk, self.dets,
+                        self.det_idx, self.det_num)
+        ops.nms_batched(self.dets, self.det_num, float(self.conf.nms_thres), self.nms_ws, self.keep, self.num_keep)
+        ops.gather_kept(self.dets, self.keep, self.num_keep, self.max_out, self.kept)
+
+    def activation_nchw(self, name):
+        """fp32 NCHW copy of a named intermediate activation (testing aid)."""
+        a = self.named[name]
+        return a.t[..., a.coff:a.coff + a.c].float().permute(0, 3, 1, 2).contiguous()
+
+    def launches_per_step(self, with_detect=True):
+        return self.n_launches + (4 if with_detect else 0)
+
+    def forward(self, images=None, detect=False):
+        """images: [B,3,H,W] fp32 CUDA (copied into the engine's input buffer) or None to reuse it.
+        Returns (cls, prob, bbox_2d, bbox_3d) views of the engine's output buffers."""
+        if images is not None:
+            assert tuple(images.shape) == tuple(self.image.shape), (images.shape, self.image.shape)
+            self.image.copy_(images, non_blocking=True)
+        if self.use_graph:
+            key = "det" if detect else "fwd"
+            if self.graph is None:
+                self.graph = {}
+            if key not in self.graph:
+                self._run_forward()  # warm-up outside capture: loads modules, sizes smem attributes
+                if detect:
+                    self._run_detect()
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run_forward()
+                    if detect:
+                        self._run_detect()
+                self.graph[key] = g
+            self.graph[key].replay()
+        else:
+            self._run_forward()
+            if detect:
+                self._run_detect()
+        return self.cls_out, self.prob_out, self.bbox_2d, self.bbox_3d
+
+    def detect(self, images=None, scale_factor=1.0):
+        """Full path: forward + decode/top-K + batched NMS.  Returns (kept [B,max_out,14], num_keep [B])."""
+        if float(scale_factor) != self.scale_factor:
+            self.scale_factor = float(scale_factor)
+            if self.graph:
+                self.graph.pop("det", None)
+        self.forward(images, detect=True)
+        return self.kept, self.num_keep

@@ -1,0 +1,68 @@
+"""The RPN helpers the model imports (mirror of the hot-path subset of lib/rpn_util.py):
+calc_output_size (:1401-1413), locate_anchors (:1329-1398), flatten_tensor (:892-901),
+bbox_transform_inv (:1137-1186) and im_detect_3d (:1416-1563).  The dataset /
+evaluation / plotting parts of that file are out of scope."""
+import numpy as np
+import torch
+
+from .nms.gpu_nms import gpu_nms
+
+
+def calc_output_size(res, stride):
+    return np.ceil(np.array(res) / stride).astype(int)
+
+
+def locate_anchors(anchors, feat_size, stride, convert_tensor=False):
+    """[(A*H*W), 5] rows (x1, y1, x2, y2, anchor index), anchor-major then row-major over the feature map."""
+    if torch.is_tensor(anchors):
+        anchors = anchors.detach().cpu().numpy()
+    H, W = int(feat_size[0]), int(feat_size[1])
+    sx = (np.arange(W, dtype=np.float64) * float(stride))[None, None, :]
+    sy = (np.arange(H, dtype=np.float64) * float(stride))[None, :, None]
+    a = anchors[:, 0:4]
+    cols = [np.broadcast_to(s + a[:, k][:, None, None], (a.shape[0], H, W))
+            for k, s in ((0, sx), (1, sy), (2, sx), (3, sy))]
+    cols.append(np.broadcast_to(np.arange(a.shape[0], dtype=np.float64)[:, None, None], (a.shape[0], H, W)))
+    rois = np.stack([c.reshape(-1) for c in cols], axis=1)
+    return torch.from_numpy(rois) if convert_tensor else rois
+
+
+def flatten_tensor(input):
+    """[B, C, H, W] -> [B, H*W, C]"""
+    return input.permute(0, 2, 3, 1).contiguous().view(input.shape[0], -1, input.shape[1])
+
+
+def bbox_transform_inv(boxes, deltas, means=None, stds=None):
+    if boxes.shape[0] == 0:
+        return torch.zeros((0, deltas.shape[1]), dtype=deltas.dtype, device=deltas.device)
+    widths = boxes[:, 2] - boxes[:, 0] + 1.0
+    heights = boxes[:, 3] - boxes[:, 1] + 1.0
+    ctr_x = boxes[:, 0] + 0.5 * widths
+    ctr_y = boxes[:, 1] + 0.5 * heights
+    d = deltas
+    if stds is not None:
+        d = d * stds[0:4]
+    if means is not None:
+        d = d + means[0:4]
+    pcx, pcy = d[:, 0] * widths + ctr_x, d[:, 1] * heights + ctr_y
+    pw, ph = torch.exp(d[:, 2]) * widths, torch.exp(d[:, 3]) * heights
+    return torch.stack((pcx - 0.5 * pw, pcy - 0.5 * ph, pcx + 0.5 * pw, pcy + 0.5 * ph), dim=1)
+
+
+def im_detect_3d(im, net, rpn_conf, obj, gpu=0, synced=False):
+    """Single-image detection with the reference's signature and return value
+    (numpy [n_kept, 14]); decode, top-K and NMS all run on the device through the
+    network's detection tail (no host round trip before NMS)."""
+    if im.dim() == 3:
+        im = im[None]
+    im = im.cuda()
+    with torch.no_grad():
+        net.eval()
+        kept, num = net.detect(im, scale_factor=float(obj.scale_factor), max_out=int(rpn_conf.nms_topN_pre))
+    aboxes = kept[0, :int(num[0].item())].cpu().numpy()
+    if rpn_conf.clip_boxes:
+        aboxes[:, 0] = np.clip(aboxes[:, 0], 0, obj.imW - 1)
+        aboxes[:, 1] = np.clip(aboxes[:, 1], 0, obj.imH - 1)
+        aboxes[:, 2] = np.clip(aboxes[:, 2], 0, obj.imW - 1)
+        aboxes[:, 3] = np.clip(aboxes[:, 3], 0, obj.imH - 1)
+    return aboxes

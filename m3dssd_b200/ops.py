@@ -106,3 +106,113 @@ def conv2d_nhwc(inputs, weight, out, *, R, S, stride=1, pad=0, dil=1, Cout=None,
     d.force_gather = int(force_gather)
     check(lib().m3d_conv2d_nhwc(C.byref(d), _stream()))
     return out
+
+
+# --------------------------------------------------------------------------- other ops
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def stem_conv7x7(image, weight, bias, out, slope=0.01):
+    """image [N,3,H,W] fp32 NCHW; weight [16,3,7,7] fp32 (BN folded); out NHWC [N,H,W,>=16]."""
+    assert image.dtype == torch.float32 and image.is_contiguous() and image.shape[1] == 3
+    N, _, H, W = image.shape
+    check(lib().m3d_stem_conv7x7(_p(image), _p(weight), _p(bias), _p(out), _dt(out), out.shape[-1], N, H, W,
+                                 float(slope), _stream()))
+    return out
+
+
+def maxpool2x2(x, out, C_=None):
+    N, H, W, cs = x.shape
+    check(lib().m3d_maxpool2x2_nhwc(_p(x), _p(out), _dt(x), N, H, W, C_ or cs, cs, out.shape[-1], _stream()))
+    return out
+
+
+def upsample_add(x, weight, skip, out, f=2):
+    """depthwise ConvTranspose2d(2f, stride f, pad f//2) of x plus skip; weight [C,1,2f,2f] or [C,2f,2f] fp32."""
+    N, H, W, cs = x.shape
+    Cc = weight.shape[0]
+    check(lib().m3d_upsample_add_nhwc(_p(x), _p(weight), _p(skip), _p(out), _dt(x), N, H, W, Cc, f, cs,
+                                      skip.shape[-1] if skip is not None else 0, out.shape[-1], _stream()))
+    return out
+
+
+def cls_softmax(logits, A, K, cls_out, prob_out, fg_max, fg_arg, score, cls_pred):
+    N, H, W, cs = logits.shape
+    check(lib().m3d_cls_softmax(_p(logits), cs, N, H, W, A, K, _p(cls_out), _p(prob_out), _p(fg_max), _p(fg_arg),
+                                _p(score), _p(cls_pred), _stream()))
+
+
+def shape_align_om(fg_max, fg_arg, anchors, feat_stride, thresh, om):
+    check(lib().m3d_shape_align_om(_p(fg_max), _p(fg_arg), _p(anchors), anchors.shape[1], float(feat_stride),
+                                   float(thresh), _p(om), fg_max.numel(), _stream()))
+
+
+def center_align_om(fg_max, fg_arg, heads, x_coff, y_coff, anchors, feat_stride, mean_xy, std_xy, thresh, om):
+    check(lib().m3d_center_align_om(_p(fg_max), _p(fg_arg), _p(heads), heads.shape[-1], x_coff, y_coff, _p(anchors),
+                                    anchors.shape[1], float(feat_stride), float(mean_xy[0]), float(mean_xy[1]),
+                                    float(std_xy[0]), float(std_xy[1]), float(thresh), _p(om), om.shape[-1],
+                                    fg_max.numel(), _stream()))
+
+
+def flatten_heads(heads, A, slots, bbox_2d, bbox_3d):
+    N, H, W, cs = heads.shape
+    arr = (C.c_int * 11)(*slots)
+    check(lib().m3d_flatten_heads(_p(heads), cs, N, H, W, A, arr, _p(bbox_2d), _p(bbox_3d), _stream()))
+
+
+def nchw_to_nhwc(x, out, coff=0):
+    N, Cc, H, W = x.shape
+    check(lib().m3d_nchw_to_nhwc(_p(x), _dt(x), _p(out), _dt(out), N, Cc, H, W, out.shape[-1], coff, _stream()))
+    return out
+
+
+def nhwc_to_nchw(x, out, coff=0):
+    N, Cc, H, W = out.shape
+    check(lib().m3d_nhwc_to_nchw(_p(x), _dt(x), _p(out), _dt(out), N, Cc, H, W, x.shape[-1], coff, _stream()))
+    return out
+
+
+def decode_topk(score, cls_pred, bbox_2d, bbox_3d, anchors, means, stds, A, H, W, feat_stride, scale_factor, topk,
+                dets, det_idx, det_num):
+    B = score.shape[0]
+    check(lib().m3d_decode_topk(_p(score), _p(cls_pred), _p(bbox_2d), _p(bbox_3d), _p(anchors), _p(means), _p(stds),
+                                B, A, H, W, float(feat_stride), float(scale_factor), topk, _p(dets), _p(det_idx),
+                                _p(det_num), _stream()))
+
+
+def nms_workspace_bytes(batch, max_n):
+    return lib().m3d_nms_workspace_bytes(batch, max_n)
+
+
+def nms_batched(boxes, num, thresh, workspace, keep, num_keep):
+    """boxes [B, max_n, stride] fp32 (x1,y1,x2,y2,...), sorted by score within each image."""
+    B, max_n, stride = boxes.shape
+    check(lib().m3d_nms_batched(_p(boxes), stride, _p(num), B, max_n, float(thresh), _p(workspace),
+                                workspace.numel() * workspace.element_size(), _p(keep), _p(num_keep), _stream()))
+
+
+def gather_kept(dets, keep, num_keep, max_out, out):
+    B, max_n, row = dets.shape
+    check(lib().m3d_gather_kept(_p(dets), row, B, max_n, _p(keep), _p(num_keep), max_out, _p(out), _stream()))
+
+
+def dcn_v2_forward(input, offset, mask, weight, bias, stride, padding, dilation, deformable_groups, precision=M3D_F32):
+    """NCHW fp32 CUDA tensors -> NCHW fp32 output (DCNv2Function.forward, model/DCNv2/dcn_v2_func.py:22-38)."""
+    B, Cin, H, W = input.shape
+    Cout, Ck, kh, kw = weight.shape
+    if Ck != Cin:
+        raise RuntimeError("Input shape and kernel channels wont match: (%d vs %d)." % (Cin, Ck))
+    Ho = (H + 2 * padding - (dilation * (kh - 1) + 1)) // stride + 1
+    Wo = (W + 2 * padding - (dilation * (kw - 1) + 1)) // stride + 1
+    if tuple(offset.shape) != (B, 2 * deformable_groups * kh * kw, Ho, Wo) or \
+            tuple(mask.shape) != (B, deformable_groups * kh * kw, Ho, Wo):
+        raise RuntimeError("offset/mask shape does not match the output size %dx%d" % (Ho, Wo))
+    ws_bytes = lib().m3d_dcn_v2_forward_workspace(B, Cin, H, W, Cout, kh, kw, stride, padding, dilation, precision)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=input.device)
+    out = torch.empty(B, Cout, Ho, Wo, dtype=torch.float32, device=input.device)
+    args = [t.contiguous().float() for t in (input, weight, bias, offset, mask)]
+    check(lib().m3d_dcn_v2_forward(_p(args[0]), _p(args[1]), _p(args[2]), _p(args[3]), _p(args[4]), _p(out), B, Cin, H,
+                                   W, Cout, kh, kw, stride, stride, padding, padding, dilation, dilation,
+                                   deformable_groups, precision, _p(ws), ws_bytes, _stream()))
+    return out

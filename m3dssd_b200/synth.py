@@ -1,0 +1,150 @@
+"""Synthetic KITTI-shaped configuration, weights and inputs.
+
+There is no dataset or checkpoint in the build/bench environment, so the
+benchmark and the parity tests use: the reference's own anchor recipe
+(lib/rpn_util.py:39-52,167-183; scripts/config/kitti_3d_base.py:75-79,130-132)
+with fixed 3-D priors, zero/one bbox statistics, and deterministic random
+weights in which the (zero-initialised, model/DCNv2/dcn_v2.py:60-62)
+conv_offset_mask layers are randomised so the deformable gather is exercised.
+"""
+import math
+
+import numpy as np
+import torch
+
+
+class Conf(dict):
+    """Attribute dict (the reference uses easydict.EasyDict, absent from this image)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def anchor_center(w, h, stride):
+    # lib/rpn_util.py:167-183
+    a = np.zeros([4], dtype=np.float32)
+    a[0] = -w / 2 + (stride - 1) / 2
+    a[1] = -h / 2 + (stride - 1) / 2
+    a[2] = w / 2 + (stride - 1) / 2
+    a[3] = h / 2 + (stride - 1) / 2
+    return a
+
+
+def make_anchors(test_scale=(384, 1280), percent_anc_h=(0.0625, 0.75), n_scales=12, ratios=(0.5, 1.0, 1.5), stride=8):
+    min_h, max_h = test_scale[0] * percent_anc_h[0], test_scale[0] * percent_anc_h[1]
+    base = (max_h / min_h) ** (1 / (n_scales - 1))
+    scales = np.array([min_h * (base ** i) for i in range(n_scales)])
+    anchors = np.zeros([n_scales * len(ratios), 9], dtype=np.float32)
+    k = 0
+    for s in scales:
+        for r in ratios:
+            anchors[k, 0:4] = anchor_center(s * r, s, stride)
+            # fixed 3-D priors: z = pinhole depth of a 1.5 m object at KITTI focal ~721 px
+            anchors[k, 4:9] = [721.0 * 1.5 / s, 1.6, 1.5, 3.9, 0.0]
+            k += 1
+    return anchors, scales, np.array(ratios)
+
+
+def make_conf(attention=None, center_align=True, shape_align=True, back_bone="dla34", batch_size=8,
+              crop_size=(384, 1280), device="cpu"):
+    c = Conf()
+    c.model = "M3d_inference_align"
+    c.ida_dcnv2 = True
+    c.attention = attention
+    c.center_align = center_align
+    c.shape_align = shape_align
+    c.back_bone = back_bone
+    c.pre_train = False
+    c.feat_stride = 8
+    c.has_3d = True
+    c.test_scale = list(crop_size)
+    c.crop_size = list(crop_size)
+    c.lbls = ["Car", "Pedestrian", "Cyclist"]
+    c.ilbls = ["Van", "ignore"]
+    c.batch_size = batch_size
+    c.nms_topN_pre = 3000
+    c.nms_topN_post = 40
+    c.nms_thres = 0.4
+    c.clip_boxes = False
+    c.rng_seed = 2
+    c.cuda_seed = 2
+    anchors, scales, ratios = make_anchors(stride=c.feat_stride)
+    c.anchors = anchors
+    c.anchor_scales = scales
+    c.anchor_ratios = ratios
+    c.bbox_means = np.zeros([1, 11], dtype=np.float32)
+    c.bbox_stds = np.ones([1, 11], dtype=np.float32)
+    c.device = device
+    return c
+
+
+@torch.no_grad()
+def randomize_weights(model, seed=2, offset_sigma_px=2.0, fg_fraction=0.01):
+    """Deterministic synthetic weights for a reference-shaped RPN (reference modules or ours).
+
+    Draws every tensor from its own generator keyed by the parameter name, so the
+    result does not depend on module construction order.
+    """
+    sd = model.state_dict()
+    mods = dict(model.named_modules())
+    new = {}
+    for name in sorted(sd.keys()):
+        t = sd[name]
+        g = torch.Generator().manual_seed((hash_name(name) + seed) % (2 ** 31))
+        mod = mods.get(name.rsplit(".", 1)[0])
+        leaf = name.rsplit(".", 1)[-1]
+        if leaf == "num_batches_tracked":
+            new[name] = t
+            continue
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            if leaf == "running_mean":
+                v = torch.randn(t.shape, generator=g) * 0.1
+            elif leaf == "running_var":
+                v = torch.rand(t.shape, generator=g) + 0.5
+            elif leaf == "weight":
+                v = torch.rand(t.shape, generator=g) + 0.5
+            else:
+                v = torch.randn(t.shape, generator=g) * 0.1
+        elif "conv_offset_mask" in name and leaf == "weight":
+            fan_in = t.shape[1] * t.shape[2] * t.shape[3]
+            # activations are O(1); offsets ~ N(0, sigma^2) need w ~ sigma / sqrt(fan_in)
+            v = torch.randn(t.shape, generator=g) * (offset_sigma_px / math.sqrt(fan_in))
+            v[18:] *= 0.5 / offset_sigma_px  # mask logits ~ N(0, 0.5^2): sigmoid spread over ~(0.25, 0.75)
+        elif "conv_offset_mask" in name:
+            v = torch.randn(t.shape, generator=g) * 0.2
+        elif isinstance(mod, torch.nn.ConvTranspose2d):
+            # bilinear kernels from fill_up_weights (model/pose_dla_dcn.py:459-468); trainable, so perturbed
+            v = t.float() * (1.0 + 0.05 * torch.randn(t.shape, generator=g))
+        elif t.dim() == 4:
+            fan_in = t.shape[1] * t.shape[2] * t.shape[3]
+            v = torch.randn(t.shape, generator=g) * math.sqrt(2.0 / fan_in)
+        else:
+            v = torch.randn(t.shape, generator=g) * 0.1
+        new[name] = v.to(t.dtype)
+    # cls head: shift the background logit so ~fg_fraction of anchors are foreground
+    key = "cls.6.bias"
+    if key in new:
+        na = new[key].shape[0] // 4
+        b = new[key].clone()
+        b[:na] += 4.5  # class 0 = background (channel = class * num_anchors + anchor)
+        new[key] = b
+    model.load_state_dict(new)
+    return new
+
+
+def hash_name(name):
+    h = 0
+    for ch in name:
+        h = (h * 131 + ord(ch)) % 1000003
+    return h
+
+
+def make_images(batch, crop_size=(384, 1280), seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(batch, 3, crop_size[0], crop_size[1], generator=g)

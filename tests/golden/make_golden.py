@@ -1,0 +1,84 @@
+"""Generate the committed golden fixtures from the UNMODIFIED reference (build container only).
+
+    python tests/golden/make_golden.py
+
+Runs /root/reference's own Python modules on CPU through oracle/ref_harness.py
+(its CUDA-only DCNv2 extension replaced by torchvision.ops.deform_conv2d, which
+the C oracle is pinned against) and its own lib/nms/py_cpu_nms.py, on seeded
+synthetic inputs that tests regenerate from the same seeds.  Outputs are stored
+sub-sampled (every STRIDE-th row) plus whole-tensor checksums to stay small.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from m3dssd_b200 import synth  # noqa: E402
+from oracle import ref_harness as RH  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+STRIDE = 11
+CONFIGS = {
+    "base": dict(attention=None, center_align=False, shape_align=False),
+    "align": dict(attention=None, center_align=True, shape_align=True),
+    "anab": dict(attention="ANAB", center_align=True, shape_align=True),
+}
+CROP = (96, 320)
+
+
+def nms_boxes(n, seed):
+    rng = np.random.default_rng(seed)
+    xy = rng.random((n, 2)) * np.array([1200, 350])
+    wh = rng.random((n, 2)) * 120 + 4
+    sc = rng.permutation(n).astype(np.float32) / max(n, 1)  # tie-free
+    return np.concatenate([xy, xy + wh, sc[:, None]], 1).astype(np.float32)
+
+
+def main():
+    ns = RH.load_reference()
+    # --- DCNv2 known-answer test of the reference (model/DCNv2/test.py:32-65), stated as data
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 2, 4, 4, generator=g)
+    np.savez(os.path.join(HERE, "dcn_zero_offset.npz"), input=x.numpy(), expected_2x_output=x.numpy())
+
+    # --- NMS: the reference's own py_cpu_nms on seeded boxes
+    out = {}
+    for n, seed in [(1, 1), (63, 2), (64, 3), (65, 4), (500, 5), (3000, 6)]:
+        d = nms_boxes(n, seed)
+        out["keep_%d" % n] = np.asarray(ns.py_cpu_nms(d, 0.4), dtype=np.int32)
+        out["seed_%d" % n] = np.int32(seed)
+    np.savez_compressed(os.path.join(HERE, "nms_py_cpu.npz"), **out)
+
+    # --- model forward + decode through the unmodified reference modules
+    torch.Tensor.cuda = lambda self, *a, **k: self  # im_detect_3d calls .cuda(); stay on CPU
+    torch.cuda.FloatTensor = torch.FloatTensor
+    for name, kw in CONFIGS.items():
+        conf = ns.EasyDict(synth.make_conf(crop_size=CROP, **kw))
+        net = ns.rpn.build(conf, "test")
+        synth.randomize_weights(net)
+        x = synth.make_images(2, CROP)
+        with torch.no_grad():
+            cls, prob, b2, b3, feat_size, rois = net(x)
+        fix = dict(stride=np.int32(STRIDE))
+        for k, t in (("cls", cls), ("prob", prob), ("bbox_2d", b2), ("bbox_3d", b3)):
+            a = t.numpy()
+            fix[k] = a[:, ::STRIDE].copy()
+            fix[k + "_sum"] = np.float64(a.astype(np.float64).sum())
+            fix[k + "_abssum"] = np.float64(np.abs(a.astype(np.float64)).sum())
+        fix["rois"] = rois.numpy()[::STRIDE].copy()
+        fix["fg_frac"] = np.float64(((1 - prob[..., 0]) > 0.5).float().mean().item())
+        # unmodified im_detect_3d (lib/rpn_util.py:1416-1563) on image 0
+        obj = types.SimpleNamespace(imH=CROP[0], imW=CROP[1], p2=np.eye(4), scale_factor=1.0)
+        ab = ns.rpn_util.im_detect_3d(x[0:1].clone(), net, conf, obj)
+        fix["aboxes"] = ab.astype(np.float32)
+        np.savez_compressed(os.path.join(HERE, "ref_model_%s_96x320.npz" % name), **fix)
+        print(name, "fg_frac=%.4f" % fix["fg_frac"], "aboxes", ab.shape,
+              {k: v.shape for k, v in fix.items() if hasattr(v, "shape") and v.ndim > 0})
+
+
+if __name__ == "__main__":
+    main()
