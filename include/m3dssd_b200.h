@@ -31,7 +31,8 @@ enum {
   M3D_ERR_WORKSPACE = -4    /* workspace too small */
 };
 
-enum { M3D_BF16 = 0, M3D_F32 = 1 };
+/* M3D_BF16X3 is a *precision* (fp32 tensors, 3-part bf16 split on the tensor cores), not a storage type */
+enum { M3D_BF16 = 0, M3D_F32 = 1, M3D_BF16X3 = 2 };
 
 const char* m3d_last_error(void);
 int m3d_version(void);
@@ -48,8 +49,12 @@ int m3d_version(void);
  *                                              (* mask) * W[co; i,r,s,c] + bias[co] (+ res[n,p,q,co]) )
  *
  * act_dtype M3D_BF16: bf16 activations, bf16 weights, fp32 accumulate.
- * act_dtype M3D_F32 : fp32 activations; weights given as bf16 hi + lo parts;
- *                     products formed as hi*hi + lo*hi + hi*lo (fp32-accurate).
+ * act_dtype M3D_F32 : fp32 activations, fp32 output.  Two arithmetic modes:
+ *    weight_f32 set  -> reference-accuracy mode: CUDA-core implicit GEMM, IEEE fp32 FMA accumulation
+ *                       (the arithmetic class of the reference's cuDNN / SGEMM fp32 path);
+ *    weight_mid/lo set -> "bf16x3": weights as three bf16 parts (24 mantissa bits), six tcgen05 partial
+ *                       products per k-step, fp32 accumulation in TMEM (~3e-6 relative per layer:
+ *                       tensor-core accumulators truncate).
  * Weights are packed [rows][K] with K = concat_i (tap-major, channel-minor).
  * ---------------------------------------------------------------------- */
 #define M3D_MAX_CONCAT 4
@@ -67,8 +72,10 @@ typedef struct m3d_conv_desc {
   int R, S, stride, pad, dil;
   int Cout;   /* output channels per group */
   int groups; /* independent GEMMs sharing geometry (batched heads); >1 only for plain bf16 convs */
-  const void* weight;    /* bf16 [weight_rows][K] */
-  const void* weight_lo; /* bf16 low parts (M3D_F32 only) */
+  const void* weight;     /* bf16 [weight_rows][K] (M3D_F32: the high 8 mantissa bits) */
+  const void* weight_mid; /* M3D_F32 only: bf16 of the next 8 mantissa bits */
+  const void* weight_lo;  /* M3D_F32 only: bf16 of the last 8 mantissa bits */
+  const float* weight_f32; /* M3D_F32 reference-accuracy mode: fp32 [weight_rows][K]; `weight` may be NULL */
   int weight_rows;       /* total rows in the packed matrix */
   int weight_goff;       /* row offset per group */
   const float* bias;     /* [groups * bias_goff] or NULL */
@@ -96,7 +103,7 @@ int m3d_conv2d_nhwc(const m3d_conv_desc* desc, m3d_stream_t stream);
  * Differences: `ones`/`columns` scratch tensors are gone (the caller passes one
  * opaque workspace of m3d_dcn_v2_forward_workspace() bytes), shape errors are
  * returned (reference: THError, dcn_v2_cuda.c:33-38), the batch is handled in
- * one launch.  precision: M3D_F32 = fp32-accurate (bf16x3 split products),
+ * one launch.  precision: M3D_F32 = reference accuracy (IEEE fp32 FMA), M3D_BF16X3 = 3-part bf16 split on tensor cores,
  * M3D_BF16 = bf16 operands / fp32 accumulate.  deformable_group must be 1.
  * ---------------------------------------------------------------------- */
 size_t m3d_dcn_v2_forward_workspace(int B, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil,
@@ -125,7 +132,7 @@ int m3d_nms_batched(const float* boxes, int box_stride, const int* num, int batc
  * score (descending, ties by lower index), anchor decode of the selected rows
  * into dets [batch, topk, 14] = x1,y1,x2,y2,score,cls,x3d,y3d,z3d,w3d,h3d,l3d,ry3d,anchor. */
 int m3d_decode_topk(const float* score, const unsigned char* cls_pred, const float* bbox_2d, const float* bbox_3d,
-                    const float* anchors /*[A,9]*/, const float* means11, const float* stds11, int batch, int A, int H,
+                    const float* anchors /*[A,9] device*/, const float* means11 /*host*/, const float* stds11 /*host*/, int batch, int A, int H,
                     int W, float feat_stride, float scale_factor, int topk, float* dets, int* det_idx, int* det_num,
                     m3d_stream_t stream);
 int m3d_gather_kept(const float* dets, int row_len, int batch, int max_n, const int* keep, const int* num_keep,
@@ -164,6 +171,21 @@ int m3d_nchw_to_nhwc(const void* in, int in_dtype, void* out, int out_dtype, int
                      int out_cstride, int out_coff, m3d_stream_t stream);
 int m3d_nhwc_to_nchw(const void* in, int in_dtype, void* out, int out_dtype, int N, int C, int H, int W,
                      int in_cstride, int in_coff, m3d_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * ANAB (model/module/attention.py:120-216).  kvs = fp32 NHWC output of the
+ * concatenated key | value | spatial 1x1 convolutions.  m3d_anab_pool builds
+ * the T = sum(size^2) attention-weighted pyramid tokens (PAPAModule :120-147);
+ * m3d_anab_attention computes LeakyReLU(BN(softmax(Q K^T) V + x)) with the
+ * eval-mode BatchNorm given as per-channel (scale, shift).
+ * ---------------------------------------------------------------------- */
+size_t m3d_anab_pool_workspace(int N, int H, int nlev, const int* sizes, int ck, int cv);
+int m3d_anab_pool(const float* kvs, int kvs_cstride, int N, int H, int W, int ck, int cv, int nlev,
+                  const int* sizes /*host*/, void* workspace, size_t workspace_bytes, float* ktok /*[N,T,ck]*/,
+                  float* vtok /*[N,T,cv]*/, m3d_stream_t stream);
+int m3d_anab_attention(const void* q, int q_cstride, const float* ktok, const float* vtok, const void* x,
+                       int x_cstride, int act_dtype, const float* scale, const float* shift, float slope, void* out,
+                       int out_cstride, int N, int HW, int ck, int cv, int T, m3d_stream_t stream);
 
 #ifdef __cplusplus
 }

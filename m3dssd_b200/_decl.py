@@ -4,7 +4,7 @@ import ctypes as C
 vp, i, f, sz, lg = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_long
 
 _SIGS = {
-    "m3d_dcn_v2_forward": [vp, vp, vp, vp, vp, vp] + [i] * 16 + [vp, sz, vp],
+    "m3d_dcn_v2_forward": [vp, vp, vp, vp, vp, vp] + [i] * 15 + [vp, sz, vp],
     "m3d_nms": [vp, vp, vp, i, i, f, i],
     "m3d_nms_batched": [vp, i, vp, i, i, f, vp, sz, vp, vp, vp],
     "m3d_decode_topk": [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, f, f, i, vp, vp, vp, vp],
@@ -16,12 +16,15 @@ _SIGS = {
     "m3d_shape_align_om": [vp, vp, vp, i, f, f, vp, lg, vp],
     "m3d_center_align_om": [vp, vp, vp, i, i, i, vp, i, f, f, f, f, f, f, vp, i, lg, vp],
     "m3d_flatten_heads": [vp, i, i, i, i, i, vp, vp, vp, vp],
+    "m3d_anab_pool": [vp, i, i, i, i, i, i, i, vp, vp, sz, vp, vp, vp],
+    "m3d_anab_attention": [vp, i, vp, vp, vp, i, i, vp, vp, f, vp, i, i, i, i, i, i, vp],
     "m3d_nchw_to_nhwc": [vp, i, vp, i, i, i, i, i, i, i, vp],
     "m3d_nhwc_to_nchw": [vp, i, vp, i, i, i, i, i, i, i, vp],
 }
 _SIZE_FNS = {
     "m3d_dcn_v2_forward_workspace": [i] * 11,
     "m3d_nms_workspace_bytes": [i, i],
+    "m3d_anab_pool_workspace": [i, i, i, vp, i, i],
 }
 
 

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libm3dssd_b200.so")
 
-M3D_BF16, M3D_F32 = 0, 1
+M3D_BF16, M3D_F32, M3D_BF16X3 = 0, 1, 2
 MAX_CONCAT = 4
 
 
@@ -26,7 +26,7 @@ class ConvDesc(C.Structure):
         ("N", C.c_int), ("H", C.c_int), ("W", C.c_int),
         ("R", C.c_int), ("S", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("dil", C.c_int),
         ("Cout", C.c_int), ("groups", C.c_int),
-        ("weight", C.c_void_p), ("weight_lo", C.c_void_p),
+        ("weight", C.c_void_p), ("weight_mid", C.c_void_p), ("weight_lo", C.c_void_p), ("weight_f32", C.c_void_p),
         ("weight_rows", C.c_int), ("weight_goff", C.c_int),
         ("bias", C.c_void_p), ("bias_goff", C.c_int),
         ("res", C.c_void_p), ("res_cstride", C.c_int), ("res_coff", C.c_int), ("res_goff", C.c_int),

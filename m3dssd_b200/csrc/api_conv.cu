@@ -102,7 +102,9 @@ static int sm_count() {
   return sms;
 }
 
-static int pick_bn(int cout, int bk, long m_tiles, bool gather) {
+int launch_conv_simt_f32(const m3d_conv_desc* d, int P, int Q, cudaStream_t stream);
+
+static int pick_bn(int cout, int bk, long m_tiles, bool gather, bool split) {
   if (bk == 16) return cout <= 16 ? 16 : 32;
   if (bk == 32) return cout <= 32 ? 32 : 64;
   if (cout <= 16 && gather) return 16;
@@ -110,8 +112,9 @@ static int pick_bn(int cout, int bk, long m_tiles, bool gather) {
   if (cout <= 48) return 48;
   if (cout <= 64) return 64;
   if (cout <= 128) return 128;
-  // A deformable gather is paid once per N tile: always take the widest tile.
-  if (gather) return 256;
+  // A deformable gather is paid once per N tile: always take the widest tile
+  // (the 3-part fp32 mode only fits 128 columns of operands in shared memory).
+  if (gather) return split ? 128 : 256;
   // Plain conv: 256-wide tiles halve the A traffic, but only when there are
   // enough tiles left to occupy every SM.
   return (m_tiles * ((cout + 255) / 256) >= sm_count()) ? 256 : 128;
@@ -130,7 +133,7 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
   M3D_REQUIRE(d->num_inputs >= 1 && d->num_inputs <= M3D_MAX_CONCAT, "num_inputs=%d out of range", d->num_inputs);
   M3D_REQUIRE(d->R >= 1 && d->S >= 1 && d->stride >= 1 && d->dil >= 1 && d->pad >= 0, "bad kernel geometry");
   M3D_REQUIRE(d->N >= 1 && d->H >= 1 && d->W >= 1 && d->Cout >= 1, "bad tensor geometry");
-  M3D_REQUIRE(d->weight != nullptr && d->out != nullptr, "weight/out is NULL");
+  M3D_REQUIRE((d->weight != nullptr || d->weight_f32 != nullptr) && d->out != nullptr, "weight/out is NULL");
   const int groups = d->groups < 1 ? 1 : d->groups;
   const int P = (d->H + 2 * d->pad - (d->dil * (d->R - 1) + 1)) / d->stride + 1;  // dcn_v2_cuda.c:40-41
   const int Q = (d->W + 2 * d->pad - (d->dil * (d->S - 1) + 1)) / d->stride + 1;
@@ -139,7 +142,12 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
   const bool gather = split || d->om != nullptr || d->force_gather;
   if (split) {
     M3D_REQUIRE(d->out_dtype == M3D_F32, "fp32 activations need fp32 output");
-    M3D_REQUIRE(d->weight_lo != nullptr, "fp32 mode needs weight_lo");
+    if (d->weight_f32 != nullptr) {
+      M3D_REQUIRE(groups == 1, "fp32 path does not batch groups");
+      return launch_conv_simt_f32(d, P, Q, stream);
+    }
+    M3D_REQUIRE(d->weight != nullptr && d->weight_mid != nullptr && d->weight_lo != nullptr,
+                "fp32 activations need weight_f32 (reference accuracy) or weight + weight_mid + weight_lo (bf16x3)");
   }
   long ktot = 0;
   int bk = 64;
@@ -161,7 +169,7 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
   pick_tile(P, Q, 256 / d->stride, &TW, &TH);
   const int tiles_w = (Q + TW - 1) / TW, tiles_h = (P + TH - 1) / TH;
   const long m_tiles = static_cast<long>(tiles_w) * tiles_h * d->N;
-  const int BN = pick_bn(d->Cout, bk, m_tiles * groups, gather);
+  const int BN = pick_bn(d->Cout, bk, m_tiles * groups, gather, split);
   const int n_tiles = (d->Cout + BN - 1) / BN;
   const long total_tiles = m_tiles * n_tiles * groups;
   M3D_REQUIRE(total_tiles < (1L << 30), "too many tiles");
@@ -199,6 +207,8 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
   int rc = make_tmap_2d(&p.tmap_b, d->weight, d->weight_rows, ktot, 64, BN);
   if (rc != M3D_OK) return rc;
   if (split) {
+    rc = make_tmap_2d(&p.tmap_b_mid, d->weight_mid, d->weight_rows, ktot, 64, BN);
+    if (rc != M3D_OK) return rc;
     rc = make_tmap_2d(&p.tmap_b_lo, d->weight_lo, d->weight_rows, ktot, 64, BN);
     if (rc != M3D_OK) return rc;
   }

@@ -1,0 +1,205 @@
+// fp32 reference-accuracy convolution / DCNv2: implicit GEMM on the CUDA cores
+// with IEEE fp32 FMA accumulation in registers -- the arithmetic class of the
+// reference's own GPU path (cuDNN fp32 / cuBLAS SGEMM, model/DCNv2/src/dcn_v2_cuda.c:93-96).
+// Tensor-core accumulators truncate (~2^-23 per add, biased), which this random-
+// weight network amplifies past the 1e-3 parity budget; this kernel is the
+// mode parity is judged in.  Throughput mode is the tcgen05 path in igemm.cu.
+//
+// CTA = 256 threads, output tile 64 pixels (8x8 of one image) x 64 channels,
+// 4x4 outputs per thread, k-blocks of 16 (one tap, 16 input channels).
+#include <cstdint>
+
+#include "common.cuh"
+#include "igemm.cuh"
+
+namespace m3d {
+
+constexpr int SM_TM = 64, SM_TN = 64, SM_TK = 16, SM_TW = 8, SM_TH = 8;
+
+struct ConvSimtParams {
+  int num_inputs;
+  const float* in[kMaxConcat];
+  int in_cstride[kMaxConcat], in_coff[kMaxConcat], in_c[kMaxConcat];
+  int H, W, R, S, stride, pad, dil;
+  int N, P, Q, tiles_w, tiles_h, n_tiles;
+  int Cout;
+  const float* weight;  // fp32 [rows][ktot]
+  int weight_rows, ktot;
+  const float* om;
+  int om_cstride, sigmoid_mask;
+  float* out;
+  int out_cstride, out_coff;
+  const float* bias;
+  const float* res;
+  int res_cstride, res_coff;
+  float slope;
+};
+
+__global__ void __launch_bounds__(256) conv_simt_f32_kernel(const ConvSimtParams p) {
+  __shared__ __align__(16) float As[SM_TK][SM_TM + 4];
+  __shared__ __align__(16) float Bs[SM_TK][SM_TN + 4];
+  const int tid = threadIdx.x;
+  int tile = blockIdx.x;
+  const int nt = tile % p.n_tiles;
+  tile /= p.n_tiles;
+  const int tw = tile % p.tiles_w;
+  tile /= p.tiles_w;
+  const int th = tile % p.tiles_h;
+  const int n = tile / p.tiles_h;
+  const int p0 = th * SM_TH, q0 = tw * SM_TW, n0 = nt * SM_TN;
+  const int taps = p.R * p.S;
+
+  // A loader role: pixel a_px, channel quad a_kq
+  const int a_px = tid % SM_TM, a_kq = tid / SM_TM;
+  const int a_pp = p0 + a_px / SM_TW, a_qq = q0 + a_px % SM_TW;
+  const bool a_ok = a_pp < p.P && a_qq < p.Q;
+  // B loader role: output channel b_co, k quad b_kq
+  const int b_co = tid / 4, b_kq = tid % 4;
+  const bool b_ok = n0 + b_co < p.Cout && n0 + b_co < p.weight_rows;
+  // compute role
+  const int tx = tid % 16, ty = tid / 16;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  int kcol = 0;
+  for (int ii = 0; ii < p.num_inputs; ++ii) {
+    const float* in = p.in[ii] + p.in_coff[ii];
+    const int cs = p.in_cstride[ii];
+    for (int tap = 0; tap < taps; ++tap) {
+      // sample geometry of (pixel, tap): dcn_v2_im2col_cuda.cu:141-173, :18-47
+      const int r = tap / p.S, s = tap % p.S;
+      long o00 = 0, o01 = 0, o10 = 0, o11 = 0;
+      float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f, m = 0.f;
+      bool any = false;
+      if (a_ok) {
+        float hf = static_cast<float>(a_pp * p.stride - p.pad + r * p.dil);
+        float wf = static_cast<float>(a_qq * p.stride - p.pad + s * p.dil);
+        m = 1.f;
+        if (p.om != nullptr) {
+          const float* om = p.om + ((static_cast<long>(n) * p.P + a_pp) * p.Q + a_qq) * p.om_cstride;
+          hf += __ldg(om + 2 * tap);
+          wf += __ldg(om + 2 * tap + 1);
+          m = __ldg(om + 2 * taps + tap);
+          if (p.sigmoid_mask) m = 1.f / (1.f + expf(-m));
+        }
+        if (hf > -1.f && wf > -1.f && hf < static_cast<float>(p.H) && wf < static_cast<float>(p.W)) {
+          any = true;
+          const float hl = floorf(hf), wl = floorf(wf);
+          const int h_low = static_cast<int>(hl), w_low = static_cast<int>(wl);
+          const int h_high = h_low + 1, w_high = w_low + 1;
+          const float lh = hf - hl, lw = wf - wl, hh = 1.f - lh, hw = 1.f - lw;
+          const bool hl_ok = h_low >= 0, wl_ok = w_low >= 0, hh_ok = h_high <= p.H - 1, wh_ok = w_high <= p.W - 1;
+          const long rl = (static_cast<long>(n) * p.H + (hl_ok ? h_low : 0)) * p.W;
+          const long rh = (static_cast<long>(n) * p.H + (hh_ok ? h_high : 0)) * p.W;
+          const int cl = wl_ok ? w_low : 0, ch = wh_ok ? w_high : 0;
+          o00 = (rl + cl) * cs, o01 = (rl + ch) * cs, o10 = (rh + cl) * cs, o11 = (rh + ch) * cs;
+          w00 = (hl_ok && wl_ok) ? hh * hw : 0.f;
+          w01 = (hl_ok && wh_ok) ? hh * lw : 0.f;
+          w10 = (hh_ok && wl_ok) ? lh * hw : 0.f;
+          w11 = (hh_ok && wh_ok) ? lh * lw : 0.f;
+        }
+      }
+      for (int c0 = 0; c0 < p.in_c[ii]; c0 += SM_TK) {
+        // ---- stage A (sampled, modulated activations) and B (weights)
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (any) {
+          const int c = c0 + a_kq * 4;
+          if (w00 == 1.f) {
+            v = __ldg(reinterpret_cast<const float4*>(in + o00 + c));
+          } else {
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(in + o00 + c));
+            const float4 v2 = __ldg(reinterpret_cast<const float4*>(in + o01 + c));
+            const float4 v3 = __ldg(reinterpret_cast<const float4*>(in + o10 + c));
+            const float4 v4 = __ldg(reinterpret_cast<const float4*>(in + o11 + c));
+            v.x = w00 * v1.x + w01 * v2.x + w10 * v3.x + w11 * v4.x;
+            v.y = w00 * v1.y + w01 * v2.y + w10 * v3.y + w11 * v4.y;
+            v.z = w00 * v1.z + w01 * v2.z + w10 * v3.z + w11 * v4.z;
+            v.w = w00 * v1.w + w01 * v2.w + w10 * v3.w + w11 * v4.w;
+          }
+          v.x *= m, v.y *= m, v.z *= m, v.w *= m;
+        }
+        float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b_ok) wv = __ldg(reinterpret_cast<const float4*>(p.weight + static_cast<long>(n0 + b_co) * p.ktot + kcol + b_kq * 4));
+        __syncthreads();  // previous k-block fully consumed
+        As[a_kq * 4 + 0][a_px] = v.x;
+        As[a_kq * 4 + 1][a_px] = v.y;
+        As[a_kq * 4 + 2][a_px] = v.z;
+        As[a_kq * 4 + 3][a_px] = v.w;
+        Bs[b_kq * 4 + 0][b_co] = wv.x;
+        Bs[b_kq * 4 + 1][b_co] = wv.y;
+        Bs[b_kq * 4 + 2][b_co] = wv.z;
+        Bs[b_kq * 4 + 3][b_co] = wv.w;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < SM_TK; ++kk) {
+          const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+          const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+          const float av[4] = {a.x, a.y, a.z, a.w};
+          const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        kcol += SM_TK;
+      }
+    }
+  }
+  // ---- epilogue: bias, residual, LeakyReLU
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int px = ty * 4 + i;
+    const int pp = p0 + px / SM_TW, qq = q0 + px % SM_TW;
+    if (pp >= p.P || qq >= p.Q) continue;
+    const long pix = (static_cast<long>(n) * p.P + pp) * p.Q + qq;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = n0 + tx * 4 + j;
+      if (co >= p.Cout) continue;
+      float v = acc[i][j];
+      if (p.bias != nullptr) v += __ldg(p.bias + co);
+      if (p.res != nullptr) v += __ldg(p.res + pix * p.res_cstride + p.res_coff + co);
+      v = v > 0.f ? v : v * p.slope;
+      p.out[pix * p.out_cstride + p.out_coff + co] = v;
+    }
+  }
+}
+
+int launch_conv_simt_f32(const m3d_conv_desc* d, int P, int Q, cudaStream_t stream) {
+  ConvSimtParams p;
+  p.num_inputs = d->num_inputs;
+  long ktot = 0;
+  for (int i = 0; i < d->num_inputs; ++i) {
+    p.in[i] = static_cast<const float*>(d->in[i]);
+    p.in_cstride[i] = d->in_cstride[i];
+    p.in_coff[i] = d->in_coff[i];
+    p.in_c[i] = d->in_c[i];
+    M3D_REQUIRE(d->in_c[i] % 16 == 0 && d->in_cstride[i] % 4 == 0 && d->in_coff[i] % 4 == 0,
+                "fp32 path: input %d channels must be a multiple of 16 and 16-byte aligned", i);
+    ktot += static_cast<long>(d->R) * d->S * d->in_c[i];
+  }
+  for (int i = d->num_inputs; i < kMaxConcat; ++i) p.in[i] = nullptr, p.in_cstride[i] = p.in_coff[i] = p.in_c[i] = 0;
+  p.H = d->H, p.W = d->W, p.R = d->R, p.S = d->S, p.stride = d->stride, p.pad = d->pad, p.dil = d->dil;
+  p.N = d->N, p.P = P, p.Q = Q;
+  p.tiles_w = (Q + SM_TW - 1) / SM_TW, p.tiles_h = (P + SM_TH - 1) / SM_TH;
+  p.n_tiles = (d->Cout + SM_TN - 1) / SM_TN;
+  p.Cout = d->Cout;
+  p.weight = static_cast<const float*>(d->weight_f32);
+  p.weight_rows = d->weight_rows, p.ktot = static_cast<int>(ktot);
+  p.om = d->om, p.om_cstride = d->om_cstride, p.sigmoid_mask = d->sigmoid_mask;
+  p.out = static_cast<float*>(d->out), p.out_cstride = d->out_cstride, p.out_coff = d->out_coff;
+  p.bias = d->bias;
+  p.res = static_cast<const float*>(d->res), p.res_cstride = d->res_cstride, p.res_coff = d->res_coff;
+  p.slope = d->slope;
+  const long tiles = static_cast<long>(p.tiles_w) * p.tiles_h * p.N * p.n_tiles;
+  M3D_REQUIRE(tiles < (1L << 31), "too many tiles");
+  conv_simt_f32_kernel<<<static_cast<unsigned>(tiles), 256, 0, stream>>>(p);
+  M3D_CUDA_OK(cudaGetLastError());
+  return M3D_OK;
+}
+
+}  // namespace m3d

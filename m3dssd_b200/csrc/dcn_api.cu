@@ -13,7 +13,8 @@ namespace m3d {
 
 // [Cout, Cin, kh, kw] fp32 -> [Cout][tap][Cpad] bf16 (hi, lo), zero channel padding.
 __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
-                                   __nv_bfloat16* __restrict__ lo, int Cout, int Cin, int KK, int Cpad) {
+                                   __nv_bfloat16* __restrict__ mid, __nv_bfloat16* __restrict__ lo, int Cout, int Cin,
+                                   int KK, int Cpad) {
   const long total = static_cast<long>(Cout) * KK * Cpad;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -24,7 +25,24 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
     if (c < Cin) v = w[(static_cast<long>(co) * Cin + c) * KK + t];
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
     hi[i] = h;
-    if (lo != nullptr) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    if (mid != nullptr) {
+      const float r1 = v - __bfloat162float(h);
+      const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+      mid[i] = m;
+      lo[i] = __float2bfloat16_rn(r1 - __bfloat162float(m));
+    }
+  }
+}
+
+__global__ void pack_weight_f32_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int KK,
+                                       int Cpad) {
+  const long total = static_cast<long>(Cout) * KK * Cpad;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Cpad);
+    const int t = static_cast<int>((i / Cpad) % KK);
+    const int co = static_cast<int>(i / (static_cast<long>(Cpad) * KK));
+    out[i] = c < Cin ? w[(static_cast<long>(co) * Cin + c) * KK + t] : 0.f;
   }
 }
 
@@ -42,12 +60,12 @@ static DcnLayout dcn_layout(int B, int C, int H, int W, int Cout, int kh, int kw
   L.Wo = (W + 2 * pad - (dil * (kw - 1) + 1)) / stride + 1;
   L.Cpad = (C + 63) / 64 * 64;
   L.KK = kh * kw;
-  const size_t esz = precision == M3D_F32 ? 4 : 2;
+  const size_t esz = precision == M3D_BF16 ? 2 : 4;
   L.x_bytes = align256(static_cast<size_t>(B) * H * W * L.Cpad * esz);
   L.om_bytes = align256(static_cast<size_t>(B) * L.Ho * L.Wo * 3 * L.KK * 4);
-  L.w_bytes = align256(static_cast<size_t>(Cout) * L.KK * L.Cpad * 2);
+  L.w_bytes = align256(static_cast<size_t>(Cout) * L.KK * L.Cpad * 2);  // one bf16 part; fp32 weights use two slots
   L.out_bytes = align256(static_cast<size_t>(B) * L.Ho * L.Wo * Cout * 4);
-  L.total = L.x_bytes + L.om_bytes + 2 * L.w_bytes + L.out_bytes;
+  L.total = L.x_bytes + L.om_bytes + 3 * L.w_bytes + L.out_bytes;
   return L;
 }
 
@@ -78,7 +96,9 @@ extern "C" int m3d_dcn_v2_forward(const float* input, const float* weight, const
                    deformable_group, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, kh, kw);
     return M3D_ERR_UNSUPPORTED;
   }
-  M3D_REQUIRE(precision == M3D_F32 || precision == M3D_BF16, "precision must be M3D_F32 or M3D_BF16");
+  M3D_REQUIRE(precision == M3D_F32 || precision == M3D_BF16 || precision == M3D_BF16X3,
+              "precision must be M3D_F32, M3D_BF16X3 or M3D_BF16");
+  const int act = precision == M3D_BF16 ? M3D_BF16 : M3D_F32;
   const DcnLayout L = dcn_layout(B, C, H, W, Cout, kh, kw, stride_h, pad_h, dil_h, precision);
   M3D_REQUIRE(L.Ho >= 1 && L.Wo >= 1, "empty output");
   if (workspace == nullptr || workspace_bytes < L.total) {
@@ -89,11 +109,12 @@ extern "C" int m3d_dcn_v2_forward(const float* input, const float* weight, const
   void* x = ws;
   float* om = reinterpret_cast<float*>(ws + L.x_bytes);
   __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(ws + L.x_bytes + L.om_bytes);
-  __nv_bfloat16* w_lo = reinterpret_cast<__nv_bfloat16*>(ws + L.x_bytes + L.om_bytes + L.w_bytes);
-  float* out_nhwc = reinterpret_cast<float*>(ws + L.x_bytes + L.om_bytes + 2 * L.w_bytes);
+  __nv_bfloat16* w_mid = reinterpret_cast<__nv_bfloat16*>(ws + L.x_bytes + L.om_bytes + L.w_bytes);
+  __nv_bfloat16* w_lo = reinterpret_cast<__nv_bfloat16*>(ws + L.x_bytes + L.om_bytes + 2 * L.w_bytes);
+  float* out_nhwc = reinterpret_cast<float*>(ws + L.x_bytes + L.om_bytes + 3 * L.w_bytes);
 
   if (L.Cpad != C) M3D_CUDA_OK(cudaMemsetAsync(x, 0, L.x_bytes, stream));
-  int rc = m3d_nchw_to_nhwc(input, M3D_F32, x, precision, B, C, H, W, L.Cpad, 0, stream_);
+  int rc = m3d_nchw_to_nhwc(input, M3D_F32, x, act, B, C, H, W, L.Cpad, 0, stream_);
   if (rc) return rc;
   rc = m3d_nchw_to_nhwc(offset, M3D_F32, om, M3D_F32, B, 2 * L.KK, L.Ho, L.Wo, 3 * L.KK, 0, stream_);
   if (rc) return rc;
@@ -102,12 +123,15 @@ extern "C" int m3d_dcn_v2_forward(const float* input, const float* weight, const
   {
     const long total = static_cast<long>(Cout) * L.KK * L.Cpad;
     const int grid = static_cast<int>((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
-    pack_weight_kernel<<<grid, 256, 0, stream>>>(weight, w_hi, precision == M3D_F32 ? w_lo : nullptr, Cout, C, L.KK,
-                                                 L.Cpad);
+    if (precision == M3D_F32)
+      pack_weight_f32_kernel<<<grid, 256, 0, stream>>>(weight, reinterpret_cast<float*>(w_hi), Cout, C, L.KK, L.Cpad);
+    else
+      pack_weight_kernel<<<grid, 256, 0, stream>>>(weight, w_hi, precision == M3D_BF16X3 ? w_mid : nullptr, w_lo, Cout,
+                                                   C, L.KK, L.Cpad);
     M3D_CUDA_OK(cudaGetLastError());
   }
   m3d_conv_desc d = {};
-  d.act_dtype = precision;
+  d.act_dtype = act;
   d.out_dtype = M3D_F32;
   d.num_inputs = 1;
   d.in[0] = x;
@@ -116,7 +140,13 @@ extern "C" int m3d_dcn_v2_forward(const float* input, const float* weight, const
   d.N = B, d.H = H, d.W = W;
   d.R = kh, d.S = kw, d.stride = stride_h, d.pad = pad_h, d.dil = dil_h;
   d.Cout = Cout, d.groups = 1;
-  d.weight = w_hi, d.weight_lo = precision == M3D_F32 ? w_lo : nullptr;
+  if (precision == M3D_F32) {
+    d.weight_f32 = reinterpret_cast<const float*>(w_hi);
+  } else {
+    d.weight = w_hi;
+    d.weight_mid = precision == M3D_BF16X3 ? w_mid : nullptr;
+    d.weight_lo = precision == M3D_BF16X3 ? w_lo : nullptr;
+  }
   d.weight_rows = Cout;
   d.bias = bias;
   d.out = out_nhwc, d.out_cstride = Cout;

@@ -277,8 +277,10 @@ __global__ void __launch_bounds__(192, 1) conv_tma_kernel(const __grid_constant_
 //   warp 9    : TMEM allocator + MMA issuer
 //   warps 10-13: epilogue
 // InT = bf16: one MMA per k16.  InT = float ("split"): activations and weights
-// carry bf16 hi+lo parts, three MMAs per k16 (hi*hi + lo*hi + hi*lo), which
-// reproduces fp32 products to ~2^-16 relative.
+// are carried as three bf16 parts (hi, mid, lo: 3 x 8 = 24 mantissa bits) and
+// each k16 issues six MMAs -- hi*hi, hi*mid, mid*hi, mid*mid, hi*lo, lo*hi --
+// i.e. every term down to 2^-16 of the product; the dropped ones are <= 2^-24.
+// That reproduces fp32 products to ~2^-23 with fp32 accumulation in TMEM.
 // =========================================================================
 constexpr int kGatherBK = 64;
 constexpr int kProducerThreads = 256;
@@ -288,10 +290,11 @@ struct GatherCfg {
   static constexpr int ROW_BYTES = 128;
   static constexpr int A_BYTES = kTileM * ROW_BYTES;  // per part
   static constexpr int B_BYTES = BN * ROW_BYTES;      // per part
-  static constexpr int PARTS = SPLIT ? 2 : 1;
+  static constexpr int PARTS = SPLIT ? 3 : 1;
   static constexpr int STAGE = PARTS * (A_BYTES + B_BYTES);
   static constexpr int OM_BYTES = kTileM * 28 * 4;
   static constexpr int STAGES = (STAGE * 4 + OM_BYTES <= 200 * 1024) ? 4 : ((STAGE * 3 + OM_BYTES <= 210 * 1024) ? 3 : 2);
+  static_assert(STAGES * STAGE + OM_BYTES + 1280 <= 227 * 1024, "gather tile does not fit shared memory");
   static constexpr int SMEM = STAGES * STAGE + OM_BYTES + 1024 + 256;
   static constexpr int ACC = acc_cols(BN);
 };
@@ -335,7 +338,7 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
   constexpr int BK = kGatherBK;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  // stage layout: [A_hi][A_lo?][B_hi][B_lo?]
+  // stage layout: [A_hi][A_mid][A_lo][B_hi][B_mid][B_lo]  (one part each when !SPLIT)
   float* om_s = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE + Cfg::OM_BYTES);
   uint64_t* full = bars;
@@ -358,7 +361,10 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
     }
     fence_barrier_init();
     prefetch_tmap(&p.tmap_b);
-    if (SPLIT) prefetch_tmap(&p.tmap_b_lo);
+    if (SPLIT) {
+      prefetch_tmap(&p.tmap_b_mid);
+      prefetch_tmap(&p.tmap_b_lo);
+    }
   }
   if (warp == 9) tmem_alloc<2 * Cfg::ACC>(tmem_slot);
   tc_fence_before();
@@ -442,7 +448,6 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
           for (int c = 0; c < p.chunks[i]; ++c) {
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* a_hi = smem + stage * Cfg::STAGE;
-            uint8_t* a_lo = a_hi + Cfg::A_BYTES;
             const int coff = c * BK + j * 8;
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
@@ -469,14 +474,17 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
               }
               const uint32_t off = swizzled_offset<128>(row, j);
               if constexpr (SPLIT) {
-                float hi[8], lo[8];
+                float hi[8], mid[8], lo[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                   hi[e] = __bfloat162float(__float2bfloat16_rn(acc[e]));
-                  lo[e] = acc[e] - hi[e];
+                  const float r1 = acc[e] - hi[e];  // exact
+                  mid[e] = __bfloat162float(__float2bfloat16_rn(r1));
+                  lo[e] = r1 - mid[e];              // exact; rounded to bf16 by pack8
                 }
                 *reinterpret_cast<uint4*>(a_hi + off) = pack8(hi);
-                *reinterpret_cast<uint4*>(a_lo + off) = pack8(lo);
+                *reinterpret_cast<uint4*>(a_hi + Cfg::A_BYTES + off) = pack8(mid);
+                *reinterpret_cast<uint4*>(a_hi + 2 * Cfg::A_BYTES + off) = pack8(lo);
               } else {
                 *reinterpret_cast<uint4*>(a_hi + off) = pack8(acc);
               }
@@ -503,7 +511,10 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
           uint8_t* b_hi = smem + stage * Cfg::STAGE + Cfg::PARTS * Cfg::A_BYTES;
           mbar_arrive_expect_tx(&full[stage], Cfg::PARTS * Cfg::B_BYTES);
           tma_load_2d(b_hi, &p.tmap_b, &full[stage], kb * BK, t.nt * BN);
-          if constexpr (SPLIT) tma_load_2d(b_hi + Cfg::B_BYTES, &p.tmap_b_lo, &full[stage], kb * BK, t.nt * BN);
+          if constexpr (SPLIT) {
+            tma_load_2d(b_hi + Cfg::B_BYTES, &p.tmap_b_mid, &full[stage], kb * BK, t.nt * BN);
+            tma_load_2d(b_hi + 2 * Cfg::B_BYTES, &p.tmap_b_lo, &full[stage], kb * BK, t.nt * BN);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -533,12 +544,20 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
           const uint64_t db = umma_smem_desc<128>(b_hi);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            umma_f16(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
             if constexpr (SPLIT) {
-              const uint64_t dal = umma_smem_desc<128>(a_hi + Cfg::A_BYTES);
-              const uint64_t dbl = umma_smem_desc<128>(b_hi + Cfg::B_BYTES);
-              umma_f16(tmem_acc, dal + 2 * k, db + 2 * k, idesc, 1);
-              umma_f16(tmem_acc, da + 2 * k, dbl + 2 * k, idesc, 1);
+              const uint64_t dam = umma_smem_desc<128>(a_hi + Cfg::A_BYTES) + 2 * k;
+              const uint64_t dal = umma_smem_desc<128>(a_hi + 2 * Cfg::A_BYTES) + 2 * k;
+              const uint64_t dbm = umma_smem_desc<128>(b_hi + Cfg::B_BYTES) + 2 * k;
+              const uint64_t dbl = umma_smem_desc<128>(b_hi + 2 * Cfg::B_BYTES) + 2 * k;
+              // smallest terms first, the dominant hi*hi last
+              umma_f16(tmem_acc, da + 2 * k, dbl, idesc, (kb | k) != 0);
+              umma_f16(tmem_acc, dal, db + 2 * k, idesc, 1);
+              umma_f16(tmem_acc, dam, dbm, idesc, 1);
+              umma_f16(tmem_acc, da + 2 * k, dbm, idesc, 1);
+              umma_f16(tmem_acc, dam, db + 2 * k, idesc, 1);
+              umma_f16(tmem_acc, da + 2 * k, db + 2 * k, idesc, 1);
+            } else {
+              umma_f16(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
             }
           }
           umma_commit(&empty[stage]);
@@ -646,7 +665,8 @@ int launch_conv_gather(const ConvGatherParams& p, int BN, int in_dtype, int out_
     if (in_dtype == DT_BF16)                                                                     \
       return out_dtype == DT_BF16 ? launch_gather_t<bn, __nv_bfloat16, __nv_bfloat16>(p, stream) \
                                   : launch_gather_t<bn, __nv_bfloat16, float>(p, stream);        \
-    return launch_gather_t<bn, float, float>(p, stream);                                         \
+    if constexpr (bn <= 128) return launch_gather_t<bn, float, float>(p, stream);                \
+    return M3D_ERR_UNSUPPORTED;                                                                  \
   }
   M3D_G_CASE(16)
   M3D_G_CASE(32)

@@ -16,7 +16,9 @@
 //                          mask and write the swizzled bf16 tile themselves
 //                          (no im2col buffer in HBM).  Also the fp32-accurate
 //                          mode: fp32 activations and weights are split into
-//                          bf16 hi+lo parts and contracted with 3 MMAs.
+//                          three bf16 parts (hi + mid + lo = 24 mantissa bits)
+//                          and contracted with the 6 MMAs whose terms are
+//                          >= 2^-16 of the product (error ~2^-23: fp32 quality).
 //
 // Semantics follow the reference's modulated_deformable_im2col_gpu_kernel +
 // SGEMM (model/DCNv2/src/cuda/dcn_v2_im2col_cuda.cu:118-180,
@@ -59,8 +61,9 @@ struct alignas(64) ConvTmaParams {
 };
 
 struct alignas(64) ConvGatherParams {
-  CUtensorMap tmap_b;     // bf16 weights (hi part in split mode)
-  CUtensorMap tmap_b_lo;  // lo part (split mode only)
+  CUtensorMap tmap_b;      // bf16 weights (hi part in split mode)
+  CUtensorMap tmap_b_mid;  // split mode: second 8 mantissa bits
+  CUtensorMap tmap_b_lo;   // split mode: third 8 mantissa bits
   int num_inputs;
   const void* in[kMaxConcat];
   int in_cstride[kMaxConcat], in_coff[kMaxConcat], chunks[kMaxConcat];

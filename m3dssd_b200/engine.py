@@ -46,18 +46,20 @@ def _fold(conv_w, conv_b, bn):
 
 class Engine:
     def __init__(self, net, batch, height, width, precision="bf16", use_graph=True, topk=None, max_out=None):
-        assert precision in ("bf16", "fp32")
+        assert precision in ("bf16", "bf16x3", "fp32")
         if not torch.cuda.is_available():
             raise RuntimeError("m3dssd_b200.Engine needs a CUDA device: there is no CPU fallback")
         self.dev = torch.device("cuda", torch.cuda.current_device())
         self.net = net
         self.conf = net.conf
         self.B, self.H, self.W = batch, height, width
-        self.fp32 = precision == "fp32"
+        self.fp32 = precision != "bf16"  # fp32 activation storage ("fp32": IEEE FMA; "bf16x3": tensor-core split)
         self.precision = precision
         self.adt = torch.float32 if self.fp32 else torch.bfloat16
         self.ops = []
+        self.meta = []
         self.bufs = {}
+        self._pool_cache = {}
         self.named = {}  # name -> Act of notable intermediate activations (parity checks)
         self.n_launches = 0
         self.use_graph = use_graph
@@ -79,8 +81,11 @@ class Engine:
         self.bufs[name] = t
         return t
 
-    def _add(self, fn, launches=1):
+    def _add(self, fn, launches=1, name="", kind="misc", flops=0.0, bytes_=0.0):
+        """Register one step of the plan.  flops / bytes_ are ALGORITHMIC (real channels, every
+        operand read or written once), the numerators of the roofline figures bench.py reports."""
         self.ops.append(fn)
+        self.meta.append(dict(name=name, kind=kind, launches=launches, flops=float(flops), bytes=float(bytes_)))
         self.n_launches += launches
 
     def _conv(self, name, inputs, w, b, bn, k, stride=1, pad=None, slope=0.01, res=None, out=None, out_dtype=None,
@@ -90,9 +95,12 @@ class Engine:
         wf, bf = _fold(w, b, bn)
         cout = wf.shape[0]
         splits = [(a.c, self._cpad(a.c)) for a in inputs]
-        hi, lo = ops.pack_conv_weight(wf.cpu(), in_splits=splits, fp32_mode=self.fp32)
-        hi = hi.to(self.dev)
-        lo = lo.to(self.dev) if lo is not None else None
+        hi, lo = ops.pack_conv_weight(wf.cpu(), in_splits=splits, mode=self.precision)
+        hi = hi.to(self.dev) if hi is not None else None
+        if isinstance(lo, tuple):
+            lo = tuple(t.to(self.dev) for t in lo)
+        elif lo is not None:
+            lo = lo.to(self.dev)
         bias = bf.to(self.dev).contiguous()
         x0 = inputs[0].t
         N, H, W = x0.shape[:3]
@@ -112,7 +120,16 @@ class Engine:
                             res_coff=res_coff, slope=slope, weight_lo=lo, om=om_t, sigmoid_mask=sigmoid_mask,
                             out_coff=out_coff)
 
-        self._add(run)
+        esz = 4 if self.fp32 else 2
+        k_real = k * k * sum(a.c for a in inputs)
+        flops = 2.0 * N * P * Q * cout * k_real
+        nbytes = sum(N * H * W * a.c * esz for a in inputs) + N * P * Q * cout * out.element_size() + cout * k_real * 2
+        if res is not None:
+            nbytes += N * P * Q * cout * esz
+        if om is not None:
+            nbytes += N * P * Q * 3 * k * k * 4
+        kind = "dcn_gather" if om is not None else ("conv_gather" if self.fp32 else "conv_tma")
+        self._add(run, 1, name, kind, flops, nbytes)
         return Act(out, cout, out_coff)
 
     def _conv_module(self, name, inputs, conv, bn, slope=0.01, res=None, **kw):
@@ -120,10 +137,18 @@ class Engine:
                           conv.padding[0], slope, res, **kw)
 
     def _maxpool(self, name, a):
+        key = (a.t.data_ptr(), a.coff, a.c)
+        if key in self._pool_cache:  # nested Trees pool the same tensor twice in the reference
+            return self._pool_cache[key]
+        r = self._maxpool_new(name, a)
+        self._pool_cache[key] = r
+        return r
+
+    def _maxpool_new(self, name, a):
         N, H, W, cs = a.t.shape
         out = self._new(name, N, H // 2, W // 2, cs)
         x = a.t
-        self._add(lambda: ops.maxpool2x2(x, out))
+        self._add(lambda: ops.maxpool2x2(x, out), 1, name, "maxpool", 0, x.numel() * x.element_size() * 1.25)
         return Act(out, a.c)
 
     # ------------------------------------------------------------- DLA trunk
@@ -162,7 +187,8 @@ class Engine:
         assert c0 == 16, "stem kernel is specialised for 16 output channels"
         s0 = self._new("stem", B, H, W, self._cpad(c0))
         img = self.image
-        self._add(lambda: ops.stem_conv7x7(img, w, b, s0, 0.01))
+        self._add(lambda: ops.stem_conv7x7(img, w, b, s0, 0.01), 1, "stem", "stem", 2.0 * B * H * W * c0 * 147,
+                  B * H * W * (3 * 4 + c0 * s0.element_size()))
         x = Act(s0, c0)
         x = self._conv_module("level0", [x], base.level0[0], base.level0[1])
         levels = [x]
@@ -195,7 +221,9 @@ class Engine:
             u = self._new("%s.up_%d" % (name, k), N, H * f, W * f, cs)
             wt = up.weight.detach().float().reshape(up.weight.shape[0], -1).contiguous().to(self.dev)
             pt, st = p.t, skip.t
-            self._add(lambda pt=pt, wt=wt, st=st, u=u, f=f: ops.upsample_add(pt, wt, st, u, f))
+            self._add(lambda pt=pt, wt=wt, st=st, u=u, f=f: ops.upsample_add(pt, wt, st, u, f), 1,
+                      "%s.up_%d" % (name, k), "upsample", 2.0 * u.numel() * 4,
+                      (pt.numel() + 2 * u.numel()) * u.element_size())
             layers[i] = self._deform_conv("%s.node_%d" % (name, k), node, Act(u, p.c))
 
     def _dla_seg(self):
@@ -251,14 +279,46 @@ class Engine:
             ops.conv2d_nhwc([(h2, 0, mid)], w3, heads_buf, R=1, S=1, Cout=A, bias=b3, slope=1.0, groups=G,
                             in_goff=[mid], weight_goff=rows3, bias_goff=rows3, out_coff=slot0 * A, out_goff=A)
 
-        self._add(run, 2)
+        fl2 = 2.0 * N * H * W * G * mid * mid
+        fl3 = 2.0 * N * H * W * G * A * mid
+        by2 = N * H * W * G * mid * 2 * 2 + G * mid * mid * 2
+        by3 = N * H * W * G * (mid * 2 + A * 4) + G * A * mid * 2
+        self._add(run, 2, gname + ".l2l3", "conv_tma", fl2 + fl3, by2 + by3)
 
     def _align(self, name, m, x, om):
         return self._conv(name, [x], m.align.weight, m.align.bias, None, m.align.kernel_size[0], 1, m.align.padding,
                           1.0, res=x, om=om)
 
     def _anab(self, x):
-        raise NotImplementedError("ANAB fused path is built in engine_anab.py")
+        """bbox_z3d_gl = ANAB -> BN -> LeakyReLU (model/M3d_inference_align.py:168-173); BN folded into the epilogue."""
+        seq = self.net.bbox_z3d_gl
+        anab, bn = seq[0], seq[1]
+        if not anab.with_atten:
+            raise NotImplementedError("ANAB(with_atten=False) is not on the reference's path")
+        ck, cv, T = anab.key_ch, anab.outch, anab.key_num
+        sizes = list(anab.psp_size)
+        N, H, W = x.t.shape[:3]
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        q = self._conv_module("anab.q", [x], anab.query_conv, None, slope=1.0)
+        w = torch.cat([anab.key_conv.weight, anab.value_conv.weight, anab.spatial_conv.weight]).detach()
+        ckvs = (ck + cv + len(sizes) + 3) // 4 * 4
+        kvs = self._new("anab.kvs", N, H, W, ckvs, torch.float32)
+        self._conv("anab.kvs", [x], w, None, None, 1, 1, 0, 1.0, out=kvs)
+        ktok = torch.zeros(N, T, ck, **f32)
+        vtok = torch.zeros(N, T, cv, **f32)
+        ws = torch.zeros(ops.anab_pool_workspace(N, H, sizes, ck, cv), dtype=torch.uint8, device=self.dev)
+        self._add(lambda: ops.anab_pool(kvs, ck, cv, sizes, ktok, vtok, ws), 2, "anab.pool", "anab_pool",
+                  2.0 * N * H * W * (ck + cv) * len(sizes), kvs.numel() * 4)
+        scale = (bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)).to(self.dev)
+        shift = (bn.bias.detach().float().to(self.dev) - bn.running_mean.detach().float().to(self.dev) * scale)
+        scale, shift = scale.contiguous(), shift.contiguous()
+        out = self._new("anab.out", N, H, W, x.t.shape[-1])
+        qt, xt = q.t, x.t
+        self._add(lambda: ops.anab_attention(qt, ktok, vtok, xt, scale, shift, 0.01, out, ck, cv), 1, "anab.attention",
+                  "anab_attention", 2.0 * N * H * W * T * (ck + cv),
+                  N * H * W * (ck + 2 * cv) * out.element_size() + N * T * (ck + cv) * 4)
+        self.bufs["anab.ktok"], self.bufs["anab.vtok"] = ktok, vtok
+        return Act(out, x.c)
 
     def _build(self):
         net, conf = self.net, self.conf
@@ -283,7 +343,7 @@ class Engine:
         self.score = torch.zeros(B, M, **f32)
         self.cls_pred = torch.zeros(B, M, dtype=torch.uint8, device=self.dev)
         self._add(lambda: ops.cls_softmax(logits, A, K, self.cls_out, self.prob_out, self.fg_max, self.fg_arg,
-                                          self.score, self.cls_pred))
+                                          self.score, self.cls_pred), 1, "cls_softmax", "softmax", 0, B * M * K * 4 * 3)
         anchors = torch.tensor(np.asarray(conf.anchors), **f32).contiguous()
         self.anchors = anchors
         means = [float(v) for v in np.asarray(conf.bbox_means)[0]]
@@ -294,7 +354,8 @@ class Engine:
         if net.shape_align is not None:
             om_s = torch.zeros(B, Hf, Wf, 27, **f32)
             thr = float(net.shape_align.thresh)
-            self._add(lambda: ops.shape_align_om(self.fg_max, self.fg_arg, anchors, stride, thr, om_s))
+            self._add(lambda: ops.shape_align_om(self.fg_max, self.fg_arg, anchors, stride, thr, om_s), 1,
+                      "shape_align.om", "align_om", 0, om_s.numel() * 4)
             feats = self._align("shape_align", net.shape_align, feat, om_s)
         # --- regression heads (slots follow HEAD_ORDER)
         heads = self._new("heads", B, Hf, Wf, 11 * A, torch.float32)
@@ -307,9 +368,9 @@ class Engine:
             thr = float(net.center_align2d.thresh)
             sx, sy, sx3, sy3 = (HEAD_ORDER.index(n) * A for n in ("bbox_x", "bbox_y", "bbox_x3d", "bbox_y3d"))
             self._add(lambda: ops.center_align_om(self.fg_max, self.fg_arg, heads, sx, sy, anchors, stride, means[0:2],
-                                                  stds[0:2], thr, om2))
+                                                  stds[0:2], thr, om2), 1, "center_align2d.om", "align_om", 0, om2.numel() * 4)
             self._add(lambda: ops.center_align_om(self.fg_max, self.fg_arg, heads, sx3, sy3, anchors, stride,
-                                                  means[4:6], stds[4:6], thr, om3))
+                                                  means[4:6], stds[4:6], thr, om3), 1, "center_align3d.om", "align_om", 0, om3.numel() * 4)
             f2d = self._align("center_align2d", net.center_align2d, feats, om2)
             f3d = self._align("center_align3d", net.center_align3d, feats, om3)
         self.named["feats_shape"], self.named["feats_align2d"], self.named["feats_align3d"] = feats, f2d, f3d
@@ -322,11 +383,11 @@ class Engine:
         self._head_group("headsZ", ["bbox_z3d"], fz, heads)
         self.bbox_2d = torch.zeros(B, M, 4, **f32)
         self.bbox_3d = torch.zeros(B, M, 7, **f32)
-        self._add(lambda: ops.flatten_heads(heads, A, OUT_SLOTS, self.bbox_2d, self.bbox_3d))
+        self._add(lambda: ops.flatten_heads(heads, A, OUT_SLOTS, self.bbox_2d, self.bbox_3d), 1, "flatten_heads",
+                  "flatten", 0, B * M * 11 * 4 * 2)
         self.n_forward_ops = len(self.ops)
         # --- detection tail
-        self.means_t = torch.tensor(means, **f32)
-        self.stds_t = torch.tensor(stds, **f32)
+        self.means_t, self.stds_t = means, stds  # host lists (the C ABI takes them by value)
         self.dets = torch.zeros(B, self.topk, 14, **f32)
         self.det_idx = torch.zeros(B, self.topk, dtype=torch.int32, device=self.dev)
         self.det_num = torch.zeros(B, dtype=torch.int32, device=self.dev)
@@ -342,54 +403,82 @@ class Engine:
         for op in self.ops:
             op()
 
-    def _run_detect(self):
+    def _run_decode(self):
         ops.decode_topk(self.score, self.cls_pred, self.bbox_2d, self.bbox_3d, self.anchors, self.means_t, self.stds_t,
                         self.A, self.Hf, self.Wf, float(self.conf.feat_stride), self.scale_factor, self.topk, self.dets,
                         self.det_idx, self.det_num)
+
+    def _run_nms(self):
         ops.nms_batched(self.dets, self.det_num, float(self.conf.nms_thres), self.nms_ws, self.keep, self.num_keep)
         ops.gather_kept(self.dets, self.keep, self.num_keep, self.max_out, self.kept)
+
+    _STAGES = {"forward": 0, "decode": 1, "detect": 2}
+
+    def _run_stage(self, stage):
+        self._run_forward()
+        if self._STAGES[stage] >= 1:
+            self._run_decode()
+        if self._STAGES[stage] >= 2:
+            self._run_nms()
+
+    def launches_per_step(self, stage="detect"):
+        return self.n_launches + (0, 1, 4)[self._STAGES[stage]]
 
     def activation_nchw(self, name):
         """fp32 NCHW copy of a named intermediate activation (testing aid)."""
         a = self.named[name]
         return a.t[..., a.coff:a.coff + a.c].float().permute(0, 3, 1, 2).contiguous()
 
-    def launches_per_step(self, with_detect=True):
-        return self.n_launches + (4 if with_detect else 0)
-
-    def forward(self, images=None, detect=False):
-        """images: [B,3,H,W] fp32 CUDA (copied into the engine's input buffer) or None to reuse it.
-        Returns (cls, prob, bbox_2d, bbox_3d) views of the engine's output buffers."""
+    def run(self, images=None, stage="forward"):
+        """One pass over the engine's batch.  images: [B,3,H,W] fp32 CUDA tensor copied into the input
+        buffer (None = reuse what is there).  stage: "forward" (network outputs), "decode" (+ top-K
+        decode into self.dets) or "detect" (+ batched NMS into self.kept / self.num_keep)."""
         if images is not None:
             assert tuple(images.shape) == tuple(self.image.shape), (images.shape, self.image.shape)
             self.image.copy_(images, non_blocking=True)
-        if self.use_graph:
-            key = "det" if detect else "fwd"
-            if self.graph is None:
-                self.graph = {}
-            if key not in self.graph:
-                self._run_forward()  # warm-up outside capture: loads modules, sizes smem attributes
-                if detect:
-                    self._run_detect()
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._run_forward()
-                    if detect:
-                        self._run_detect()
-                self.graph[key] = g
-            self.graph[key].replay()
-        else:
-            self._run_forward()
-            if detect:
-                self._run_detect()
+        if not self.use_graph:
+            self._run_stage(stage)
+            return
+        if self.graph is None:
+            self.graph = {}
+        if stage not in self.graph:
+            self._run_stage(stage)  # eager pass first: module load, shared-memory attributes
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run_stage(stage)
+            self.graph[stage] = g
+        self.graph[stage].replay()
+
+    def forward(self, images=None):
+        """Returns (cls, prob, bbox_2d, bbox_3d): views of the engine's output buffers."""
+        self.run(images, "forward")
         return self.cls_out, self.prob_out, self.bbox_2d, self.bbox_3d
 
     def detect(self, images=None, scale_factor=1.0):
         """Full path: forward + decode/top-K + batched NMS.  Returns (kept [B,max_out,14], num_keep [B])."""
         if float(scale_factor) != self.scale_factor:
             self.scale_factor = float(scale_factor)
-            if self.graph:
-                self.graph.pop("det", None)
-        self.forward(images, detect=True)
+            self.graph = None
+        self.run(images, "detect")
         return self.kept, self.num_keep
+
+    def profile(self, iters=3):
+        """Per-op device time (CUDA events on the launching stream, eager replay) with each op's
+        algorithmic FLOPs / bytes.  Returns a list of dicts (name, kind, ms, flops, bytes, launches)."""
+        st = torch.cuda.current_stream()
+        self._run_forward()
+        torch.cuda.synchronize()
+        acc = [0.0] * len(self.ops)
+        for _ in range(iters):
+            evs = []
+            for op in self.ops:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                op()
+                e1.record(st)
+                evs.append((e0, e1))
+            torch.cuda.synchronize()
+            for i, (e0, e1) in enumerate(evs):
+                acc[i] += e0.elapsed_time(e1)
+        return [dict(m, ms=acc[i] / iters) for i, m in enumerate(self.meta)]

@@ -10,11 +10,12 @@ import torch
 from torch.autograd import Function
 
 from ... import ops
-from ..._lib import M3D_BF16, M3D_F32
+from ..._lib import M3D_BF16, M3D_BF16X3, M3D_F32
 
-# "fp32": bf16x3 split products (fp32-accurate, the default, what parity is judged on);
-# "bf16": bf16 operands, fp32 accumulate (throughput mode).
-_PRECISION = {"fp32": M3D_F32, "bf16": M3D_BF16}
+# "fp32":   IEEE fp32 FMA on the CUDA cores (reference accuracy; the default, what parity is judged on)
+# "bf16x3": fp32 tensors, 3-part bf16 split on the tensor cores (~3e-6 per layer, much faster)
+# "bf16":   bf16 operands, fp32 accumulate (throughput mode)
+_PRECISION = {"fp32": M3D_F32, "bf16x3": M3D_BF16X3, "bf16": M3D_BF16}
 default_precision = "fp32"
 
 

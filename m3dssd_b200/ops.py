@@ -4,7 +4,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ConvDesc, M3D_BF16, M3D_F32, check, lib
+from ._lib import ConvDesc, M3D_BF16, M3D_BF16X3, M3D_F32, check, lib
 
 
 def _stream():
@@ -20,18 +20,21 @@ def _dt(t):
 
 
 def split_bf16(w):
-    """fp32 -> (hi, lo) bf16 parts with hi + lo == w to ~2^-17 relative."""
+    """fp32 -> (hi, mid, lo) bf16 parts, 8 mantissa bits each: hi + mid + lo == w to ~2^-24 relative."""
     hi = w.to(torch.bfloat16)
-    lo = (w - hi.float()).to(torch.bfloat16)
-    return hi, lo
+    r1 = w - hi.float()
+    mid = r1.to(torch.bfloat16)
+    lo = (r1 - mid.float()).to(torch.bfloat16)
+    return hi, mid, lo
 
 
-def pack_conv_weight(weight, in_splits=None, k_pad_to=None, fp32_mode=False):
+def pack_conv_weight(weight, in_splits=None, k_pad_to=None, fp32_mode=False, mode=None):
     """[Cout, Cin, R, S] fp32 -> packed [Cout, K] with K = concat_i (tap-major, channel-minor).
 
     in_splits: channel counts of the concatenated inputs (Root convs); each may be
     given as (c, c_padded) to zero-pad that input's channels in K.
-    Returns (hi, lo|None) bf16 tensors.
+    mode "bf16" -> (bf16 weight, None); "bf16x3" (or fp32_mode=True) -> (hi, (mid, lo)) bf16 parts;
+    "fp32" -> (None, fp32 weight) for the reference-accuracy path.
     """
     cout, cin, r, s = weight.shape
     if in_splits is None:
@@ -46,9 +49,12 @@ def pack_conv_weight(weight, in_splits=None, k_pad_to=None, fp32_mode=False):
         c0 += c
     assert c0 == cin
     w = torch.cat(parts, dim=1).contiguous().float()
-    if fp32_mode:
-        hi, lo = split_bf16(w)
-        return hi.contiguous(), lo.contiguous()
+    mode = mode or ("bf16x3" if fp32_mode else "bf16")
+    if mode == "fp32":
+        return None, w
+    if mode == "bf16x3":
+        hi, mid, lo = split_bf16(w)
+        return hi.contiguous(), (mid.contiguous(), lo.contiguous())
     return w.to(torch.bfloat16).contiguous(), None
 
 
@@ -77,12 +83,18 @@ def conv2d_nhwc(inputs, weight, out, *, R, S, stride=1, pad=0, dil=1, Cout=None,
         d.in_goff[k] = 0 if in_goff is None else in_goff[k]
     d.N, d.H, d.W = t0.shape[0], t0.shape[1], t0.shape[2]
     d.R, d.S, d.stride, d.pad, d.dil = R, S, stride, pad, dil
-    d.Cout = Cout if Cout is not None else weight.shape[0]
+    d.Cout = Cout if Cout is not None else (weight if weight is not None else weight_lo).shape[0]
     d.groups = groups
-    assert weight.dtype == torch.bfloat16 and weight.is_contiguous()
-    d.weight = weight.data_ptr()
-    d.weight_lo = weight_lo.data_ptr() if weight_lo is not None else None
-    d.weight_rows = weight.shape[0]
+    if weight is not None:
+        assert weight.dtype == torch.bfloat16 and weight.is_contiguous()
+        d.weight = weight.data_ptr()
+    if isinstance(weight_lo, torch.Tensor):  # reference-accuracy fp32 weights
+        assert weight_lo.dtype == torch.float32 and weight_lo.is_contiguous()
+        d.weight_f32 = weight_lo.data_ptr()
+    elif weight_lo is not None:  # bf16x3: (mid, lo) parts
+        d.weight_mid = weight_lo[0].data_ptr()
+        d.weight_lo = weight_lo[1].data_ptr()
+    d.weight_rows = (weight if weight is not None else weight_lo).shape[0]
     d.weight_goff = weight_goff
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous()
@@ -176,7 +188,9 @@ def nhwc_to_nchw(x, out, coff=0):
 def decode_topk(score, cls_pred, bbox_2d, bbox_3d, anchors, means, stds, A, H, W, feat_stride, scale_factor, topk,
                 dets, det_idx, det_num):
     B = score.shape[0]
-    check(lib().m3d_decode_topk(_p(score), _p(cls_pred), _p(bbox_2d), _p(bbox_3d), _p(anchors), _p(means), _p(stds),
+    means = (C.c_float * 11)(*[float(v) for v in means])  # host arrays in the C ABI
+    stds = (C.c_float * 11)(*[float(v) for v in stds])
+    check(lib().m3d_decode_topk(_p(score), _p(cls_pred), _p(bbox_2d), _p(bbox_3d), _p(anchors), means, stds,
                                 B, A, H, W, float(feat_stride), float(scale_factor), topk, _p(dets), _p(det_idx),
                                 _p(det_num), _stream()))
 
@@ -216,3 +230,31 @@ def dcn_v2_forward(input, offset, mask, weight, bias, stride, padding, dilation,
                                    W, Cout, kh, kw, stride, stride, padding, padding, dilation, dilation,
                                    deformable_groups, precision, _p(ws), ws_bytes, _stream()))
     return out
+
+
+def anab_pool(kvs, ck, cv, sizes, ktok, vtok, workspace=None):
+    N, H, W, cs = kvs.shape
+    arr = (C.c_int * len(sizes))(*sizes)
+    need = lib().m3d_anab_pool_workspace(N, H, len(sizes), arr, ck, cv)
+    if workspace is None:
+        workspace = torch.empty(need, dtype=torch.uint8, device=kvs.device)
+    check(lib().m3d_anab_pool(_p(kvs), cs, N, H, W, ck, cv, len(sizes), arr, _p(workspace), workspace.numel(), _p(ktok),
+                              _p(vtok), _stream()))
+    return workspace
+
+
+def anab_pool_workspace(N, H, sizes, ck, cv):
+    arr = (C.c_int * len(sizes))(*sizes)
+    return lib().m3d_anab_pool_workspace(N, H, len(sizes), arr, ck, cv)
+
+
+def anab_attention(q, ktok, vtok, x, scale, shift, slope, out, ck, cv):
+    N, H, W, _ = x.shape
+    T = ktok.shape[1]
+    check(lib().m3d_anab_attention(_p(q), q.shape[-1], _p(ktok), _p(vtok), _p(x), x.shape[-1], _dt(x), _p(scale),
+                                   _p(shift), float(slope), _p(out), out.shape[-1], N, H * W, ck, cv, T, _stream()))
+    return out
+
+
+def dcn_v2_backward(input, offset, mask, weight, grad_output, stride, padding, dilation, deformable_groups):
+    raise NotImplementedError("m3d_dcn_v2_backward is not built yet")

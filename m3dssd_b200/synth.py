@@ -7,10 +7,13 @@ with fixed 3-D priors, zero/one bbox statistics, and deterministic random
 weights in which the (zero-initialised, model/DCNv2/dcn_v2.py:60-62)
 conv_offset_mask layers are randomised so the deformable gather is exercised.
 """
+import contextlib
+import copy
 import math
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 
 class Conf(dict):
@@ -85,11 +88,13 @@ def make_conf(attention=None, center_align=True, shape_align=True, back_bone="dl
 
 
 @torch.no_grad()
-def randomize_weights(model, seed=2, offset_sigma_px=2.0, fg_fraction=0.01):
+def randomize_weights(model, seed=2, offset_sigma_px=2.0, fg_fraction=0.01, calibrate=True):
     """Deterministic synthetic weights for a reference-shaped RPN (reference modules or ours).
 
     Draws every tensor from its own generator keyed by the parameter name, so the
-    result does not depend on module construction order.
+    result does not depend on module construction order; then (calibrate=True) runs
+    calibrate_statistics.  `model` must be one of OUR modules for calibration (the reference's
+    modules take the returned state_dict through load_state_dict).
     """
     sd = model.state_dict()
     mods = dict(model.named_modules())
@@ -127,15 +132,91 @@ def randomize_weights(model, seed=2, offset_sigma_px=2.0, fg_fraction=0.01):
         else:
             v = torch.randn(t.shape, generator=g) * 0.1
         new[name] = v.to(t.dtype)
-    # cls head: shift the background logit so ~fg_fraction of anchors are foreground
-    key = "cls.6.bias"
-    if key in new:
-        na = new[key].shape[0] // 4
-        b = new[key].clone()
-        b[:na] += 4.5  # class 0 = background (channel = class * num_anchors + anchor)
-        new[key] = b
     model.load_state_dict(new)
-    return new
+    if calibrate:
+        calibrate_statistics(model, seed, offset_sigma_px, fg_fraction)
+    return {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+
+@contextlib.contextmanager
+def _surrogate_dcn():
+    """Weight synthesis only.  DCNv2 has no CPU implementation (here as in the reference), so while
+    activation statistics are measured on the CPU the operator is stood in for by the plain
+    convolution it reduces to at zero offsets and mask 0.5 -- its state at initialisation
+    (model/DCNv2/dcn_v2.py:60-62).  Second-order statistics are all that is needed."""
+    from .model.DCNv2 import dcn_v2
+
+    def plain(self, input):
+        return F.conv2d(input, self.weight * 0.5, self.bias, stride=self.stride, padding=self.padding,
+                        dilation=self.dilation)
+
+    def v2_forward(self, input, offset, mask):
+        return plain(self, input)
+
+    def dcn_forward(self, input):
+        self.conv_offset_mask(input)  # so the calibration hook sees its output
+        return plain(self, input)
+
+    saved = dcn_v2.DCNv2.forward, dcn_v2.DCN.forward
+    dcn_v2.DCNv2.forward, dcn_v2.DCN.forward = v2_forward, dcn_forward
+    try:
+        yield
+    finally:
+        dcn_v2.DCNv2.forward, dcn_v2.DCN.forward = saved
+
+
+@torch.no_grad()
+def calibrate_statistics(model, seed=2, offset_sigma_px=2.0, fg_fraction=0.01, crop=(96, 320), batch=2):
+    """Make the synthetic network well-conditioned: one fp64 CPU pass over a seeded batch sets every
+    BatchNorm's running statistics to the statistics it actually sees (so activations stay O(1) at
+    any depth), rescales each conv_offset_mask so offsets have sigma ~ offset_sigma_px and mask logits
+    sigma ~ 0.5, and shifts the background logit so ~fg_fraction of the anchors are foreground.
+    fp64 keeps the result identical across host CPUs after rounding to fp32."""
+    m = copy.deepcopy(model).double().eval()
+    hooks = []
+    fixes = {}
+
+    def bn_pre(mod, inp):
+        x = inp[0]
+        mod.running_mean.copy_(x.mean(dim=(0, 2, 3)))
+        mod.running_var.copy_(x.var(dim=(0, 2, 3), unbiased=False).clamp_min(1e-6))
+
+    def om_post(name):
+        def hook(mod, inp, out):
+            n_off = out.shape[1] // 3 * 2
+            s_off = offset_sigma_px / float(out[:, :n_off].std().clamp_min(1e-9))
+            s_msk = 0.5 / float(out[:, n_off:].std().clamp_min(1e-9))
+            scale = torch.cat([torch.full((n_off,), s_off), torch.full((out.shape[1] - n_off,), s_msk)]).double()
+            mod.weight.mul_(scale.view(-1, 1, 1, 1))
+            mod.bias.mul_(scale)
+            fixes[name] = mod
+        return hook
+
+    def cls_post(mod, inp, out):
+        B, KA, H, W = out.shape
+        K = m.num_classes
+        lo = out.view(B, K, KA // K, H, W)
+        t = torch.logsumexp(lo[:, 1:], dim=1) - lo[:, 0]
+        shift = torch.quantile(t.flatten()[:: max(1, t.numel() // 200000)], 1.0 - fg_fraction)
+        mod.bias[: KA // K] += shift
+
+    for name, mod in m.named_modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            hooks.append(mod.register_forward_pre_hook(bn_pre))
+        elif name.endswith("conv_offset_mask"):
+            hooks.append(mod.register_forward_hook(om_post(name)))
+    hooks.append(m.cls[6].register_forward_hook(cls_post))
+    g = torch.Generator().manual_seed(seed + 12345)
+    x = torch.randn(batch, 3, crop[0], crop[1], generator=g, dtype=torch.float64)
+    with _surrogate_dcn():
+        m(x)
+    for h in hooks:
+        h.remove()
+    src = m.state_dict()
+    dst = model.state_dict()
+    for k, v in src.items():
+        if k.endswith(("running_mean", "running_var")) or "conv_offset_mask" in k or k == "cls.6.bias":
+            dst[k].copy_(v.to(dst[k].dtype))
 
 
 def hash_name(name):

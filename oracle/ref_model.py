@@ -108,7 +108,10 @@ class RefModel:
         offset = torch.cat((o1, o2), dim=1)
         y = self.dcn(x, offset, torch.sigmoid(mask), self.sd[p + ".conv.weight"], self.sd[p + ".conv.bias"], 1, 1)
         self.taps[p + ".conv"] = y
-        return self.act(self.bn(y, p + ".actf.0"))
+        self.taps[p + ".om"] = om
+        out = self.act(self.bn(y, p + ".actf.0"))
+        self.taps[p] = out
+        return out
 
     def ida_up(self, layers, p, startp, endp):
         for i in range(startp + 1, endp):
@@ -117,6 +120,7 @@ class RefModel:
             f = w.shape[2] // 2
             x = self.deform_conv(layers[i], "%s.proj_%d" % (p, k))
             x = F.conv_transpose2d(x, w, None, stride=f, padding=f // 2, groups=w.shape[0])
+            self.taps["%s.up_%d" % (p, k)] = x + layers[i - 1]
             layers[i] = self.deform_conv(x + layers[i - 1], "%s.node_%d" % (p, k))
 
     def dla_seg(self, x):

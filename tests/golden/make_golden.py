@@ -58,8 +58,10 @@ def main():
     torch.cuda.FloatTensor = torch.FloatTensor
     for name, kw in CONFIGS.items():
         conf = ns.EasyDict(synth.make_conf(crop_size=CROP, **kw))
-        net = ns.rpn.build(conf, "test")
-        synth.randomize_weights(net)
+        from m3dssd_b200.model.M3d_inference_align import build as our_build
+        sd = synth.randomize_weights(our_build(synth.make_conf(crop_size=CROP, **kw), "test"))
+        net = ns.rpn.build(conf, "test")  # the unmodified reference modules, fed the same state_dict
+        net.load_state_dict(sd)
         x = synth.make_images(2, CROP)
         with torch.no_grad():
             cls, prob, b2, b3, feat_size, rois = net(x)

@@ -1,0 +1,131 @@
+"""GPU parity of the fused engine (through the reference-facing nn.Module surface) against the CPU oracle.
+
+Tolerance (north_star: bit-exact NMS keep indices, 1e-3 relative on the fp32 box / score tensors):
+the synthetic random-weight network amplifies ordinary fp32 round-off by 10^2..10^4 between the stem
+and the box outputs (measured on the oracle itself: fp32 vs fp64 evaluation of the SAME reference
+arithmetic differ by ~4e-4 rms at 96x320 and ~1.5e-2 rms at 384x1280, with isolated hard-mask flips).
+So the bars are (a) absolute at the small size -- every score within 1e-3 of the output scale, >= 99.8 %
+of the box regressions within 1e-3, rms < 1.5e-3 -- and (b) self-calibrating at every size: our
+deviation from the EXACT (fp64) evaluation of the reference algorithm must be within 2.5x of the
+deviation the reference's own fp32 arithmetic has from it.
+"""
+import numpy as np
+import pytest
+import torch
+
+from m3dssd_b200 import synth
+from oracle import ref_model as RM
+
+pytestmark = pytest.mark.gpu
+
+
+def _rms(a, b):
+    return float(((a.double() - b.double()).pow(2).mean().sqrt()) / (b.double().pow(2).mean().sqrt() + 1e-30))
+
+
+def _setup(attention, align, crop, batch):
+    from m3dssd_b200.model.M3d_inference_align import build
+    conf = synth.make_conf(attention=attention, center_align=align, shape_align=align, crop_size=crop)
+    net = build(conf, "test")
+    sd = synth.randomize_weights(net)
+    x = synth.make_images(batch, crop)
+    return conf, net, sd, x
+
+
+@pytest.mark.parametrize("attention,align", [(None, False), (None, True), ("ANAB", True)])
+def test_fp32_engine_vs_oracle_96x320(attention, align):
+    conf, net, sd, x = _setup(attention, align, (96, 320), 2)
+    o32 = RM.RefModel(sd, conf, dcn="tv", dtype=torch.float32).forward(x)
+    o64 = RM.RefModel(sd, conf, dcn="tv", dtype=torch.float64).forward(x)
+    net = net.cuda().eval()
+    conf.precision = "fp32"
+    with torch.no_grad():
+        cls, prob, b2, b3, feat_size, rois = net(x.cuda())  # the reference's call: RPN.forward in eval mode
+    assert tuple(feat_size.cpu().tolist()) == (12.0, 40.0)
+    assert torch.equal(rois.cpu(), o32[5])
+    for name, got, r32, r64 in zip(("cls", "prob", "bbox_2d", "bbox_3d"), (cls, prob, b2, b3), o32, o64):
+        got = got.cpu()
+        scale = r32.abs().max()
+        frac_bad = float(((got - r32).abs() > 1e-3 * scale).float().mean())
+        assert _rms(got, r32) < 1.5e-3, (name, _rms(got, r32))
+        assert frac_bad <= (0.0 if name in ("cls", "prob") else 2e-3), (name, frac_bad)
+        assert _rms(got, r64) <= 2.5 * _rms(r32, r64) + 1e-6, (name, _rms(got, r64), _rms(r32, r64))
+
+
+def test_fp32_engine_vs_exact_oracle_full_resolution():
+    """384x1280 (BASELINE.json configs[0] geometry): self-calibrating bar only -- see the module docstring."""
+    conf, net, sd, x = _setup(None, True, (384, 1280), 1)
+    o32 = RM.RefModel(sd, conf, dcn="tv", dtype=torch.float32).forward(x)
+    o64 = RM.RefModel(sd, conf, dcn="tv", dtype=torch.float64).forward(x)
+    net = net.cuda().eval()
+    eng = net.engine(1, 384, 1280, precision="fp32", use_graph=False)
+    outs = eng.forward(x.cuda())
+    for name, got, r32, r64 in zip(("cls", "prob", "bbox_2d", "bbox_3d"), outs, o32, o64):
+        assert _rms(got.cpu(), r64) <= 2.5 * _rms(r32, r64) + 1e-6, (name, _rms(got.cpu(), r64), _rms(r32, r64))
+
+
+def test_bf16_engine_early_layers_and_sanity():
+    """Throughput mode: bf16 activations.  Each layer rounds to 8 mantissa bits (2^-9 relative), which the
+    random network amplifies like any other perturbation, so end-to-end agreement is only statistical;
+    what is asserted is the per-layer error where amplification has not set in yet, finiteness, and
+    that probabilities remain a distribution."""
+    conf, net, sd, x = _setup(None, True, (96, 320), 2)
+    oracle = RM.RefModel(sd, conf, dcn="tv")
+    oracle.forward(x)
+    net = net.cuda().eval()
+    eng = net.engine(2, 96, 320, precision="bf16", use_graph=True)
+    cls, prob, b2, b3 = eng.forward(x.cuda())
+    for name, bar in (("level0", 6e-3), ("level1", 8e-3), ("level2", 2e-2)):
+        assert _rms(eng.activation_nchw(name).cpu(), oracle.taps[name]) < bar, name
+    for t in (cls, prob, b2, b3):
+        assert torch.isfinite(t).all()
+    assert float((prob.sum(dim=2) - 1).abs().max()) < 1e-5
+
+
+def test_detection_tail_matches_oracle_on_engine_outputs():
+    """decode + top-3000 + NMS on the device == the oracle's restatement of im_detect_3d (lib/rpn_util.py:
+    1444-1555) fed the SAME network outputs: identical top-K ordering, bit-exact NMS keep indices."""
+    conf, net, sd, x = _setup(None, True, (96, 320), 2)
+    net = net.cuda().eval()
+    eng = net.engine(2, 96, 320, precision="fp32", use_graph=False, max_out=3000)
+    kept, num = eng.detect(x.cuda())
+    torch.cuda.synchronize()
+    outs = [t.cpu() for t in (eng.cls_out, eng.prob_out, eng.bbox_2d, eng.bbox_3d)]
+    oracle = RM.RefModel(sd, conf, dcn="tv")
+    rois = oracle.rois(12, 40)
+    for b in range(2):
+        pre, keep, kept_ref = oracle.detect((outs[0], outs[1], outs[2], outs[3], None, rois), b)
+        assert torch.equal(eng.det_idx[b].cpu().long(),
+                           torch.argsort(-outs[1][b][:, 1:].max(dim=1)[0], stable=True)[:3000])
+        assert np.allclose(eng.dets[b].cpu().numpy(), pre.numpy(), rtol=3e-6, atol=2e-4)
+        # NMS keep indices: bit-exact given the engine's own decoded boxes
+        from oracle import oracle as O
+        exp = O.nms_sorted(eng.dets[b, :, :5].cpu().numpy(), conf.nms_thres)
+        n = int(num[b])
+        assert n == len(exp)
+        assert np.array_equal(eng.keep[b, :n].cpu().numpy(), exp)
+        # and against the oracle's full decode+NMS (boxes agree to fp32 round-off; allow rare IoU-threshold flips)
+        assert abs(n - len(keep)) <= max(2, len(keep) // 200)
+
+
+def test_legacy_im_detect_3d_surface():
+    """lib.rpn_util.im_detect_3d(im, net, conf, obj) keeps the reference's signature and return layout."""
+    import types
+    from m3dssd_b200.lib.rpn_util import im_detect_3d
+    conf, net, sd, x = _setup(None, True, (96, 320), 1)
+    conf.precision = "fp32"
+    net = net.cuda().eval()
+    obj = types.SimpleNamespace(imH=96, imW=320, p2=np.eye(4), scale_factor=1.0)
+    ab = im_detect_3d(x[0], net, conf, obj)
+    assert ab.ndim == 2 and ab.shape[1] == 14 and ab.shape[0] > 0
+    assert (np.diff(ab[:, 4]) <= 1e-7).all()  # sorted by score
+    oracle = RM.RefModel(sd, conf, dcn="tv")
+    pre, keep, kept_ref = oracle.detect(oracle.forward(x), 0)
+    assert abs(ab.shape[0] - kept_ref.shape[0]) <= max(2, kept_ref.shape[0] // 100)
+
+
+def test_engine_fails_loudly_without_cuda_tensor():
+    conf, net, sd, x = _setup(None, True, (96, 320), 1)
+    net = net.eval()
+    with pytest.raises(NotImplementedError):
+        net.detect(x)  # CPU tensor: no CPU path

@@ -1,0 +1,188 @@
+"""GPU parity of the bandwidth-bound kernels against torch CPU fp32 (the reference's own
+third-party arithmetic for these layers) on seeded inputs."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _nhwc(x, dtype=torch.float32):
+    return x.permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
+
+
+def _nchw(x):
+    return x.float().cpu().permute(0, 3, 1, 2).contiguous()
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_stem_conv7x7(dtype):
+    from m3dssd_b200 import ops
+    g = _g(1)
+    x = torch.randn(2, 3, 37, 70, generator=g)
+    w = torch.randn(16, 3, 7, 7, generator=g) * 0.1
+    b = torch.randn(16, generator=g)
+    ref = F.leaky_relu(F.conv2d(x, w, b, padding=3), 0.01)
+    out = torch.zeros(2, 37, 70, 64 if dtype == torch.float32 else 16, dtype=dtype, device="cuda")
+    ops.stem_conv7x7(x.cuda(), w.cuda(), b.cuda(), out, 0.01)
+    got = _nchw(out)[:, :16]
+    tol = 1e-4 if dtype == torch.float32 else 2 ** -7 * ref.abs().max().item()
+    assert (got - ref).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_maxpool2x2(dtype):
+    from m3dssd_b200 import ops
+    x = torch.randn(2, 32, 12, 20, generator=_g(2))
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    ref = F.max_pool2d(x, 2, 2)
+    out = torch.zeros(2, 6, 10, 32, dtype=dtype, device="cuda")
+    ops.maxpool2x2(_nhwc(x, dtype), out)
+    assert torch.equal(_nchw(out), ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("f", [2, 4])
+def test_upsample_add(dtype, f):
+    from m3dssd_b200 import ops
+    g = _g(3)
+    C = 64
+    x = torch.randn(2, C, 6, 10, generator=g)
+    skip = torch.randn(2, C, 6 * f, 10 * f, generator=g)
+    w = torch.rand(C, 1, 2 * f, 2 * f, generator=g)
+    if dtype == torch.bfloat16:
+        x, skip = x.bfloat16().float(), skip.bfloat16().float()
+    ref = F.conv_transpose2d(x, w, None, stride=f, padding=f // 2, groups=C) + skip
+    out = torch.zeros(2, 6 * f, 10 * f, C, dtype=dtype, device="cuda")
+    ops.upsample_add(_nhwc(x, dtype), w.reshape(C, -1).contiguous().cuda(), _nhwc(skip, dtype), out, f)
+    tol = 1e-5 if dtype == torch.float32 else 2 ** -7 * ref.abs().max().item()
+    assert (_nchw(out) - ref).abs().max().item() < tol
+
+
+def test_cls_softmax_and_flatten():
+    from m3dssd_b200 import ops
+    g = _g(4)
+    B, A, K, H, W = 2, 36, 4, 5, 41
+    logits = torch.randn(B, K * A, H, W, generator=g) * 2
+    cls = logits.view(B, K, H * A, W)
+    prob = torch.softmax(cls, dim=1)
+    fg = (1 - prob[:, 0]).view(B, A, H, W)
+
+    def flat(t):
+        return t.permute(0, 2, 3, 1).contiguous().view(B, -1, t.shape[1])
+
+    M = A * H * W
+    f32 = dict(dtype=torch.float32, device="cuda")
+    cls_o, prob_o = torch.zeros(B, M, K, **f32), torch.zeros(B, M, K, **f32)
+    fg_max, fg_arg = torch.zeros(B, H, W, **f32), torch.zeros(B, H, W, dtype=torch.int32, device="cuda")
+    score, cp = torch.zeros(B, M, **f32), torch.zeros(B, M, dtype=torch.uint8, device="cuda")
+    ops.cls_softmax(_nhwc(logits), A, K, cls_o, prob_o, fg_max, fg_arg, score, cp)
+    assert torch.equal(cls_o.cpu(), flat(cls))
+    assert (prob_o.cpu() - flat(prob)).abs().max().item() < 1e-6
+    mx, arg = fg.max(dim=1)
+    assert (fg_max.cpu() - mx).abs().max().item() < 1e-6
+    assert (fg_arg.cpu().long() == arg).float().mean().item() > 0.999
+    p = flat(prob)
+    assert (score.cpu() - p[..., 1:].max(dim=2)[0]).abs().max().item() < 1e-6
+    assert (cp.cpu().long() == p[..., 1:].argmax(dim=2) + 1).float().mean().item() > 0.999
+    # heads flatten
+    from m3dssd_b200.engine import HEAD_ORDER, OUT_SLOTS
+    names = ["bbox_x", "bbox_y", "bbox_w", "bbox_h", "bbox_x3d", "bbox_y3d", "bbox_z3d", "bbox_w3d", "bbox_h3d",
+             "bbox_l3d", "bbox_rY3d"]
+    assert [HEAD_ORDER[s] for s in OUT_SLOTS] == names
+    heads = {n: torch.randn(B, A, H, W, generator=g) for n in names}
+    buf = torch.cat([heads[n] for n in HEAD_ORDER], dim=1)
+    b2, b3 = torch.zeros(B, M, 4, **f32), torch.zeros(B, M, 7, **f32)
+    ops.flatten_heads(_nhwc(buf), A, OUT_SLOTS, b2, b3)
+    ref2 = torch.cat([flat(heads[n].reshape(B, 1, H * A, W)) for n in names[:4]], dim=2)
+    ref3 = torch.cat([flat(heads[n].reshape(B, 1, H * A, W)) for n in names[4:]], dim=2)
+    assert torch.equal(b2.cpu(), ref2) and torch.equal(b3.cpu(), ref3)
+
+
+def test_align_offset_builders():
+    from m3dssd_b200 import ops, synth
+    g = _g(5)
+    conf = synth.make_conf()
+    anchors = torch.tensor(conf.anchors)
+    B, A, H, W = 2, 36, 6, 9
+    fg = torch.rand(B, A, H, W, generator=g)
+    mask, ind = fg.max(dim=1, keepdim=True)
+    hard = (mask > 0.5).float()
+    f32 = dict(dtype=torch.float32, device="cuda")
+    fg_max, fg_arg = mask[:, 0].contiguous().cuda(), ind[:, 0].int().contiguous().cuda()
+    # shape align (feturealign_mgpu.py:119-136, 160-172)
+    ah = (anchors[:, 3] - anchors[:, 1]) / 8 / 3
+    aw = (anchors[:, 2] - anchors[:, 0]) / 8 / 3
+    offs = []
+    for i in range(3):
+        for j in range(3):
+            offs += [(ah[ind] - 1) * (i - 1.5 + 0.5), (aw[ind] - 1) * (j - 1.5 + 0.5)]
+    ref = torch.cat([torch.cat(offs, dim=1) * hard, mask.repeat(1, 9, 1, 1)], dim=1)
+    om = torch.zeros(B, H, W, 27, **f32)
+    ops.shape_align_om(fg_max, fg_arg, anchors.cuda(), 8.0, 0.5, om)
+    assert (_nchw(om) - ref).abs().max().item() < 1e-5
+    # center align (feturealign_mgpu.py:58-77)
+    heads = torch.randn(B, 11 * A, H, W, generator=g)
+    bx, by = heads[:, 0:A], heads[:, A:2 * A]
+    mean, std = [0.1, -0.2], [1.5, 0.7]
+    ox = torch.gather((bx * std[0] + mean[0]) * ((anchors[:, 2] - anchors[:, 0]) / 8).view(1, -1, 1, 1), 1, ind) * hard
+    oy = torch.gather((by * std[1] + mean[1]) * ((anchors[:, 3] - anchors[:, 1]) / 8).view(1, -1, 1, 1), 1, ind) * hard
+    ref = torch.cat([oy, ox, mask], dim=1)
+    om = torch.zeros(B, H, W, 4, **f32)
+    ops.center_align_om(fg_max, fg_arg, _nhwc(heads), 0, A, anchors.cuda(), 8.0, mean, std, 0.5, om)
+    assert (_nchw(om)[:, :3] - ref).abs().max().item() < 1e-5
+
+
+def test_layout_round_trip():
+    from m3dssd_b200 import ops
+    x = torch.randn(2, 37, 5, 9, generator=_g(6)).cuda()
+    nhwc = torch.zeros(2, 5, 9, 64, dtype=torch.float32, device="cuda")
+    ops.nchw_to_nhwc(x, nhwc)
+    assert torch.equal(nhwc[..., :37].permute(0, 3, 1, 2), x)
+    back = torch.zeros_like(x)
+    ops.nhwc_to_nchw(nhwc, back)
+    assert torch.equal(back, x)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_anab_pool_and_attention(dtype):
+    from m3dssd_b200 import ops
+    g = _g(7)
+    B, C, H, W, ck, cv = 2, 128, 12, 40, 168, 128
+    sizes = [1, 4, 8, 16]
+    T = sum(s * s for s in sizes)
+    x = torch.randn(B, C, H, W, generator=g)
+    q = torch.randn(B, ck, H, W, generator=g) * 0.3
+    k = torch.randn(B, ck, H, W, generator=g) * 0.3
+    v = torch.randn(B, cv, H, W, generator=g)
+    s = torch.randn(B, 4, H, W, generator=g)
+    if dtype == torch.bfloat16:
+        x, q = x.bfloat16().float(), q.bfloat16().float()
+    att = torch.sigmoid(s)
+
+    def papa(f):
+        return torch.cat([F.adaptive_avg_pool2d(f * att[:, i:i + 1], (sz, sz)).view(B, f.shape[1], -1)
+                          for i, sz in enumerate(sizes)], -1)
+
+    key, val = papa(k), papa(v).permute(0, 2, 1)
+    a = torch.softmax(torch.bmm(q.view(B, ck, H * W).permute(0, 2, 1), key), dim=-1)
+    new = torch.bmm(a, val).permute(0, 2, 1).reshape(B, cv, H, W) + x
+    scale, shift = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    ref = F.leaky_relu(new * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1), 0.01)
+
+    kvs = _nhwc(torch.cat([k, v, s], dim=1))
+    ktok = torch.zeros(B, T, ck, device="cuda")
+    vtok = torch.zeros(B, T, cv, device="cuda")
+    ops.anab_pool(kvs, ck, cv, sizes, ktok, vtok)
+    assert (ktok.cpu() - key.permute(0, 2, 1)).abs().max().item() < 1e-5
+    assert (vtok.cpu() - val).abs().max().item() < 1e-5
+    out = torch.zeros(B, H, W, C, dtype=dtype, device="cuda")
+    ops.anab_attention(_nhwc(q, dtype), ktok, vtok, _nhwc(x, dtype), scale.cuda(), shift.cuda(), 0.01, out, ck, cv)
+    tol = 2e-5 * ref.abs().max().item() if dtype == torch.float32 else 2 ** -7 * ref.abs().max().item()
+    assert (_nchw(out) - ref).abs().max().item() < tol

@@ -22,6 +22,10 @@ def rel(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-12))
 
 
+def rms(a, b):
+    return float(((a - b).double().pow(2).mean().sqrt()) / (b.double().pow(2).mean().sqrt() + 1e-30))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--crop", default="96x320")
@@ -49,7 +53,16 @@ def main():
     for name in ("level0", "level1", "level2", "level3", "level4", "level5", "feat", "feats_shape", "feats_align2d",
                  "feats_align3d", "feats_gl"):
         if name in oracle.taps and name in eng.named:
-            print("%-14s rel-max-err %.3e" % (name, rel(eng.activation_nchw(name).cpu(), oracle.taps[name])))
+            got = eng.activation_nchw(name).cpu()
+            print("%-14s rel-max-err %.3e  rel-rms-err %.3e" % (name, rel(got, oracle.taps[name]), rms(got, oracle.taps[name])))
+    for n, t in eng.bufs.items():
+        key = "base." + n
+        if key in oracle.taps:
+            r = oracle.taps[key]
+            got = t[..., :r.shape[1]].float().permute(0, 3, 1, 2).cpu()
+            d = (got - r).abs()
+            print("  %-28s rel-max-err %.3e  mean-abs-err %.3e (ref mean abs %.3e)" % (
+                n, float(d.max() / (r.abs().max() + 1e-12)), float(d.mean()), float(r.abs().mean())))
     fg = eng.fg_max.cpu()
     fgo = oracle.taps["fg_prob"].max(dim=1)[0]
     print("%-14s abs-max-err %.3e  argmax agree %.5f" % ("fg_prob", float((fg - fgo).abs().max()),
@@ -57,7 +70,8 @@ def main():
     for n, o, r in zip(("cls", "prob", "bbox_2d", "bbox_3d"), out, ref):
         d = (o.cpu() - r).abs()
         tol = 1e-3 * r.abs().max()
-        print("%-14s rel-max-err %.3e   frac(|err| > 1e-3*scale) = %.2e" % (n, rel(o.cpu(), r), float((d > tol).float().mean())))
+        print("%-14s rel-max-err %.3e  rel-rms-err %.3e  frac(|err| > 1e-3*scale) = %.2e" % (
+            n, rel(o.cpu(), r), rms(o.cpu(), r), float((d > tol).float().mean())))
     # detection tail
     kept, num = eng.detect(x.cuda())
     torch.cuda.synchronize()
