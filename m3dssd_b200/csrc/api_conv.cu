@@ -174,9 +174,21 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
   const long total_tiles = m_tiles * n_tiles * groups;
   M3D_REQUIRE(total_tiles < (1L << 30), "too many tiles");
 
+  // bf16 tiles of whole 64-channel slabs leave through shared memory + TMA stores
+  const bool staged = d->act_dtype == M3D_BF16 && d->out_dtype == M3D_BF16 && bk == 64 && BN % 64 == 0 &&
+                      d->Cout % 64 == 0 && d->out_cstride % 8 == 0 && d->out_coff % 8 == 0 && d->out_goff % 8 == 0 &&
+                      (d->res == nullptr || (d->res_cstride % 8 == 0 && d->res_coff % 8 == 0 && d->res_goff % 8 == 0));
   if (!gather) {
     ConvTmaParams p;
     memset(&p, 0, sizeof(p));
+    if (staged) {
+      int rc2 = make_tmap_nhwc(&p.tmap_out, d->out, d->N, P, Q, d->out_cstride, 64, TW, TH, 1);
+      if (rc2 != M3D_OK) return rc2;
+      if (d->res != nullptr) {
+        rc2 = make_tmap_nhwc(&p.tmap_res, d->res, d->N, P, Q, d->res_cstride, 64, TW, TH, 1);
+        if (rc2 != M3D_OK) return rc2;
+      }
+    }
     for (int i = 0; i < d->num_inputs; ++i) {
       M3D_REQUIRE(d->in_cstride[i] % 8 == 0, "input %d: channel stride %d not a multiple of 8", i, d->in_cstride[i]);
       int rc = make_tmap_nhwc(&p.tmap_a[i], d->in[i], d->N, d->H, d->W, d->in_cstride[i], bk, TW, TH, d->stride);
@@ -197,7 +209,7 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
     p.res = d->res, p.res_cstride = d->res_cstride, p.res_coff = d->res_coff, p.res_goff = d->res_goff;
     p.slope = d->slope;
     p.total_tiles = static_cast<int>(total_tiles);
-    rc = launch_conv_tma(p, BN, bk, d->out_dtype, stream);
+    rc = launch_conv_tma(p, BN, bk, d->out_dtype, staged, stream);
     if (rc == M3D_ERR_UNSUPPORTED) set_last_error("no TMA conv kernel for BN=%d BK=%d", BN, bk);
     return rc;
   }
@@ -206,6 +218,14 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
   memset(&p, 0, sizeof(p));
   int rc = make_tmap_2d(&p.tmap_b, d->weight, d->weight_rows, ktot, 64, BN);
   if (rc != M3D_OK) return rc;
+  if (staged) {
+    rc = make_tmap_nhwc(&p.tmap_out, d->out, d->N, P, Q, d->out_cstride, 64, TW, TH, 1);
+    if (rc != M3D_OK) return rc;
+    if (d->res != nullptr) {
+      rc = make_tmap_nhwc(&p.tmap_res, d->res, d->N, P, Q, d->res_cstride, 64, TW, TH, 1);
+      if (rc != M3D_OK) return rc;
+    }
+  }
   if (split) {
     rc = make_tmap_2d(&p.tmap_b_mid, d->weight_mid, d->weight_rows, ktot, 64, BN);
     if (rc != M3D_OK) return rc;
@@ -234,7 +254,7 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
   p.slope = d->slope;
   p.total_tiles = static_cast<int>(total_tiles);
   rc = launch_conv_gather(p, BN, d->act_dtype == M3D_F32 ? DT_F32 : DT_BF16, d->out_dtype == M3D_F32 ? DT_F32 : DT_BF16,
-                          stream);
+                          staged, stream);
   if (rc == M3D_ERR_UNSUPPORTED) set_last_error("no gather conv kernel for BN=%d", BN);
   return rc;
 }

@@ -1,0 +1,215 @@
+// Accumulator drains shared by the conv kernels (TMEM -> bias/residual/LeakyReLU -> global).
+//
+//  * epilogue_tile_staged: bf16 outputs whose channel count is a multiple of 64.  The 128 x BN tile
+//    leaves through shared memory in 64-channel slabs (one swizzled 128-byte row per pixel) written by
+//    TMA stores; the residual slab arrives in the same buffer by TMA load.  One bulk transaction per
+//    slab instead of 32 scattered 16-byte stores per warp instruction; TMA clips tiles that overhang
+//    the image.
+//  * epilogue_tile_direct: everything else (fp32 outputs, odd channel counts: 27-ch offsets, 36-ch
+//    heads): each thread owns one pixel and stores its channels itself.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "ptx.cuh"
+
+namespace m3d {
+
+constexpr int kEpiThreads = 128;
+constexpr int kEpiBarrier = 2;         // named barrier id of the 4 epilogue warps
+constexpr int kSlabBytes = 128 * 128;  // 128 pixels x 64 bf16 channels
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+// ---------------------------------------------------------------- direct
+template <typename OutT, typename ResT>
+__device__ __forceinline__ void epilogue_chunk16(const uint32_t (&acc)[16], const float* __restrict__ bias,
+                                                 const ResT* __restrict__ res, OutT* __restrict__ out, int nvalid,
+                                                 float slope) {
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
+  const bool full = nvalid >= 16;
+  if (bias != nullptr) {
+    if (full && (reinterpret_cast<uintptr_t>(bias) & 15) == 0) {
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + h);
+        v[4 * h] += b.x, v[4 * h + 1] += b.y, v[4 * h + 2] += b.z, v[4 * h + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < nvalid) v[i] += __ldg(bias + i);
+    }
+  }
+  if (res != nullptr) {
+    if (full && (reinterpret_cast<uintptr_t>(res) & 15) == 0) {
+      if constexpr (sizeof(ResT) == 2) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(res);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint4 u = __ldg(r4 + h);
+          v[h * 8 + 0] += __uint_as_float(u.x << 16), v[h * 8 + 1] += __uint_as_float(u.x & 0xffff0000u);
+          v[h * 8 + 2] += __uint_as_float(u.y << 16), v[h * 8 + 3] += __uint_as_float(u.y & 0xffff0000u);
+          v[h * 8 + 4] += __uint_as_float(u.z << 16), v[h * 8 + 5] += __uint_as_float(u.z & 0xffff0000u);
+          v[h * 8 + 6] += __uint_as_float(u.w << 16), v[h * 8 + 7] += __uint_as_float(u.w & 0xffff0000u);
+        }
+      } else {
+        const float4* r4 = reinterpret_cast<const float4*>(res);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float4 u = __ldg(r4 + h);
+          v[4 * h] += u.x, v[4 * h + 1] += u.y, v[4 * h + 2] += u.z, v[4 * h + 3] += u.w;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < nvalid) v[i] += static_cast<float>(res[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], slope);
+  if (full && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    if constexpr (sizeof(OutT) == 2) {
+      uint32_t w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<uint32_t*>(&b);
+      }
+      uint4* o4 = reinterpret_cast<uint4*>(out);
+      o4[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      o4[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    } else {
+      float4* o4 = reinterpret_cast<float4*>(out);
+#pragma unroll
+      for (int h = 0; h < 4; ++h) o4[h] = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)  // compile-time indices: stays in registers
+      if (i < nvalid) out[i] = static_cast<OutT>(v[i]);
+  }
+}
+
+template <int BN, typename OutT, typename ResT>
+__device__ __forceinline__ void epilogue_tile_direct(uint32_t tmem_acc, int quarter, int lane, int n, int p0, int q0,
+                                                     int TW, int P, int Q, int col_base, int cout, const float* bias,
+                                                     const ResT* res, int res_cstride, OutT* out, int out_cstride,
+                                                     float slope) {
+  const int row = quarter * 32 + lane;
+  const int p = p0 + row / TW;
+  const int q = q0 + row % TW;
+  const bool pix_ok = (p < P) && (q < Q);
+  const long pix = (static_cast<long>(n) * P + p) * Q + q;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 16) {
+    uint32_t acc[16];
+    tmem_ld16(tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + c0, acc);  // warp-collective
+    tmem_ld_wait();
+    const int col = col_base + c0;
+    const int nvalid = cout - col;
+    if (pix_ok && nvalid > 0) {
+      epilogue_chunk16<OutT, ResT>(acc, bias ? bias + col : nullptr, res ? res + pix * res_cstride + col : nullptr,
+                                   out + pix * out_cstride + col, nvalid, slope);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- staged
+struct StagedEpilogue {
+  uint8_t* slab[2];    // two 16 KB swizzled staging buffers (1024-byte aligned)
+  float* bias_s;       // BN floats
+  uint64_t* res_bar;   // [2] residual-landed barriers
+  uint32_t res_uses[2];
+  uint32_t slab_count;  // running slab index: selects the buffer
+  __device__ __forceinline__ void init(uint8_t* stage, float* bias_smem, uint64_t* bars) {
+    slab[0] = stage, slab[1] = stage + kSlabBytes;
+    bias_s = bias_smem, res_bar = bars;
+    res_uses[0] = res_uses[1] = 0;
+    slab_count = 0;
+  }
+};
+
+// One 128 x BN bf16 tile.  `ep_tid` in [0,128) numbers the epilogue threads; thread 0 issues every
+// TMA operation (bulk groups are per thread).  c_out / c_res: first channel of the tile inside the
+// output / residual buffers.  `on_tmem_drained` is called once the accumulator has been read.
+template <int BN, typename F>
+__device__ __forceinline__ void epilogue_tile_staged(StagedEpilogue& st, uint32_t tmem_acc, int quarter, int lane,
+                                                     int ep_tid, int n, int p0, int q0, const void* tmap_out, int c_out,
+                                                     const void* tmap_res, int c_res, const float* bias, int nbias,
+                                                     float slope, F on_tmem_drained) {
+  static_assert(BN % 64 == 0, "staged epilogue works on 64-channel slabs");
+  constexpr int NSLAB = BN / 64;
+  const int row = quarter * 32 + lane;
+  const bool leader = ep_tid == 0;
+  const bool has_res = tmap_res != nullptr;
+
+  named_bar_sync(kEpiBarrier, kEpiThreads);  // previous tile no longer reads bias_s
+  for (int i = ep_tid; i < BN; i += kEpiThreads) st.bias_s[i] = (bias != nullptr && i < nbias) ? __ldg(bias + i) : 0.f;
+  if (has_res && leader) {
+    const int b = st.slab_count & 1;
+    tma_store_wait_read<1>();  // the store that last used buffer b (two slabs ago) has drained it
+    mbar_arrive_expect_tx(&st.res_bar[b], kSlabBytes);
+    tma_load_4d(st.slab[b], tmap_res, &st.res_bar[b], c_res, q0, p0, n);
+  }
+  named_bar_sync(kEpiBarrier, kEpiThreads);  // bias_s visible
+
+#pragma unroll 1
+  for (int s = 0; s < NSLAB; ++s) {
+    const int b = st.slab_count & 1;
+    uint8_t* buf = st.slab[b];
+    if (has_res) {
+      if (leader && s + 1 < NSLAB) {  // prefetch the next residual slab into the other buffer
+        tma_store_wait_read<0>();
+        mbar_arrive_expect_tx(&st.res_bar[b ^ 1], kSlabBytes);
+        tma_load_4d(st.slab[b ^ 1], tmap_res, &st.res_bar[b ^ 1], c_res + (s + 1) * 64, q0, p0, n);
+      }
+      mbar_wait(&st.res_bar[b], st.res_uses[b] & 1);
+      st.res_uses[b]++;
+    } else {
+      if (leader) tma_store_wait_read<1>();
+      named_bar_sync(kEpiBarrier, kEpiThreads);  // buffer b is free for everybody
+    }
+    uint32_t a0[32], a1[32];
+    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + s * 64;
+    tmem_ld32(taddr, a0);
+    tmem_ld32(taddr + 32, a1);
+    tmem_ld_wait();
+    if (s == NSLAB - 1) on_tmem_drained();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // 8 chunks of 8 channels
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(j < 4 ? a0[j * 8 + e] : a1[(j - 4) * 8 + e]);
+      const float4 b0 = *reinterpret_cast<const float4*>(st.bias_s + s * 64 + j * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(st.bias_s + s * 64 + j * 8 + 4);
+      v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w, v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
+      uint4* cell = reinterpret_cast<uint4*>(buf + swizzled_offset<128>(row, j));
+      if (has_res) {
+        const uint4 u = *cell;
+        v[0] += __uint_as_float(u.x << 16), v[1] += __uint_as_float(u.x & 0xffff0000u);
+        v[2] += __uint_as_float(u.y << 16), v[3] += __uint_as_float(u.y & 0xffff0000u);
+        v[4] += __uint_as_float(u.z << 16), v[5] += __uint_as_float(u.z & 0xffff0000u);
+        v[6] += __uint_as_float(u.w << 16), v[7] += __uint_as_float(u.w & 0xffff0000u);
+      }
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __nv_bfloat162 t = __floats2bfloat162_rn(lrelu(v[2 * e], slope), lrelu(v[2 * e + 1], slope));
+        w[e] = *reinterpret_cast<uint32_t*>(&t);
+      }
+      *cell = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(kEpiBarrier, kEpiThreads);  // slab complete
+    if (leader) {
+      tma_store_4d(tmap_out, buf, c_out + s * 64, q0, p0, n);
+      tma_store_commit();
+    }
+    st.slab_count++;
+  }
+}
+
+}  // namespace m3d

@@ -4,6 +4,7 @@
 #include <cstdio>
 
 #include "common.cuh"
+#include "epilogue.cuh"
 #include "ptx.cuh"
 
 namespace m3d {
@@ -29,103 +30,8 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, int n_tiles, int tile
   return t;
 }
 
-template <typename T>
-struct Out16;
-
-// Epilogue for 16 accumulator columns of one output pixel: + bias, + residual,
-// LeakyReLU, convert, store.  `nvalid` = number of real channels in the chunk.
-template <typename OutT, typename ResT>
-__device__ __forceinline__ void epilogue_chunk16(const uint32_t (&acc)[16], const float* __restrict__ bias,
-                                                 const ResT* __restrict__ res, OutT* __restrict__ out, int nvalid,
-                                                 float slope) {
-  float v[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
-  if (bias != nullptr) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (i < nvalid) v[i] += __ldg(bias + i);
-  }
-  if (res != nullptr) {
-    if (nvalid == 16 && (reinterpret_cast<uintptr_t>(res) & 15) == 0) {
-      if constexpr (sizeof(ResT) == 2) {
-        const uint4* r4 = reinterpret_cast<const uint4*>(res);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint4 u = __ldg(r4 + h);
-          uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            v[h * 8 + 2 * i] += __uint_as_float(w[i] << 16);
-            v[h * 8 + 2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
-          }
-        }
-      } else {
-        const float4* r4 = reinterpret_cast<const float4*>(res);
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          float4 u = __ldg(r4 + h);
-          v[4 * h] += u.x;
-          v[4 * h + 1] += u.y;
-          v[4 * h + 2] += u.z;
-          v[4 * h + 3] += u.w;
-        }
-      }
-    } else {
-      for (int i = 0; i < nvalid; ++i) v[i] += static_cast<float>(res[i]);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * slope;
-
-  if (nvalid == 16 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-    if constexpr (sizeof(OutT) == 2) {
-      uint32_t w[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-        w[i] = *reinterpret_cast<uint32_t*>(&b);
-      }
-      uint4* o4 = reinterpret_cast<uint4*>(out);
-      o4[0] = make_uint4(w[0], w[1], w[2], w[3]);
-      o4[1] = make_uint4(w[4], w[5], w[6], w[7]);
-    } else {
-      float4* o4 = reinterpret_cast<float4*>(out);
-#pragma unroll
-      for (int h = 0; h < 4; ++h) o4[h] = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
-    }
-  } else {
-    for (int i = 0; i < nvalid; ++i) out[i] = static_cast<OutT>(v[i]);
-  }
-}
-
 // TMEM columns per accumulator stage (power of two >= 32).
 __host__ __device__ constexpr int acc_cols(int bn) { return bn <= 32 ? 32 : (bn <= 64 ? 64 : (bn <= 128 ? 128 : 256)); }
-
-// Drain one 128 x BN accumulator tile: TMEM -> registers -> global (NHWC).
-template <int BN, typename OutT, typename ResT>
-__device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int quarter, int lane, int n, int p0, int q0, int TW,
-                                              int P, int Q, int col_base, int cout, const float* bias, const ResT* res,
-                                              int res_cstride, OutT* out, int out_cstride, float slope) {
-  const int row = quarter * 32 + lane;
-  const int p = p0 + row / TW;
-  const int q = q0 + row % TW;
-  const bool pix_ok = (p < P) && (q < Q);
-  const long pix = (static_cast<long>(n) * P + p) * Q + q;
-#pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 16) {
-    uint32_t acc[16];
-    tmem_ld16(tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + c0, acc);  // warp-collective
-    tmem_ld_wait();
-    const int col = col_base + c0;
-    int nvalid = cout - col;
-    nvalid = nvalid > 16 ? 16 : nvalid;
-    if (pix_ok && nvalid > 0) {
-      epilogue_chunk16<OutT, ResT>(acc, bias ? bias + col : nullptr, res ? res + pix * res_cstride + col : nullptr,
-                                   out + pix * out_cstride + col, nvalid, slope);
-    }
-  }
-}
 
 // =========================================================================
 // Plain convolution: TMA-fed A operand.
@@ -133,32 +39,37 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int quarter, in
 //   warp 1: TMEM allocator + MMA issuer
 //   warps 2-5: epilogue (TMEM lane quarter = warp % 4)
 // =========================================================================
-template <int BN, int BK>
+template <int BN, int BK, bool STAGED>
 struct TmaCfg {
   static constexpr int ROW_BYTES = BK * 2;
   static constexpr int A_BYTES = kTileM * ROW_BYTES;
   static constexpr int B_BYTES = BN * ROW_BYTES;
   static constexpr int B_STRIDE = (B_BYTES + 1023) & ~1023;
   static constexpr int STAGE = A_BYTES + B_STRIDE;
-  static constexpr int STAGES = (STAGE * 6 <= 96 * 1024) ? 6 : ((STAGE * 4 <= 200 * 1024) ? 4 : 3);
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int EXTRA = STAGED ? (2 * kSlabBytes + 1024) : 0;  // staging slabs + bias
+  static constexpr int BUDGET = 224 * 1024 - EXTRA;
+  static constexpr int STAGES = (STAGE * 6 <= 96 * 1024) ? 6 : (BUDGET / STAGE >= 4 ? 4 : (BUDGET / STAGE >= 3 ? 3 : 2));
+  static constexpr int SMEM = STAGES * STAGE + EXTRA + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int ACC = acc_cols(BN);
+  static_assert(SMEM <= 227 * 1024, "conv tile does not fit shared memory");
 };
 
-template <int BN, int BK, typename OutT>
+template <int BN, int BK, typename OutT, bool STAGED>
 __global__ void __launch_bounds__(192, 1) conv_tma_kernel(const __grid_constant__ ConvTmaParams p) {
-  using Cfg = TmaCfg<BN, BK>;
+  using Cfg = TmaCfg<BN, BK, STAGED>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE);
+  uint8_t* stage_out = smem + STAGES * Cfg::STAGE;  // STAGED: 2 slabs + bias (1 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE + Cfg::EXTRA);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* res_bar = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -171,10 +82,12 @@ __global__ void __launch_bounds__(192, 1) conv_tma_kernel(const __grid_constant_
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], 128);
+      mbar_init(&res_bar[s], 1);
     }
     fence_barrier_init();
     for (int i = 0; i < p.num_inputs; ++i) prefetch_tmap(&p.tmap_a[i]);
     prefetch_tmap(&p.tmap_b);
+    if (STAGED) prefetch_tmap(&p.tmap_out);
   }
   if (warp == 1) tmem_alloc<2 * Cfg::ACC>(tmem_slot);
   tc_fence_before();
@@ -245,6 +158,9 @@ __global__ void __launch_bounds__(192, 1) conv_tma_kernel(const __grid_constant_
     }
   } else {
     const int quarter = warp & 3;
+    const int ep_tid = threadIdx.x - 64;
+    StagedEpilogue st;
+    if constexpr (STAGED) st.init(stage_out, reinterpret_cast<float*>(stage_out + 2 * kSlabBytes), res_bar);
     int local = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
       const TileCoord t = decode_tile(tile, p.n_tiles, p.tiles_w, p.tiles_h, p.N, p.TW, p.TH);
@@ -253,14 +169,27 @@ __global__ void __launch_bounds__(192, 1) conv_tma_kernel(const __grid_constant_
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const float* bias = p.bias ? p.bias + t.g * p.bias_goff : nullptr;
-      const __nv_bfloat16* res =
-          p.res ? static_cast<const __nv_bfloat16*>(p.res) + p.res_coff + t.g * p.res_goff : nullptr;
-      OutT* out = static_cast<OutT*>(p.out) + p.out_coff + t.g * p.out_goff;
-      epilogue_tile<BN, OutT, __nv_bfloat16>(tmem_base + as * Cfg::ACC, quarter, lane, t.n, t.p0, t.q0, p.TW, p.P, p.Q,
-                                             t.nt * BN, p.Cout, bias, res, p.res_cstride, out, p.out_cstride, p.slope);
-      tc_fence_before();
-      mbar_arrive(&tempty[as]);
+      if constexpr (STAGED) {
+        const int col0 = t.nt * BN;
+        epilogue_tile_staged<BN>(st, tmem_base + as * Cfg::ACC, quarter, lane, ep_tid, t.n, t.p0, t.q0, &p.tmap_out,
+                                 p.out_coff + t.g * p.out_goff + col0, p.res ? &p.tmap_res : nullptr,
+                                 p.res_coff + t.g * p.res_goff + col0, bias ? bias + col0 : nullptr, p.Cout - col0,
+                                 p.slope, [&]() {
+                                   tc_fence_before();
+                                   mbar_arrive(&tempty[as]);
+                                 });
+      } else {
+        const __nv_bfloat16* res =
+            p.res ? static_cast<const __nv_bfloat16*>(p.res) + p.res_coff + t.g * p.res_goff : nullptr;
+        OutT* out = static_cast<OutT*>(p.out) + p.out_coff + t.g * p.out_goff;
+        epilogue_tile_direct<BN, OutT, __nv_bfloat16>(tmem_base + as * Cfg::ACC, quarter, lane, t.n, t.p0, t.q0, p.TW,
+                                                      p.P, p.Q, t.nt * BN, p.Cout, bias, res, p.res_cstride, out,
+                                                      p.out_cstride, p.slope);
+        tc_fence_before();
+        mbar_arrive(&tempty[as]);
+      }
     }
+    if (STAGED && ep_tid == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -285,7 +214,7 @@ __global__ void __launch_bounds__(192, 1) conv_tma_kernel(const __grid_constant_
 constexpr int kGatherBK = 64;
 constexpr int kProducerThreads = 256;
 
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, bool STAGED>
 struct GatherCfg {
   static constexpr int ROW_BYTES = 128;
   static constexpr int A_BYTES = kTileM * ROW_BYTES;  // per part
@@ -293,9 +222,11 @@ struct GatherCfg {
   static constexpr int PARTS = SPLIT ? 3 : 1;
   static constexpr int STAGE = PARTS * (A_BYTES + B_BYTES);
   static constexpr int OM_BYTES = kTileM * 28 * 4;
-  static constexpr int STAGES = (STAGE * 4 + OM_BYTES <= 200 * 1024) ? 4 : ((STAGE * 3 + OM_BYTES <= 210 * 1024) ? 3 : 2);
-  static_assert(STAGES * STAGE + OM_BYTES + 1280 <= 227 * 1024, "gather tile does not fit shared memory");
-  static constexpr int SMEM = STAGES * STAGE + OM_BYTES + 1024 + 256;
+  static constexpr int EXTRA = STAGED ? (2 * kSlabBytes + 1024) : 0;
+  static constexpr int BUDGET = 224 * 1024 - OM_BYTES - EXTRA;
+  static constexpr int STAGES = BUDGET / STAGE >= 4 ? 4 : (BUDGET / STAGE >= 3 ? 3 : 2);
+  static constexpr int SMEM = STAGES * STAGE + EXTRA + OM_BYTES + 1024 + 256;
+  static_assert(SMEM <= 227 * 1024, "gather tile does not fit shared memory");
   static constexpr int ACC = acc_cols(BN);
 };
 
@@ -330,37 +261,41 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-template <int BN, typename InT, typename OutT>
+template <int BN, typename InT, typename OutT, bool STAGED>
 __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_constant__ ConvGatherParams p) {
   constexpr bool SPLIT = sizeof(InT) == 4;
-  using Cfg = GatherCfg<BN, SPLIT>;
+  using Cfg = GatherCfg<BN, SPLIT, STAGED>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BK = kGatherBK;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   // stage layout: [A_hi][A_mid][A_lo][B_hi][B_mid][B_lo]  (one part each when !SPLIT)
-  float* om_s = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE + Cfg::OM_BYTES);
+  uint8_t* stage_out = smem + STAGES * Cfg::STAGE;  // STAGED: 2 slabs + bias (1 KB)
+  float* om_s = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE + Cfg::EXTRA);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE + Cfg::EXTRA + Cfg::OM_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* res_bar = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], kProducerThreads + 1);
+      mbar_init(&full[s], kProducerThreads / 32 + 1);  // one arrival per producer warp + the weight TMA
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], 128);
+      mbar_init(&res_bar[s], 1);
     }
     fence_barrier_init();
     prefetch_tmap(&p.tmap_b);
+    if (STAGED) prefetch_tmap(&p.tmap_out);
     if (SPLIT) {
       prefetch_tmap(&p.tmap_b_mid);
       prefetch_tmap(&p.tmap_b_lo);
@@ -449,21 +384,42 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* a_hi = smem + stage * Cfg::STAGE;
             const int coff = c * BK + j * 8;
+            if constexpr (!SPLIT) {
+              // all 16 corner loads of this thread's 4 rows go out before the first blend: invalid corners
+              // carry weight 0 and a clamped (in-range) address, so there is nothing to branch on
+              uint4 cv[4][4];
 #pragma unroll
-            for (int ii = 0; ii < 4; ++ii) {
-              const int row = rbase + 32 * ii;
-              const SampleInfo& x = si[ii];
-              float acc[8];
-              if (x.mask == 0.f && x.w00 == 0.f && x.w01 == 0.f && x.w10 == 0.f && x.w11 == 0.f) {
+              for (int ii = 0; ii < 4; ++ii) {
+                cv[ii][0] = __ldg(reinterpret_cast<const uint4*>(in + si[ii].o00 + coff));
+                cv[ii][1] = __ldg(reinterpret_cast<const uint4*>(in + si[ii].o01 + coff));
+                cv[ii][2] = __ldg(reinterpret_cast<const uint4*>(in + si[ii].o10 + coff));
+                cv[ii][3] = __ldg(reinterpret_cast<const uint4*>(in + si[ii].o11 + coff));
+              }
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-              } else if (x.w00 == 1.f) {
-                // integer sample position (plain convolution): one corner
-                load8(in + x.o00 + coff, acc);
+              for (int ii = 0; ii < 4; ++ii) {
+                const SampleInfo& x = si[ii];
+                const uint32_t* q0 = reinterpret_cast<const uint32_t*>(&cv[ii][0]);
+                const uint32_t* q1 = reinterpret_cast<const uint32_t*>(&cv[ii][1]);
+                const uint32_t* q2 = reinterpret_cast<const uint32_t*>(&cv[ii][2]);
+                const uint32_t* q3 = reinterpret_cast<const uint32_t*>(&cv[ii][3]);
+                uint32_t w[4];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] *= x.mask;
-              } else {
-                float v1[8], v2[8], v3[8], v4[8];
+                for (int e = 0; e < 4; ++e) {
+                  const float lo = (x.w00 * __uint_as_float(q0[e] << 16) + x.w01 * __uint_as_float(q1[e] << 16) +
+                                    x.w10 * __uint_as_float(q2[e] << 16) + x.w11 * __uint_as_float(q3[e] << 16)) * x.mask;
+                  const float hi = (x.w00 * __uint_as_float(q0[e] & 0xffff0000u) + x.w01 * __uint_as_float(q1[e] & 0xffff0000u) +
+                                    x.w10 * __uint_as_float(q2[e] & 0xffff0000u) + x.w11 * __uint_as_float(q3[e] & 0xffff0000u)) * x.mask;
+                  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+                  w[e] = *reinterpret_cast<uint32_t*>(&t);
+                }
+                *reinterpret_cast<uint4*>(a_hi + swizzled_offset<128>(rbase + 32 * ii, j)) = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+            } else {
+#pragma unroll 1
+              for (int ii = 0; ii < 4; ++ii) {
+                const int row = rbase + 32 * ii;
+                const SampleInfo& x = si[ii];
+                float v1[8], v2[8], v3[8], v4[8], acc[8];
                 load8(in + x.o00 + coff, v1);
                 load8(in + x.o01 + coff, v2);
                 load8(in + x.o10 + coff, v3);
@@ -471,9 +427,7 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
 #pragma unroll
                 for (int e = 0; e < 8; ++e)
                   acc[e] = (x.w00 * v1[e] + x.w01 * v2[e] + x.w10 * v3[e] + x.w11 * v4[e]) * x.mask;
-              }
-              const uint32_t off = swizzled_offset<128>(row, j);
-              if constexpr (SPLIT) {
+                const uint32_t off = swizzled_offset<128>(row, j);
                 float hi[8], mid[8], lo[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -485,12 +439,11 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
                 *reinterpret_cast<uint4*>(a_hi + off) = pack8(hi);
                 *reinterpret_cast<uint4*>(a_hi + Cfg::A_BYTES + off) = pack8(mid);
                 *reinterpret_cast<uint4*>(a_hi + 2 * Cfg::A_BYTES + off) = pack8(lo);
-              } else {
-                *reinterpret_cast<uint4*>(a_hi + off) = pack8(acc);
               }
             }
             fence_proxy_async_smem();
-            mbar_arrive(&full[stage]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[stage]);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -572,6 +525,9 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
   } else {
     // --------------------------------------------------------------- epilogue
     const int quarter = warp & 3;
+    const int ep_tid = threadIdx.x - 320;
+    StagedEpilogue st;
+    if constexpr (STAGED) st.init(stage_out, reinterpret_cast<float*>(stage_out + 2 * kSlabBytes), res_bar);
     int local = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
       const TileCoord t = decode_tile(tile, p.n_tiles, p.tiles_w, p.tiles_h, p.N, p.TW, p.TH);
@@ -579,13 +535,24 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
       const uint32_t aphase = (local >> 1) & 1;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      const InT* res = p.res ? static_cast<const InT*>(p.res) + p.res_coff : nullptr;
-      OutT* out = static_cast<OutT*>(p.out) + p.out_coff;
-      epilogue_tile<BN, OutT, InT>(tmem_base + as * Cfg::ACC, quarter, lane, t.n, t.p0, t.q0, p.TW, p.P, p.Q, t.nt * BN,
-                                   p.Cout, p.bias, res, p.res_cstride, out, p.out_cstride, p.slope);
-      tc_fence_before();
-      mbar_arrive(&tempty[as]);
+      if constexpr (STAGED) {
+        const int col0 = t.nt * BN;
+        epilogue_tile_staged<BN>(st, tmem_base + as * Cfg::ACC, quarter, lane, ep_tid, t.n, t.p0, t.q0, &p.tmap_out,
+                                 p.out_coff + col0, p.res ? &p.tmap_res : nullptr, p.res_coff + col0,
+                                 p.bias ? p.bias + col0 : nullptr, p.Cout - col0, p.slope, [&]() {
+                                   tc_fence_before();
+                                   mbar_arrive(&tempty[as]);
+                                 });
+      } else {
+        const InT* res = p.res ? static_cast<const InT*>(p.res) + p.res_coff : nullptr;
+        OutT* out = static_cast<OutT*>(p.out) + p.out_coff;
+        epilogue_tile_direct<BN, OutT, InT>(tmem_base + as * Cfg::ACC, quarter, lane, t.n, t.p0, t.q0, p.TW, p.P, p.Q,
+                                            t.nt * BN, p.Cout, p.bias, res, p.res_cstride, out, p.out_cstride, p.slope);
+        tc_fence_before();
+        mbar_arrive(&tempty[as]);
+      }
     }
+    if (STAGED && ep_tid == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -606,10 +573,10 @@ static int num_sms() {
   return sms;
 }
 
-template <int BN, int BK, typename OutT>
+template <int BN, int BK, typename OutT, bool STAGED>
 static int launch_tma_t(const ConvTmaParams& p, cudaStream_t stream) {
-  using Cfg = TmaCfg<BN, BK>;
-  auto kern = conv_tma_kernel<BN, BK, OutT>;
+  using Cfg = TmaCfg<BN, BK, STAGED>;
+  auto kern = conv_tma_kernel<BN, BK, OutT, STAGED>;
   static bool configured = false;
   if (!configured) {
     M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
@@ -624,12 +591,18 @@ static int launch_tma_t(const ConvTmaParams& p, cudaStream_t stream) {
   return M3D_OK;
 }
 
-int launch_conv_tma(const ConvTmaParams& p, int BN, int BK, int out_dtype, cudaStream_t stream) {
-#define M3D_TMA_CASE(bn, bk)                                                        \
-  if (BN == bn && BK == bk) {                                                       \
-    return out_dtype == DT_BF16 ? launch_tma_t<bn, bk, __nv_bfloat16>(p, stream)    \
-                                : launch_tma_t<bn, bk, float>(p, stream);           \
+int launch_conv_tma(const ConvTmaParams& p, int BN, int BK, int out_dtype, bool staged, cudaStream_t stream) {
+#define M3D_TMA_CASE(bn, bk)                                                               \
+  if (BN == bn && BK == bk) {                                                              \
+    return out_dtype == DT_BF16 ? launch_tma_t<bn, bk, __nv_bfloat16, false>(p, stream)    \
+                                : launch_tma_t<bn, bk, float, false>(p, stream);           \
   }
+#define M3D_TMA_STAGED(bn)                                                                 \
+  if (staged && BN == bn && BK == 64 && out_dtype == DT_BF16)                              \
+    return launch_tma_t<bn, 64, __nv_bfloat16, true>(p, stream);
+  M3D_TMA_STAGED(64)
+  M3D_TMA_STAGED(128)
+  M3D_TMA_STAGED(256)
   M3D_TMA_CASE(16, 16)
   M3D_TMA_CASE(32, 16)
   M3D_TMA_CASE(32, 32)
@@ -640,13 +613,14 @@ int launch_conv_tma(const ConvTmaParams& p, int BN, int BK, int out_dtype, cudaS
   M3D_TMA_CASE(128, 64)
   M3D_TMA_CASE(256, 64)
 #undef M3D_TMA_CASE
+#undef M3D_TMA_STAGED
   return M3D_ERR_UNSUPPORTED;
 }
 
-template <int BN, typename InT, typename OutT>
+template <int BN, typename InT, typename OutT, bool STAGED>
 static int launch_gather_t(const ConvGatherParams& p, cudaStream_t stream) {
-  using Cfg = GatherCfg<BN, sizeof(InT) == 4>;
-  auto kern = conv_gather_kernel<BN, InT, OutT>;
+  using Cfg = GatherCfg<BN, sizeof(InT) == 4, STAGED>;
+  auto kern = conv_gather_kernel<BN, InT, OutT, STAGED>;
   static bool configured = false;
   if (!configured) {
     M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
@@ -659,15 +633,22 @@ static int launch_gather_t(const ConvGatherParams& p, cudaStream_t stream) {
   return M3D_OK;
 }
 
-int launch_conv_gather(const ConvGatherParams& p, int BN, int in_dtype, int out_dtype, cudaStream_t stream) {
-#define M3D_G_CASE(bn)                                                                           \
-  if (BN == bn) {                                                                                \
-    if (in_dtype == DT_BF16)                                                                     \
-      return out_dtype == DT_BF16 ? launch_gather_t<bn, __nv_bfloat16, __nv_bfloat16>(p, stream) \
-                                  : launch_gather_t<bn, __nv_bfloat16, float>(p, stream);        \
-    if constexpr (bn <= 128) return launch_gather_t<bn, float, float>(p, stream);                \
-    return M3D_ERR_UNSUPPORTED;                                                                  \
+int launch_conv_gather(const ConvGatherParams& p, int BN, int in_dtype, int out_dtype, bool staged,
+                       cudaStream_t stream) {
+#define M3D_G_STAGED(bn)                                                    \
+  if (staged && BN == bn && in_dtype == DT_BF16 && out_dtype == DT_BF16)    \
+    return launch_gather_t<bn, __nv_bfloat16, __nv_bfloat16, true>(p, stream);
+#define M3D_G_CASE(bn)                                                                                  \
+  if (BN == bn) {                                                                                       \
+    if (in_dtype == DT_BF16)                                                                            \
+      return out_dtype == DT_BF16 ? launch_gather_t<bn, __nv_bfloat16, __nv_bfloat16, false>(p, stream) \
+                                  : launch_gather_t<bn, __nv_bfloat16, float, false>(p, stream);        \
+    if constexpr (bn <= 128) return launch_gather_t<bn, float, float, false>(p, stream);                \
+    return M3D_ERR_UNSUPPORTED;                                                                         \
   }
+  M3D_G_STAGED(64)
+  M3D_G_STAGED(128)
+  M3D_G_STAGED(256)
   M3D_G_CASE(16)
   M3D_G_CASE(32)
   M3D_G_CASE(48)
@@ -675,6 +656,7 @@ int launch_conv_gather(const ConvGatherParams& p, int BN, int in_dtype, int out_
   M3D_G_CASE(128)
   M3D_G_CASE(256)
 #undef M3D_G_CASE
+#undef M3D_G_STAGED
   return M3D_ERR_UNSUPPORTED;
 }
 

@@ -39,6 +39,7 @@ enum : int { DT_BF16 = 0, DT_F32 = 1 };
 struct alignas(64) ConvTmaParams {
   CUtensorMap tmap_a[kMaxConcat];  // NHWC inputs as 4-D (C, W, H, N) maps, box {BK, TW*stride, TH*stride, 1}
   CUtensorMap tmap_b;              // packed weights as 2-D (K, rows) map, box {BK, BN}
+  CUtensorMap tmap_out, tmap_res;  // staged epilogue: output / residual as (C, Q, P, N), box {64, TW, TH, 1}
   int num_inputs;
   int chunks[kMaxConcat];  // k-blocks per tap for each concat input (= C_i / BK)
   int a_coff[kMaxConcat];  // first channel of input i inside its buffer
@@ -64,6 +65,7 @@ struct alignas(64) ConvGatherParams {
   CUtensorMap tmap_b;      // bf16 weights (hi part in split mode)
   CUtensorMap tmap_b_mid;  // split mode: second 8 mantissa bits
   CUtensorMap tmap_b_lo;   // split mode: third 8 mantissa bits
+  CUtensorMap tmap_out, tmap_res;  // staged epilogue (bf16 out, Cout % 64 == 0)
   int num_inputs;
   const void* in[kMaxConcat];
   int in_cstride[kMaxConcat], in_coff[kMaxConcat], chunks[kMaxConcat];
@@ -87,7 +89,8 @@ struct alignas(64) ConvGatherParams {
 };
 
 // Host launchers (igemm.cu).  Return 0 or a negative m3d error code.
-int launch_conv_tma(const ConvTmaParams& p, int BN, int BK, int out_dtype, cudaStream_t stream);
-int launch_conv_gather(const ConvGatherParams& p, int BN, int in_dtype, int out_dtype, cudaStream_t stream);
+int launch_conv_tma(const ConvTmaParams& p, int BN, int BK, int out_dtype, bool staged, cudaStream_t stream);
+int launch_conv_gather(const ConvGatherParams& p, int BN, int in_dtype, int out_dtype, bool staged,
+                       cudaStream_t stream);
 
 }  // namespace m3d
