@@ -70,6 +70,7 @@ typedef struct m3d_conv_desc {
   int in_goff[M3D_MAX_CONCAT];    /* extra channel offset per group */
   int N, H, W;                    /* input geometry */
   int R, S, stride, pad, dil;
+  int out_h, out_w; /* 0 = (H + 2 pad - dil (R-1) - 1) / stride + 1; set to crop the output (pad is then top/left only) */
   int Cout;   /* output channels per group */
   int groups; /* independent GEMMs sharing geometry (batched heads); >1 only for plain bf16 convs */
   const void* weight;     /* bf16 [weight_rows][K] (M3D_F32: the high 8 mantissa bits) */
@@ -144,11 +145,17 @@ int m3d_gather_kept(const float* dets, int row_len, int batch, int max_n, const 
 /* DLA.base_layer (model/pose_dla_dcn.py:336-340): 7x7 conv on the NCHW fp32 image, BN folded, LeakyReLU. */
 int m3d_stem_conv7x7(const float* image_nchw, const float* weight /*[16,3,7,7]*/, const float* bias, void* out,
                      int out_dtype, int out_cstride, int N, int H, int W, float slope, m3d_stream_t stream);
+/* The same layer on the tensor cores, written in 2x2 space-to-depth form: out [N, H/2, W/2, 64] bf16 with
+ * channel (dy*2 + dx)*16 + c = stem output channel c at pixel (2Y+dy, 2X+dx).  The 7x7 conv becomes a
+ * K = 3*8*8 implicit GEMM (stride-2 8x8 windows of the fp32 NCHW image gathered straight into the
+ * swizzled A tile).  weight: bf16 [64][192] packed by the host (m3dssd_b200.ops.pack_stem_s2d). */
+int m3d_stem_conv7x7_s2d(const float* image_nchw, const void* weight_bf16, const float* bias64, void* out, int N,
+                         int H, int W, float slope, m3d_stream_t stream);
 /* nn.MaxPool2d(2) (model/pose_dla_dcn.py:306). */
 int m3d_maxpool2x2_nhwc(const void* in, void* out, int dtype, int N, int H, int W, int C, int in_cstride,
                         int out_cstride, m3d_stream_t stream);
 /* IDAUp up_i + skip add (model/pose_dla_dcn.py:536-552): depthwise ConvTranspose2d(2f, stride f, pad f/2). */
-int m3d_upsample_add_nhwc(const void* x, const float* weight /*[C,2f,2f]*/, const void* skip, void* out, int dtype,
+int m3d_upsample_add_nhwc(const void* x, const float* weight /*tap-major [(2f)^2, C]*/, const void* skip, void* out, int dtype,
                           int N, int H, int W, int C, int f, int x_cstride, int skip_cstride, int out_cstride,
                           m3d_stream_t stream);
 /* softmax over classes + fg prob + top-1 anchor + score/class (model/M3d_inference_align.py:229-234). */

@@ -10,6 +10,7 @@ _SIGS = {
     "m3d_decode_topk": [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, f, f, i, vp, vp, vp, vp],
     "m3d_gather_kept": [vp, i, i, i, vp, vp, i, vp, vp],
     "m3d_stem_conv7x7": [vp, vp, vp, vp, i, i, i, i, i, f, vp],
+    "m3d_stem_conv7x7_s2d": [vp, vp, vp, vp, i, i, i, f, vp],
     "m3d_maxpool2x2_nhwc": [vp, vp, i, i, i, i, i, i, i, vp],
     "m3d_upsample_add_nhwc": [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp],
     "m3d_cls_softmax": [vp, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp],

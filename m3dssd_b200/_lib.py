@@ -25,6 +25,7 @@ class ConvDesc(C.Structure):
         ("in_coff", C.c_int * MAX_CONCAT), ("in_goff", C.c_int * MAX_CONCAT),
         ("N", C.c_int), ("H", C.c_int), ("W", C.c_int),
         ("R", C.c_int), ("S", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("dil", C.c_int),
+        ("out_h", C.c_int), ("out_w", C.c_int),
         ("Cout", C.c_int), ("groups", C.c_int),
         ("weight", C.c_void_p), ("weight_mid", C.c_void_p), ("weight_lo", C.c_void_p), ("weight_f32", C.c_void_p),
         ("weight_rows", C.c_int), ("weight_goff", C.c_int),

@@ -124,6 +124,35 @@ static int pick_bn(int cout, int bk, long m_tiles, bool gather, bool split) {
 
 using namespace m3d;
 
+extern "C" int m3d_stem_conv7x7_s2d(const float* image, const void* weight, const float* bias, void* out, int N, int H,
+                                    int W, float slope, m3d_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3D_REQUIRE(image && weight && bias && out, "NULL pointer");
+  M3D_REQUIRE(H % 2 == 0 && W % 2 == 0 && H >= 2 && W >= 2, "space-to-depth stem needs even H, W (got %dx%d)", H, W);
+  const int P = H / 2, Q = W / 2;
+  int TW = 16, TH = 8;
+  pick_tile(P, Q, 256, &TW, &TH);
+  ConvGatherParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = make_tmap_2d(&p.tmap_b, weight, 64, 192, 64, 64);
+  if (rc != M3D_OK) return rc;
+  rc = make_tmap_nhwc(&p.tmap_out, out, N, P, Q, 64, 64, TW, TH, 1);
+  if (rc != M3D_OK) return rc;
+  p.num_inputs = 1;
+  p.chunks[0] = 3;  // one k-block per image channel
+  p.stem_img = image;
+  p.H = H, p.W = W;
+  p.R = 1, p.S = 1, p.stride = 1, p.pad = 0, p.dil = 1;
+  p.N = N, p.P = P, p.Q = Q;
+  p.TW = TW, p.TH = TH, p.tiles_w = (Q + TW - 1) / TW, p.tiles_h = (P + TH - 1) / TH;
+  p.Cout = 64, p.n_tiles = 1;
+  p.out = out, p.out_cstride = 64;
+  p.bias = bias;
+  p.slope = slope;
+  p.total_tiles = p.tiles_w * p.tiles_h * N;
+  return launch_conv_gather(p, 64, DT_BF16, DT_BF16, true, stream);
+}
+
 extern "C" const char* m3d_last_error(void) { return g_last_error; }
 extern "C" int m3d_version(void) { return 100; }
 
@@ -135,8 +164,8 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
   M3D_REQUIRE(d->N >= 1 && d->H >= 1 && d->W >= 1 && d->Cout >= 1, "bad tensor geometry");
   M3D_REQUIRE((d->weight != nullptr || d->weight_f32 != nullptr) && d->out != nullptr, "weight/out is NULL");
   const int groups = d->groups < 1 ? 1 : d->groups;
-  const int P = (d->H + 2 * d->pad - (d->dil * (d->R - 1) + 1)) / d->stride + 1;  // dcn_v2_cuda.c:40-41
-  const int Q = (d->W + 2 * d->pad - (d->dil * (d->S - 1) + 1)) / d->stride + 1;
+  const int P = d->out_h > 0 ? d->out_h : (d->H + 2 * d->pad - (d->dil * (d->R - 1) + 1)) / d->stride + 1;  // dcn_v2_cuda.c:40-41
+  const int Q = d->out_w > 0 ? d->out_w : (d->W + 2 * d->pad - (d->dil * (d->S - 1) + 1)) / d->stride + 1;
   M3D_REQUIRE(P >= 1 && Q >= 1, "empty output %dx%d", P, Q);
   const bool split = d->act_dtype == M3D_F32;
   const bool gather = split || d->om != nullptr || d->force_gather;

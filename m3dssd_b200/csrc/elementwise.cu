@@ -146,7 +146,8 @@ __global__ void maxpool2x2_kernel(const T* __restrict__ in, T* __restrict__ out,
 
 // ---------------------------------------------------------------------------
 // IDAUp: depthwise ConvTranspose2d(k = 2f, stride f, pad f/2, groups = C, no
-// bias) followed by "+ skip" (model/pose_dla_dcn.py:536-552).  Output pixel
+// bias) followed by "+ skip" (model/pose_dla_dcn.py:536-552); weights are passed tap-major,
+// [k*k][C], so a thread's 8 channels of one tap are two 16-byte loads.  Output pixel
 // (oy, ox) gathers the <= ceil(k/f)^2 = 4 input pixels that reach it:
 //   oy = iy * f - pad + ky   <=>   iy = (oy + pad - ky) / f   when divisible.
 // ---------------------------------------------------------------------------
@@ -189,8 +190,12 @@ __global__ void upsample_add_kernel(const T* __restrict__ x, const float* __rest
         T v[V];
         *reinterpret_cast<uint4*>(v) =
             __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<long>(n) * H + iy) * W + ix) * x_cstride + c));
+        float wv[V];
 #pragma unroll
-        for (int q = 0; q < V; ++q) up[q] = fmaf(to_f(v[q]), __ldg(wt + (c + q) * k * k + ky * k + kx), up[q]);
+        for (int q = 0; q < V; q += 4)
+          *reinterpret_cast<float4*>(wv + q) = __ldg(reinterpret_cast<const float4*>(wt + (ky * k + kx) * C + c + q));
+#pragma unroll
+        for (int q = 0; q < V; ++q) up[q] = fmaf(to_f(v[q]), wv[q], up[q]);
       }
     }
     T o[V];
@@ -345,23 +350,32 @@ __global__ void __launch_bounds__(256) flatten_heads_kernel(const float* __restr
   const int w0 = blockIdx.x * SM_PIX, h = blockIdx.y, n = blockIdx.z;
   const int npix = min(SM_PIX, W - w0);
   const float* src = heads + ((static_cast<long>(n) * H + h) * W + w0) * hc_stride;
-  for (int i = threadIdx.x; i < npix * C; i += blockDim.x) {
-    const int px = i / C, c = i - px * C;
-    s_tile[px * ld + c] = __ldg(src + static_cast<long>(px) * hc_stride + c);
+  if ((C & 3) == 0 && (hc_stride & 3) == 0) {
+    const int c4 = C / 4;
+    for (int i = threadIdx.x; i < npix * c4; i += blockDim.x) {
+      const int px = i / c4, c = (i - px * c4) * 4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + static_cast<long>(px) * hc_stride + c));
+      float* d = s_tile + px * ld + c;
+      d[0] = v.x, d[1] = v.y, d[2] = v.z, d[3] = v.w;
+    }
+  } else {
+    for (int i = threadIdx.x; i < npix * C; i += blockDim.x) {
+      const int px = i / C, c = i - px * C;
+      s_tile[px * ld + c] = __ldg(src + static_cast<long>(px) * hc_stride + c);
+    }
   }
   __syncthreads();
-  // bbox_2d: 4 floats per row; thread -> (a, px, j) with (px, j) fastest
-  for (int i = threadIdx.x; i < A * SM_PIX * 4; i += blockDim.x) {
-    const int j = i & 3, px = (i >> 2) % SM_PIX, a = i / (4 * SM_PIX);
+  // thread -> (anchor, pixel) with the pixel fastest: one 16-byte bbox_2d row and one 28-byte bbox_3d row
+  for (int i = threadIdx.x; i < A * SM_PIX; i += blockDim.x) {
+    const int px = i % SM_PIX, a = i / SM_PIX;
     if (px >= npix) continue;
+    const float* t = s_tile + px * ld + a;
     const long row = (static_cast<long>(n) * A + a) * H * W + static_cast<long>(h) * W + (w0 + px);
-    bbox_2d[row * 4 + j] = s_tile[px * ld + slots.s[j] * A + a];
-  }
-  for (int i = threadIdx.x; i < A * SM_PIX * 7; i += blockDim.x) {
-    const int j = i % 7, px = (i / 7) % SM_PIX, a = i / (7 * SM_PIX);
-    if (px >= npix) continue;
-    const long row = (static_cast<long>(n) * A + a) * H * W + static_cast<long>(h) * W + (w0 + px);
-    bbox_3d[row * 7 + j] = s_tile[px * ld + slots.s[4 + j] * A + a];
+    *reinterpret_cast<float4*>(bbox_2d + row * 4) =
+        make_float4(t[slots.s[0] * A], t[slots.s[1] * A], t[slots.s[2] * A], t[slots.s[3] * A]);
+    float* o3 = bbox_3d + row * 7;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) o3[j] = t[slots.s[4 + j] * A];
   }
 }
 

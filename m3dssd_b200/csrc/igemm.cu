@@ -319,6 +319,40 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
     const int omc = 3 * taps;
     int stage = 0;
     uint32_t phase = 0;
+    if (!SPLIT && p.stem_img != nullptr) {
+      // ---- stem: 7x7 conv of the fp32 NCHW image in 2x2 space-to-depth form.  Row (Y, X) of the tile
+      // is the 8x8 window at (2Y-3, 2X-3); k-block kb = image channel kb, 16-byte chunk j = window row
+      // j, its 8 elements = 8 consecutive image columns.
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(tile, p.n_tiles, p.tiles_w, p.tiles_h, p.N, p.TW, p.TH);
+        for (int kb = 0; kb < 3; ++kb) {
+          const float* plane = p.stem_img + (static_cast<long>(t.n) * 3 + kb) * p.H * p.W;
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* a_hi = smem + stage * Cfg::STAGE;
+#pragma unroll
+          for (int ii = 0; ii < 4; ++ii) {
+            const int row = rbase + 32 * ii;
+            const int Y = t.p0 + row / p.TW, X = t.q0 + row % p.TW;
+            const int y = 2 * Y - 3 + j, x0 = 2 * X - 3;
+            float v[8];
+            const bool yok = Y < p.P && X < p.Q && y >= 0 && y < p.H;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int x = x0 + e;
+              v[e] = (yok && x >= 0 && x < p.W) ? __ldg(plane + static_cast<long>(y) * p.W + x) : 0.f;
+            }
+            *reinterpret_cast<uint4*>(a_hi + swizzled_offset<128>(row, j)) = pack8(v);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    } else
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(tile, p.n_tiles, p.tiles_w, p.tiles_h, p.N, p.TW, p.TH);
       if (p.om != nullptr) {

@@ -79,6 +79,8 @@ struct alignas(64) ConvGatherParams {
   const float* om;
   int om_cstride;
   int sigmoid_mask;
+  // stem mode: A rows are stride-2 8x8 windows of this fp32 NCHW 3-channel image (k-block = channel)
+  const float* stem_img;
   void* out;
   int out_cstride, out_coff;
   const float* bias;

@@ -30,8 +30,8 @@ OUT_SLOTS = [0, 1, 4, 5, 2, 3, 10, 6, 7, 8, 9]
 class Act:
     """An NHWC activation: `c` real channels inside a buffer with t.shape[-1] channels per pixel."""
 
-    def __init__(self, t, c, coff=0):
-        self.t, self.c, self.coff = t, c, coff
+    def __init__(self, t, c, coff=0, s2d=False):
+        self.t, self.c, self.coff, self.s2d = t, c, coff, s2d  # s2d: 2x2 space-to-depth packed ((dy*2+dx)*c/4 + ch)
 
 
 def _fold(conv_w, conv_b, bn):
@@ -89,7 +89,7 @@ class Engine:
         self.n_launches += launches
 
     def _conv(self, name, inputs, w, b, bn, k, stride=1, pad=None, slope=0.01, res=None, out=None, out_dtype=None,
-              om=None, sigmoid_mask=False, out_coff=0):
+              om=None, sigmoid_mask=False, out_coff=0, out_hw=None):
         """Register conv(+BN)(+res)(+LeakyReLU) over concatenated NHWC inputs; returns the output Act."""
         pad = k // 2 if pad is None else pad
         wf, bf = _fold(w, b, bn)
@@ -106,6 +106,8 @@ class Engine:
         N, H, W = x0.shape[:3]
         P = (H + 2 * pad - k) // stride + 1
         Q = (W + 2 * pad - k) // stride + 1
+        if out_hw is not None:
+            P, Q = out_hw
         if out is None:
             odt = out_dtype or self.adt
             cbuf = self._cpad(cout) if odt == self.adt else cout
@@ -118,7 +120,7 @@ class Engine:
         def run():
             ops.conv2d_nhwc(ins, hi, out, R=k, S=k, stride=stride, pad=pad, Cout=cout, bias=bias, res=res_t,
                             res_coff=res_coff, slope=slope, weight_lo=lo, om=om_t, sigmoid_mask=sigmoid_mask,
-                            out_coff=out_coff)
+                            out_coff=out_coff, out_hw=out_hw)
 
         esz = 4 if self.fp32 else 2
         k_real = k * k * sum(a.c for a in inputs)
@@ -182,9 +184,13 @@ class Engine:
         base = self.net.base.base
         B, H, W = self.B, self.H, self.W
         w, b = _fold(base.base_layer[0].weight, None, base.base_layer[1])
-        w, b = w.to(self.dev).contiguous(), b.to(self.dev).contiguous()
         c0 = w.shape[0]
         assert c0 == 16, "stem kernel is specialised for 16 output channels"
+        l0, l1 = base.level0, base.level1
+        if (not self.fp32 and H % 2 == 0 and W % 2 == 0 and len(l0) == 3 and len(l1) == 3
+                and l0[0].out_channels == 16 and l1[0].stride[0] == 2):
+            return self._trunk_s2d(base, w, b)
+        w, b = w.to(self.dev).contiguous(), b.to(self.dev).contiguous()
         s0 = self._new("stem", B, H, W, self._cpad(c0))
         img = self.image
         self._add(lambda: ops.stem_conv7x7(img, w, b, s0, 0.01), 1, "stem", "stem", 2.0 * B * H * W * c0 * 147,
@@ -200,6 +206,42 @@ class Engine:
         for i, a in enumerate(levels):
             self.named["level%d" % i] = a
         return levels
+
+    def _trunk_s2d(self, base, w_stem, b_stem):
+        """bf16 trunk head in 2x2 space-to-depth form: the three full-resolution 16-channel layers (stem 7x7,
+        level0 3x3, level1 3x3 s2) become well-shaped GEMMs on [N, H/2, W/2, 64] tensors -- same arithmetic,
+        zero-padded weights -- instead of 32-byte-per-pixel tiles the TMA / tensor pipes handle poorly."""
+        B, H, W = self.B, self.H, self.W
+        wp, bp = ops.pack_stem_s2d(w_stem, b_stem)
+        wp, bp = wp.to(self.dev), bp.to(self.dev)
+        s0 = self._new("stem", B, H // 2, W // 2, 64)
+        img = self.image
+        self._add(lambda: ops.stem_conv7x7_s2d(img, wp, bp, s0, 0.01), 1, "stem", "stem_s2d",
+                  2.0 * B * H * W * 16 * 147, B * H * W * (3 * 4 + 16 * 2))
+        x = Act(s0, 64, s2d=True)
+        w0, b0 = _fold(base.level0[0].weight, None, base.level0[1])
+        w0p, b0p = ops.s2d_conv3x3_weight(w0, b0)
+        x = self._conv("level0", [x], w0p, b0p, None, 3, 1, 1, 0.01)
+        x.s2d = True
+        self._fix_meta("level0", 2.0 * B * H * W * 16 * 144, B * H * W * 16 * 2 * 2)
+        levels = [x]
+        w1, b1 = _fold(base.level1[0].weight, None, base.level1[1])
+        x = self._conv("level1", [x], ops.s2d_conv3x3_s2_weight(w1), b1, None, 2, 1, 1, 0.01, out_hw=(H // 2, W // 2))
+        self._fix_meta("level1", 2.0 * B * (H // 2) * (W // 2) * w1.shape[0] * 144,
+                       B * H * W * 16 * 2 + B * (H // 2) * (W // 2) * w1.shape[0] * 2)
+        levels.append(x)
+        for i in range(2, 6):
+            x = self._tree("level%d" % i, getattr(base, "level%d" % i), x)
+            levels.append(x)
+        for i, a in enumerate(levels):
+            self.named["level%d" % i] = a
+        return levels
+
+    def _fix_meta(self, name, flops, bytes_):
+        """Roofline numerators stay ALGORITHMIC: the zero-padded s2d weights do not count as work."""
+        for m in self.meta:
+            if m["name"] == name:
+                m["flops"], m["bytes"] = float(flops), float(bytes_)
 
     # ----------------------------------------------------------- aggregation
     def _deform_conv(self, name, m, x):
@@ -219,7 +261,7 @@ class Engine:
             N, H, W, cs = p.t.shape
             skip = layers[i - 1]
             u = self._new("%s.up_%d" % (name, k), N, H * f, W * f, cs)
-            wt = up.weight.detach().float().reshape(up.weight.shape[0], -1).contiguous().to(self.dev)
+            wt = ops.pack_upsample_weight(up.weight).to(self.dev)
             pt, st = p.t, skip.t
             self._add(lambda pt=pt, wt=wt, st=st, u=u, f=f: ops.upsample_add(pt, wt, st, u, f), 1,
                       "%s.up_%d" % (name, k), "upsample", 2.0 * u.numel() * 4,
@@ -324,6 +366,7 @@ class Engine:
         net, conf = self.net, self.conf
         A, K, B = self.A, self.K, self.B
         feat = self._dla_seg()
+        self.n_trunk_ops = len(self.ops)  # ops [0, n_trunk_ops) never touch the buffers the detection tail reads
         self.named["feat"] = feat
         N, Hf, Wf = feat.t.shape[:3]
         self.Hf, self.Wf = Hf, Wf
@@ -427,7 +470,11 @@ class Engine:
     def activation_nchw(self, name):
         """fp32 NCHW copy of a named intermediate activation (testing aid)."""
         a = self.named[name]
-        return a.t[..., a.coff:a.coff + a.c].float().permute(0, 3, 1, 2).contiguous()
+        t = a.t[..., a.coff:a.coff + a.c].float()
+        if a.s2d:  # [N, Y, X, (dy, dx, c)] -> [N, 2Y+dy, 2X+dx, c]
+            n, hh, ww, c4 = t.shape
+            t = t.view(n, hh, ww, 2, 2, c4 // 4).permute(0, 1, 3, 2, 4, 5).reshape(n, 2 * hh, 2 * ww, c4 // 4)
+        return t.permute(0, 3, 1, 2).contiguous()
 
     def run(self, images=None, stage="forward"):
         """One pass over the engine's batch.  images: [B,3,H,W] fp32 CUDA tensor copied into the input
@@ -462,6 +509,74 @@ class Engine:
             self.graph = None
         self.run(images, "detect")
         return self.kept, self.num_keep
+
+    # ------------------------------------------------------------- pipelined
+    def _pipe_init(self):
+        """Three CUDA graphs and a side stream: trunk (DLA + aggregation), heads (everything that writes
+        the score / box buffers) and the detection tail.  The tail of batch i runs on the side stream
+        under the trunk of batch i+1; only the heads of batch i+1 wait for it (they overwrite its inputs)."""
+        self._pipe = {}
+        self._tail_stream = torch.cuda.Stream()
+        self._ev_fwd = torch.cuda.Event()
+        self._ev_tail = torch.cuda.Event()
+        self._ev_tail.record(self._tail_stream)
+
+        def capture(fn):
+            fn()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            return g
+
+        def trunk():
+            for op in self.ops[:self.n_trunk_ops]:
+                op()
+
+        def heads():
+            for op in self.ops[self.n_trunk_ops:]:
+                op()
+
+        if self.use_graph:
+            self._pipe["trunk"], self._pipe["heads"] = capture(trunk), capture(heads)
+            self._pipe["decode"], self._pipe["nms"] = capture(self._run_decode), capture(self._run_nms)
+            self._pipe = {k: g.replay for k, g in self._pipe.items()}
+        else:
+            self._pipe = dict(trunk=trunk, heads=heads, decode=self._run_decode, nms=self._run_nms)
+
+    def detect_pipelined(self, images=None, between=None):
+        """Asynchronous detect: enqueues batch i and returns immediately.  self.kept / self.num_keep hold
+        batch i's detections once `self.tail_done` (an event on self.tail_stream) has fired; the caller
+        must consume them (e.g. enqueue a D2H copy on self.tail_stream) before the next call's tail runs.
+        `between(dets, det_num) -> (dets, det_num)` runs on the side stream after decode (the multi-GPU
+        all-gather hooks in here) and must then drive the NMS itself by returning None."""
+        if not hasattr(self, "_pipe"):
+            self._pipe_init()
+        cur = torch.cuda.current_stream()
+        if images is not None:
+            self.image.copy_(images, non_blocking=True)
+        self._pipe["trunk"]()
+        cur.wait_event(self._ev_tail)  # the previous tail has finished reading score / box buffers
+        self._pipe["heads"]()
+        self._ev_fwd.record(cur)
+        ts = self._tail_stream
+        ts.wait_event(self._ev_fwd)
+        with torch.cuda.stream(ts):
+            self._pipe["decode"]()
+            if between is not None:
+                between()
+            else:
+                self._pipe["nms"]()
+            self._ev_tail.record(ts)
+        return self.kept, self.num_keep
+
+    @property
+    def tail_stream(self):
+        return self._tail_stream
+
+    @property
+    def tail_done(self):
+        return self._ev_tail
 
     def profile(self, iters=3):
         """Per-op device time (CUDA events on the launching stream, eager replay) with each op's

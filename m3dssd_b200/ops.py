@@ -61,7 +61,7 @@ def pack_conv_weight(weight, in_splits=None, k_pad_to=None, fp32_mode=False, mod
 def conv2d_nhwc(inputs, weight, out, *, R, S, stride=1, pad=0, dil=1, Cout=None, bias=None, res=None,
                 slope=1.0, weight_lo=None, om=None, sigmoid_mask=False, groups=1, in_goff=None,
                 weight_goff=0, bias_goff=0, out_coff=0, out_goff=0, res_coff=0, res_goff=0,
-                force_gather=False):
+                force_gather=False, out_hw=None):
     """inputs: list of (tensor[N,H,W,Cbuf], coff, c) or bare tensors; out: tensor[N,P,Q,Cbuf_out]."""
     d = ConvDesc()
     ins = []
@@ -83,6 +83,8 @@ def conv2d_nhwc(inputs, weight, out, *, R, S, stride=1, pad=0, dil=1, Cout=None,
         d.in_goff[k] = 0 if in_goff is None else in_goff[k]
     d.N, d.H, d.W = t0.shape[0], t0.shape[1], t0.shape[2]
     d.R, d.S, d.stride, d.pad, d.dil = R, S, stride, pad, dil
+    if out_hw is not None:
+        d.out_h, d.out_w = out_hw
     d.Cout = Cout if Cout is not None else (weight if weight is not None else weight_lo).shape[0]
     d.groups = groups
     if weight is not None:
@@ -134,6 +136,67 @@ def stem_conv7x7(image, weight, bias, out, slope=0.01):
     return out
 
 
+def pack_stem_s2d(w, b):
+    """Stem weights [16,3,7,7] (BN folded) + bias [16] -> bf16 [64, 192] and bias [64] for m3d_stem_conv7x7_s2d:
+    output channel (ey*2+ex)*16 + co, K index c*64 + r8*8 + s8 over the 8x8 stride-2 window."""
+    co, ci, kh, kw = w.shape
+    assert (co, ci, kh, kw) == (16, 3, 7, 7)
+    wp = torch.zeros(2, 2, co, ci, 8, 8, dtype=torch.float32)
+    for ey in range(2):
+        for ex in range(2):
+            wp[ey, ex, :, :, ey:ey + 7, ex:ex + 7] = w.float().cpu()
+    return wp.reshape(4 * co, ci * 64).to(torch.bfloat16).contiguous(), b.float().cpu().repeat(4).contiguous()
+
+
+def s2d_conv3x3_weight(w, b):
+    """3x3 / stride 1 / pad 1 conv [Co, Ci, 3, 3] acting on a 2x2 space-to-depth tensor: the equivalent dense
+    3x3 conv [4*Co, 4*Ci, 3, 3] (75 % zeros) whose in/out channels are (dy*2+dx)*C + c."""
+    co, ci = w.shape[:2]
+    wp = torch.zeros(2, 2, co, 2, 2, ci, 3, 3, dtype=torch.float32)  # [ey, ex, co, dy, dx, ci, R, S]
+    w = w.float().cpu()
+    for ey in range(2):
+        for dy in range(2):
+            for R in (-1, 0, 1):
+                r = 2 * R + dy - ey
+                if not -1 <= r <= 1:
+                    continue
+                for ex in range(2):
+                    for dx in range(2):
+                        for S in (-1, 0, 1):
+                            s = 2 * S + dx - ex
+                            if -1 <= s <= 1:
+                                wp[ey, ex, :, dy, dx, :, R + 1, S + 1] = w[:, :, r + 1, s + 1]
+    return wp.reshape(4 * co, 4 * ci, 3, 3), b.float().cpu().repeat(4)
+
+
+def s2d_conv3x3_s2_weight(w):
+    """3x3 / stride 2 / pad 1 conv [Co, Ci, 3, 3] reading a 2x2 space-to-depth tensor and writing a plain one:
+    the equivalent 2x2 conv [Co, 4*Ci, 2, 2] with top/left padding 1 (taps R, S in {-1, 0})."""
+    co, ci = w.shape[:2]
+    wp = torch.zeros(co, 2, 2, ci, 2, 2, dtype=torch.float32)  # [co, dy, dx, ci, R+1, S+1]
+    w = w.float().cpu()
+    for dy in range(2):
+        for R in (-1, 0):
+            r = 2 * R + dy
+            if not -1 <= r <= 1:
+                continue
+            for dx in range(2):
+                for S in (-1, 0):
+                    s = 2 * S + dx
+                    if -1 <= s <= 1:
+                        wp[:, dy, dx, :, R + 1, S + 1] = w[:, :, r + 1, s + 1]
+    return wp.reshape(co, 4 * ci, 2, 2)
+
+
+def stem_conv7x7_s2d(image, weight, bias, out, slope=0.01):
+    """image [N,3,H,W] fp32 NCHW; weight/bias from pack_stem_s2d; out bf16 [N,H/2,W/2,64]."""
+    assert image.dtype == torch.float32 and image.is_contiguous() and image.shape[1] == 3
+    assert out.dtype == torch.bfloat16 and out.shape[-1] == 64
+    N, _, H, W = image.shape
+    check(lib().m3d_stem_conv7x7_s2d(_p(image), _p(weight), _p(bias), _p(out), N, H, W, float(slope), _stream()))
+    return out
+
+
 def maxpool2x2(x, out, C_=None):
     N, H, W, cs = x.shape
     check(lib().m3d_maxpool2x2_nhwc(_p(x), _p(out), _dt(x), N, H, W, C_ or cs, cs, out.shape[-1], _stream()))
@@ -141,12 +204,20 @@ def maxpool2x2(x, out, C_=None):
 
 
 def upsample_add(x, weight, skip, out, f=2):
-    """depthwise ConvTranspose2d(2f, stride f, pad f//2) of x plus skip; weight [C,1,2f,2f] or [C,2f,2f] fp32."""
+    """depthwise ConvTranspose2d(2f, stride f, pad f//2) of x plus skip; weight tap-major [(2f)^2, C] fp32
+    (pack with pack_upsample_weight)."""
     N, H, W, cs = x.shape
-    Cc = weight.shape[0]
+    Cc = weight.shape[1]
+    assert weight.shape[0] == 4 * f * f and weight.is_contiguous()
     check(lib().m3d_upsample_add_nhwc(_p(x), _p(weight), _p(skip), _p(out), _dt(x), N, H, W, Cc, f, cs,
                                       skip.shape[-1] if skip is not None else 0, out.shape[-1], _stream()))
     return out
+
+
+def pack_upsample_weight(w):
+    """ConvTranspose2d weight [C, 1, k, k] -> tap-major [k*k, C] fp32."""
+    C_ = w.shape[0]
+    return w.detach().float().reshape(C_, -1).t().contiguous()
 
 
 def cls_softmax(logits, A, K, cls_out, prob_out, fg_max, fg_arg, score, cls_pred):

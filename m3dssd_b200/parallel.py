@@ -48,6 +48,22 @@ class ShardedDetector:
         self.nms_ws = torch.zeros(ops.nms_workspace_bytes(gb, e.topk), dtype=torch.uint8, device=dev)
         self.launches_per_step = e.launches_per_step("decode") + 3
 
+    def _gather_and_nms(self):
+        e = self.engine
+        dets, num = gather_detections(e.dets, e.det_num)
+        ops.nms_batched(dets, num, float(e.conf.nms_thres), self.nms_ws, self.keep, self.num_keep)
+        ops.gather_kept(dets, self.keep, self.num_keep, e.max_out, self.kept)
+
+    def step_pipelined(self, images=None):
+        """Asynchronous step (see Engine.detect_pipelined): batch i's tail -- decode, [all-gather,] NMS --
+        runs on the engine's side stream under batch i+1's trunk.  Results are valid once
+        self.engine.tail_done has fired; returns the (kept, num_keep) buffers."""
+        e = self.engine
+        if self.world == 1:
+            return e.detect_pipelined(images)
+        e.detect_pipelined(images, between=self._gather_and_nms)
+        return self.kept, self.num_keep
+
     def step(self, images=None):
         """Returns (kept [world*local_batch, max_out, 14], num_keep [world*local_batch])."""
         e = self.engine

@@ -60,7 +60,7 @@ def test_upsample_add(dtype, f):
         x, skip = x.bfloat16().float(), skip.bfloat16().float()
     ref = F.conv_transpose2d(x, w, None, stride=f, padding=f // 2, groups=C) + skip
     out = torch.zeros(2, 6 * f, 10 * f, C, dtype=dtype, device="cuda")
-    ops.upsample_add(_nhwc(x, dtype), w.reshape(C, -1).contiguous().cuda(), _nhwc(skip, dtype), out, f)
+    ops.upsample_add(_nhwc(x, dtype), ops.pack_upsample_weight(w).cuda(), _nhwc(skip, dtype), out, f)
     tol = 1e-5 if dtype == torch.float32 else 2 ** -7 * ref.abs().max().item()
     assert (_nchw(out) - ref).abs().max().item() < tol
 
