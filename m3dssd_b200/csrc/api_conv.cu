@@ -75,6 +75,23 @@ int make_tmap_nhwc(CUtensorMap* map, const void* base, int N, int H, int W, int 
   return M3D_OK;
 }
 
+// fp32 NCHW 3-channel image as (W, H, 3, N); box {box_w, box_h, 3, 1}, no swizzle, zero fill outside.
+int make_tmap_img(CUtensorMap* map, const void* base, int N, int H, int W, int box_w, int box_h) {
+  auto enc = get_encode();
+  M3D_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), 3, static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(W) * 4, static_cast<cuuint64_t>(H) * W * 4,
+                           static_cast<cuuint64_t>(H) * W * 12};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 3, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  M3D_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(image %dx%dx%d box %dx%d) failed: %d", N, H, W, box_w, box_h,
+              static_cast<int>(r));
+  return M3D_OK;
+}
+
 // Output tile = TH x TW pixels with TH * TW = 128: pick the shape wasting the
 // fewest padded pixels (ties go to the squarest, which shares the most halo).
 void pick_tile(int P, int Q, int max_tw, int* TW, int* TH) {
@@ -128,15 +145,17 @@ extern "C" int m3d_stem_conv7x7_s2d(const float* image, const void* weight, cons
                                     int W, float slope, m3d_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   M3D_REQUIRE(image && weight && bias && out, "NULL pointer");
-  M3D_REQUIRE(H % 2 == 0 && W % 2 == 0 && H >= 2 && W >= 2, "space-to-depth stem needs even H, W (got %dx%d)", H, W);
+  M3D_REQUIRE(H % 2 == 0 && W % 4 == 0 && H >= 2 && W >= 4, "space-to-depth stem needs H %% 2 == 0, W %% 4 == 0 (got %dx%d)", H, W);
   const int P = H / 2, Q = W / 2;
   int TW = 16, TH = 8;
-  pick_tile(P, Q, 256, &TW, &TH);
+  pick_tile(P, Q, 64, &TW, &TH);  // image tile (2TW+8) x (2TH+6) x 3 fp32 must fit the producer scratch
   ConvGatherParams p;
   memset(&p, 0, sizeof(p));
   int rc = make_tmap_2d(&p.tmap_b, weight, 64, 192, 64, 64);
   if (rc != M3D_OK) return rc;
   rc = make_tmap_nhwc(&p.tmap_out, out, N, P, Q, 64, 64, TW, TH, 1);
+  if (rc != M3D_OK) return rc;
+  rc = make_tmap_img(&p.tmap_img, image, N, H, W, 2 * TW + 8, 2 * TH + 6);
   if (rc != M3D_OK) return rc;
   p.num_inputs = 1;
   p.chunks[0] = 3;  // one k-block per image channel
@@ -193,6 +212,9 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
     M3D_REQUIRE(bk == 64, "gather/DCN path needs input channels in multiples of 64");
     M3D_REQUIRE(groups == 1, "gather/DCN path does not batch groups");
     M3D_REQUIRE(d->R * d->S <= 9 || d->om == nullptr, "deformable kernels above 3x3 unsupported");
+    if (!split) {
+      M3D_REQUIRE(d->num_inputs == 1 && d->R * d->S <= 9, "bf16 gather path: one input, at most 9 taps");
+    }
   }
   int TW = 16, TH = 8;
   pick_tile(P, Q, 256 / d->stride, &TW, &TH);

@@ -221,7 +221,9 @@ struct GatherCfg {
   static constexpr int B_BYTES = BN * ROW_BYTES;      // per part
   static constexpr int PARTS = SPLIT ? 3 : 1;
   static constexpr int STAGE = PARTS * (A_BYTES + B_BYTES);
-  static constexpr int OM_BYTES = kTileM * 28 * 4;
+  // producer scratch: SPLIT: the tile's offsets/masks [128][27+1] fp32; bf16: the per-tile sample table
+  // [128 rows][9 taps] x {int4 corner offsets, float4 corner weights * mask} (also the stem's image tile)
+  static constexpr int OM_BYTES = SPLIT ? kTileM * 28 * 4 : kTileM * 9 * 32;
   static constexpr int EXTRA = STAGED ? (2 * kSlabBytes + 1024) : 0;
   static constexpr int BUDGET = 224 * 1024 - OM_BYTES - EXTRA;
   static constexpr int STAGES = BUDGET / STAGE >= 4 ? 4 : (BUDGET / STAGE >= 3 ? 3 : 2);
@@ -317,32 +319,171 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
     const int j = pt & 7;        // 16-byte chunk (8 channels) inside the 64-channel k-block
     const int rbase = pt >> 3;   // rows rbase + 32*i
     const int omc = 3 * taps;
+    const int tw_shift = 31 - __clz(p.TW);  // TW is a power of two
     int stage = 0;
     uint32_t phase = 0;
     if (!SPLIT && p.stem_img != nullptr) {
       // ---- stem: 7x7 conv of the fp32 NCHW image in 2x2 space-to-depth form.  Row (Y, X) of the tile
       // is the 8x8 window at (2Y-3, 2X-3); k-block kb = image channel kb, 16-byte chunk j = window row
-      // j, its 8 elements = 8 consecutive image columns.
+      // j, its 8 elements = 8 consecutive image columns.  The image tile (3 x (2TH+6) x (2TW+6)) is
+      // staged once per tile in shared memory with coalesced loads.
+      float* s_img = om_s;
+      const int th2 = 2 * p.TH + 6, ld = 2 * p.TW + 8;  // TMA box: ld x th2 x 3 fp32, zero outside the image
+      uint32_t img_phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(tile, p.n_tiles, p.tiles_w, p.tiles_h, p.N, p.TW, p.TH);
+        named_bar_sync(1, kProducerThreads);  // previous tile's readers are done
+        if (pt == 0) {
+          mbar_arrive_expect_tx(&res_bar[1], static_cast<uint32_t>(3 * th2 * ld * 4));
+          // x origin 2*q0 - 4 keeps the innermost coordinate 16-byte aligned (window columns start at +1)
+          tma_load_4d(s_img, &p.tmap_img, &res_bar[1], 2 * t.q0 - 4, 2 * t.p0 - 3, 0, t.n);
+        }
+        mbar_wait(&res_bar[1], img_phase);
+        img_phase ^= 1;
         for (int kb = 0; kb < 3; ++kb) {
-          const float* plane = p.stem_img + (static_cast<long>(t.n) * 3 + kb) * p.H * p.W;
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* a_hi = smem + stage * Cfg::STAGE;
 #pragma unroll
           for (int ii = 0; ii < 4; ++ii) {
             const int row = rbase + 32 * ii;
-            const int Y = t.p0 + row / p.TW, X = t.q0 + row % p.TW;
-            const int y = 2 * Y - 3 + j, x0 = 2 * X - 3;
+            const float* src = s_img + (kb * th2 + 2 * (row >> tw_shift) + j) * ld + 2 * (row & (p.TW - 1)) + 1;
             float v[8];
-            const bool yok = Y < p.P && X < p.Q && y >= 0 && y < p.H;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int x = x0 + e;
-              v[e] = (yok && x >= 0 && x < p.W) ? __ldg(plane + static_cast<long>(y) * p.W + x) : 0.f;
-            }
+            for (int e = 0; e < 8; ++e) v[e] = src[e];
             *reinterpret_cast<uint4*>(a_hi + swizzled_offset<128>(row, j)) = pack8(v);
           }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    } else if constexpr (!SPLIT) {
+      // ---- bf16 deformable gather.  Phase 0 per tile: the 256 producers fill a shared-memory table with, for
+      // every (row, tap), the four clamped corner offsets and the four bilinear weights already multiplied by
+      // validity and by the modulation mask (dcn_v2_im2col_cuda.cu:18-47,151-175).  Main loop: software
+      // pipeline over half k-blocks (2 of the thread's 4 rows): the 8 corner loads of unit u+1 are issued
+      // before unit u is blended, so the L1/L2 latency overlaps the fp32 blend instead of serialising.
+      struct Entry {
+        int4 off;
+        float4 w;
+      };
+      Entry* table = reinterpret_cast<Entry*>(om_s);
+      const InT* in0 = static_cast<const InT*>(p.in[0]) + p.in_coff[0];
+      const int cs = p.in_cstride[0];
+      const int nchunk = p.chunks[0];
+      const int units = taps * nchunk * 2;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(tile, p.n_tiles, p.tiles_w, p.tiles_h, p.N, p.TW, p.TH);
+        named_bar_sync(1, kProducerThreads);  // previous tile's table readers are done
+        // thread pt owns row pt/2 and the taps of parity pt%2: at most 5 entries, their 15 offset / mask
+        // loads issued together
+        const int trow = pt >> 1;
+        const int tpp = t.p0 + (trow >> tw_shift), tqq = t.q0 + (trow & (p.TW - 1));
+        const bool tok = tpp < p.P && tqq < p.Q;
+        const float* om_px = p.om + ((static_cast<long>(t.n) * p.P + tpp) * p.Q + tqq) * p.om_cstride;
+        float o_h[5], o_w[5], o_m[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const int tap = (pt & 1) + 2 * k;
+          o_h[k] = o_w[k] = 0.f, o_m[k] = 1.f;
+          if (tok && tap < taps && p.om != nullptr) {
+            o_h[k] = __ldg(om_px + 2 * tap);
+            o_w[k] = __ldg(om_px + 2 * tap + 1);
+            o_m[k] = __ldg(om_px + 2 * taps + tap);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const int tap = (pt & 1) + 2 * k;
+          if (tap >= taps) break;
+          const int row = trow, pp = tpp, qq = tqq;
+          Entry e;
+          e.off = make_int4(0, 0, 0, 0);
+          e.w = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (tok) {
+            const int r = taps == 9 ? tap / 3 : tap / p.S, sx = tap - r * p.S;
+            float hf = static_cast<float>(pp * p.stride - p.pad + r * p.dil) + o_h[k];
+            float wf = static_cast<float>(qq * p.stride - p.pad + sx * p.dil) + o_w[k];
+            float m = o_m[k];
+            if (p.om != nullptr && p.sigmoid_mask) m = 1.f / (1.f + __expf(-m));
+            {
+            }
+            if (hf > -1.f && wf > -1.f && hf < static_cast<float>(p.H) && wf < static_cast<float>(p.W)) {
+              const float hl = floorf(hf), wl = floorf(wf);
+              const int h_low = static_cast<int>(hl), w_low = static_cast<int>(wl);
+              const int h_high = h_low + 1, w_high = w_low + 1;
+              const float lh = hf - hl, lw = wf - wl, hh = 1.f - lh, hw = 1.f - lw;
+              const bool hl_ok = h_low >= 0, wl_ok = w_low >= 0, hh_ok = h_high <= p.H - 1, wh_ok = w_high <= p.W - 1;
+              const int rl = (t.n * p.H + (hl_ok ? h_low : 0)) * p.W, rh = (t.n * p.H + (hh_ok ? h_high : 0)) * p.W;
+              const int cl = wl_ok ? w_low : 0, ch = wh_ok ? w_high : 0;
+              e.off = make_int4((rl + cl) * cs, (rl + ch) * cs, (rh + cl) * cs, (rh + ch) * cs);
+              e.w = make_float4((hl_ok && wl_ok) ? hh * hw * m : 0.f, (hl_ok && wh_ok) ? hh * lw * m : 0.f,
+                                (hh_ok && wl_ok) ? lh * hw * m : 0.f, (hh_ok && wh_ok) ? lh * lw * m : 0.f);
+            }
+          }
+          table[row * taps + tap] = e;
+        }
+        named_bar_sync(1, kProducerThreads);
+
+        // unit u -> (tap, chunk, half); rows rbase + 32 * (2*half + {0,1})
+        uint4 cv[2][2][4];
+        float4 cw[2][2];
+        int nx_tap = 0, nx_c = 0;  // (tap, chunk) of the next unit to issue
+        auto issue = [&](int u, int buf) {
+          const int half = u & 1;
+          const int tap = nx_tap, c = nx_c;
+          if (half) {
+            if (++nx_c == nchunk) nx_c = 0, ++nx_tap;
+          }
+          const int coff = c * BK + j * 8;
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const Entry& e = table[(rbase + 32 * (2 * half + rr)) * taps + tap];  // taps is 1 or 9: cheap multiply
+            const int4 o = e.off;
+            cw[buf][rr] = e.w;
+            cv[buf][rr][0] = __ldg(reinterpret_cast<const uint4*>(in0 + o.x + coff));
+            cv[buf][rr][1] = __ldg(reinterpret_cast<const uint4*>(in0 + o.y + coff));
+            cv[buf][rr][2] = __ldg(reinterpret_cast<const uint4*>(in0 + o.z + coff));
+            cv[buf][rr][3] = __ldg(reinterpret_cast<const uint4*>(in0 + o.w + coff));
+          }
+        };
+        auto blend = [&](int u, int buf, uint8_t* a_hi) {
+          const int half = u & 1;
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const float4 w4 = cw[buf][rr];
+            const uint32_t* q0 = reinterpret_cast<const uint32_t*>(&cv[buf][rr][0]);
+            const uint32_t* q1 = reinterpret_cast<const uint32_t*>(&cv[buf][rr][1]);
+            const uint32_t* q2 = reinterpret_cast<const uint32_t*>(&cv[buf][rr][2]);
+            const uint32_t* q3 = reinterpret_cast<const uint32_t*>(&cv[buf][rr][3]);
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float lo = w4.x * __uint_as_float(q0[e] << 16) + w4.y * __uint_as_float(q1[e] << 16) +
+                               w4.z * __uint_as_float(q2[e] << 16) + w4.w * __uint_as_float(q3[e] << 16);
+              const float hi = w4.x * __uint_as_float(q0[e] & 0xffff0000u) + w4.y * __uint_as_float(q1[e] & 0xffff0000u) +
+                               w4.z * __uint_as_float(q2[e] & 0xffff0000u) + w4.w * __uint_as_float(q3[e] & 0xffff0000u);
+              __nv_bfloat162 tt = __floats2bfloat162_rn(lo, hi);
+              w[e] = *reinterpret_cast<uint32_t*>(&tt);
+            }
+            *reinterpret_cast<uint4*>(a_hi + swizzled_offset<128>(rbase + 32 * (2 * half + rr), j)) =
+                make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        };
+        issue(0, 0);
+#pragma unroll 1
+        for (int u = 0; u < units; u += 2) {
+          // half 0 of k-block u/2 (buffer 0), then half 1 (buffer 1)
+          issue(u + 1, 1);
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* a_hi = smem + stage * Cfg::STAGE;
+          blend(u, 0, a_hi);
+          if (u + 2 < units) issue(u + 2, 0);
+          blend(u + 1, 1, a_hi);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&full[stage]);

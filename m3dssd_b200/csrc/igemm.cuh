@@ -66,6 +66,7 @@ struct alignas(64) ConvGatherParams {
   CUtensorMap tmap_b_mid;  // split mode: second 8 mantissa bits
   CUtensorMap tmap_b_lo;   // split mode: third 8 mantissa bits
   CUtensorMap tmap_out, tmap_res;  // staged epilogue (bf16 out, Cout % 64 == 0)
+  CUtensorMap tmap_img;            // stem mode: fp32 NCHW image as (W, H, 3, N), box {2TW+8, 2TH+6, 3, 1}
   int num_inputs;
   const void* in[kMaxConcat];
   int in_cstride[kMaxConcat], in_coff[kMaxConcat], chunks[kMaxConcat];
