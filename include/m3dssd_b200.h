@@ -114,6 +114,17 @@ int m3d_dcn_v2_forward(const float* input, const float* weight, const float* bia
                        int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int deformable_group,
                        int precision, void* workspace, size_t workspace_bytes, m3d_stream_t stream);
 
+/* DCNv2 backward, reference FFI shape (replaces dcn_v2_cuda_backward, dcn_v2_cuda.h:19-29).  All five
+ * gradients are OVERWRITTEN (the reference accumulates into buffers its Python wrapper zero-fills,
+ * dcn_v2_func.py:44-48).  fp32; grad_input / grad_weight / grad_bias use float atomics, so -- as in the
+ * reference -- the summation order is not reproducible bit for bit.  deformable_group must be 1. */
+size_t m3d_dcn_v2_backward_workspace(int B, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil);
+int m3d_dcn_v2_backward(const float* input, const float* weight, const float* offset, const float* mask,
+                        const float* grad_output, float* grad_input, float* grad_weight, float* grad_bias,
+                        float* grad_offset, float* grad_mask, int B, int C, int H, int W, int Cout, int kh, int kw,
+                        int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int deformable_group,
+                        void* workspace, size_t workspace_bytes, m3d_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * gpu_nms.  m3d_nms is the drop-in for `_nms` (lib/nms/gpu_nms.hpp:1-2): HOST
  * pointers, boxes [n, boxes_dim] already sorted by score, keep_out receives the

@@ -5,6 +5,7 @@ vp, i, f, sz, lg = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_long
 
 _SIGS = {
     "m3d_dcn_v2_forward": [vp, vp, vp, vp, vp, vp] + [i] * 15 + [vp, sz, vp],
+    "m3d_dcn_v2_backward": [vp] * 10 + [i] * 14 + [vp, sz, vp],
     "m3d_nms": [vp, vp, vp, i, i, f, i],
     "m3d_nms_batched": [vp, i, vp, i, i, f, vp, sz, vp, vp, vp],
     "m3d_decode_topk": [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, f, f, i, vp, vp, vp, vp],
@@ -24,6 +25,7 @@ _SIGS = {
 }
 _SIZE_FNS = {
     "m3d_dcn_v2_forward_workspace": [i] * 11,
+    "m3d_dcn_v2_backward_workspace": [i] * 10,
     "m3d_nms_workspace_bytes": [i, i],
     "m3d_anab_pool_workspace": [i, i, i, vp, i, i],
 }

@@ -328,4 +328,17 @@ def anab_attention(q, ktok, vtok, x, scale, shift, slope, out, ck, cv):
 
 
 def dcn_v2_backward(input, offset, mask, weight, grad_output, stride, padding, dilation, deformable_groups):
-    raise NotImplementedError("m3d_dcn_v2_backward is not built yet")
+    """DCNv2Function.backward (model/DCNv2/dcn_v2_func.py:40-62): returns (grad_input, grad_offset, grad_mask,
+    grad_weight, grad_bias), fp32 NCHW CUDA tensors."""
+    B, Cin, H, W = input.shape
+    Cout, _, kh, kw = weight.shape
+    args = [t.contiguous().float() for t in (input, weight, offset, mask, grad_output)]
+    gi, go, gm = torch.empty_like(args[0]), torch.empty_like(args[2]), torch.empty_like(args[3])
+    gw = torch.empty_like(args[1])
+    gb = torch.empty(Cout, dtype=torch.float32, device=input.device)
+    n = lib().m3d_dcn_v2_backward_workspace(B, Cin, H, W, Cout, kh, kw, stride, padding, dilation)
+    ws = torch.empty(n, dtype=torch.uint8, device=input.device)
+    check(lib().m3d_dcn_v2_backward(*[_p(t) for t in args], _p(gi), _p(gw), _p(gb), _p(go), _p(gm), B, Cin, H, W, Cout,
+                                    kh, kw, stride, stride, padding, padding, dilation, dilation, deformable_groups,
+                                    _p(ws), n, _stream()))
+    return gi, go, gm, gw, gb

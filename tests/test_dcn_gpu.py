@@ -103,3 +103,27 @@ def test_oracle_im2col_vs_reference_cuda_kernel():
         exp = O.dcn_v2_im2col(x, off, m, k, k, s, p, 1, 1)
         # same fp32 expressions; nvcc may contract a*b+c into FMA, so allow an ulp-level difference
         assert np.abs(col.cpu().numpy() - exp).max() < 2e-6 * max(np.abs(exp).max(), 1.0)
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 9, 11, 8, 3, 1, 1), (1, 64, 12, 20, 32, 3, 1, 1), (1, 6, 7, 9, 5, 1, 1, 0),
+                                   (1, 32, 10, 13, 20, 3, 2, 1)])
+def test_dcn_v2_backward_vs_oracle(shape):
+    """DCNv2Function under autograd vs the C oracle's restatement of dcn_v2_cuda_backward (fp32 inputs,
+    the oracle accumulates in double): all five gradients."""
+    from m3dssd_b200.model.DCNv2.dcn_v2_func import DCNv2Function
+    B, Cin, H, W, Cout, k, s, p = shape
+    rng = np.random.default_rng(sum(shape) + 1)
+    x = rng.standard_normal((B, Cin, H, W)).astype(np.float32)
+    Ho, Wo = O.dcn_out_shape(H, W, k, k, s, p, 1)
+    off = (rng.standard_normal((B, 2 * k * k, Ho, Wo)) * 2.5).astype(np.float32)
+    m = rng.random((B, k * k, Ho, Wo)).astype(np.float32)
+    w = (rng.standard_normal((Cout, Cin, k, k)) / np.sqrt(Cin * k * k)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    gy = rng.standard_normal((B, Cout, Ho, Wo)).astype(np.float32)
+    ref = O.dcn_v2_backward(x, off, m, w, gy, s, p, 1, 1)
+    ts = [torch.from_numpy(a).cuda().requires_grad_(True) for a in (x, off, m, w, b)]
+    out = DCNv2Function(s, p, 1, 1, precision="fp32")(*ts)
+    out.backward(torch.from_numpy(gy).cuda())
+    for name, t, r in zip(("input", "offset", "mask", "weight", "bias"), ts, ref):
+        err = np.abs(t.grad.cpu().numpy() - r).max() / max(np.abs(r).max(), 1e-6)
+        assert err < 2e-5, (name, err)
