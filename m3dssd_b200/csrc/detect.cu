@@ -27,21 +27,48 @@ __device__ __forceinline__ uint32_t score_key(float s) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // total order for any sign
 }
 
+// One histogram pass over the image's scores.  8 elements per thread per trip (two 16-byte loads in
+// flight), same-bin lanes of a warp combined with match_any before the shared-memory atomic.
 template <int BITS>
 __device__ void radix_pass(const float* __restrict__ score, int M, uint32_t prefix, uint32_t prefix_mask, int shift,
-                           uint32_t* hist /*smem [1<<BITS]*/, int need, uint32_t* out_digit, int* out_need) {
+                           uint32_t* hist /*smem [1<<BITS]*/, int need, uint32_t* out_digit, int* out_need,
+                           int* out_count) {
   constexpr int NB = 1 << BITS;
   for (int i = threadIdx.x; i < NB; i += blockDim.x) hist[i] = 0;
   __syncthreads();
-  for (int i = threadIdx.x; i < M; i += blockDim.x) {
-    const uint32_t k = score_key(score[i]);
-    if ((k & prefix_mask) == prefix) atomicAdd(&hist[(k >> shift) & (NB - 1)], 1u);
+  const int lane = threadIdx.x & 31;
+  auto add = [&](float v, bool live) {
+    const uint32_t k = score_key(v);
+    const bool in = live && (k & prefix_mask) == prefix;
+    const uint32_t bin = (k >> shift) & (NB - 1);
+    const uint32_t act = __ballot_sync(0xffffffffu, in);
+    if (in) {
+      const uint32_t peers = __match_any_sync(act, bin);
+      if (lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+    }
+  };
+  const int M8 = M & ~7;
+  for (int i0 = threadIdx.x * 8; i0 < ((M8 + blockDim.x * 8 - 1) / (blockDim.x * 8)) * (blockDim.x * 8);
+       i0 += blockDim.x * 8) {
+    const bool live = i0 < M8;  // uniform trip count: the warp-collective ops above need every lane
+    float4 a = make_float4(0, 0, 0, 0), b = a;
+    if (live) {
+      a = __ldg(reinterpret_cast<const float4*>(score + i0));
+      b = __ldg(reinterpret_cast<const float4*>(score + i0) + 1);
+    }
+    add(a.x, live), add(a.y, live), add(a.z, live), add(a.w, live);
+    add(b.x, live), add(b.y, live), add(b.z, live), add(b.w, live);
+  }
+  for (int i0 = M8; i0 < M8 + 32; i0 += 32) {  // tail (< 8 elements)
+    const int i = i0 + lane;
+    const bool live = threadIdx.x < 32 && i < M;
+    if (threadIdx.x < 32) add(live ? score[i] : 0.f, live);
   }
   __syncthreads();
   // two-level descending scan: 32 warp partial sums, then inside the crossing group
   {
     constexpr int PER = NB / 32;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5;
     uint32_t v = 0;
     for (int i = lane; i < PER; i += 32) v += hist[warp * PER + i];
 #pragma unroll
@@ -63,6 +90,7 @@ __device__ void radix_pass(const float* __restrict__ score, int M, uint32_t pref
       }
       *out_digit = static_cast<uint32_t>(d);
       *out_need = need - acc;  // how many still to take from inside digit d
+      *out_count = static_cast<int>(hist[d]);
     }
   }
   __syncthreads();
@@ -87,7 +115,7 @@ __global__ void __launch_bounds__(kSelThreads) topk_decode_kernel(const DecodePa
   __shared__ uint32_t hist[2048];
   __shared__ unsigned long long keys[kMaxTopK];
   __shared__ uint32_t s_digit;
-  __shared__ int s_need, s_cnt_gt, s_cnt_eq;
+  __shared__ int s_need, s_count, s_cnt_gt, s_cnt_eq;
   __shared__ int s_warp_gt[32], s_warp_eq[32];
   const int n = blockIdx.x;
   const float* score = p.score + static_cast<long>(n) * p.M;
@@ -96,50 +124,82 @@ __global__ void __launch_bounds__(kSelThreads) topk_decode_kernel(const DecodePa
   // ---- threshold key T: the K-th largest
   uint32_t prefix = 0, mask = 0;
   int need = K;
-  radix_pass<11>(score, p.M, prefix, mask, 21, hist, need, &s_digit, &s_need);
+  radix_pass<11>(score, p.M, prefix, mask, 21, hist, need, &s_digit, &s_need, &s_count);
   prefix |= s_digit << 21, mask |= 0x7FFu << 21, need = s_need;
-  radix_pass<11>(score, p.M, prefix, mask, 10, hist, need, &s_digit, &s_need);
+  radix_pass<11>(score, p.M, prefix, mask, 10, hist, need, &s_digit, &s_need, &s_count);
   prefix |= s_digit << 10, mask |= 0x7FFu << 10, need = s_need;
-  radix_pass<10>(score, p.M, prefix, mask, 0, hist, need, &s_digit, &s_need);
+  radix_pass<10>(score, p.M, prefix, mask, 0, hist, need, &s_digit, &s_need, &s_count);
   const uint32_t T = prefix | s_digit;
-  const int need_eq = s_need;  // number of elements equal to T to take (lowest indices)
+  const int need_eq = s_need;        // number of elements equal to T to take (lowest indices)
+  const int count_eq = s_count;      // number of elements equal to T in the image
 
-  // ---- ordered compaction: keys > T (all) and == T (first need_eq by index)
   if (threadIdx.x == 0) s_cnt_gt = 0, s_cnt_eq = 0;
   for (int i = threadIdx.x; i < kMaxTopK; i += blockDim.x) keys[i] = 0ull;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int base = 0; base < p.M; base += kSelThreads) {
-    const int i = base + threadIdx.x;
-    uint32_t k = 0;
-    bool gt = false, eq = false;
-    if (i < p.M) {
-      k = score_key(score[i]);
-      gt = k > T;
-      eq = k == T;
+  if (count_eq == need_eq) {
+    // ---- fast path (no tie straddles the cut): every key >= T is selected, order is irrelevant here
+    // because the bitonic sort below orders by (key, index).  Warp-aggregated slot allocation.
+    const int M4 = p.M & ~3;
+    for (int i0 = threadIdx.x * 4; i0 < ((p.M + blockDim.x * 4 - 1) / (blockDim.x * 4)) * (blockDim.x * 4);
+         i0 += blockDim.x * 4) {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (i0 < M4) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(score + i0));
+        v[0] = f.x, v[1] = f.y, v[2] = f.z, v[3] = f.w;
+      } else {
+        for (int e = 0; e < 4; ++e)
+          if (i0 + e < p.M) v[e] = score[i0 + e];
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = i0 + e;
+        const uint32_t k = score_key(v[e]);
+        const bool take = i < p.M && k >= T;
+        const uint32_t b = __ballot_sync(0xffffffffu, take);
+        if (b) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&s_cnt_gt, __popc(b));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (take)
+            keys[base + __popc(b & ((1u << lane) - 1))] =
+                (static_cast<unsigned long long>(k) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(i));
+        }
+      }
     }
-    const uint32_t bgt = __ballot_sync(0xffffffffu, gt), beq = __ballot_sync(0xffffffffu, eq);
-    if (lane == 0) s_warp_gt[warp] = __popc(bgt), s_warp_eq[warp] = __popc(beq);
     __syncthreads();
-    int off_gt = s_cnt_gt, off_eq = s_cnt_eq;
-    for (int w = 0; w < warp; ++w) off_gt += s_warp_gt[w], off_eq += s_warp_eq[w];
-    const uint32_t lt = (1u << lane) - 1;
-    const unsigned long long packed = (static_cast<unsigned long long>(k) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(i));
-    if (gt) {
-      const int pos = off_gt + __popc(bgt & lt);
-      keys[pos] = packed;  // pos < K - need_eq by construction
+  } else {
+    // ---- ties straddle the cut: ordered compaction, keys > T (all) and == T (first need_eq by index)
+    for (int base = 0; base < p.M; base += kSelThreads) {
+      const int i = base + threadIdx.x;
+      uint32_t k = 0;
+      bool gt = false, eq = false;
+      if (i < p.M) {
+        k = score_key(score[i]);
+        gt = k > T;
+        eq = k == T;
+      }
+      const uint32_t bgt = __ballot_sync(0xffffffffu, gt), beq = __ballot_sync(0xffffffffu, eq);
+      if (lane == 0) s_warp_gt[warp] = __popc(bgt), s_warp_eq[warp] = __popc(beq);
+      __syncthreads();
+      int off_gt = s_cnt_gt, off_eq = s_cnt_eq;
+      for (int w = 0; w < warp; ++w) off_gt += s_warp_gt[w], off_eq += s_warp_eq[w];
+      const uint32_t lt = (1u << lane) - 1;
+      const unsigned long long packed =
+          (static_cast<unsigned long long>(k) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(i));
+      if (gt) keys[off_gt + __popc(bgt & lt)] = packed;  // < K - need_eq by construction
+      if (eq) {
+        const int r = off_eq + __popc(beq & lt);
+        if (r < need_eq) keys[(K - need_eq) + r] = packed;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int tg = 0, te = 0;
+        for (int w = 0; w < kSelThreads / 32; ++w) tg += s_warp_gt[w], te += s_warp_eq[w];
+        s_cnt_gt += tg, s_cnt_eq += te;
+      }
+      __syncthreads();
     }
-    if (eq) {
-      const int r = off_eq + __popc(beq & lt);
-      if (r < need_eq) keys[(K - need_eq) + r] = packed;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int tg = 0, te = 0;
-      for (int w = 0; w < kSelThreads / 32; ++w) tg += s_warp_gt[w], te += s_warp_eq[w];
-      s_cnt_gt += tg, s_cnt_eq += te;
-    }
-    __syncthreads();
   }
 
   // ---- bitonic sort, descending on (key, ~index): higher score first, lower index first on ties
@@ -262,61 +322,72 @@ __global__ void __launch_bounds__(128) nms_mask_kernel(const float* __restrict__
   }
 }
 
-// Greedy sweep (nms_kernel.cu:124-139), one warp per image.  Lane l keeps the
-// "removed" words l and l+32 in registers.  Each 64-box block is resolved
-// sequentially from its diagonal mask words (held one row per lane pair), then
-// the kept rows are OR-ed into the later words in parallel across lanes.
-__global__ void __launch_bounds__(32) nms_sweep_kernel(const unsigned long long* __restrict__ mask,
-                                                       const int* __restrict__ num, int max_n, int col_blocks,
-                                                       int* __restrict__ keep, int* __restrict__ num_keep) {
-  const int n = blockIdx.x, lane = threadIdx.x;
+// Greedy sweep (nms_kernel.cu:124-139), one 256-thread block per image.  For each 64-box block: thread 0
+// resolves the block from its 64 diagonal mask words held in registers (pure ALU, no memory in the
+// dependent chain); then all threads OR the kept rows' mask words into the shared "removed" words of
+// the later blocks (independent loads, 4 row groups x 64 words).
+constexpr int kSweepThreads = 256;
+
+__global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const unsigned long long* __restrict__ mask,
+                                                                   const int* __restrict__ num, int max_n,
+                                                                   int col_blocks, int* __restrict__ keep,
+                                                                   int* __restrict__ num_keep) {
+  __shared__ unsigned long long remv[64];
+  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long s_keptbits;
+  __shared__ int s_kept;
+  const int n = blockIdx.x, tid = threadIdx.x;
   const int nb = num ? num[n] : max_n;
   const unsigned long long* m = mask + static_cast<long>(n) * max_n * col_blocks;
   int* kp = keep + static_cast<long>(n) * max_n;
   const int nblocks = (nb + 63) / 64;
-  unsigned long long remv0 = 0, remv1 = 0;  // words lane and lane + 32
-  int kept = 0;
+  if (tid < 64) remv[tid] = 0ull;
+  if (tid == 0) s_kept = 0;
+  __syncthreads();
   for (int blk = 0; blk < nblocks; ++blk) {
-    const int r0 = blk * 64 + lane, r1 = r0 + 32;
-    const unsigned long long d0 = r0 < nb ? m[static_cast<long>(r0) * col_blocks + blk] : 0ull;
-    const unsigned long long d1 = r1 < nb ? m[static_cast<long>(r1) * col_blocks + blk] : 0ull;
-    unsigned long long cur = __shfl_sync(0xffffffffu, blk < 32 ? remv0 : remv1, blk & 31);
-    unsigned long long keptbits = 0;
-    const int lim = min(64, nb - blk * 64);
-    for (int b = 0; b < lim; ++b) {
-      const unsigned long long drow = __shfl_sync(0xffffffffu, b < 32 ? d0 : d1, b & 31);
-      if (!((cur >> b) & 1ull)) {
-        keptbits |= 1ull << b;
-        cur |= drow;
-      }
+    if (tid < 64) {
+      const int r = blk * 64 + tid;
+      diag[tid] = r < nb ? m[static_cast<long>(r) * col_blocks + blk] : 0ull;
     }
-    // record kept indices (in order) and OR their rows into later words
-    unsigned long long kb = keptbits;
-    while (kb) {  // four kept rows per trip so their mask loads overlap
-      int rows4[4];
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long d[64];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        rows4[u] = -1;
-        if (kb) {
-          const int b = __ffsll(static_cast<long long>(kb)) - 1;
-          kb &= kb - 1;
-          rows4[u] = blk * 64 + b;
-          if (lane == 0) kp[kept] = rows4[u];
-          ++kept;
+      for (int b = 0; b < 64; ++b) d[b] = diag[b];
+      unsigned long long cur = remv[blk], kept = 0ull;
+      const int lim = min(64, nb - blk * 64);
+#pragma unroll
+      for (int b = 0; b < 64; ++b) {
+        if (b < lim && !((cur >> b) & 1ull)) {
+          kept |= 1ull << b;
+          cur |= d[b];
         }
       }
-      unsigned long long v0[4], v1[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const unsigned long long* mr = m + static_cast<long>(rows4[u] < 0 ? 0 : rows4[u]) * col_blocks;
-        v0[u] = (rows4[u] >= 0 && lane > blk && lane < col_blocks) ? mr[lane] : 0ull;
-        v1[u] = (rows4[u] >= 0 && lane + 32 > blk && lane + 32 < col_blocks) ? mr[lane + 32] : 0ull;
-      }
-      remv0 |= v0[0] | v0[1] | v0[2] | v0[3];
-      remv1 |= v1[0] | v1[1] | v1[2] | v1[3];
+      s_keptbits = kept;
     }
+    __syncthreads();
+    const unsigned long long kept = s_keptbits;
+    const int base = s_kept;
+    // kept indices in order: thread b < 64 writes its own slot
+    if (tid < 64 && ((kept >> tid) & 1ull)) kp[base + __popcll(kept & ((1ull << tid) - 1))] = blk * 64 + tid;
+    // OR kept rows into later words: thread -> (word w, row group g of 4)
+    const int w = tid & 63, g = tid >> 6;
+    if (w > blk && w < col_blocks) {
+      unsigned long long acc = 0ull;
+      unsigned long long kb = kept;
+      int idx = 0;
+      while (kb) {
+        const int b = __ffsll(static_cast<long long>(kb)) - 1;
+        kb &= kb - 1;
+        if ((idx++ & 3) == g) acc |= m[static_cast<long>(blk * 64 + b) * col_blocks + w];
+      }
+      if (acc) atomicOr(&remv[w], acc);
+    }
+    __syncthreads();
+    if (tid == 0) s_kept = base + __popcll(kept);
   }
-  if (lane == 0) num_keep[n] = kept;
+  __syncthreads();
+  if (tid == 0) num_keep[n] = s_kept;
 }
 
 // Gather the first `max_out` kept rows of every image (im_detect_3d's aboxes[keep]).
@@ -367,7 +438,7 @@ extern "C" int m3d_nms_batched(const float* boxes, int box_stride, const int* nu
   dim3 grid(cb, cb, batch);
   nms_mask_kernel<<<grid, 128, 0, S(stream)>>>(boxes, box_stride, num, max_n, thresh, mask, cb);
   M3D_CUDA_OK(cudaGetLastError());
-  nms_sweep_kernel<<<batch, 32, 0, S(stream)>>>(mask, num, max_n, cb, keep, num_keep);
+  nms_sweep_kernel<<<batch, kSweepThreads, 0, S(stream)>>>(mask, num, max_n, cb, keep, num_keep);
   M3D_CUDA_OK(cudaGetLastError());
   return M3D_OK;
 }
@@ -405,7 +476,7 @@ extern "C" int m3d_nms(int* keep_out, int* num_out, const float* boxes_host, int
   dim3 grid(cb, cb, 1);
   nms_mask_kernel<<<grid, 128, 0, st>>>(ws.boxes, boxes_dim, nullptr, boxes_num, nms_overlap_thresh, ws.mask, cb);
   M3D_CUDA_OK(cudaGetLastError());
-  nms_sweep_kernel<<<1, 32, 0, st>>>(ws.mask, nullptr, boxes_num, cb, ws.keep, ws.num_keep);
+  nms_sweep_kernel<<<1, kSweepThreads, 0, st>>>(ws.mask, nullptr, boxes_num, cb, ws.keep, ws.num_keep);
   M3D_CUDA_OK(cudaGetLastError());
   M3D_CUDA_OK(cudaMemcpyAsync(num_out, ws.num_keep, sizeof(int), cudaMemcpyDeviceToHost, st));
   M3D_CUDA_OK(cudaStreamSynchronize(st));
