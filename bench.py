@@ -183,10 +183,26 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL writes its version banner to stdout when the communicator is created; stdout carries
+        # exactly one JSON line, so point fd 1 at stderr until the first collective has run.
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     W = max(3, args.warmup)
     K = args.steps
     peaks = load_peaks()
+
+    def note(msg):
+        if os.environ.get("M3D_BENCH_VERBOSE"):
+            print("[bench rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
 
     conf = synth.make_conf(attention=args.attention, center_align=True, shape_align=True, crop_size=CROP,
                            batch_size=LOCAL_BATCH)
@@ -194,7 +210,9 @@ def main():
     net = build(conf, "test")
     synth.randomize_weights(net)
     net = net.cuda()
+    note("weights ready")
     det = ShardedDetector(net, LOCAL_BATCH, CROP[0], CROP[1], precision="bf16", use_graph=True)
+    note("engine built")
     eng = det.engine
 
     NB = 4  # distinct input batches, rotated; activations per step (>1 GB) exceed the 126 MB L2 by themselves
@@ -225,6 +243,7 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     clk = clocks.stop()
+    note("device-resident loop done: %.3f ms/step" % (ms / K))
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -265,6 +284,7 @@ def main():
 
     e2e_loop(W)
     barrier()
+    note("e2e warm-up done")
     t0 = time.perf_counter()
     e0.record()
     e2e_loop(K)
@@ -328,11 +348,15 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line))
+        sys.stdout.write(json.dumps(line) + "\n")
+        sys.stdout.flush()
+    if world > 1:
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception as e:  # noqa: BLE001  (the measurement is already printed)
+            print("[bench] process-group teardown: %r" % (e,), file=sys.stderr)
     return 0
 
 
