@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "igemm.cuh"
@@ -52,6 +53,45 @@ int make_tmap_2d(CUtensorMap* map, const void* base, long rows, long cols, int b
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   M3D_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d rows=%ld cols=%ld box=%dx%d) failed: %d", rows, cols,
               box_cols, box_rows, static_cast<int>(r));
+  return M3D_OK;
+}
+
+// Packed bf16 weights [rows][K] as (bk, rows, K/bk): box {bk, box_rows, ksub} lands as ksub consecutive
+// [box_rows][bk] k-block tiles.
+int make_tmap_b3d(CUtensorMap* map, const void* base, long rows, long cols, int bk, int box_rows, int ksub) {
+  auto enc = get_encode();
+  M3D_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  M3D_REQUIRE(cols % bk == 0, "weight K=%ld is not a multiple of the k-block %d", cols, bk);
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(bk), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(cols / bk)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(cols) * 2, static_cast<cuuint64_t>(bk) * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(ksub)};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  M3D_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights rows=%ld cols=%ld box=%dx%dx%d) failed: %d", rows, cols,
+              bk, box_rows, ksub, static_cast<int>(r));
+  return M3D_OK;
+}
+
+// NHWC bf16 activation as (bk, W, H, N, C/bk): box {bk, tw*stride, th*stride, 1, ksub} lands as ksub
+// consecutive [th*tw][bk] channel-chunk tiles of the same window.
+int make_tmap_nhwc5(CUtensorMap* map, const void* base, int N, int H, int W, int C, int bk, int tw, int th, int stride,
+                    int ksub) {
+  auto enc = get_encode();
+  M3D_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint64_t dims[5] = {static_cast<cuuint64_t>(bk), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(C / bk)};
+  cuuint64_t strides[4] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
+                           static_cast<cuuint64_t>(H) * W * C * 2, static_cast<cuuint64_t>(bk) * 2};
+  cuuint32_t box[5] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(tw * stride),
+                       static_cast<cuuint32_t>(th * stride), 1, static_cast<cuuint32_t>(ksub)};
+  cuuint32_t es[5] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  M3D_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(nhwc5 N=%d H=%d W=%d C=%d box=%dx%dx%dx%d) failed: %d", N, H, W,
+              C, bk, tw * stride, th * stride, ksub, static_cast<int>(r));
   return M3D_OK;
 }
 
@@ -240,15 +280,37 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
         if (rc2 != M3D_OK) return rc2;
       }
     }
+    // k-blocks per pipeline stage: enough tensor-pipe clocks per stage (N/2 per k16) to cover the
+    // issue cost of the stage's barrier hand-shakes and TMA instructions
+    const long total_kb = ktot / bk;
+    int ksub = 1;
+    if (staged) {
+      for (int k = (BN >= 256 ? 1 : (BN >= 128 ? 2 : 4)); k > 1; --k)
+        if (total_kb % k == 0) {
+          ksub = k;
+          break;
+        }
+      const char* e = getenv("M3D_KSUB");  // development override
+      if (e != nullptr && atoi(e) >= 1 && total_kb % atoi(e) == 0 && (atoi(e) <= 2 || BN == 64)) ksub = atoi(e);
+    }
+    bool wide = ksub > 1;
     for (int i = 0; i < d->num_inputs; ++i) {
       M3D_REQUIRE(d->in_cstride[i] % 8 == 0, "input %d: channel stride %d not a multiple of 8", i, d->in_cstride[i]);
-      int rc = make_tmap_nhwc(&p.tmap_a[i], d->in[i], d->N, d->H, d->W, d->in_cstride[i], bk, TW, TH, d->stride);
+      if ((d->in_c[i] / bk) % ksub != 0 || d->in_cstride[i] % bk != 0 || d->in_coff[i] % bk != 0 ||
+          d->in_goff[i] % bk != 0)
+        wide = false;
+    }
+    for (int i = 0; i < d->num_inputs; ++i) {
+      int rc = wide ? make_tmap_nhwc5(&p.tmap_a[i], d->in[i], d->N, d->H, d->W, d->in_cstride[i], bk, TW, TH, d->stride,
+                                      ksub)
+                    : make_tmap_nhwc(&p.tmap_a[i], d->in[i], d->N, d->H, d->W, d->in_cstride[i], bk, TW, TH, d->stride);
       if (rc != M3D_OK) return rc;
       p.chunks[i] = d->in_c[i] / bk;
       p.a_coff[i] = d->in_coff[i];
       p.a_goff[i] = d->in_goff[i];
     }
-    int rc = make_tmap_2d(&p.tmap_b, d->weight, d->weight_rows, ktot, bk, BN);
+    p.a_wide = wide ? 1 : 0;
+    int rc = make_tmap_b3d(&p.tmap_b, d->weight, d->weight_rows, ktot, bk, BN, ksub);
     if (rc != M3D_OK) return rc;
     p.num_inputs = d->num_inputs;
     p.R = d->R, p.S = d->S, p.stride = d->stride, p.pad = d->pad, p.dil = d->dil;
@@ -260,7 +322,7 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
     p.res = d->res, p.res_cstride = d->res_cstride, p.res_coff = d->res_coff, p.res_goff = d->res_goff;
     p.slope = d->slope;
     p.total_tiles = static_cast<int>(total_tiles);
-    rc = launch_conv_tma(p, BN, bk, d->out_dtype, staged, stream);
+    rc = launch_conv_tma(p, BN, bk, ksub, d->out_dtype, staged, stream);
     if (rc == M3D_ERR_UNSUPPORTED) set_last_error("no TMA conv kernel for BN=%d BK=%d", BN, bk);
     return rc;
   }

@@ -39,29 +39,51 @@ __host__ __device__ constexpr int acc_cols(int bn) { return bn <= 32 ? 32 : (bn 
 //   warp 1: TMEM allocator + MMA issuer
 //   warps 2-5: epilogue (TMEM lane quarter = warp % 4)
 // =========================================================================
-template <int BN, int BK, bool STAGED>
+// A pipeline stage holds KSUB k-blocks (KSUB x BK channels of K): the producer / MMA hand-shake
+// (mbarrier wait + arrive, ~100 clocks each on a lone warp, plus ~80 clocks per TMA issue) is paid once
+// per stage, so a stage must carry several hundred tensor-pipe clocks (M128 x N x K16 = N/2 clocks) for
+// the issuing warps to stay ahead of the MMAs.
+template <int BN, int BK, int KSUB, bool STAGED>
 struct TmaCfg {
   static constexpr int ROW_BYTES = BK * 2;
-  static constexpr int A_BYTES = kTileM * ROW_BYTES;
+  static constexpr int A_BYTES = kTileM * ROW_BYTES;  // one k-block of A
   static constexpr int B_BYTES = BN * ROW_BYTES;
   static constexpr int B_STRIDE = (B_BYTES + 1023) & ~1023;
-  static constexpr int STAGE = A_BYTES + B_STRIDE;
+  static constexpr int STAGE = KSUB * (A_BYTES + B_STRIDE);
   static constexpr int EXTRA = STAGED ? (2 * kSlabBytes + 1024) : 0;  // staging slabs + bias
-  static constexpr int BUDGET = 224 * 1024 - EXTRA;
-  static constexpr int STAGES = (STAGE * 6 <= 96 * 1024) ? 6 : (BUDGET / STAGE >= 4 ? 4 : (BUDGET / STAGE >= 3 ? 3 : 2));
+  static constexpr int BUDGET = 225 * 1024 + 512 - EXTRA;
+  static constexpr int FIT = BUDGET / STAGE;
+  static constexpr int STAGES = (STAGE * 6 <= 96 * 1024) ? 6 : (FIT >= 5 ? 5 : FIT);
   static constexpr int SMEM = STAGES * STAGE + EXTRA + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int ACC = acc_cols(BN);
+  static_assert(STAGES >= 2, "conv tile does not fit shared memory");
   static_assert(SMEM <= 227 * 1024, "conv tile does not fit shared memory");
+  static_assert(KSUB == 1 || B_STRIDE == B_BYTES, "multi-k-block stages need 1024-byte weight sub-tiles");
 };
 
-template <int BN, int BK, typename OutT, bool STAGED>
+// Position of a k-block in the (input, tap, channel chunk) walk of K.
+struct KWalk {
+  int i, r, sx, c;
+  __device__ __forceinline__ void reset() { i = 0, r = 0, sx = 0, c = 0; }
+  __device__ __forceinline__ void advance(int n, const ConvTmaParams& p) {
+    c += n;
+    if (c >= p.chunks[i]) {
+      c = 0;
+      if (++sx == p.S) {
+        sx = 0;
+        if (++r == p.R) r = 0, ++i;
+      }
+    }
+  }
+};
+
+template <int BN, int BK, int KSUB, typename OutT, bool STAGED>
 __global__ void __launch_bounds__(192, 1) conv_tma_kernel(const __grid_constant__ ConvTmaParams p) {
-  using Cfg = TmaCfg<BN, BK, STAGED>;
+  using Cfg = TmaCfg<BN, BK, KSUB, STAGED>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+  // stage layout: [A k-block 0..KSUB-1][B k-block 0..KSUB-1]
   uint8_t* stage_out = smem + STAGES * Cfg::STAGE;  // STAGED: 2 slabs + bias (1 KB)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE + Cfg::EXTRA);
   uint64_t* full = bars;
@@ -95,66 +117,92 @@ __global__ void __launch_bounds__(192, 1) conv_tma_kernel(const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int taps = p.R * p.S;
+  int total_kb = 0;
+  for (int i = 0; i < p.num_inputs; ++i) total_kb += p.R * p.S * p.chunks[i];
+  const int n_stages = total_kb / KSUB;  // host guarantees divisibility
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(tile, p.n_tiles, p.tiles_w, p.tiles_h, p.N, p.TW, p.TH);
-        const int brow = t.g * p.b_goff + t.nt * BN;
-        int kcol = 0;
-        for (int i = 0; i < p.num_inputs; ++i) {
-          const int c_base = p.a_coff[i] + t.g * p.a_goff[i];
-          for (int tap = 0; tap < taps; ++tap) {
-            const int r = tap / p.S, s = tap % p.S;
-            const int h0 = t.p0 * p.stride - p.pad + r * p.dil;
-            const int w0 = t.q0 * p.stride - p.pad + s * p.dil;
-            for (int c = 0; c < p.chunks[i]; ++c) {
-              mbar_wait(&empty[stage], phase ^ 1);
-              mbar_arrive_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
-              tma_load_4d(smem_a + stage * Cfg::A_BYTES, &p.tmap_a[i], &full[stage], c_base + c * BK, w0, h0, t.n);
-              tma_load_2d(smem_b + stage * Cfg::B_STRIDE, &p.tmap_b, &full[stage], kcol, brow);
-              kcol += BK;
-              if (++stage == STAGES) {
-                stage = 0;
-                phase ^= 1;
-              }
-            }
+    // The whole warp walks the loop (convergent control flow keeps addresses and descriptors in
+    // uniform registers); one elected lane issues the TMA operations.
+    int stage = 0;
+    uint32_t phase = 0;
+    const bool wide_a = KSUB > 1 && p.a_wide;  // one 5-D box brings the stage's KSUB channel chunks of one tap
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(tile, p.n_tiles, p.tiles_w, p.tiles_h, p.N, p.TW, p.TH);
+      const int brow = t.g * p.b_goff + t.nt * BN;
+      const int hbase = t.p0 * p.stride - p.pad, wbase = t.q0 * p.stride - p.pad;
+      KWalk kw;
+      kw.reset();
+      for (int st = 0; st < n_stages; ++st) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE;
+        uint8_t* sb = sa + KSUB * Cfg::A_BYTES;
+        if (wide_a) {
+          const int cb = p.a_coff[kw.i] + t.g * p.a_goff[kw.i];
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full[stage], KSUB * (Cfg::A_BYTES + Cfg::B_BYTES));
+            tma_load_5d(sa, &p.tmap_a[kw.i], &full[stage], cb & (BK - 1), wbase + kw.sx * p.dil, hbase + kw.r * p.dil,
+                        t.n, cb / BK + kw.c);
+            tma_load_3d(sb, &p.tmap_b, &full[stage], 0, brow, st * KSUB);
           }
+          kw.advance(KSUB, p);
+        } else {
+          const bool leader = elect_one();
+          if (leader) {
+            mbar_arrive_expect_tx(&full[stage], KSUB * (Cfg::A_BYTES + Cfg::B_BYTES));
+            tma_load_3d(sb, &p.tmap_b, &full[stage], 0, brow, st * KSUB);
+          }
+#pragma unroll
+          for (int u = 0; u < KSUB; ++u) {
+            const int cb = p.a_coff[kw.i] + t.g * p.a_goff[kw.i] + kw.c * BK;
+            if (leader)
+              tma_load_4d(sa + u * Cfg::A_BYTES, &p.tmap_a[kw.i], &full[stage], cb, wbase + kw.sx * p.dil,
+                          hbase + kw.r * p.dil, t.n);
+            kw.advance(1, p);
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BN);
-      int total_kb = 0;
-      for (int i = 0; i < p.num_inputs; ++i) total_kb += taps * p.chunks[i];
-      int stage = 0;
-      uint32_t phase = 0;
-      int local = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
-        const int as = local & 1;
-        const uint32_t aphase = (local >> 1) & 1;
-        mbar_wait(&tempty[as], aphase ^ 1);
+    constexpr uint32_t idesc = umma_idesc_bf16(BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + as * Cfg::ACC;
+      for (int st = 0; st < n_stages; ++st) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + as * Cfg::ACC;
-        for (int kb = 0; kb < total_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint64_t da = umma_smem_desc<Cfg::ROW_BYTES>(smem_u32(smem_a + stage * Cfg::A_BYTES));
-          const uint64_t db = umma_smem_desc<Cfg::ROW_BYTES>(smem_u32(smem_b + stage * Cfg::B_STRIDE));
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE);
+          const uint64_t da = umma_smem_desc<Cfg::ROW_BYTES>(sa);
+          const uint64_t db = umma_smem_desc<Cfg::ROW_BYTES>(sa + KSUB * Cfg::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-          umma_commit(&empty[stage]);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
+          for (int u = 0; u < KSUB; ++u) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_f16(tmem_acc, da + (u * Cfg::A_BYTES >> 4) + 2 * k, db + (u * Cfg::B_BYTES >> 4) + 2 * k, idesc,
+                       (st | u | k) != 0);
           }
+          umma_commit(&empty[stage]);
         }
-        umma_commit(&tfull[as]);
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      if (elect_one()) umma_commit(&tfull[as]);
+      __syncwarp();
     }
   } else {
     const int quarter = warp & 3;
@@ -748,10 +796,10 @@ static int num_sms() {
   return sms;
 }
 
-template <int BN, int BK, typename OutT, bool STAGED>
+template <int BN, int BK, int KSUB, typename OutT, bool STAGED>
 static int launch_tma_t(const ConvTmaParams& p, cudaStream_t stream) {
-  using Cfg = TmaCfg<BN, BK, STAGED>;
-  auto kern = conv_tma_kernel<BN, BK, OutT, STAGED>;
+  using Cfg = TmaCfg<BN, BK, KSUB, STAGED>;
+  auto kern = conv_tma_kernel<BN, BK, KSUB, OutT, STAGED>;
   static bool configured = false;
   if (!configured) {
     M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
@@ -766,18 +814,24 @@ static int launch_tma_t(const ConvTmaParams& p, cudaStream_t stream) {
   return M3D_OK;
 }
 
-int launch_conv_tma(const ConvTmaParams& p, int BN, int BK, int out_dtype, bool staged, cudaStream_t stream) {
-#define M3D_TMA_CASE(bn, bk)                                                               \
-  if (BN == bn && BK == bk) {                                                              \
-    return out_dtype == DT_BF16 ? launch_tma_t<bn, bk, __nv_bfloat16, false>(p, stream)    \
-                                : launch_tma_t<bn, bk, float, false>(p, stream);           \
+int launch_conv_tma(const ConvTmaParams& p, int BN, int BK, int ksub, int out_dtype, bool staged,
+                    cudaStream_t stream) {
+#define M3D_TMA_CASE(bn, bk)                                                                  \
+  if (BN == bn && BK == bk && ksub == 1) {                                                    \
+    return out_dtype == DT_BF16 ? launch_tma_t<bn, bk, 1, __nv_bfloat16, false>(p, stream)    \
+                                : launch_tma_t<bn, bk, 1, float, false>(p, stream);           \
   }
-#define M3D_TMA_STAGED(bn)                                                                 \
-  if (staged && BN == bn && BK == 64 && out_dtype == DT_BF16)                              \
-    return launch_tma_t<bn, 64, __nv_bfloat16, true>(p, stream);
-  M3D_TMA_STAGED(64)
-  M3D_TMA_STAGED(128)
-  M3D_TMA_STAGED(256)
+#define M3D_TMA_STAGED(bn, ks)                                                             \
+  if (staged && BN == bn && BK == 64 && ksub == ks && out_dtype == DT_BF16)                \
+    return launch_tma_t<bn, 64, ks, __nv_bfloat16, true>(p, stream);
+  M3D_TMA_STAGED(64, 1)
+  M3D_TMA_STAGED(64, 2)
+  M3D_TMA_STAGED(64, 3)
+  M3D_TMA_STAGED(64, 4)
+  M3D_TMA_STAGED(128, 1)
+  M3D_TMA_STAGED(128, 2)
+  M3D_TMA_STAGED(256, 1)
+  M3D_TMA_STAGED(256, 2)
   M3D_TMA_CASE(16, 16)
   M3D_TMA_CASE(32, 16)
   M3D_TMA_CASE(32, 32)

@@ -38,7 +38,7 @@ enum : int { DT_BF16 = 0, DT_F32 = 1 };
 
 struct alignas(64) ConvTmaParams {
   CUtensorMap tmap_a[kMaxConcat];  // NHWC inputs as 4-D (C, W, H, N) maps, box {BK, TW*stride, TH*stride, 1}
-  CUtensorMap tmap_b;              // packed weights as 2-D (K, rows) map, box {BK, BN}
+  CUtensorMap tmap_b;              // packed weights as 3-D (BK, rows, K/BK) map, box {BK, BN, KSUB}
   CUtensorMap tmap_out, tmap_res;  // staged epilogue: output / residual as (C, Q, P, N), box {64, TW, TH, 1}
   int num_inputs;
   int chunks[kMaxConcat];  // k-blocks per tap for each concat input (= C_i / BK)
@@ -59,6 +59,7 @@ struct alignas(64) ConvTmaParams {
   int res_cstride, res_coff, res_goff;
   float slope;  // LeakyReLU negative slope; 1.0 = identity
   int total_tiles;
+  int a_wide;  // tmap_a are 5-D (BK, W, H, N, C/BK) maps whose box holds the stage's KSUB channel chunks
 };
 
 struct alignas(64) ConvGatherParams {
@@ -92,7 +93,8 @@ struct alignas(64) ConvGatherParams {
 };
 
 // Host launchers (igemm.cu).  Return 0 or a negative m3d error code.
-int launch_conv_tma(const ConvTmaParams& p, int BN, int BK, int out_dtype, bool staged, cudaStream_t stream);
+int launch_conv_tma(const ConvTmaParams& p, int BN, int BK, int ksub, int out_dtype, bool staged,
+                    cudaStream_t stream);
 int launch_conv_gather(const ConvGatherParams& p, int BN, int in_dtype, int out_dtype, bool staged,
                        cudaStream_t stream);
 

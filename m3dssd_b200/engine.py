@@ -587,6 +587,9 @@ class Engine:
         acc = [0.0] * len(self.ops)
         for _ in range(iters):
             evs = []
+            # keep the device busy while the host enqueues the whole step (a ctypes call costs more than most
+            # of these kernels run): the events then bracket device time, not launch latency
+            torch.cuda._sleep(40_000_000)
             for op in self.ops:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(st)
