@@ -180,6 +180,15 @@ int m3d_center_align_om(const float* fg_max, const int* fg_arg, const float* hea
                         int y_coff, const float* anchors, int anchor_ld, float feat_stride, float mean_x, float mean_y,
                         float std_x, float std_y, float thresh, float* om, int om_cstride, long npix,
                         m3d_stream_t stream);
+/* G three-layer 1x1 regression heads that share the input x, fused in one kernel (conv1x1 + BN + LeakyReLU,
+ * conv1x1 + BN + LeakyReLU, conv1x1: model/M3d_inference_align.py:66-210, 236-277; BatchNorm folded into w/b).
+ * x: bf16 NHWC [N,H,W,x_cstride], channels [x_coff, x_coff+Cx), Cx in {64,128}.  w1: bf16 [G*256][Cx],
+ * w2: bf16 [G*256][256], w3: bf16 [G*rows3][256] (rows >= A of each head zero), b1,b2: fp32 [G*256], b3: fp32 [G*rows3].
+ * out: fp32 NHWC [N,H,W,out_cstride]; head g -> channels [out_coff + g*A, out_coff + (g+1)*A).  The 256-channel
+ * intermediates stay in shared memory / TMEM (rounded to bf16 between layers, like the layer-by-layer bf16 path). */
+int m3d_head_mlp(const void* x, int N, int H, int W, int x_cstride, int x_coff, int Cx, const void* w1, const float* b1,
+                 const void* w2, const float* b2, const void* w3, const float* b3, int G, int A, int rows3, float* out,
+                 int out_cstride, int out_coff, float slope, m3d_stream_t stream);
 /* flatten_tensor + cat of the 11 regression heads (model/M3d_inference_align.py:280-295). */
 int m3d_flatten_heads(const float* heads, int heads_cstride, int N, int H, int W, int A,
                       const int* slot_of_output /*host, 11 ints: slot of x,y,w,h,x3d,y3d,z3d,w3d,h3d,l3d,rY3d*/,

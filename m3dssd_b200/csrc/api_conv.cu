@@ -284,14 +284,14 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
     // issue cost of the stage's barrier hand-shakes and TMA instructions
     const long total_kb = ktot / bk;
     int ksub = 1;
-    if (staged) {
+    if (staged || (bk == 64 && (BN == 32 || BN == 48))) {
       for (int k = (BN >= 256 ? 1 : (BN >= 128 ? 2 : 4)); k > 1; --k)
         if (total_kb % k == 0) {
           ksub = k;
           break;
         }
       const char* e = getenv("M3D_KSUB");  // development override
-      if (e != nullptr && atoi(e) >= 1 && total_kb % atoi(e) == 0 && (atoi(e) <= 2 || BN == 64)) ksub = atoi(e);
+      if (e != nullptr && atoi(e) >= 1 && total_kb % atoi(e) == 0 && (atoi(e) <= 2 || BN <= 64)) ksub = atoi(e);
     }
     bool wide = ksub > 1;
     for (int i = 0; i < d->num_inputs; ++i) {

@@ -1,0 +1,342 @@
+// Fused bf16 DCNv2 layer (throughput mode): bilinear offset/mask sampling + output GEMM in one kernel,
+// following modulated_deformable_im2col_gpu_kernel + SGEMM of the reference
+// (model/DCNv2/src/cuda/dcn_v2_im2col_cuda.cu:18-47,118-180; model/DCNv2/src/dcn_v2_cuda.c:61-97) with no
+// `columns` buffer.  Same GEMM view as igemm.cu (M = 128 output pixels, N = BN, k-blocks of 64 channels) but
+// sized for what bounds this layer: the fp32 bilinear blend costs ~8.5 CUDA-core instructions per A element
+// (unpack + FMA per corner), i.e. >= 544 issue clocks per k-block against 2*BN/... tensor clocks, so the
+// kernel spends its warps on the blend:
+//
+//   warps 0-15 : A producers.  Per tile a shared table holds, for every (row, tap), the four clamped corner
+//                offsets and the bilinear weights already multiplied by validity and modulation mask; per
+//                k-block each thread blends 2 rows x 8 channels (4 x 16-byte corner loads per row, issued one
+//                row ahead of the blend) and writes the swizzled bf16 A tile.
+//   warp 16    : weight tiles by TMA (K walked chunk-major: the 9 taps of a 64-channel chunk re-read one
+//                input window, which keeps the corner loads in L1/L2).
+//   warp 17    : tcgen05.mma issue, accumulators in TMEM (two stages).
+//   warps 18-21: epilogue: TMEM -> bias (+ residual) -> LeakyReLU -> bf16 NHWC.
+#include <cstdlib>
+
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "igemm.cuh"
+#include "ptx.cuh"
+
+namespace m3d {
+
+namespace {
+
+constexpr int kProd = 512;  // producer threads
+constexpr int kDcnThreads = kProd + 6 * 32;
+constexpr int kBK = 64;
+
+template <int BN, int NSTG>
+struct DcnCfg {
+  static constexpr int A_BYTES = kTileM * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int STAGES = NSTG;
+  static constexpr int TABLE = kTileM * 9 * 32;
+  static constexpr int SMEM = STAGES * STAGE + TABLE + 1024 + 256;
+  static constexpr int ACC = BN <= 128 ? 128 : 256;
+  static_assert(SMEM <= 227 * 1024, "DCN tile does not fit shared memory");
+};
+
+struct Entry {
+  int4 off;
+  float4 w;
+};
+
+struct Tile {
+  int nt, n, p0, q0;
+};
+__device__ __forceinline__ Tile tile_of(int tile, const ConvGatherParams& p) {
+  Tile t;
+  t.nt = tile % p.n_tiles;
+  int r = tile / p.n_tiles;
+  const int tw = r % p.tiles_w;
+  r /= p.tiles_w;
+  const int th = r % p.tiles_h;
+  t.n = r / p.tiles_h;
+  t.p0 = th * p.TH;
+  t.q0 = tw * p.TW;
+  return t;
+}
+
+template <int BN, int NSTG>
+__global__ void __launch_bounds__(kDcnThreads, 1) dcn_fused_kernel(const __grid_constant__ ConvGatherParams p) {
+  using Cfg = DcnCfg<BN, NSTG>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  Entry* table = reinterpret_cast<Entry*>(smem + STAGES * Cfg::STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE + Cfg::TABLE);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], kProd / 32 + 1);  // one arrival per producer warp + the weight TMA
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 128);
+    }
+    fence_barrier_init();
+    prefetch_tmap(&p.tmap_b);
+  }
+  if (warp == 17) tmem_alloc<2 * Cfg::ACC>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int taps = p.R * p.S;
+  const int nchunk = p.chunks[0];
+  const int total_kb = taps * nchunk;
+
+  if (warp < 16) {
+    // ------------------------------------------------------------ A producers
+    const int pt = threadIdx.x;
+    const int j = pt & 7;       // 16-byte chunk (8 channels) of the 64-channel k-block
+    const int rbase = pt >> 3;  // rows rbase and rbase + 64
+    const int tw_shift = 31 - __clz(p.TW);
+    const __nv_bfloat16* in0 = static_cast<const __nv_bfloat16*>(p.in[0]) + p.in_coff[0];
+    const int cs = p.in_cstride[0];
+    const int units = total_kb * 2;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const Tile t = tile_of(tile, p);
+      named_bar_sync(1, kProd);  // previous tile's table readers are done
+      {
+        // thread pt fills row pt/4, taps (pt%4) + 4k  (dcn_v2_im2col_cuda.cu:18-47,151-175)
+        const int trow = pt >> 2;
+        const int pp = t.p0 + (trow >> tw_shift), qq = t.q0 + (trow & (p.TW - 1));
+        const bool tok = pp < p.P && qq < p.Q;
+        const float* om_px = p.om + ((static_cast<long>(t.n) * p.P + pp) * p.Q + qq) * p.om_cstride;
+        float o_h[3], o_w[3], o_m[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int tap = (pt & 3) + 4 * k;
+          o_h[k] = o_w[k] = 0.f, o_m[k] = 1.f;
+          if (tok && tap < taps) {
+            o_h[k] = __ldg(om_px + 2 * tap);
+            o_w[k] = __ldg(om_px + 2 * tap + 1);
+            o_m[k] = __ldg(om_px + 2 * taps + tap);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int tap = (pt & 3) + 4 * k;
+          if (tap >= taps) break;
+          Entry e;
+          e.off = make_int4(0, 0, 0, 0);
+          e.w = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (tok) {
+            const int r = taps == 9 ? tap / 3 : tap / p.S, sx = tap - r * p.S;
+            const float hf = static_cast<float>(pp * p.stride - p.pad + r * p.dil) + o_h[k];
+            const float wf = static_cast<float>(qq * p.stride - p.pad + sx * p.dil) + o_w[k];
+            float m = o_m[k];
+            if (p.sigmoid_mask) m = 1.f / (1.f + __expf(-m));
+            if (hf > -1.f && wf > -1.f && hf < static_cast<float>(p.H) && wf < static_cast<float>(p.W)) {
+              const float hl = floorf(hf), wl = floorf(wf);
+              const int h_low = static_cast<int>(hl), w_low = static_cast<int>(wl);
+              const int h_high = h_low + 1, w_high = w_low + 1;
+              const float lh = hf - hl, lw = wf - wl, hh = 1.f - lh, hw = 1.f - lw;
+              const bool hl_ok = h_low >= 0, wl_ok = w_low >= 0, hh_ok = h_high <= p.H - 1, wh_ok = w_high <= p.W - 1;
+              const int rl = (t.n * p.H + (hl_ok ? h_low : 0)) * p.W, rh = (t.n * p.H + (hh_ok ? h_high : 0)) * p.W;
+              const int cl = wl_ok ? w_low : 0, ch = wh_ok ? w_high : 0;
+              e.off = make_int4((rl + cl) * cs, (rl + ch) * cs, (rh + cl) * cs, (rh + ch) * cs);
+              e.w = make_float4((hl_ok && wl_ok) ? hh * hw * m : 0.f, (hl_ok && wh_ok) ? hh * lw * m : 0.f,
+                                (hh_ok && wl_ok) ? lh * hw * m : 0.f, (hh_ok && wh_ok) ? lh * lw * m : 0.f);
+            }
+          }
+          table[trow * taps + tap] = e;
+        }
+      }
+      named_bar_sync(1, kProd);
+
+      // unit u = (k-block u/2, row half u%2); K is walked chunk-major: k-block -> (chunk, tap)
+      uint4 cv[2][4];
+      float4 cw[2];
+      int nx_tap = 0, nx_c = 0;
+      auto issue = [&](int u, int buf) {
+        const int half = u & 1;
+        const int tap = nx_tap, c = nx_c;
+        if (half) {
+          if (++nx_tap == taps) nx_tap = 0, ++nx_c;
+        }
+        const Entry& e = table[(rbase + 64 * half) * taps + tap];
+        const int4 o = e.off;
+        cw[buf] = e.w;
+        const __nv_bfloat16* base = in0 + c * kBK + j * 8;
+        cv[buf][0] = __ldg(reinterpret_cast<const uint4*>(base + o.x));
+        cv[buf][1] = __ldg(reinterpret_cast<const uint4*>(base + o.y));
+        cv[buf][2] = __ldg(reinterpret_cast<const uint4*>(base + o.z));
+        cv[buf][3] = __ldg(reinterpret_cast<const uint4*>(base + o.w));
+      };
+      auto blend = [&](int half, int buf, uint8_t* a_tile) {
+        const float4 w4 = cw[buf];
+        const uint32_t* q0 = reinterpret_cast<const uint32_t*>(&cv[buf][0]);
+        const uint32_t* q1 = reinterpret_cast<const uint32_t*>(&cv[buf][1]);
+        const uint32_t* q2 = reinterpret_cast<const uint32_t*>(&cv[buf][2]);
+        const uint32_t* q3 = reinterpret_cast<const uint32_t*>(&cv[buf][3]);
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float lo = w4.x * __uint_as_float(q0[e] << 16) + w4.y * __uint_as_float(q1[e] << 16) +
+                           w4.z * __uint_as_float(q2[e] << 16) + w4.w * __uint_as_float(q3[e] << 16);
+          const float hi = w4.x * __uint_as_float(q0[e] & 0xffff0000u) + w4.y * __uint_as_float(q1[e] & 0xffff0000u) +
+                           w4.z * __uint_as_float(q2[e] & 0xffff0000u) + w4.w * __uint_as_float(q3[e] & 0xffff0000u);
+          __nv_bfloat162 tt = __floats2bfloat162_rn(lo, hi);
+          w[e] = *reinterpret_cast<uint32_t*>(&tt);
+        }
+        *reinterpret_cast<uint4*>(a_tile + swizzled_offset<128>(rbase + 64 * half, j)) = make_uint4(w[0], w[1], w[2], w[3]);
+      };
+      issue(0, 0);
+#pragma unroll 1
+      for (int u = 0; u < units; u += 2) {
+        issue(u + 1, 1);
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* a_tile = smem + stage * Cfg::STAGE;
+        blend(0, 0, a_tile);
+        if (u + 2 < units) issue(u + 2, 0);
+        blend(1, 1, a_tile);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 16) {
+    // ---------------------------------------------------- weight TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const Tile t = tile_of(tile, p);
+      int tap = 0, c = 0;
+      for (int kb = 0; kb < total_kb; ++kb) {
+        const int kblk = tap * nchunk + c;  // weights are packed tap-major
+        if (++tap == taps) tap = 0, ++c;
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full[stage], Cfg::B_BYTES);
+          tma_load_2d(smem + stage * Cfg::STAGE + Cfg::A_BYTES, &p.tmap_b, &full[stage], kblk * kBK, t.nt * BN);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 17) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + as * Cfg::ACC;
+      for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE);
+          const uint64_t da = umma_smem_desc<128>(sa);
+          const uint64_t db = umma_smem_desc<128>(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) umma_f16(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (elect_one()) umma_commit(&tfull[as]);
+      __syncwarp();
+    }
+  } else {
+    // --------------------------------------------------------------- epilogue
+    const int quarter = warp & 3;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+      const Tile t = tile_of(tile, p);
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const __nv_bfloat16* res = p.res ? static_cast<const __nv_bfloat16*>(p.res) + p.res_coff : nullptr;
+      __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out) + p.out_coff;
+      epilogue_tile_direct<BN, __nv_bfloat16, __nv_bfloat16>(tmem_base + as * Cfg::ACC, quarter, lane, t.n, t.p0, t.q0,
+                                                             p.TW, p.P, p.Q, t.nt * BN, p.Cout, p.bias, res,
+                                                             p.res_cstride, out, p.out_cstride, p.slope);
+      tc_fence_before();
+      mbar_arrive(&tempty[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    tc_fence_after();
+    tmem_dealloc<2 * Cfg::ACC>(tmem_base);
+  }
+}
+
+template <int BN, int NSTG>
+int launch_t(const ConvGatherParams& p, cudaStream_t stream) {
+  using Cfg = DcnCfg<BN, NSTG>;
+  auto kern = dcn_fused_kernel<BN, NSTG>;
+  static bool configured = false;
+  if (!configured) {
+    M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    // what the operand ring does not need goes to L1: the 9 taps of a chunk re-read one input window
+    const int pct = (Cfg::SMEM + 2048) * 100 / (228 * 1024) + 1;
+    M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct));
+    configured = true;
+  }
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = sms;
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  kern<<<grid, kDcnThreads, Cfg::SMEM, stream>>>(p);
+  M3D_CUDA_OK(cudaGetLastError());
+  return M3D_OK;
+}
+
+}  // namespace
+
+// bf16 in / bf16 out 3x3 deformable layers with one input and BN in {128, 256}; anything else (incl. the 1x1
+// centre-align layers, which are bounded by their per-tile table build, not the blend) stays on
+// conv_gather_kernel (igemm.cu).
+bool dcn_fused_supported(const ConvGatherParams& p, int BN, int in_dtype, int out_dtype) {
+  if (getenv("M3D_DCN_LEGACY") != nullptr) return false;
+  return p.om != nullptr && p.stem_img == nullptr && p.num_inputs == 1 && in_dtype == DT_BF16 &&
+         out_dtype == DT_BF16 && (BN == 128 || BN == 256) && p.R * p.S == 9 && (p.TW & (p.TW - 1)) == 0;
+}
+
+int launch_dcn_fused(const ConvGatherParams& p, int BN, cudaStream_t stream) {
+  const char* e = getenv("M3D_DCN_STAGES");
+  const int nstg = e ? atoi(e) : 2;
+  if (nstg == 3) return BN == 128 ? launch_t<128, 3>(p, stream) : launch_t<256, 3>(p, stream);
+  return BN == 128 ? launch_t<128, 2>(p, stream) : launch_t<256, 2>(p, stream);
+}
+
+}  // namespace m3d

@@ -152,58 +152,58 @@ __global__ void maxpool2x2_kernel(const T* __restrict__ in, T* __restrict__ out,
 //   oy = iy * f - pad + ky   <=>   iy = (oy + pad - ky) / f   when divisible.
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void upsample_add_kernel(const T* __restrict__ x, const float* __restrict__ wt, const T* __restrict__ skip,
-                                    T* __restrict__ out, int N, int H, int W, int C, int f, int x_cstride,
-                                    int skip_cstride, int out_cstride) {
+__global__ void __launch_bounds__(256) upsample_add_kernel(const T* __restrict__ x, const float* __restrict__ wt,
+                                                           const T* __restrict__ skip, T* __restrict__ out, int N, int H,
+                                                           int W, int C, int f, int x_cstride, int skip_cstride,
+                                                           int out_cstride) {
+  // grid = (segments of an output row, output row, image): 32-bit index math only
   constexpr int V = 16 / sizeof(T);
   const int k = 2 * f, pad = f / 2;
   const int Ho = H * f, Wo = W * f, cv = C / V;
-  const long total = static_cast<long>(N) * Ho * Wo * cv;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv) * V;
-    long r = i / cv;
-    const int ox = static_cast<int>(r % Wo);
-    r /= Wo;
-    const int oy = static_cast<int>(r % Ho);
-    const int n = static_cast<int>(r / Ho);
-    float acc[V];
-    if (skip != nullptr) {
-      T s[V];
-      *reinterpret_cast<uint4*>(s) =
-          __ldg(reinterpret_cast<const uint4*>(skip + ((static_cast<long>(n) * Ho + oy) * Wo + ox) * skip_cstride + c));
+  const int n = blockIdx.z, oy = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Wo * cv) return;
+  const int ox = idx / cv;
+  const int c = (idx - ox * cv) * V;
+  float acc[V];
+  const long opix = (static_cast<long>(n) * Ho + oy) * Wo + ox;
+  if (skip != nullptr) {
+    T s[V];
+    *reinterpret_cast<uint4*>(s) = __ldg(reinterpret_cast<const uint4*>(skip + opix * skip_cstride + c));
 #pragma unroll
-      for (int q = 0; q < V; ++q) acc[q] = to_f(s[q]);
-    } else {
+    for (int q = 0; q < V; ++q) acc[q] = to_f(s[q]);
+  } else {
 #pragma unroll
-      for (int q = 0; q < V; ++q) acc[q] = 0.f;
-    }
-    float up[V];
-#pragma unroll
-    for (int q = 0; q < V; ++q) up[q] = 0.f;
-    for (int ky = (oy + pad) % f; ky < k; ky += f) {
-      const int iy = (oy + pad - ky) / f;
-      if (iy < 0 || iy >= H) continue;
-      for (int kx = (ox + pad) % f; kx < k; kx += f) {
-        const int ix = (ox + pad - kx) / f;
-        if (ix < 0 || ix >= W) continue;
-        T v[V];
-        *reinterpret_cast<uint4*>(v) =
-            __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<long>(n) * H + iy) * W + ix) * x_cstride + c));
-        float wv[V];
-#pragma unroll
-        for (int q = 0; q < V; q += 4)
-          *reinterpret_cast<float4*>(wv + q) = __ldg(reinterpret_cast<const float4*>(wt + (ky * k + kx) * C + c + q));
-#pragma unroll
-        for (int q = 0; q < V; ++q) up[q] = fmaf(to_f(v[q]), wv[q], up[q]);
-      }
-    }
-    T o[V];
-#pragma unroll
-    for (int q = 0; q < V; ++q) o[q] = from_f<T>(up[q] + acc[q]);
-    *reinterpret_cast<uint4*>(out + ((static_cast<long>(n) * Ho + oy) * Wo + ox) * out_cstride + c) =
-        *reinterpret_cast<uint4*>(o);
+    for (int q = 0; q < V; ++q) acc[q] = 0.f;
   }
+  float up[V];
+#pragma unroll
+  for (int q = 0; q < V; ++q) up[q] = 0.f;
+  const int ky0 = (oy + pad) % f, kx0 = (ox + pad) % f;
+  const int iy0 = (oy + pad - ky0) / f, ix0 = (ox + pad - kx0) / f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {  // k = 2f: exactly two taps per axis reach an output pixel
+    const int ky = ky0 + a * f, iy = iy0 - a;
+    if (iy < 0 || iy >= H) continue;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int kx = kx0 + b * f, ix = ix0 - b;
+      if (ix < 0 || ix >= W) continue;
+      T v[V];
+      *reinterpret_cast<uint4*>(v) =
+          __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<long>(n) * H + iy) * W + ix) * x_cstride + c));
+      float wv[V];
+#pragma unroll
+      for (int q = 0; q < V; q += 4)
+        *reinterpret_cast<float4*>(wv + q) = __ldg(reinterpret_cast<const float4*>(wt + (ky * k + kx) * C + c + q));
+#pragma unroll
+      for (int q = 0; q < V; ++q) up[q] = fmaf(to_f(v[q]), wv[q], up[q]);
+    }
+  }
+  T o[V];
+#pragma unroll
+  for (int q = 0; q < V; ++q) o[q] = from_f<T>(up[q] + acc[q]);
+  *reinterpret_cast<uint4*>(out + opix * out_cstride + c) = *reinterpret_cast<uint4*>(o);
 }
 
 // ---------------------------------------------------------------------------
@@ -464,8 +464,9 @@ extern "C" int m3d_upsample_add_nhwc(const void* x, const float* weight, const v
   const int V = dtype == M3D_BF16 ? 8 : 4;
   M3D_REQUIRE(C % V == 0 && x_cstride % V == 0 && out_cstride % V == 0 && (skip == nullptr || skip_cstride % V == 0),
               "channels must keep 16-byte vectors");
-  const long total = static_cast<long>(N) * H * f * W * f * (C / V);
-  const int grid = static_cast<int>(std::min<long>((total + 255) / 256, 148L * 16));
+  M3D_REQUIRE(H * f <= 65535 && N <= 65535, "upsample: output too tall for the launch grid");
+  const dim3 grid(static_cast<unsigned>((static_cast<long>(W) * f * (C / V) + 255) / 256), static_cast<unsigned>(H * f),
+                  static_cast<unsigned>(N));
   if (dtype == M3D_BF16)
     upsample_add_kernel<__nv_bfloat16><<<grid, 256, 0, S(stream)>>>(
         static_cast<const __nv_bfloat16*>(x), weight, static_cast<const __nv_bfloat16*>(skip),

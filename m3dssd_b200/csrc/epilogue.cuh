@@ -18,7 +18,8 @@ constexpr int kEpiThreads = 128;
 constexpr int kEpiBarrier = 2;         // named barrier id of the 4 epilogue warps
 constexpr int kSlabBytes = 128 * 128;  // 128 pixels x 64 bf16 channels
 
-__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+// LeakyReLU; slope in [0,1] (1 = identity): max(v, slope*v) is the same value in two instructions
+__device__ __forceinline__ float lrelu(float v, float slope) { return fmaxf(v, v * slope); }
 
 // ---------------------------------------------------------------- direct
 template <typename OutT, typename ResT>

@@ -2,6 +2,7 @@
 #include "igemm.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "epilogue.cuh"
@@ -484,8 +485,8 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
         auto issue = [&](int u, int buf) {
           const int half = u & 1;
           const int tap = nx_tap, c = nx_c;
-          if (half) {
-            if (++nx_c == nchunk) nx_c = 0, ++nx_tap;
+          if (half) {  // chunk-major walk of K: the 9 taps of one 64-channel chunk share their input window
+            if (++nx_tap == taps) nx_tap = 0, ++nx_c;
           }
           const int coff = c * BK + j * 8;
 #pragma unroll
@@ -677,43 +678,49 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
     }
   } else if (warp == 8) {
     // ---------------------------------------------------- weight TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(tile, p.n_tiles, p.tiles_w, p.tiles_h, p.N, p.TW, p.TH);
-        for (int kb = 0; kb < total_kb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+    const bool chunk_major = !SPLIT && p.stem_img == nullptr;  // must match the A producers' walk of K
+    const int nchunk0 = p.chunks[0];
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(tile, p.n_tiles, p.tiles_w, p.tiles_h, p.N, p.TW, p.TH);
+      int tap = 0, c = 0;
+      for (int kb = 0; kb < total_kb; ++kb) {
+        const int kblk = chunk_major ? tap * nchunk0 + c : kb;
+        if (++tap == taps) tap = 0, ++c;
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* b_hi = smem + stage * Cfg::STAGE + Cfg::PARTS * Cfg::A_BYTES;
           mbar_arrive_expect_tx(&full[stage], Cfg::PARTS * Cfg::B_BYTES);
-          tma_load_2d(b_hi, &p.tmap_b, &full[stage], kb * BK, t.nt * BN);
+          tma_load_2d(b_hi, &p.tmap_b, &full[stage], kblk * BK, t.nt * BN);
           if constexpr (SPLIT) {
-            tma_load_2d(b_hi + Cfg::B_BYTES, &p.tmap_b_mid, &full[stage], kb * BK, t.nt * BN);
-            tma_load_2d(b_hi + 2 * Cfg::B_BYTES, &p.tmap_b_lo, &full[stage], kb * BK, t.nt * BN);
+            tma_load_2d(b_hi + Cfg::B_BYTES, &p.tmap_b_mid, &full[stage], kblk * BK, t.nt * BN);
+            tma_load_2d(b_hi + 2 * Cfg::B_BYTES, &p.tmap_b_lo, &full[stage], kblk * BK, t.nt * BN);
           }
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int local = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
-        const int as = local & 1;
-        const uint32_t aphase = (local >> 1) & 1;
-        mbar_wait(&tempty[as], aphase ^ 1);
+    constexpr uint32_t idesc = umma_idesc_bf16(BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + as * Cfg::ACC;
+      for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + as * Cfg::ACC;
-        for (int kb = 0; kb < total_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE);
           const uint32_t b_hi = a_hi + Cfg::PARTS * Cfg::A_BYTES;
           const uint64_t da = umma_smem_desc<128>(a_hi);
@@ -737,13 +744,15 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
             }
           }
           umma_commit(&empty[stage]);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        umma_commit(&tfull[as]);
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      if (elect_one()) umma_commit(&tfull[as]);
+      __syncwarp();
     }
   } else {
     // --------------------------------------------------------------- epilogue
@@ -832,6 +841,18 @@ int launch_conv_tma(const ConvTmaParams& p, int BN, int BK, int ksub, int out_dt
   M3D_TMA_STAGED(128, 2)
   M3D_TMA_STAGED(256, 1)
   M3D_TMA_STAGED(256, 2)
+#define M3D_TMA_SMALLN(bn, ks)                                                                \
+  if (!staged && BN == bn && BK == 64 && ksub == ks) {                                        \
+    return out_dtype == DT_BF16 ? launch_tma_t<bn, 64, ks, __nv_bfloat16, false>(p, stream)   \
+                                : launch_tma_t<bn, 64, ks, float, false>(p, stream);          \
+  }
+  M3D_TMA_SMALLN(32, 2)
+  M3D_TMA_SMALLN(32, 3)
+  M3D_TMA_SMALLN(32, 4)
+  M3D_TMA_SMALLN(48, 2)
+  M3D_TMA_SMALLN(48, 3)
+  M3D_TMA_SMALLN(48, 4)
+#undef M3D_TMA_SMALLN
   M3D_TMA_CASE(16, 16)
   M3D_TMA_CASE(32, 16)
   M3D_TMA_CASE(32, 32)
@@ -875,6 +896,7 @@ int launch_conv_gather(const ConvGatherParams& p, int BN, int in_dtype, int out_
     if constexpr (bn <= 128) return launch_gather_t<bn, float, float, false>(p, stream);                \
     return M3D_ERR_UNSUPPORTED;                                                                         \
   }
+  if (dcn_fused_supported(p, BN, in_dtype, out_dtype)) return launch_dcn_fused(p, BN, stream);
   M3D_G_STAGED(64)
   M3D_G_STAGED(128)
   M3D_G_STAGED(256)

@@ -98,4 +98,8 @@ int launch_conv_tma(const ConvTmaParams& p, int BN, int BK, int ksub, int out_dt
 int launch_conv_gather(const ConvGatherParams& p, int BN, int in_dtype, int out_dtype, bool staged,
                        cudaStream_t stream);
 
+// Dedicated bf16 DCNv2 kernel (dcn_fused.cu): 16 producer warps for the bilinear blend.
+bool dcn_fused_supported(const ConvGatherParams& p, int BN, int in_dtype, int out_dtype);
+int launch_dcn_fused(const ConvGatherParams& p, int BN, cudaStream_t stream);
+
 }  // namespace m3d

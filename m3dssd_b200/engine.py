@@ -298,34 +298,29 @@ class Engine:
                 self._conv_module("%s.%d.l3" % (gname, g), [h2], m[6], None, slope=1.0, out=heads_buf,
                                   out_coff=(slot0 + g) * A)
             return
-        # layer 1: concatenated output channels
-        w1 = torch.cat([_fold(m[0].weight, m[0].bias, m[1])[0] for m in mods])
-        b1 = torch.cat([_fold(m[0].weight, m[0].bias, m[1])[1] for m in mods])
-        h1 = self._conv("%s.l1" % gname, [x], w1, b1, None, 1, 1, 0, 0.01)
-        # layers 2 and 3: groups
-        h2 = self._new("%s.l2" % gname, N, H, W, G * mid)
-        w2 = torch.cat([ops.pack_conv_weight(_fold(m[3].weight, m[3].bias, m[4])[0].cpu())[0] for m in mods]).to(self.dev)
-        b2 = torch.cat([_fold(m[3].weight, m[3].bias, m[4])[1] for m in mods]).to(self.dev).contiguous()
-        rows3 = (A + 15) // 16 * 16
+        # one fused kernel: the 256-channel intermediates never leave the SM (csrc/heads.cu)
+        rows3 = 48
+        assert mid == 256 and A <= rows3 and x.c in (64, 128)
+        f1 = [_fold(m[0].weight, m[0].bias, m[1]) for m in mods]
+        f2 = [_fold(m[3].weight, m[3].bias, m[4]) for m in mods]
+        w1 = torch.cat([ops.pack_conv_weight(w.cpu())[0] for w, _ in f1]).to(self.dev).contiguous()
+        b1 = torch.cat([b for _, b in f1]).to(self.dev).float().contiguous()
+        w2 = torch.cat([ops.pack_conv_weight(w.cpu())[0] for w, _ in f2]).to(self.dev).contiguous()
+        b2 = torch.cat([b for _, b in f2]).to(self.dev).float().contiguous()
         w3 = torch.zeros(G * rows3, mid, dtype=torch.bfloat16)
         b3 = torch.zeros(G * rows3, dtype=torch.float32)
         for g, m in enumerate(mods):
             w3[g * rows3:g * rows3 + A] = ops.pack_conv_weight(m[6].weight.detach().float().cpu())[0]
             b3[g * rows3:g * rows3 + A] = m[6].bias.detach().float().cpu()
         w3, b3 = w3.to(self.dev), b3.to(self.dev)
-        h1t = h1.t
+        xt, xc, xoff = x.t, x.c, x.coff
 
         def run():
-            ops.conv2d_nhwc([(h1t, 0, mid)], w2, h2, R=1, S=1, Cout=mid, bias=b2, slope=0.01, groups=G, in_goff=[mid],
-                            weight_goff=mid, bias_goff=mid, out_goff=mid)
-            ops.conv2d_nhwc([(h2, 0, mid)], w3, heads_buf, R=1, S=1, Cout=A, bias=b3, slope=1.0, groups=G,
-                            in_goff=[mid], weight_goff=rows3, bias_goff=rows3, out_coff=slot0 * A, out_goff=A)
+            ops.head_mlp(xt, xoff, xc, w1, b1, w2, b2, w3, b3, G, A, rows3, heads_buf, slot0 * A, 0.01)
 
-        fl2 = 2.0 * N * H * W * G * mid * mid
-        fl3 = 2.0 * N * H * W * G * A * mid
-        by2 = N * H * W * G * mid * 2 * 2 + G * mid * mid * 2
-        by3 = N * H * W * G * (mid * 2 + A * 4) + G * A * mid * 2
-        self._add(run, 2, gname + ".l2l3", "conv_tma", fl2 + fl3, by2 + by3)
+        fl = 2.0 * N * H * W * G * (xc * mid + mid * mid + A * mid)
+        by = N * H * W * (xc * 2 + G * A * 4) + G * (xc * mid + mid * mid + A * mid) * 2
+        self._add(run, 1, gname + ".mlp", "head_mlp", fl, by)
 
     def _align(self, name, m, x, om):
         return self._conv(name, [x], m.align.weight, m.align.bias, None, m.align.kernel_size[0], 1, m.align.padding,

@@ -238,6 +238,15 @@ def center_align_om(fg_max, fg_arg, heads, x_coff, y_coff, anchors, feat_stride,
                                     fg_max.numel(), _stream()))
 
 
+def head_mlp(x, x_coff, cx, w1, b1, w2, b2, w3, b3, G, A, rows3, out, out_coff, slope=0.01):
+    """G fused three-layer 1x1 heads on x[..., x_coff:x_coff+cx] (bf16 NHWC) -> out[..., out_coff + g*A + a] (fp32 NHWC)."""
+    N, H, W, cs = x.shape
+    assert x.dtype == torch.bfloat16 and out.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
+    assert w1.shape == (G * 256, cx) and w2.shape == (G * 256, 256) and w3.shape == (G * rows3, 256)
+    check(lib().m3d_head_mlp(_p(x), N, H, W, cs, x_coff, cx, _p(w1), _p(b1), _p(w2), _p(b2), _p(w3), _p(b3), G, A, rows3,
+                             _p(out), out.shape[-1], out_coff, float(slope), _stream()))
+
+
 def flatten_heads(heads, A, slots, bbox_2d, bbox_3d):
     N, H, W, cs = heads.shape
     arr = (C.c_int * 11)(*slots)

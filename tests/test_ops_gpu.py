@@ -186,3 +186,44 @@ def test_anab_pool_and_attention(dtype):
     ops.anab_attention(_nhwc(q, dtype), ktok, vtok, _nhwc(x, dtype), scale.cuda(), shift.cuda(), 0.01, out, ck, cv)
     tol = 2e-5 * ref.abs().max().item() if dtype == torch.float32 else 2 ** -7 * ref.abs().max().item()
     assert (_nchw(out) - ref).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("shape", [(2, 12, 20, 128, 3), (1, 9, 37, 128, 1), (2, 48, 160, 128, 4), (1, 8, 16, 64, 2)])
+def test_head_mlp(shape):
+    """Fused three-layer 1x1 heads vs the layer-by-layer fp32 evaluation with the same bf16 roundings
+    (inputs / weights bf16, fp32 accumulation, intermediates rounded to bf16 after bias + LeakyReLU)."""
+    from m3dssd_b200 import ops
+    N, H, W, Cx, G = shape
+    A, rows3 = 36, 48
+    g = _g(11)
+    x = torch.randn(N, H, W, Cx + 64, generator=g).bfloat16()  # a channel window of a wider buffer
+    xoff = 64
+    w1 = (torch.randn(G * 256, Cx, generator=g) / Cx ** 0.5).bfloat16()
+    w2 = (torch.randn(G * 256, 256, generator=g) / 16).bfloat16()
+    w3 = torch.zeros(G * rows3, 256)
+    b3 = torch.zeros(G * rows3)
+    for k in range(G):
+        w3[k * rows3:k * rows3 + A] = torch.randn(A, 256, generator=g) / 16
+        b3[k * rows3:k * rows3 + A] = torch.randn(A, generator=g)
+    w3 = w3.bfloat16()
+    b1 = torch.randn(G * 256, generator=g)
+    b2 = torch.randn(G * 256, generator=g)
+    out = torch.full((N, H, W, 11 * A), 7.0, device="cuda")
+    coff = 2 * A
+    ops.head_mlp(x.cuda(), xoff, Cx, w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), w3.cuda(), b3.cuda(), G, A, rows3, out,
+                 coff, 0.01)
+    got = out.cpu()
+    xs = x[..., xoff:xoff + Cx].float().reshape(-1, Cx).double()
+    for k in range(G):
+        h1 = F.leaky_relu(xs @ w1[k * 256:(k + 1) * 256].double().t() + b1[k * 256:(k + 1) * 256].double(), 0.01)
+        h1 = h1.float().bfloat16().double()
+        h2 = F.leaky_relu(h1 @ w2[k * 256:(k + 1) * 256].double().t() + b2[k * 256:(k + 1) * 256].double(), 0.01)
+        h2 = h2.float().bfloat16().double()
+        ref = (h2 @ w3[k * rows3:k * rows3 + A].double().t() + b3[k * rows3:k * rows3 + A].double()).float()
+        o = got[..., coff + k * A:coff + (k + 1) * A].reshape(-1, A)
+        # a bf16 rounding of an intermediate can flip on an fp32-accumulation-order difference: 1 bf16 ulp of one
+        # of 256 terms, i.e. ~2^-9 * |h| * |w| ~ 1e-3 absolute; typical error is ~1e-5
+        assert (o - ref).abs().max().item() < 5e-3 * max(1.0, ref.abs().max().item()), k
+        assert (o - ref).abs().mean().item() < 2e-4
+    # untouched channels stay untouched
+    assert torch.all(got[..., :coff] == 7.0) and torch.all(got[..., coff + G * A:] == 7.0)
