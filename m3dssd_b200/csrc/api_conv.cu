@@ -74,6 +74,24 @@ int make_tmap_b3d(CUtensorMap* map, const void* base, long rows, long cols, int 
   return M3D_OK;
 }
 
+// Packed bf16 weights [rows][K] of a 3x3 conv, K = ((r*3+s)*nchunk + c)*64 + ch, as (64, rows, 3*nchunk, 3):
+// box {64, bn, 1, 3} brings the three kernel rows r of one (s, chunk) as consecutive [bn][64] tiles (conv_halo.cu).
+int make_tmap_b_halo(CUtensorMap* map, const void* base, long rows, int nchunk, int bn) {
+  auto enc = get_encode();
+  M3D_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  const cuuint64_t K = static_cast<cuuint64_t>(9) * nchunk * 64;
+  cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(3 * nchunk), 3};
+  cuuint64_t strides[3] = {K * 2, 128, static_cast<cuuint64_t>(3 * nchunk) * 128};
+  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bn), 1, 3};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  M3D_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(halo weights rows=%ld nchunk=%d bn=%d) failed: %d", rows, nchunk,
+              bn, static_cast<int>(r));
+  return M3D_OK;
+}
+
 // NHWC bf16 activation as (bk, W, H, N, C/bk): box {bk, tw*stride, th*stride, 1, ksub} lands as ksub
 // consecutive [th*tw][bk] channel-chunk tiles of the same window.
 int make_tmap_nhwc5(CUtensorMap* map, const void* base, int N, int H, int W, int C, int bk, int tw, int th, int stride,
@@ -160,6 +178,8 @@ static int sm_count() {
 }
 
 int launch_conv_simt_f32(const m3d_conv_desc* d, int P, int Q, cudaStream_t stream);
+bool conv_halo_supported(int BN, int out_dtype, bool staged);
+int launch_conv_halo(const ConvTmaParams& p, int BN, int out_dtype, bool staged, cudaStream_t stream);
 
 static int pick_bn(int cout, int bk, long m_tiles, bool gather, bool split) {
   if (bk == 16) return cout <= 16 ? 16 : 32;
@@ -280,18 +300,43 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
         if (rc2 != M3D_OK) return rc2;
       }
     }
+    // 3x3 stride-1 convs: one (TH+2)-row window per kernel column serves its three taps (conv_halo.cu)
+    const bool halo = d->R == 3 && d->S == 3 && d->stride == 1 && d->dil == 1 && d->pad == 1 && d->num_inputs == 1 &&
+                      groups == 1 && bk == 64 && d->out_h <= 0 && d->out_w <= 0 && TW <= 16 &&
+                      d->in_cstride[0] % 8 == 0 && d->in_coff[0] % 8 == 0 &&
+                      conv_halo_supported(BN, d->out_dtype == M3D_F32 ? DT_F32 : DT_BF16, staged) &&
+                      getenv("M3D_NO_HALO") == nullptr;
+    if (halo) {
+      int rc = make_tmap_nhwc(&p.tmap_a[0], d->in[0], d->N, d->H, d->W, d->in_cstride[0], 64, TW, TH + 2, 1);
+      if (rc != M3D_OK) return rc;
+      rc = make_tmap_b_halo(&p.tmap_b, d->weight, d->weight_rows, d->in_c[0] / 64, BN);
+      if (rc != M3D_OK) return rc;
+      p.num_inputs = 1;
+      p.chunks[0] = d->in_c[0] / 64;
+      p.a_coff[0] = d->in_coff[0];
+      p.R = 3, p.S = 3, p.stride = 1, p.pad = 1, p.dil = 1;
+      p.N = d->N, p.P = P, p.Q = Q;
+      p.TW = TW, p.TH = TH, p.tiles_w = tiles_w, p.tiles_h = tiles_h;
+      p.Cout = d->Cout, p.n_tiles = n_tiles, p.groups = 1;
+      p.out = d->out, p.out_cstride = d->out_cstride, p.out_coff = d->out_coff;
+      p.bias = d->bias;
+      p.res = d->res, p.res_cstride = d->res_cstride, p.res_coff = d->res_coff;
+      p.slope = d->slope;
+      p.total_tiles = static_cast<int>(total_tiles);
+      return launch_conv_halo(p, BN, d->out_dtype == M3D_F32 ? DT_F32 : DT_BF16, staged, stream);
+    }
     // k-blocks per pipeline stage: enough tensor-pipe clocks per stage (N/2 per k16) to cover the
     // issue cost of the stage's barrier hand-shakes and TMA instructions
     const long total_kb = ktot / bk;
     int ksub = 1;
-    if (staged || (bk == 64 && (BN == 32 || BN == 48))) {
+    if (staged) {
       for (int k = (BN >= 256 ? 1 : (BN >= 128 ? 2 : 4)); k > 1; --k)
         if (total_kb % k == 0) {
           ksub = k;
           break;
         }
       const char* e = getenv("M3D_KSUB");  // development override
-      if (e != nullptr && atoi(e) >= 1 && total_kb % atoi(e) == 0 && (atoi(e) <= 2 || BN <= 64)) ksub = atoi(e);
+      if (e != nullptr && atoi(e) >= 1 && total_kb % atoi(e) == 0 && (atoi(e) <= 2 || BN == 64)) ksub = atoi(e);
     }
     bool wide = ksub > 1;
     for (int i = 0; i < d->num_inputs; ++i) {

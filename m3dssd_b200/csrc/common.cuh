@@ -24,3 +24,43 @@ void set_last_error(const char* fmt, ...);
       return M3D_ERR_INVALID;                 \
     }                                         \
   } while (0)
+
+// Kernel launch with programmatic dependent launch (PDL): the grid may be scheduled while its predecessor
+// in the stream drains (SM by SM), runs its prologue (barrier init, TMEM allocation, descriptor prefetch)
+// and blocks in griddepcontrol.wait until the predecessor has completed and flushed.  Only kernels that
+// execute m3d::grid_dep_sync() before their first global access may be launched this way.
+// M3D_PDL=0 falls back to ordinary stream serialisation.
+#ifdef __CUDACC__
+#include <cstdlib>
+#include <utility>
+namespace m3d {
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("M3D_PDL");
+    on = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  return on == 1;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+// Device side: let the successor start launching, then wait for the predecessor's results.
+__device__ __forceinline__ void grid_dep_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+}  // namespace m3d
+#endif

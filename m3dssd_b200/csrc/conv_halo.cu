@@ -1,0 +1,243 @@
+// 3x3 stride-1 convolution with a vertically shared A window.
+//
+// The plain implicit-GEMM kernel (igemm.cu) fetches one 128-pixel A tile per tap: 9 x 16 KB per 64-channel chunk,
+// and the SM's ~64 B/clk L2 port -- not the tensor pipe -- bounds every layer whose N is small (A bytes per
+// tensor clock = 8192 / N).  Here a pipeline stage is (kernel column s, channel chunk): ONE TMA box of
+// (TH + 2) x TW pixels serves the three taps r = 0, 1, 2 of that column, because with TW a multiple of 8 the
+// tile for tap r is the same shared-memory image shifted by r * TW rows = a whole number of 1024-byte
+// swizzle atoms: the UMMA descriptor just starts r * TW * 128 bytes later.  A traffic drops 3 * TH / (TH + 2)
+// = 2.4x (TH = 8); the stage's three weight k-blocks arrive as one 4-D TMA box.  12 MMAs per stage also
+// amortise the barrier hand-shakes.  Same warp roles / TMEM double buffering / epilogues as conv_tma_kernel.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "igemm.cuh"
+#include "ptx.cuh"
+
+namespace m3d {
+
+namespace {
+
+__host__ __device__ constexpr int halo_acc_cols(int bn) { return bn <= 32 ? 32 : (bn <= 64 ? 64 : (bn <= 128 ? 128 : 256)); }
+
+template <int BN, bool STAGED>
+struct HaloCfg {
+  static constexpr int A_ROWS = 160;                 // (TH + 2) * TW with TH * TW = 128, TH = 8... see host
+  static constexpr int A_BYTES = 20 * 1024;          // host guarantees (TH + 2) * TW * 128 <= A_BYTES
+  static constexpr int B_BYTES = BN * 128;           // one tap
+  static constexpr int STAGE = A_BYTES + 3 * B_BYTES;
+  static constexpr int EXTRA = STAGED ? (2 * kSlabBytes + 1024) : 0;
+  static constexpr int BUDGET = 225 * 1024 + 512 - EXTRA;
+  static constexpr int FIT = BUDGET / STAGE;
+  static constexpr int STAGES = FIT >= 6 ? 6 : FIT;
+  static constexpr int SMEM = STAGES * STAGE + EXTRA + 1024 + 256;
+  static constexpr int ACC = halo_acc_cols(BN);
+  static_assert(STAGES >= 2, "halo conv tile does not fit shared memory");
+  static_assert(B_BYTES % 1024 == 0, "weight tap tiles must keep the 1024-byte swizzle alignment");
+};
+
+struct HTile {
+  int nt, n, p0, q0;
+};
+__device__ __forceinline__ HTile htile(int tile, const ConvTmaParams& p) {
+  HTile t;
+  t.nt = tile % p.n_tiles;
+  int r = tile / p.n_tiles;
+  const int tw = r % p.tiles_w;
+  r /= p.tiles_w;
+  const int th = r % p.tiles_h;
+  t.n = r / p.tiles_h;
+  t.p0 = th * p.TH;
+  t.q0 = tw * p.TW;
+  return t;
+}
+
+template <int BN, typename OutT, bool STAGED>
+__global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant__ ConvTmaParams p) {
+  using Cfg = HaloCfg<BN, STAGED>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* stage_out = smem + STAGES * Cfg::STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE + Cfg::EXTRA);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* res_bar = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 128);
+      mbar_init(&res_bar[s], 1);
+    }
+    fence_barrier_init();
+    prefetch_tmap(&p.tmap_a[0]);
+    prefetch_tmap(&p.tmap_b);
+    if (STAGED) prefetch_tmap(&p.tmap_out);
+  }
+  if (warp == 1) tmem_alloc<2 * Cfg::ACC>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  grid_dep_sync();
+
+  const int nchunk = p.chunks[0];
+  const int n_stages = 3 * nchunk;  // (s, chunk) pairs
+  const uint32_t a_bytes = static_cast<uint32_t>((p.TH + 2) * p.TW * 128);
+  const uint32_t tap_shift = static_cast<uint32_t>(p.TW * 128) >> 4;  // descriptor units (16 B) per kernel row
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const HTile t = htile(tile, p);
+      const int brow = t.nt * BN;
+      int s = 0, c = 0;
+      for (int st = 0; st < n_stages; ++st) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* sa = smem + stage * Cfg::STAGE;
+          mbar_arrive_expect_tx(&full[stage], a_bytes + 3 * Cfg::B_BYTES);
+          tma_load_4d(sa, &p.tmap_a[0], &full[stage], p.a_coff[0] + c * 64, t.q0 - 1 + s, t.p0 - 1, t.n);
+          tma_load_4d(sa + Cfg::A_BYTES, &p.tmap_b, &full[stage], 0, brow, s * nchunk + c, 0);
+        }
+        __syncwarp();
+        if (++c == nchunk) c = 0, ++s;
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16(BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + as * Cfg::ACC;
+      for (int st = 0; st < n_stages; ++st) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE);
+          const uint64_t da = umma_smem_desc<128>(sa);
+          const uint64_t db = umma_smem_desc<128>(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(tmem_acc, da + r * tap_shift + 2 * k, db + r * (Cfg::B_BYTES >> 4) + 2 * k, idesc,
+                       (st | r | k) != 0);
+          }
+          umma_commit(&empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (elect_one()) umma_commit(&tfull[as]);
+      __syncwarp();
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int ep_tid = threadIdx.x - 64;
+    StagedEpilogue st;
+    if constexpr (STAGED) st.init(stage_out, reinterpret_cast<float*>(stage_out + 2 * kSlabBytes), res_bar);
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+      const HTile t = htile(tile, p);
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      if constexpr (STAGED) {
+        const int col0 = t.nt * BN;
+        epilogue_tile_staged<BN>(st, tmem_base + as * Cfg::ACC, quarter, lane, ep_tid, t.n, t.p0, t.q0, &p.tmap_out,
+                                 p.out_coff + col0, p.res ? &p.tmap_res : nullptr, p.res_coff + col0,
+                                 p.bias ? p.bias + col0 : nullptr, p.Cout - col0, p.slope, [&]() {
+                                   tc_fence_before();
+                                   mbar_arrive(&tempty[as]);
+                                 });
+      } else {
+        const __nv_bfloat16* res = p.res ? static_cast<const __nv_bfloat16*>(p.res) + p.res_coff : nullptr;
+        OutT* out = static_cast<OutT*>(p.out) + p.out_coff;
+        epilogue_tile_direct<BN, OutT, __nv_bfloat16>(tmem_base + as * Cfg::ACC, quarter, lane, t.n, t.p0, t.q0, p.TW,
+                                                      p.P, p.Q, t.nt * BN, p.Cout, p.bias, res, p.res_cstride, out,
+                                                      p.out_cstride, p.slope);
+        tc_fence_before();
+        mbar_arrive(&tempty[as]);
+      }
+    }
+    if (STAGED && ep_tid == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<2 * Cfg::ACC>(tmem_base);
+  }
+}
+
+template <int BN, typename OutT, bool STAGED>
+int launch_t(const ConvTmaParams& p, cudaStream_t stream) {
+  using Cfg = HaloCfg<BN, STAGED>;
+  auto kern = conv_halo_kernel<BN, OutT, STAGED>;
+  static bool configured = false;
+  if (!configured) {
+    M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    configured = true;
+  }
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int per_sm = (2 * (Cfg::SMEM + 1024) <= 227 * 1024 && 4 * Cfg::ACC <= 512) ? 2 : 1;
+  int grid = sms * per_sm;
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  M3D_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(192), Cfg::SMEM, stream, p));
+  return M3D_OK;
+}
+
+}  // namespace
+
+// Packed bf16 weights [rows][K], K = (r, s, chunk, 64) as (64, rows, 3 * nchunk, 3): box {64, bn, 1, 3} brings the
+// three kernel rows of one (s, chunk) as consecutive [bn][64] tiles.
+int make_tmap_b_halo(CUtensorMap* map, const void* base, long rows, int nchunk, int bn);
+
+bool conv_halo_supported(int BN, int out_dtype, bool staged) {
+  if (staged) return out_dtype == DT_BF16 && (BN == 64 || BN == 128);
+  return BN == 32 || BN == 64;
+}
+
+int launch_conv_halo(const ConvTmaParams& p, int BN, int out_dtype, bool staged, cudaStream_t stream) {
+  if (staged) {
+    if (BN == 64) return launch_t<64, __nv_bfloat16, true>(p, stream);
+    if (BN == 128) return launch_t<128, __nv_bfloat16, true>(p, stream);
+    return M3D_ERR_UNSUPPORTED;
+  }
+  if (BN == 32)
+    return out_dtype == DT_BF16 ? launch_t<32, __nv_bfloat16, false>(p, stream) : launch_t<32, float, false>(p, stream);
+  if (BN == 64)
+    return out_dtype == DT_BF16 ? launch_t<64, __nv_bfloat16, false>(p, stream) : launch_t<64, float, false>(p, stream);
+  return M3D_ERR_UNSUPPORTED;
+}
+
+}  // namespace m3d

@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(kDcnThreads, 1) dcn_fused_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dep_sync();
 
   const int taps = p.R * p.S;
   const int nchunk = p.chunks[0];
@@ -153,7 +154,8 @@ __global__ void __launch_bounds__(kDcnThreads, 1) dcn_fused_kernel(const __grid_
               const bool hl_ok = h_low >= 0, wl_ok = w_low >= 0, hh_ok = h_high <= p.H - 1, wh_ok = w_high <= p.W - 1;
               const int rl = (t.n * p.H + (hl_ok ? h_low : 0)) * p.W, rh = (t.n * p.H + (hh_ok ? h_high : 0)) * p.W;
               const int cl = wl_ok ? w_low : 0, ch = wh_ok ? w_high : 0;
-              e.off = make_int4((rl + cl) * cs, (rl + ch) * cs, (rh + cl) * cs, (rh + ch) * cs);
+              // byte offsets of the four corner pixels (unsigned 32-bit: one IMAD.WIDE.U32 per load in the main loop)
+              e.off = make_int4((rl + cl) * cs * 2, (rl + ch) * cs * 2, (rh + cl) * cs * 2, (rh + ch) * cs * 2);
               e.w = make_float4((hl_ok && wl_ok) ? hh * hw * m : 0.f, (hl_ok && wh_ok) ? hh * lw * m : 0.f,
                                 (hh_ok && wl_ok) ? lh * hw * m : 0.f, (hh_ok && wh_ok) ? lh * lw * m : 0.f);
             }
@@ -176,11 +178,11 @@ __global__ void __launch_bounds__(kDcnThreads, 1) dcn_fused_kernel(const __grid_
         const Entry& e = table[(rbase + 64 * half) * taps + tap];
         const int4 o = e.off;
         cw[buf] = e.w;
-        const __nv_bfloat16* base = in0 + c * kBK + j * 8;
-        cv[buf][0] = __ldg(reinterpret_cast<const uint4*>(base + o.x));
-        cv[buf][1] = __ldg(reinterpret_cast<const uint4*>(base + o.y));
-        cv[buf][2] = __ldg(reinterpret_cast<const uint4*>(base + o.z));
-        cv[buf][3] = __ldg(reinterpret_cast<const uint4*>(base + o.w));
+        const char* base = reinterpret_cast<const char*>(in0 + c * kBK + j * 8);
+        cv[buf][0] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<uint32_t>(o.x)));
+        cv[buf][1] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<uint32_t>(o.y)));
+        cv[buf][2] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<uint32_t>(o.z)));
+        cv[buf][3] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<uint32_t>(o.w)));
       };
       auto blend = [&](int half, int buf, uint8_t* a_tile) {
         const float4 w4 = cw[buf];
@@ -316,8 +318,7 @@ int launch_t(const ConvGatherParams& p, cudaStream_t stream) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = sms;
   if (grid > p.total_tiles) grid = p.total_tiles;
-  kern<<<grid, kDcnThreads, Cfg::SMEM, stream>>>(p);
-  M3D_CUDA_OK(cudaGetLastError());
+  M3D_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kDcnThreads), Cfg::SMEM, stream, p));
   return M3D_OK;
 }
 
@@ -329,7 +330,8 @@ int launch_t(const ConvGatherParams& p, cudaStream_t stream) {
 bool dcn_fused_supported(const ConvGatherParams& p, int BN, int in_dtype, int out_dtype) {
   if (getenv("M3D_DCN_LEGACY") != nullptr) return false;
   return p.om != nullptr && p.stem_img == nullptr && p.num_inputs == 1 && in_dtype == DT_BF16 &&
-         out_dtype == DT_BF16 && (BN == 128 || BN == 256) && p.R * p.S == 9 && (p.TW & (p.TW - 1)) == 0;
+         out_dtype == DT_BF16 && (BN == 128 || BN == 256) && p.R * p.S == 9 && (p.TW & (p.TW - 1)) == 0 &&
+         static_cast<long>(p.N) * p.H * p.W * p.in_cstride[0] * 2 < (1L << 32);  // 32-bit byte offsets in the table
 }
 
 int launch_dcn_fused(const ConvGatherParams& p, int BN, cudaStream_t stream) {

@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(256) stem_conv7x7_kernel(const float* __restri
 template <typename T>
 __global__ void maxpool2x2_kernel(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int C,
                                   int in_cstride, int out_cstride) {
+  grid_dep_sync();  // PDL: launched while the previous kernel drains
   constexpr int V = 16 / sizeof(T);
   const int Ho = H / 2, Wo = W / 2, cv = C / V;
   const long total = static_cast<long>(N) * Ho * Wo * cv;
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(256) upsample_add_kernel(const T* __restrict__
                                                            const T* __restrict__ skip, T* __restrict__ out, int N, int H,
                                                            int W, int C, int f, int x_cstride, int skip_cstride,
                                                            int out_cstride) {
+  grid_dep_sync();  // PDL: launched while the previous kernel drains
   // grid = (segments of an output row, output row, image): 32-bit index math only
   constexpr int V = 16 / sizeof(T);
   const int k = 2 * f, pad = f / 2;
@@ -223,6 +225,7 @@ __global__ void __launch_bounds__(256) cls_softmax_kernel(const float* __restric
                                                           float* __restrict__ prob_out, float* __restrict__ fg_max,
                                                           int* __restrict__ fg_arg, float* __restrict__ score,
                                                           unsigned char* __restrict__ cls_pred) {
+  grid_dep_sync();  // PDL: launched while the previous kernel drains
   extern __shared__ float s_tile[];  // [SM_PIX][K*A + 1]
   const int KA = K * A, ld = KA + 1;
   const int w0 = blockIdx.x * SM_PIX, h = blockIdx.y, n = blockIdx.z;
@@ -292,6 +295,7 @@ __global__ void __launch_bounds__(256) cls_softmax_kernel(const float* __restric
 __global__ void shape_align_om_kernel(const float* __restrict__ fg_max, const int* __restrict__ fg_arg,
                                       const float* __restrict__ anchors, int anchor_ld, float feat_stride, float thresh,
                                       float* __restrict__ om, long npix) {
+  grid_dep_sync();  // PDL: launched while the previous kernel drains
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (i >= npix) return;
   const float fg = fg_max[i];
@@ -319,6 +323,7 @@ __global__ void center_align_om_kernel(const float* __restrict__ fg_max, const i
                                        const float* __restrict__ anchors, int anchor_ld, float feat_stride,
                                        float mean_x, float mean_y, float std_x, float std_y, float thresh,
                                        float* __restrict__ om, int om_cstride, long npix) {
+  grid_dep_sync();  // PDL: launched while the previous kernel drains
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (i >= npix) return;
   const float fg = fg_max[i];
@@ -345,6 +350,7 @@ struct HeadSlots {
 __global__ void __launch_bounds__(256) flatten_heads_kernel(const float* __restrict__ heads, int hc_stride, int N, int H,
                                                             int W, int A, const HeadSlots slots,
                                                             float* __restrict__ bbox_2d, float* __restrict__ bbox_3d) {
+  grid_dep_sync();  // PDL: launched while the previous kernel drains
   extern __shared__ float s_tile[];  // [SM_PIX][11*A + 1]
   const int C = 11 * A, ld = C + 1;
   const int w0 = blockIdx.x * SM_PIX, h = blockIdx.y, n = blockIdx.z;
@@ -447,11 +453,11 @@ extern "C" int m3d_maxpool2x2_nhwc(const void* in, void* out, int dtype, int N, 
   const long total = static_cast<long>(N) * (H / 2) * (W / 2) * (C / V);
   const int grid = static_cast<int>(std::min<long>((total + 255) / 256, 148L * 16));
   if (dtype == M3D_BF16)
-    maxpool2x2_kernel<__nv_bfloat16><<<grid, 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(in),
-                                                                  static_cast<__nv_bfloat16*>(out), N, H, W, C, in_cstride, out_cstride);
+    M3D_CUDA_OK(launch_pdl(maxpool2x2_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, S(stream), static_cast<const __nv_bfloat16*>(in),
+                                                                  static_cast<__nv_bfloat16*>(out), N, H, W, C, in_cstride, out_cstride));
   else
-    maxpool2x2_kernel<float><<<grid, 256, 0, S(stream)>>>(static_cast<const float*>(in), static_cast<float*>(out), N, H,
-                                                          W, C, in_cstride, out_cstride);
+    M3D_CUDA_OK(launch_pdl(maxpool2x2_kernel<float>, dim3(grid), dim3(256), 0, S(stream), static_cast<const float*>(in), static_cast<float*>(out), N, H,
+                                                          W, C, in_cstride, out_cstride));
   M3D_CUDA_OK(cudaGetLastError());
   return M3D_OK;
 }
@@ -468,13 +474,13 @@ extern "C" int m3d_upsample_add_nhwc(const void* x, const float* weight, const v
   const dim3 grid(static_cast<unsigned>((static_cast<long>(W) * f * (C / V) + 255) / 256), static_cast<unsigned>(H * f),
                   static_cast<unsigned>(N));
   if (dtype == M3D_BF16)
-    upsample_add_kernel<__nv_bfloat16><<<grid, 256, 0, S(stream)>>>(
+    M3D_CUDA_OK(launch_pdl(upsample_add_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, S(stream), 
         static_cast<const __nv_bfloat16*>(x), weight, static_cast<const __nv_bfloat16*>(skip),
-        static_cast<__nv_bfloat16*>(out), N, H, W, C, f, x_cstride, skip_cstride, out_cstride);
+        static_cast<__nv_bfloat16*>(out), N, H, W, C, f, x_cstride, skip_cstride, out_cstride));
   else
-    upsample_add_kernel<float><<<grid, 256, 0, S(stream)>>>(static_cast<const float*>(x), weight,
+    M3D_CUDA_OK(launch_pdl(upsample_add_kernel<float>, dim3(grid), dim3(256), 0, S(stream), static_cast<const float*>(x), weight,
                                                             static_cast<const float*>(skip), static_cast<float*>(out), N,
-                                                            H, W, C, f, x_cstride, skip_cstride, out_cstride);
+                                                            H, W, C, f, x_cstride, skip_cstride, out_cstride));
   M3D_CUDA_OK(cudaGetLastError());
   return M3D_OK;
 }
@@ -487,8 +493,8 @@ extern "C" int m3d_cls_softmax(const float* logits, int logits_cstride, int N, i
   const size_t smem = static_cast<size_t>(SM_PIX) * (K * A + 1) * sizeof(float);
   M3D_REQUIRE(smem <= 48 * 1024, "K*A too large");
   dim3 grid(cdiv(W, SM_PIX), H, N);
-  cls_softmax_kernel<<<grid, 256, smem, S(stream)>>>(logits, logits_cstride, N, H, W, A, K, cls_out, prob_out, fg_max,
-                                                     fg_arg, score, cls_pred);
+  M3D_CUDA_OK(launch_pdl(cls_softmax_kernel, dim3(grid), dim3(256), smem, S(stream), logits, logits_cstride, N, H, W, A, K, cls_out, prob_out, fg_max,
+                                                     fg_arg, score, cls_pred));
   M3D_CUDA_OK(cudaGetLastError());
   return M3D_OK;
 }
@@ -496,8 +502,8 @@ extern "C" int m3d_cls_softmax(const float* logits, int logits_cstride, int N, i
 extern "C" int m3d_shape_align_om(const float* fg_max, const int* fg_arg, const float* anchors, int anchor_ld,
                                   float feat_stride, float thresh, float* om, long npix, m3d_stream_t stream) {
   M3D_REQUIRE(fg_max && fg_arg && anchors && om, "NULL pointer");
-  shape_align_om_kernel<<<cdiv(npix, 256), 256, 0, S(stream)>>>(fg_max, fg_arg, anchors, anchor_ld, feat_stride, thresh,
-                                                                om, npix);
+  M3D_CUDA_OK(launch_pdl(shape_align_om_kernel, dim3(cdiv(npix, 256)), dim3(256), 0, S(stream), fg_max, fg_arg, anchors, anchor_ld, feat_stride, thresh,
+                                                                om, npix));
   M3D_CUDA_OK(cudaGetLastError());
   return M3D_OK;
 }
@@ -508,9 +514,9 @@ extern "C" int m3d_center_align_om(const float* fg_max, const int* fg_arg, const
                                    int om_cstride, long npix, m3d_stream_t stream) {
   M3D_REQUIRE(fg_max && fg_arg && heads && anchors && om, "NULL pointer");
   M3D_REQUIRE(om_cstride >= 3, "om_cstride=%d", om_cstride);
-  center_align_om_kernel<<<cdiv(npix, 256), 256, 0, S(stream)>>>(fg_max, fg_arg, heads, heads_cstride, x_coff, y_coff,
+  M3D_CUDA_OK(launch_pdl(center_align_om_kernel, dim3(cdiv(npix, 256)), dim3(256), 0, S(stream), fg_max, fg_arg, heads, heads_cstride, x_coff, y_coff,
                                                                  anchors, anchor_ld, feat_stride, mean_x, mean_y, std_x,
-                                                                 std_y, thresh, om, om_cstride, npix);
+                                                                 std_y, thresh, om, om_cstride, npix));
   M3D_CUDA_OK(cudaGetLastError());
   return M3D_OK;
 }
@@ -531,7 +537,7 @@ extern "C" int m3d_flatten_heads(const float* heads, int heads_cstride, int N, i
     configured = true;
   }
   dim3 grid(cdiv(W, SM_PIX), H, N);
-  flatten_heads_kernel<<<grid, 256, smem, S(stream)>>>(heads, heads_cstride, N, H, W, A, slots, bbox_2d, bbox_3d);
+  M3D_CUDA_OK(launch_pdl(flatten_heads_kernel, dim3(grid), dim3(256), smem, S(stream), heads, heads_cstride, N, H, W, A, slots, bbox_2d, bbox_3d));
   M3D_CUDA_OK(cudaGetLastError());
   return M3D_OK;
 }

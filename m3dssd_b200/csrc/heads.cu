@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dep_sync();
 
   // contiguous, balanced share of the (tile, head) items: consecutive items of a CTA mostly share the x tile
   const int start = static_cast<int>(static_cast<long>(blockIdx.x) * p.total_items / gridDim.x);
@@ -416,8 +417,7 @@ extern "C" int m3d_head_mlp(const void* x, int N, int H, int W, int x_cstride, i
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = sms;
   if (grid > p.total_items) grid = p.total_items;
-  kern<<<grid, kHeadThreads, kHeadSmem, stream>>>(p);
-  M3D_CUDA_OK(cudaGetLastError());
+  M3D_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kHeadThreads), kHeadSmem, stream, p));
   return M3D_OK;
 }
 

@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(192, 1) conv_tma_kernel(const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dep_sync();  // everything above overlapped the previous kernel's tail
 
   int total_kb = 0;
   for (int i = 0; i < p.num_inputs; ++i) total_kb += p.R * p.S * p.chunks[i];
@@ -357,6 +358,7 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dep_sync();
 
   const int taps = p.R * p.S;
   int total_kb = 0;
@@ -376,19 +378,23 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
       // is the 8x8 window at (2Y-3, 2X-3); k-block kb = image channel kb, 16-byte chunk j = window row
       // j, its 8 elements = 8 consecutive image columns.  The image tile (3 x (2TH+6) x (2TW+6)) is
       // staged once per tile in shared memory with coalesced loads.
-      float* s_img = om_s;
       const int th2 = 2 * p.TH + 6, ld = 2 * p.TW + 8;  // TMA box: ld x th2 x 3 fp32, zero outside the image
-      uint32_t img_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(tile, p.n_tiles, p.tiles_w, p.tiles_h, p.N, p.TW, p.TH);
-        named_bar_sync(1, kProducerThreads);  // previous tile's readers are done
-        if (pt == 0) {
-          mbar_arrive_expect_tx(&res_bar[1], static_cast<uint32_t>(3 * th2 * ld * 4));
-          // x origin 2*q0 - 4 keeps the innermost coordinate 16-byte aligned (window columns start at +1)
-          tma_load_4d(s_img, &p.tmap_img, &res_bar[1], 2 * t.q0 - 4, 2 * t.p0 - 3, 0, t.n);
-        }
-        mbar_wait(&res_bar[1], img_phase);
-        img_phase ^= 1;
+      const uint32_t img_bytes = static_cast<uint32_t>(3 * th2 * ld * 4);
+      float* s_img2[2] = {om_s, om_s + ((img_bytes + 127) / 128) * 32};  // double-buffered (host checks the fit)
+      auto load_img = [&](int tl, int buf) {
+        const TileCoord tn = decode_tile(tl, p.n_tiles, p.tiles_w, p.tiles_h, p.N, p.TW, p.TH);
+        mbar_arrive_expect_tx(&res_bar[buf], img_bytes);
+        // x origin 2*q0 - 4 keeps the innermost coordinate 16-byte aligned (window columns start at +1)
+        tma_load_4d(s_img2[buf], &p.tmap_img, &res_bar[buf], 2 * tn.q0 - 4, 2 * tn.p0 - 3, 0, tn.n);
+      };
+      if (pt == 0 && blockIdx.x < p.total_tiles) load_img(blockIdx.x, 0);
+      int local = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+        const int buf = local & 1;
+        named_bar_sync(1, kProducerThreads);  // the previous tile's readers are done with the other buffer
+        if (pt == 0 && tile + gridDim.x < p.total_tiles) load_img(tile + gridDim.x, buf ^ 1);  // next tile's image
+        mbar_wait(&res_bar[buf], (local >> 1) & 1);
+        const float* s_img = s_img2[buf];
         for (int kb = 0; kb < 3; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* a_hi = smem + stage * Cfg::STAGE;
@@ -818,8 +824,7 @@ static int launch_tma_t(const ConvTmaParams& p, cudaStream_t stream) {
   const int per_sm = (2 * (Cfg::SMEM + 1024) <= 227 * 1024 && 4 * Cfg::ACC <= 512) ? 2 : 1;
   int grid = num_sms() * per_sm;
   if (grid > p.total_tiles) grid = p.total_tiles;
-  kern<<<grid, 192, Cfg::SMEM, stream>>>(p);
-  M3D_CUDA_OK(cudaGetLastError());
+  M3D_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(192), Cfg::SMEM, stream, p));
   return M3D_OK;
 }
 
@@ -841,18 +846,6 @@ int launch_conv_tma(const ConvTmaParams& p, int BN, int BK, int ksub, int out_dt
   M3D_TMA_STAGED(128, 2)
   M3D_TMA_STAGED(256, 1)
   M3D_TMA_STAGED(256, 2)
-#define M3D_TMA_SMALLN(bn, ks)                                                                \
-  if (!staged && BN == bn && BK == 64 && ksub == ks) {                                        \
-    return out_dtype == DT_BF16 ? launch_tma_t<bn, 64, ks, __nv_bfloat16, false>(p, stream)   \
-                                : launch_tma_t<bn, 64, ks, float, false>(p, stream);          \
-  }
-  M3D_TMA_SMALLN(32, 2)
-  M3D_TMA_SMALLN(32, 3)
-  M3D_TMA_SMALLN(32, 4)
-  M3D_TMA_SMALLN(48, 2)
-  M3D_TMA_SMALLN(48, 3)
-  M3D_TMA_SMALLN(48, 4)
-#undef M3D_TMA_SMALLN
   M3D_TMA_CASE(16, 16)
   M3D_TMA_CASE(32, 16)
   M3D_TMA_CASE(32, 32)
@@ -878,8 +871,7 @@ static int launch_gather_t(const ConvGatherParams& p, cudaStream_t stream) {
   }
   int grid = num_sms();
   if (grid > p.total_tiles) grid = p.total_tiles;
-  kern<<<grid, 448, Cfg::SMEM, stream>>>(p);
-  M3D_CUDA_OK(cudaGetLastError());
+  M3D_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(448), Cfg::SMEM, stream, p));
   return M3D_OK;
 }
 
