@@ -36,6 +36,11 @@ enum { M3D_BF16 = 0, M3D_F32 = 1, M3D_BF16X3 = 2 };
 
 const char* m3d_last_error(void);
 int m3d_version(void);
+/* Cap the number of SMs the persistent tensor-core kernels launched (or graph-captured) after this call occupy;
+ * 0 = the whole device.  The engine leaves one SM per image free while the detection tail of the previous batch
+ * (one CTA per image, minutes of L2 latency each) runs under the trunk of the next: a persistent CTA needs a
+ * whole SM's shared memory, so a grid of all SMs would otherwise run as two waves. */
+int m3d_set_sm_limit(int sms);
 
 /* ------------------------------------------------------------------------
  * Engine-level convolution / DCNv2 on NHWC activations (tcgen05 implicit GEMM).

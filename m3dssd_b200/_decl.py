@@ -17,6 +17,7 @@ _SIGS = {
     "m3d_cls_softmax": [vp, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp],
     "m3d_shape_align_om": [vp, vp, vp, i, f, f, vp, lg, vp],
     "m3d_center_align_om": [vp, vp, vp, i, i, i, vp, i, f, f, f, f, f, f, vp, i, lg, vp],
+    "m3d_set_sm_limit": [i],
     "m3d_head_mlp": [vp, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, i, i, i, vp, i, i, f, vp],
     "m3d_flatten_heads": [vp, i, i, i, i, i, vp, vp, vp, vp],
     "m3d_anab_pool": [vp, i, i, i, i, i, i, i, vp, vp, sz, vp, vp, vp],

@@ -232,6 +232,20 @@ extern "C" int m3d_stem_conv7x7_s2d(const float* image, const void* weight, cons
   return launch_conv_gather(p, 64, DT_BF16, DT_BF16, true, stream);
 }
 
+namespace m3d {
+static int g_sm_limit = 0;
+int persistent_sms() {
+  const int all = sm_count();
+  return (g_sm_limit > 0 && g_sm_limit < all) ? g_sm_limit : all;
+}
+}  // namespace m3d
+
+extern "C" int m3d_set_sm_limit(int sms) {
+  M3D_REQUIRE(sms >= 0, "sm limit must be >= 0 (0 = the whole device)");
+  m3d::g_sm_limit = sms;
+  return M3D_OK;
+}
+
 extern "C" const char* m3d_last_error(void) { return g_last_error; }
 extern "C" int m3d_version(void) { return 100; }
 

@@ -6,6 +6,8 @@
 
 namespace m3d {
 void set_last_error(const char* fmt, ...);
+// SMs the persistent kernels launched from now on may occupy (m3d_set_sm_limit; default: all of the device)
+int persistent_sms();
 }
 
 #define M3D_CUDA_OK(expr)                                                                     \

@@ -10,6 +10,8 @@
 // amortise the barrier hand-shakes.  Same warp roles / TMEM double buffering / epilogues as conv_tma_kernel.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "igemm.cuh"
@@ -21,13 +23,17 @@ namespace {
 
 __host__ __device__ constexpr int halo_acc_cols(int bn) { return bn <= 32 ? 32 : (bn <= 64 ? 64 : (bn <= 128 ? 128 : 256)); }
 
-template <int BN, bool STAGED>
+// BRES: the whole weight matrix (9 taps x BN x 64 channels, Cin = 64 layers) is loaded once per CTA and stays in
+// shared memory; stages then carry only the 20 KB A window (level0 / level2: 50+ tiles per CTA re-used 72 KB of
+// weights per tile through the L2 port).
+template <int BN, bool STAGED, bool BRES>
 struct HaloCfg {
   static constexpr int A_ROWS = 160;                 // (TH + 2) * TW with TH * TW = 128, TH = 8... see host
   static constexpr int A_BYTES = 20 * 1024;          // host guarantees (TH + 2) * TW * 128 <= A_BYTES
   static constexpr int B_BYTES = BN * 128;           // one tap
-  static constexpr int STAGE = A_BYTES + 3 * B_BYTES;
-  static constexpr int EXTRA = STAGED ? (2 * kSlabBytes + 1024) : 0;
+  static constexpr int STAGE = A_BYTES + (BRES ? 0 : 3 * B_BYTES);
+  static constexpr int RES_BYTES = BRES ? 9 * B_BYTES : 0;
+  static constexpr int EXTRA = (STAGED ? (2 * kSlabBytes + 1024) : 0) + RES_BYTES;
   static constexpr int BUDGET = 225 * 1024 + 512 - EXTRA;
   static constexpr int FIT = BUDGET / STAGE;
   static constexpr int STAGES = FIT >= 6 ? 6 : FIT;
@@ -40,33 +46,31 @@ struct HaloCfg {
 struct HTile {
   int nt, n, p0, q0;
 };
-__device__ __forceinline__ HTile htile(int tile, const ConvTmaParams& p) {
+__device__ __forceinline__ HTile htile(const TileWalk& w, const ConvTmaParams& p) {
   HTile t;
-  t.nt = tile % p.n_tiles;
-  int r = tile / p.n_tiles;
-  const int tw = r % p.tiles_w;
-  r /= p.tiles_w;
-  const int th = r % p.tiles_h;
-  t.n = r / p.tiles_h;
-  t.p0 = th * p.TH;
-  t.q0 = tw * p.TW;
+  t.nt = w.nt, t.n = w.n, t.p0 = w.th * p.TH, t.q0 = w.tw * p.TW;
   return t;
 }
+#define HALO_WALK_INIT TileWalk tw_; tw_.init(p.total_tiles, p.n_tiles, p.tiles_w, p.tiles_h, p.N)
+#define HALO_WALK_NEXT tw_.next(p.n_tiles, p.tiles_w, p.tiles_h, p.N)
 
-template <int BN, typename OutT, bool STAGED>
-__global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant__ ConvTmaParams p) {
-  using Cfg = HaloCfg<BN, STAGED>;
+template <int BN, typename OutT, bool STAGED, bool BRES>
+__global__ void __launch_bounds__(STAGED ? 320 : 192, 1) conv_halo_kernel(const __grid_constant__ ConvTmaParams p) {
+  using Cfg = HaloCfg<BN, STAGED, BRES>;
+  constexpr int NW = STAGED ? 8 : 4;  // epilogue warps (see conv_tma_kernel)
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* stage_out = smem + STAGES * Cfg::STAGE;
+  uint8_t* b_res = smem + STAGES * Cfg::STAGE;               // BRES: [s][r][BN][64] resident weights
+  uint8_t* stage_out = b_res + Cfg::RES_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE + Cfg::EXTRA);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = tfull + 2;
   uint64_t* res_bar = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
+  uint64_t* bres_bar = res_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -78,9 +82,10 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 128);
+      mbar_init(&tempty[s], NW);  // one arrival per epilogue warp
       mbar_init(&res_bar[s], 1);
     }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
     prefetch_tmap(&p.tmap_a[0]);
     prefetch_tmap(&p.tmap_b);
@@ -101,17 +106,23 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
   if (warp == 0) {
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const HTile t = htile(tile, p);
+    if (BRES && elect_one()) {  // nchunk == 1, n_tiles == 1: the whole weight matrix, once
+      mbar_arrive_expect_tx(bres_bar, 9 * Cfg::B_BYTES);
+      for (int s = 0; s < 3; ++s) tma_load_4d(b_res + s * 3 * Cfg::B_BYTES, &p.tmap_b, bres_bar, 0, 0, s, 0);
+    }
+    __syncwarp();
+    HALO_WALK_INIT;
+    for (int tile = tw_.first; tile < tw_.last; ++tile, HALO_WALK_NEXT) {
+      const HTile t = htile(tw_, p);
       const int brow = t.nt * BN;
       int s = 0, c = 0;
       for (int st = 0; st < n_stages; ++st) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::STAGE;
-          mbar_arrive_expect_tx(&full[stage], a_bytes + 3 * Cfg::B_BYTES);
-          tma_load_4d(sa, &p.tmap_a[0], &full[stage], p.a_coff[0] + c * 64, t.q0 - 1 + s, t.p0 - 1, t.n);
-          tma_load_4d(sa + Cfg::A_BYTES, &p.tmap_b, &full[stage], 0, brow, s * nchunk + c, 0);
+          mbar_arrive_expect_tx(&full[stage], ((p.dbg & 1) ? 0 : a_bytes) + (BRES ? 0 : 3 * Cfg::B_BYTES));
+          if (!(p.dbg & 1)) tma_load_4d(sa, &p.tmap_a[0], &full[stage], p.a_coff[0] + c * 64, t.q0 - 1 + s, t.p0 - 1, t.n);
+          if (!BRES) tma_load_4d(sa + Cfg::A_BYTES, &p.tmap_b, &full[stage], 0, brow, s * nchunk + c, 0);
         }
         __syncwarp();
         if (++c == nchunk) c = 0, ++s;
@@ -126,7 +137,9 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+    if (BRES) mbar_wait(bres_bar, 0);
+    HALO_WALK_INIT;
+    for (int tile = tw_.first; tile < tw_.last; ++tile, ++local) {
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
       mbar_wait(&tempty[as], aphase ^ 1);
@@ -138,12 +151,13 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE);
           const uint64_t da = umma_smem_desc<128>(sa);
-          const uint64_t db = umma_smem_desc<128>(sa + Cfg::A_BYTES);
+          // resident weights: stage st == kernel column s (nchunk == 1)
+          const uint64_t db = umma_smem_desc<128>(BRES ? smem_u32(b_res) + st * 3 * Cfg::B_BYTES : sa + Cfg::A_BYTES);
 #pragma unroll
           for (int r = 0; r < 3; ++r) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_f16(tmem_acc, da + r * tap_shift + 2 * k, db + r * (Cfg::B_BYTES >> 4) + 2 * k, idesc,
+              if (!(p.dbg & 8)) umma_f16(tmem_acc, da + r * tap_shift + 2 * k, db + r * (Cfg::B_BYTES >> 4) + 2 * k, idesc,
                        (st | r | k) != 0);
           }
           umma_commit(&empty[stage]);
@@ -163,19 +177,27 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
     StagedEpilogue st;
     if constexpr (STAGED) st.init(stage_out, reinterpret_cast<float*>(stage_out + 2 * kSlabBytes), res_bar);
     int local = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
-      const HTile t = htile(tile, p);
+    HALO_WALK_INIT;
+    for (int tile = tw_.first; tile < tw_.last; ++tile, ++local, HALO_WALK_NEXT) {
+      const HTile t = htile(tw_, p);
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
+      if (p.dbg & 4) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);
+        continue;
+      }
       if constexpr (STAGED) {
         const int col0 = t.nt * BN;
-        epilogue_tile_staged<BN>(st, tmem_base + as * Cfg::ACC, quarter, lane, ep_tid, t.n, t.p0, t.q0, &p.tmap_out,
+        epilogue_tile_staged<BN, NW>(st, tmem_base + as * Cfg::ACC, quarter, lane, ep_tid, t.n, t.p0, t.q0, &p.tmap_out,
                                  p.out_coff + col0, p.res ? &p.tmap_res : nullptr, p.res_coff + col0,
                                  p.bias ? p.bias + col0 : nullptr, p.Cout - col0, p.slope, [&]() {
                                    tc_fence_before();
-                                   mbar_arrive(&tempty[as]);
+                                   __syncwarp();
+                                   if (lane == 0) mbar_arrive(&tempty[as]);
                                  });
       } else {
         const __nv_bfloat16* res = p.res ? static_cast<const __nv_bfloat16*>(p.res) + p.res_coff : nullptr;
@@ -184,7 +206,8 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
                                                       p.P, p.Q, t.nt * BN, p.Cout, p.bias, res, p.res_cstride, out,
                                                       p.out_cstride, p.slope);
         tc_fence_before();
-        mbar_arrive(&tempty[as]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);
       }
     }
     if (STAGED && ep_tid == 0) tma_store_wait_all();
@@ -197,22 +220,22 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
   }
 }
 
-template <int BN, typename OutT, bool STAGED>
+template <int BN, typename OutT, bool STAGED, bool BRES = false>
 int launch_t(const ConvTmaParams& p, cudaStream_t stream) {
-  using Cfg = HaloCfg<BN, STAGED>;
-  auto kern = conv_halo_kernel<BN, OutT, STAGED>;
+  using Cfg = HaloCfg<BN, STAGED, BRES>;
+  auto kern = conv_halo_kernel<BN, OutT, STAGED, BRES>;
   static bool configured = false;
   if (!configured) {
     M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     configured = true;
   }
-  int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = persistent_sms();
   const int per_sm = (2 * (Cfg::SMEM + 1024) <= 227 * 1024 && 4 * Cfg::ACC <= 512) ? 2 : 1;
   int grid = sms * per_sm;
   if (grid > p.total_tiles) grid = p.total_tiles;
-  M3D_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(192), Cfg::SMEM, stream, p));
+  ConvTmaParams q = p;
+  q.dbg = getenv("M3D_DBG") ? atoi(getenv("M3D_DBG")) : 0;
+  M3D_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(STAGED ? 320 : 192), Cfg::SMEM, stream, q));
   return M3D_OK;
 }
 
@@ -229,6 +252,7 @@ bool conv_halo_supported(int BN, int out_dtype, bool staged) {
 
 int launch_conv_halo(const ConvTmaParams& p, int BN, int out_dtype, bool staged, cudaStream_t stream) {
   if (staged) {
+    if (BN == 64 && p.chunks[0] == 1 && p.n_tiles == 1) return launch_t<64, __nv_bfloat16, true, true>(p, stream);
     if (BN == 64) return launch_t<64, __nv_bfloat16, true>(p, stream);
     if (BN == 128) return launch_t<128, __nv_bfloat16, true>(p, stream);
     return M3D_ERR_UNSUPPORTED;

@@ -313,9 +313,7 @@ int launch_t(const ConvGatherParams& p, cudaStream_t stream) {
     M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct));
     configured = true;
   }
-  int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = persistent_sms();
   int grid = sms;
   if (grid > p.total_tiles) grid = p.total_tiles;
   M3D_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kDcnThreads), Cfg::SMEM, stream, p));

@@ -133,29 +133,34 @@ struct StagedEpilogue {
   }
 };
 
-// One 128 x BN bf16 tile.  `ep_tid` in [0,128) numbers the epilogue threads; thread 0 issues every
+// One 128 x BN bf16 tile.  `ep_tid` in [0, 32*NW) numbers the epilogue threads (NW = 4 or 8 warps; with 8 the
+// two warps of a TMEM lane quarter each take 32 of a slab's 64 columns: `half`); thread 0 issues every
 // TMA operation (bulk groups are per thread).  c_out / c_res: first channel of the tile inside the
 // output / residual buffers.  `on_tmem_drained` is called once the accumulator has been read.
-template <int BN, typename F>
+template <int BN, int NW, typename F>
 __device__ __forceinline__ void epilogue_tile_staged(StagedEpilogue& st, uint32_t tmem_acc, int quarter, int lane,
                                                      int ep_tid, int n, int p0, int q0, const void* tmap_out, int c_out,
                                                      const void* tmap_res, int c_res, const float* bias, int nbias,
                                                      float slope, F on_tmem_drained) {
   static_assert(BN % 64 == 0, "staged epilogue works on 64-channel slabs");
+  static_assert(NW == 4 || NW == 8, "4 or 8 epilogue warps");
   constexpr int NSLAB = BN / 64;
+  constexpr int NT = 32 * NW;
+  constexpr int CPT = 64 / (NW / 4);  // columns of a slab per thread: 64 or 32
+  const int half = NW == 8 ? (ep_tid >> 7) : 0;
   const int row = quarter * 32 + lane;
   const bool leader = ep_tid == 0;
   const bool has_res = tmap_res != nullptr;
 
-  named_bar_sync(kEpiBarrier, kEpiThreads);  // previous tile no longer reads bias_s
-  for (int i = ep_tid; i < BN; i += kEpiThreads) st.bias_s[i] = (bias != nullptr && i < nbias) ? __ldg(bias + i) : 0.f;
+  named_bar_sync(kEpiBarrier, NT);  // previous tile no longer reads bias_s
+  for (int i = ep_tid; i < BN; i += NT) st.bias_s[i] = (bias != nullptr && i < nbias) ? __ldg(bias + i) : 0.f;
   if (has_res && leader) {
     const int b = st.slab_count & 1;
     tma_store_wait_read<1>();  // the store that last used buffer b (two slabs ago) has drained it
     mbar_arrive_expect_tx(&st.res_bar[b], kSlabBytes);
     tma_load_4d(st.slab[b], tmap_res, &st.res_bar[b], c_res, q0, p0, n);
   }
-  named_bar_sync(kEpiBarrier, kEpiThreads);  // bias_s visible
+  named_bar_sync(kEpiBarrier, NT);  // bias_s visible
 
 #pragma unroll 1
   for (int s = 0; s < NSLAB; ++s) {
@@ -171,23 +176,28 @@ __device__ __forceinline__ void epilogue_tile_staged(StagedEpilogue& st, uint32_
       st.res_uses[b]++;
     } else {
       if (leader) tma_store_wait_read<1>();
-      named_bar_sync(kEpiBarrier, kEpiThreads);  // buffer b is free for everybody
+      named_bar_sync(kEpiBarrier, NT);  // buffer b is free for everybody
     }
-    uint32_t a0[32], a1[32];
-    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + s * 64;
-    tmem_ld32(taddr, a0);
-    tmem_ld32(taddr + 32, a1);
+    uint32_t a[CPT];
+    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + s * 64 + half * 32;
+    if constexpr (CPT == 64) {
+      tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(a));
+      tmem_ld32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(a + 32));
+    } else {
+      tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(a));
+    }
     tmem_ld_wait();
     if (s == NSLAB - 1) on_tmem_drained();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {  // 8 chunks of 8 channels
+    for (int j = 0; j < CPT / 8; ++j) {  // chunks of 8 channels
+      const int chunk = half * 4 + j;
       float v[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(j < 4 ? a0[j * 8 + e] : a1[(j - 4) * 8 + e]);
-      const float4 b0 = *reinterpret_cast<const float4*>(st.bias_s + s * 64 + j * 8);
-      const float4 b1 = *reinterpret_cast<const float4*>(st.bias_s + s * 64 + j * 8 + 4);
+      for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(a[j * 8 + e]);
+      const float4 b0 = *reinterpret_cast<const float4*>(st.bias_s + s * 64 + chunk * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(st.bias_s + s * 64 + chunk * 8 + 4);
       v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w, v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
-      uint4* cell = reinterpret_cast<uint4*>(buf + swizzled_offset<128>(row, j));
+      uint4* cell = reinterpret_cast<uint4*>(buf + swizzled_offset<128>(row, chunk));
       if (has_res) {
         const uint4 u = *cell;
         v[0] += __uint_as_float(u.x << 16), v[1] += __uint_as_float(u.x & 0xffff0000u);
@@ -204,7 +214,7 @@ __device__ __forceinline__ void epilogue_tile_staged(StagedEpilogue& st, uint32_
       *cell = make_uint4(w[0], w[1], w[2], w[3]);
     }
     fence_proxy_async_smem();
-    named_bar_sync(kEpiBarrier, kEpiThreads);  // slab complete
+    named_bar_sync(kEpiBarrier, NT);  // slab complete
     if (leader) {
       tma_store_4d(tmap_out, buf, c_out + s * 64, q0, p0, n);
       tma_store_commit();

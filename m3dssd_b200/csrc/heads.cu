@@ -412,9 +412,7 @@ extern "C" int m3d_head_mlp(const void* x, int N, int H, int W, int x_cstride, i
     M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem));
     configured = true;
   }
-  int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = persistent_sms();
   int grid = sms;
   if (grid > p.total_items) grid = p.total_items;
   M3D_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kHeadThreads), kHeadSmem, stream, p));

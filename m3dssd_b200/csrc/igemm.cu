@@ -78,9 +78,16 @@ struct KWalk {
   }
 };
 
+// Epilogue warps: 8 for the staged (bf16, TMA-store) epilogue -- small-N full-resolution layers are bounded by
+// the accumulator drain, and two warps per scheduler hide its TMEM-load / shared-memory latencies -- else 4.
+template <bool STAGED>
+constexpr int conv_epi_warps() { return STAGED ? 8 : 4; }
+
 template <int BN, int BK, int KSUB, typename OutT, bool STAGED>
-__global__ void __launch_bounds__(192, 1) conv_tma_kernel(const __grid_constant__ ConvTmaParams p) {
+__global__ void __launch_bounds__(64 + 32 * conv_epi_warps<STAGED>(), 1)
+    conv_tma_kernel(const __grid_constant__ ConvTmaParams p) {
   using Cfg = TmaCfg<BN, BK, KSUB, STAGED>;
+  constexpr int NW = conv_epi_warps<STAGED>();
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -104,7 +111,7 @@ __global__ void __launch_bounds__(192, 1) conv_tma_kernel(const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 128);
+      mbar_init(&tempty[s], 32 * NW);
       mbar_init(&res_bar[s], 1);
     }
     fence_barrier_init();
@@ -221,7 +228,7 @@ __global__ void __launch_bounds__(192, 1) conv_tma_kernel(const __grid_constant_
       const float* bias = p.bias ? p.bias + t.g * p.bias_goff : nullptr;
       if constexpr (STAGED) {
         const int col0 = t.nt * BN;
-        epilogue_tile_staged<BN>(st, tmem_base + as * Cfg::ACC, quarter, lane, ep_tid, t.n, t.p0, t.q0, &p.tmap_out,
+        epilogue_tile_staged<BN, NW>(st, tmem_base + as * Cfg::ACC, quarter, lane, ep_tid, t.n, t.p0, t.q0, &p.tmap_out,
                                  p.out_coff + t.g * p.out_goff + col0, p.res ? &p.tmap_res : nullptr,
                                  p.res_coff + t.g * p.res_goff + col0, bias ? bias + col0 : nullptr, p.Cout - col0,
                                  p.slope, [&]() {
@@ -775,7 +782,7 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
       tc_fence_after();
       if constexpr (STAGED) {
         const int col0 = t.nt * BN;
-        epilogue_tile_staged<BN>(st, tmem_base + as * Cfg::ACC, quarter, lane, ep_tid, t.n, t.p0, t.q0, &p.tmap_out,
+        epilogue_tile_staged<BN, 4>(st, tmem_base + as * Cfg::ACC, quarter, lane, ep_tid, t.n, t.p0, t.q0, &p.tmap_out,
                                  p.out_coff + col0, p.res ? &p.tmap_res : nullptr, p.res_coff + col0,
                                  p.bias ? p.bias + col0 : nullptr, p.Cout - col0, p.slope, [&]() {
                                    tc_fence_before();
@@ -801,15 +808,6 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------ host launchers
-static int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return sms;
-}
 
 template <int BN, int BK, int KSUB, typename OutT, bool STAGED>
 static int launch_tma_t(const ConvTmaParams& p, cudaStream_t stream) {
@@ -822,9 +820,9 @@ static int launch_tma_t(const ConvTmaParams& p, cudaStream_t stream) {
   }
   // Two co-resident CTAs per SM when shared memory allows (small tiles).
   const int per_sm = (2 * (Cfg::SMEM + 1024) <= 227 * 1024 && 4 * Cfg::ACC <= 512) ? 2 : 1;
-  int grid = num_sms() * per_sm;
+  int grid = persistent_sms() * per_sm;
   if (grid > p.total_tiles) grid = p.total_tiles;
-  M3D_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(192), Cfg::SMEM, stream, p));
+  M3D_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(64 + 32 * conv_epi_warps<STAGED>()), Cfg::SMEM, stream, p));
   return M3D_OK;
 }
 
@@ -869,7 +867,7 @@ static int launch_gather_t(const ConvGatherParams& p, cudaStream_t stream) {
     M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     configured = true;
   }
-  int grid = num_sms();
+  int grid = persistent_sms();
   if (grid > p.total_tiles) grid = p.total_tiles;
   M3D_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(448), Cfg::SMEM, stream, p));
   return M3D_OK;

@@ -59,6 +59,7 @@ struct alignas(64) ConvTmaParams {
   int res_cstride, res_coff, res_goff;
   float slope;  // LeakyReLU negative slope; 1.0 = identity
   int total_tiles;
+  int dbg;     // development probe bits (M3D_DBG): 1 skip A loads, 4 skip the epilogue body, 8 skip MMAs, 16 skip the TMA store
   int a_wide;  // tmap_a are 5-D (BK, W, H, N, C/BK) maps whose box holds the stage's KSUB channel chunks
 };
 

@@ -23,6 +23,39 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ------------------------------------------------------------ tile schedule
+// Every CTA of a persistent kernel owns a contiguous, balanced range of the tile list (neighbouring tiles share
+// halo rows and weights in L2) and walks it with carry increments: the per-tile integer divisions of a strided
+// schedule cost a lone producer warp ~500 clocks per tile, more than a small tile's MMAs.
+struct TileWalk {
+  int first, last;         // this CTA's tiles
+  int nt, tw, th, n, g;    // coordinates of the current tile: N tile (innermost), tile column / row, image, group
+  __device__ __forceinline__ void init(int total, int n_tiles, int tiles_w, int tiles_h, int N) {
+    first = static_cast<int>(static_cast<long>(blockIdx.x) * total / gridDim.x);
+    last = static_cast<int>(static_cast<long>(blockIdx.x + 1) * total / gridDim.x);
+    nt = first % n_tiles;
+    int r = first / n_tiles;
+    tw = r % tiles_w;
+    r /= tiles_w;
+    th = r % tiles_h;
+    r /= tiles_h;
+    n = r % N;
+    g = r / N;
+  }
+  __device__ __forceinline__ void next(int n_tiles, int tiles_w, int tiles_h, int N) {
+    if (++nt == n_tiles) {
+      nt = 0;
+      if (++tw == tiles_w) {
+        tw = 0;
+        if (++th == tiles_h) {
+          th = 0;
+          if (++n == N) n = 0, ++g;
+        }
+      }
+    }
+  }
+};
+
 // ----------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

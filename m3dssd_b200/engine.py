@@ -14,6 +14,8 @@ Forward path covered (reference file:line):
   ANAB .................. model/module/attention.py:183-216
   decode + NMS .......... lib/rpn_util.py:1444-1555; lib/nms/nms_kernel.cu
 """
+import os
+
 import numpy as np
 import torch
 from torch import nn
@@ -533,7 +535,16 @@ class Engine:
                 op()
 
         if self.use_graph:
-            self._pipe["trunk"], self._pipe["heads"] = capture(trunk), capture(heads)
+            # the trunk of batch i+1 shares the device with the detection tail of batch i (one CTA per image on
+            # the side stream): leave those SMs free, or every persistent kernel of the trunk runs as two waves
+            nsm = torch.cuda.get_device_properties(self.dev).multi_processor_count
+            reserve = int(os.environ.get("M3D_TAIL_SMS", str(self.B)))
+            ops.set_sm_limit(nsm - reserve if 0 < reserve < nsm else 0)
+            try:
+                self._pipe["trunk"] = capture(trunk)
+            finally:
+                ops.set_sm_limit(0)
+            self._pipe["heads"] = capture(heads)
             self._pipe["decode"], self._pipe["nms"] = capture(self._run_decode), capture(self._run_nms)
             self._pipe = {k: g.replay for k, g in self._pipe.items()}
         else:

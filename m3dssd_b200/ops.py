@@ -238,6 +238,11 @@ def center_align_om(fg_max, fg_arg, heads, x_coff, y_coff, anchors, feat_stride,
                                     fg_max.numel(), _stream()))
 
 
+def set_sm_limit(sms):
+    """SMs the persistent kernels launched / captured from now on may use (0 = all)."""
+    check(lib().m3d_set_sm_limit(int(sms)))
+
+
 def head_mlp(x, x_coff, cx, w1, b1, w2, b2, w3, b3, G, A, rows3, out, out_coff, slope=0.01):
     """G fused three-layer 1x1 heads on x[..., x_coff:x_coff+cx] (bf16 NHWC) -> out[..., out_coff + g*A + a] (fp32 NHWC)."""
     N, H, W, cs = x.shape

@@ -12,6 +12,7 @@ import torch  # noqa: E402
 from m3dssd_b200 import ops  # noqa: E402
 
 SHAPES = [
+    ("l0 64->64 3x3 @192x640", 8, 192, 640, 64, 64, 3, 1),
     # name, N, H, W, Cin, Cout, R, stride
     ("l3 128->128 3x3 @48x160", 8, 48, 160, 128, 128, 3, 1),
     ("l4 256->256 3x3 @24x80", 8, 24, 80, 256, 256, 3, 1),
@@ -70,11 +71,11 @@ def main():
     log = open(os.path.join(ROOT, "gpurun_out", "probe_perf.log"), "w")
     for name, N, H, W, Cin, Cout, R, stride in SHAPES:
         gf = 2.0 * N * (H // stride) * (W // stride) * Cin * Cout * R * R / 1e9
-        for ksub in (1, 2, 3, 4):
-            if ksub > 2 and Cout != 64:
-                continue
-            cold, warm = time_conv(N, H, W, Cin, Cout, R, stride, ksub)
-            line = "%-28s ksub=%d  best %7.1f us  median %7.1f us  (%.0f TF/s)" % (name, ksub, cold, warm, gf / cold * 1e-3)
+        for dbg in (0, 4, 1, 5, 8, 13):
+            os.environ["M3D_DBG"] = str(dbg)
+            ksub = dbg
+            cold, warm = time_conv(N, H, W, Cin, Cout, R, stride, 0)
+            line = "%-28s dbg=%d  best %7.1f us  median %7.1f us  (%.0f TF/s)" % (name, ksub, cold, warm, gf / cold * 1e-3)
             print(line, flush=True)
             log.write(line + "\n")
     os.environ.pop("M3D_KSUB", None)
