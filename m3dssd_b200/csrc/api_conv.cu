@@ -300,7 +300,8 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
   M3D_REQUIRE(total_tiles < (1L << 30), "too many tiles");
 
   // bf16 tiles of whole 64-channel slabs leave through shared memory + TMA stores
-  const bool staged = d->act_dtype == M3D_BF16 && d->out_dtype == M3D_BF16 && bk == 64 && BN % 64 == 0 &&
+  const bool staged = d->act_dtype == M3D_BF16 && d->out_dtype == M3D_BF16 && (bk == 64 || (bk == 32 && BN == 64 && !gather)) &&
+                      BN % 64 == 0 &&
                       d->Cout % 64 == 0 && d->out_cstride % 8 == 0 && d->out_coff % 8 == 0 && d->out_goff % 8 == 0 &&
                       (d->res == nullptr || (d->res_cstride % 8 == 0 && d->res_coff % 8 == 0 && d->res_goff % 8 == 0));
   if (!gather) {
@@ -343,7 +344,7 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
     // issue cost of the stage's barrier hand-shakes and TMA instructions
     const long total_kb = ktot / bk;
     int ksub = 1;
-    if (staged) {
+    if (staged && bk == 64) {
       for (int k = (BN >= 256 ? 1 : (BN >= 128 ? 2 : 4)); k > 1; --k)
         if (total_kb % k == 0) {
           ksub = k;

@@ -836,6 +836,8 @@ int launch_conv_tma(const ConvTmaParams& p, int BN, int BK, int ksub, int out_dt
 #define M3D_TMA_STAGED(bn, ks)                                                             \
   if (staged && BN == bn && BK == 64 && ksub == ks && out_dtype == DT_BF16)                \
     return launch_tma_t<bn, 64, ks, __nv_bfloat16, true>(p, stream);
+  if (staged && BN == 64 && BK == 32 && ksub == 1 && out_dtype == DT_BF16)
+    return launch_tma_t<64, 32, 1, __nv_bfloat16, true>(p, stream);
   M3D_TMA_STAGED(64, 1)
   M3D_TMA_STAGED(64, 2)
   M3D_TMA_STAGED(64, 3)

@@ -26,7 +26,12 @@ x = synth.make_images(a.batch, (384, 1280)).cuda()
 for _ in range(a.iters):
     eng.detect(x)
 torch.cuda.synchronize()
-if a.ops:
+if a.ops == "step":  # one whole warm step inside the profiler range (ncu --profile-from-start off)
+    torch.cuda.profiler.start()
+    eng.detect(x)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+elif a.ops:
     want = a.ops.split(",")
     torch.cuda.profiler.start()
     for name in want:
