@@ -110,7 +110,6 @@ __global__ void __launch_bounds__(kDcnThreads, 1) dcn_fused_kernel(const __grid_
     const int tw_shift = 31 - __clz(p.TW);
     const __nv_bfloat16* in0 = static_cast<const __nv_bfloat16*>(p.in[0]) + p.in_coff[0];
     const int cs = p.in_cstride[0];
-    const int units = total_kb * 2;
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -165,52 +164,54 @@ __global__ void __launch_bounds__(kDcnThreads, 1) dcn_fused_kernel(const __grid_
       }
       named_bar_sync(1, kProd);
 
-      // unit u = (k-block u/2, row half u%2); K is walked chunk-major: k-block -> (chunk, tap)
-      uint4 cv[2][4];
-      float4 cw[2];
-      int nx_tap = 0, nx_c = 0;
-      auto issue = [&](int u, int buf) {
-        const int half = u & 1;
-        const int tap = nx_tap, c = nx_c;
+      // unit = (k-block, row half); K is walked chunk-major: k-block -> (chunk, tap).  The corner loads of a unit
+      // are issued two units (one k-block) before its blend, into a ring of three register buffers; the bilinear
+      // weights are re-read from the table at blend time so the ring fits the 88-register budget of 704 threads.
+      uint4 cv[3][4];
+      int nx_tap = 0, nx_c = 0;  // k-block of the next unit to issue
+      auto issue = [&](int half, uint4 (&buf)[4]) {
+        const Entry& e = table[(rbase + 64 * half) * taps + nx_tap];
+        const int4 o = e.off;
+        const char* base = reinterpret_cast<const char*>(in0 + nx_c * kBK + j * 8);
         if (half) {
           if (++nx_tap == taps) nx_tap = 0, ++nx_c;
         }
-        const Entry& e = table[(rbase + 64 * half) * taps + tap];
-        const int4 o = e.off;
-        cw[buf] = e.w;
-        const char* base = reinterpret_cast<const char*>(in0 + c * kBK + j * 8);
-        cv[buf][0] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<uint32_t>(o.x)));
-        cv[buf][1] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<uint32_t>(o.y)));
-        cv[buf][2] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<uint32_t>(o.z)));
-        cv[buf][3] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<uint32_t>(o.w)));
+        buf[0] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<uint32_t>(o.x)));
+        buf[1] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<uint32_t>(o.y)));
+        buf[2] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<uint32_t>(o.z)));
+        buf[3] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<uint32_t>(o.w)));
       };
-      auto blend = [&](int half, int buf, uint8_t* a_tile) {
-        const float4 w4 = cw[buf];
-        const uint32_t* q0 = reinterpret_cast<const uint32_t*>(&cv[buf][0]);
-        const uint32_t* q1 = reinterpret_cast<const uint32_t*>(&cv[buf][1]);
-        const uint32_t* q2 = reinterpret_cast<const uint32_t*>(&cv[buf][2]);
-        const uint32_t* q3 = reinterpret_cast<const uint32_t*>(&cv[buf][3]);
+      auto blend = [&](int half, int tap, const uint4 (&buf)[4], uint8_t* a_tile) {
+        const float4 w4 = table[(rbase + 64 * half) * taps + tap].w;
+        const uint32_t* q0 = reinterpret_cast<const uint32_t*>(&buf[0]);
+        const uint32_t* q1 = reinterpret_cast<const uint32_t*>(&buf[1]);
+        const uint32_t* q2 = reinterpret_cast<const uint32_t*>(&buf[2]);
+        const uint32_t* q3 = reinterpret_cast<const uint32_t*>(&buf[3]);
+        // same arithmetic as the scalar fp32 blend of conv_gather_kernel, two channels per FFMA2
+        const unsigned long long wx = pack_f32x2(w4.x, w4.x), wy = pack_f32x2(w4.y, w4.y);
+        const unsigned long long wz = pack_f32x2(w4.z, w4.z), ww = pack_f32x2(w4.w, w4.w);
         uint32_t w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float lo = w4.x * __uint_as_float(q0[e] << 16) + w4.y * __uint_as_float(q1[e] << 16) +
-                           w4.z * __uint_as_float(q2[e] << 16) + w4.w * __uint_as_float(q3[e] << 16);
-          const float hi = w4.x * __uint_as_float(q0[e] & 0xffff0000u) + w4.y * __uint_as_float(q1[e] & 0xffff0000u) +
-                           w4.z * __uint_as_float(q2[e] & 0xffff0000u) + w4.w * __uint_as_float(q3[e] & 0xffff0000u);
-          __nv_bfloat162 tt = __floats2bfloat162_rn(lo, hi);
-          w[e] = *reinterpret_cast<uint32_t*>(&tt);
+          // (operation order of the scalar expression as nvcc contracts it: y*q1 first, then fma x, z, w)
+          unsigned long long acc =
+              mul_f32x2(wy, pack_f32x2(__uint_as_float(q1[e] << 16), __uint_as_float(q1[e] & 0xffff0000u)));
+          acc = fma_f32x2(wx, pack_f32x2(__uint_as_float(q0[e] << 16), __uint_as_float(q0[e] & 0xffff0000u)), acc);
+          acc = fma_f32x2(wz, pack_f32x2(__uint_as_float(q2[e] << 16), __uint_as_float(q2[e] & 0xffff0000u)), acc);
+          acc = fma_f32x2(ww, pack_f32x2(__uint_as_float(q3[e] << 16), __uint_as_float(q3[e] & 0xffff0000u)), acc);
+          w[e] = f32x2_to_bf16x2(acc);
         }
         *reinterpret_cast<uint4*>(a_tile + swizzled_offset<128>(rbase + 64 * half, j)) = make_uint4(w[0], w[1], w[2], w[3]);
       };
-      issue(0, 0);
-#pragma unroll 1
-      for (int u = 0; u < units; u += 2) {
-        issue(u + 1, 1);
+      int cur_tap = 0;  // tap of the k-block being blended
+      // one k-block: its halves sit in buffers A / B; the next k-block's halves are issued into NA / NB
+      auto kblock = [&](const uint4 (&A)[4], const uint4 (&B)[4], uint4 (&NA)[4], uint4 (&NB)[4], bool more) {
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* a_tile = smem + stage * Cfg::STAGE;
-        blend(0, 0, a_tile);
-        if (u + 2 < units) issue(u + 2, 0);
-        blend(1, 1, a_tile);
+        if (more) issue(0, NA);
+        blend(0, cur_tap, A, a_tile);
+        if (more) issue(1, NB);  // NB is A's storage when the ring wraps: A has just been consumed
+        blend(1, cur_tap, B, a_tile);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[stage]);
@@ -218,6 +219,15 @@ __global__ void __launch_bounds__(kDcnThreads, 1) dcn_fused_kernel(const __grid_
           stage = 0;
           phase ^= 1;
         }
+        if (++cur_tap == taps) cur_tap = 0;
+      };
+      issue(0, cv[0]);
+      issue(1, cv[1]);
+#pragma unroll 1
+      for (int kb = 0; kb < total_kb; kb += 3) {  // total_kb = 9 * nchunk: three k-blocks per trip keep the ring static
+        kblock(cv[0], cv[1], cv[2], cv[0], true);
+        kblock(cv[2], cv[0], cv[1], cv[2], true);
+        kblock(cv[1], cv[2], cv[0], cv[1], kb + 3 < total_kb);
       }
     }
   } else if (warp == 16) {

@@ -23,6 +23,32 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ------------------------------------------------------------ packed fp32 math
+// Blackwell issues two IEEE fp32 FMAs per instruction on a 64-bit register pair (FFMA2 / FMUL2).
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// (lo, hi) fp32 pair -> packed bf16x2 (lo in the low half), round to nearest even
+__device__ __forceinline__ uint32_t f32x2_to_bf16x2(unsigned long long v) {
+  float lo, hi;
+  uint32_t r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // ------------------------------------------------------------ tile schedule
 // Every CTA of a persistent kernel owns a contiguous, balanced range of the tile list (neighbouring tiles share
 // halo rows and weights in L2) and walks it with carry increments: the per-tile integer divisions of a strided
