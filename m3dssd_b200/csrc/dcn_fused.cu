@@ -62,7 +62,37 @@ __device__ __forceinline__ Tile tile_of(int tile, const ConvGatherParams& p) {
   return t;
 }
 
-template <int BN, int NSTG>
+// One sample-table entry: clamped corner byte offsets + bilinear weights x validity x modulation mask
+// (dcn_v2_im2col_cuda.cu:18-47,151-175).  (pp, qq): output pixel, assumed inside the image.
+__device__ __forceinline__ Entry make_entry(const ConvGatherParams& p, int n, int pp, int qq, int tap, int taps, int cs,
+                                            float o_h, float o_w, float m) {
+  Entry e;
+  e.off = make_int4(0, 0, 0, 0);
+  e.w = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int r = taps == 9 ? tap / 3 : tap / p.S, sx = tap - r * p.S;
+  const float hf = static_cast<float>(pp * p.stride - p.pad + r * p.dil) + o_h;
+  const float wf = static_cast<float>(qq * p.stride - p.pad + sx * p.dil) + o_w;
+  if (p.sigmoid_mask) m = 1.f / (1.f + __expf(-m));
+  if (hf > -1.f && wf > -1.f && hf < static_cast<float>(p.H) && wf < static_cast<float>(p.W)) {
+    const float hl = floorf(hf), wl = floorf(wf);
+    const int h_low = static_cast<int>(hl), w_low = static_cast<int>(wl);
+    const int h_high = h_low + 1, w_high = w_low + 1;
+    const float lh = hf - hl, lw = wf - wl, hh = 1.f - lh, hw = 1.f - lw;
+    const bool hl_ok = h_low >= 0, wl_ok = w_low >= 0, hh_ok = h_high <= p.H - 1, wh_ok = w_high <= p.W - 1;
+    const int rl = (n * p.H + (hl_ok ? h_low : 0)) * p.W, rh = (n * p.H + (hh_ok ? h_high : 0)) * p.W;
+    const int cl = wl_ok ? w_low : 0, ch = wh_ok ? w_high : 0;
+    // byte offsets of the four corner pixels (unsigned 32-bit: one IMAD.WIDE.U32 per load in the main loop)
+    e.off = make_int4((rl + cl) * cs * 2, (rl + ch) * cs * 2, (rh + cl) * cs * 2, (rh + ch) * cs * 2);
+    e.w = make_float4((hl_ok && wl_ok) ? hh * hw * m : 0.f, (hl_ok && wh_ok) ? hh * lw * m : 0.f,
+                      (hh_ok && wl_ok) ? lh * hw * m : 0.f, (hh_ok && wh_ok) ? lh * lw * m : 0.f);
+  }
+  return e;
+}
+
+// HALF: 64-pixel tiles (A rows 64-127 are never written; their accumulator rows are never read).  The layer is
+// bounded by the producers' blend, which scales with the rows, so half tiles cost little extra per pixel and the
+// device gets filled when there are fewer full tiles than SMs (ida_0.proj_1: 30 tiles -> 72).
+template <int BN, int NSTG, bool HALF>
 __global__ void __launch_bounds__(kDcnThreads, 1) dcn_fused_kernel(const __grid_constant__ ConvGatherParams p) {
   using Cfg = DcnCfg<BN, NSTG>;
   constexpr int STAGES = Cfg::STAGES;
@@ -115,8 +145,8 @@ __global__ void __launch_bounds__(kDcnThreads, 1) dcn_fused_kernel(const __grid_
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const Tile t = tile_of(tile, p);
       named_bar_sync(1, kProd);  // previous tile's table readers are done
-      {
-        // thread pt fills row pt/4, taps (pt%4) + 4k  (dcn_v2_im2col_cuda.cu:18-47,151-175)
+      if constexpr (!HALF) {
+        // thread pt fills row pt/4, taps (pt%4) + 4k: its offset / mask loads are issued together
         const int trow = pt >> 2;
         const int pp = t.p0 + (trow >> tw_shift), qq = t.q0 + (trow & (p.TW - 1));
         const bool tok = pp < p.P && qq < p.Q;
@@ -139,27 +169,34 @@ __global__ void __launch_bounds__(kDcnThreads, 1) dcn_fused_kernel(const __grid_
           Entry e;
           e.off = make_int4(0, 0, 0, 0);
           e.w = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (tok) {
-            const int r = taps == 9 ? tap / 3 : tap / p.S, sx = tap - r * p.S;
-            const float hf = static_cast<float>(pp * p.stride - p.pad + r * p.dil) + o_h[k];
-            const float wf = static_cast<float>(qq * p.stride - p.pad + sx * p.dil) + o_w[k];
-            float m = o_m[k];
-            if (p.sigmoid_mask) m = 1.f / (1.f + __expf(-m));
-            if (hf > -1.f && wf > -1.f && hf < static_cast<float>(p.H) && wf < static_cast<float>(p.W)) {
-              const float hl = floorf(hf), wl = floorf(wf);
-              const int h_low = static_cast<int>(hl), w_low = static_cast<int>(wl);
-              const int h_high = h_low + 1, w_high = w_low + 1;
-              const float lh = hf - hl, lw = wf - wl, hh = 1.f - lh, hw = 1.f - lw;
-              const bool hl_ok = h_low >= 0, wl_ok = w_low >= 0, hh_ok = h_high <= p.H - 1, wh_ok = w_high <= p.W - 1;
-              const int rl = (t.n * p.H + (hl_ok ? h_low : 0)) * p.W, rh = (t.n * p.H + (hh_ok ? h_high : 0)) * p.W;
-              const int cl = wl_ok ? w_low : 0, ch = wh_ok ? w_high : 0;
-              // byte offsets of the four corner pixels (unsigned 32-bit: one IMAD.WIDE.U32 per load in the main loop)
-              e.off = make_int4((rl + cl) * cs * 2, (rl + ch) * cs * 2, (rh + cl) * cs * 2, (rh + ch) * cs * 2);
-              e.w = make_float4((hl_ok && wl_ok) ? hh * hw * m : 0.f, (hl_ok && wh_ok) ? hh * lw * m : 0.f,
-                                (hh_ok && wl_ok) ? lh * hw * m : 0.f, (hh_ok && wh_ok) ? lh * lw * m : 0.f);
-            }
-          }
+          if (tok) e = make_entry(p, t.n, pp, qq, tap, taps, cs, o_h[k], o_w[k], o_m[k]);
           table[trow * taps + tap] = e;
+        }
+      } else {
+        // 64 rows x 9 taps: thread pt fills (row pt/8, tap pt%8); threads with pt%8 == 0 also fill tap 8
+        const int trow = pt >> 3;
+        const int pp = t.p0 + (trow >> tw_shift), qq = t.q0 + (trow & (p.TW - 1));
+        const bool tok = pp < p.P && qq < p.Q;
+        const float* om_px = p.om + ((static_cast<long>(t.n) * p.P + pp) * p.Q + qq) * p.om_cstride;
+        float o_h[2], o_w[2], o_m[2];
+        int tp[2] = {pt & 7, 8};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          o_h[k] = o_w[k] = 0.f, o_m[k] = 1.f;
+          if (tok && tp[k] < taps && (k == 0 || (pt & 7) == 0)) {
+            o_h[k] = __ldg(om_px + 2 * tp[k]);
+            o_w[k] = __ldg(om_px + 2 * tp[k] + 1);
+            o_m[k] = __ldg(om_px + 2 * taps + tp[k]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (tp[k] >= taps || (k == 1 && (pt & 7) != 0)) continue;
+          Entry e;
+          e.off = make_int4(0, 0, 0, 0);
+          e.w = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (tok) e = make_entry(p, t.n, pp, qq, tp[k], taps, cs, o_h[k], o_w[k], o_m[k]);
+          table[trow * taps + tp[k]] = e;
         }
       }
       named_bar_sync(1, kProd);
@@ -204,14 +241,7 @@ __global__ void __launch_bounds__(kDcnThreads, 1) dcn_fused_kernel(const __grid_
         *reinterpret_cast<uint4*>(a_tile + swizzled_offset<128>(rbase + 64 * half, j)) = make_uint4(w[0], w[1], w[2], w[3]);
       };
       int cur_tap = 0;  // tap of the k-block being blended
-      // one k-block: its halves sit in buffers A / B; the next k-block's halves are issued into NA / NB
-      auto kblock = [&](const uint4 (&A)[4], const uint4 (&B)[4], uint4 (&NA)[4], uint4 (&NB)[4], bool more) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* a_tile = smem + stage * Cfg::STAGE;
-        if (more) issue(0, NA);
-        blend(0, cur_tap, A, a_tile);
-        if (more) issue(1, NB);  // NB is A's storage when the ring wraps: A has just been consumed
-        blend(1, cur_tap, B, a_tile);
+      auto finish_kblock = [&]() {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[stage]);
@@ -221,13 +251,51 @@ __global__ void __launch_bounds__(kDcnThreads, 1) dcn_fused_kernel(const __grid_
         }
         if (++cur_tap == taps) cur_tap = 0;
       };
-      issue(0, cv[0]);
-      issue(1, cv[1]);
+      if constexpr (!HALF) {
+        // one k-block: its halves sit in buffers A / B; the next k-block's halves are issued into NA / NB
+        auto kblock = [&](const uint4 (&A)[4], const uint4 (&B)[4], uint4 (&NA)[4], uint4 (&NB)[4], bool more) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* a_tile = smem + stage * Cfg::STAGE;
+          if (more) issue(0, NA);
+          blend(0, cur_tap, A, a_tile);
+          if (more) issue(1, NB);  // NB is A's storage when the ring wraps: A has just been consumed
+          blend(1, cur_tap, B, a_tile);
+          finish_kblock();
+        };
+        issue(0, cv[0]);
+        issue(1, cv[1]);
 #pragma unroll 1
-      for (int kb = 0; kb < total_kb; kb += 3) {  // total_kb = 9 * nchunk: three k-blocks per trip keep the ring static
-        kblock(cv[0], cv[1], cv[2], cv[0], true);
-        kblock(cv[2], cv[0], cv[1], cv[2], true);
-        kblock(cv[1], cv[2], cv[0], cv[1], kb + 3 < total_kb);
+        for (int kb = 0; kb < total_kb; kb += 3) {  // total_kb = 9 * nchunk: three k-blocks per trip keep the ring static
+          kblock(cv[0], cv[1], cv[2], cv[0], true);
+          kblock(cv[2], cv[0], cv[1], cv[2], true);
+          kblock(cv[1], cv[2], cv[0], cv[1], kb + 3 < total_kb);
+        }
+      } else {
+        // one row per thread and k-block; loads run two k-blocks ahead of the blend
+        auto issue1 = [&](uint4 (&buf)[4]) {
+          const Entry& e = table[rbase * taps + nx_tap];
+          const int4 o = e.off;
+          const char* base = reinterpret_cast<const char*>(in0 + nx_c * kBK + j * 8);
+          if (++nx_tap == taps) nx_tap = 0, ++nx_c;
+          buf[0] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<uint32_t>(o.x)));
+          buf[1] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<uint32_t>(o.y)));
+          buf[2] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<uint32_t>(o.z)));
+          buf[3] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<uint32_t>(o.w)));
+        };
+        auto kblock1 = [&](const uint4 (&A)[4], uint4 (&NA)[4], bool more) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (more) issue1(NA);
+          blend(0, cur_tap, A, smem + stage * Cfg::STAGE);
+          finish_kblock();
+        };
+        issue1(cv[0]);
+        issue1(cv[1]);
+#pragma unroll 1
+        for (int kb = 0; kb < total_kb; kb += 3) {
+          kblock1(cv[0], cv[2], true);
+          kblock1(cv[1], cv[0], kb + 3 < total_kb);
+          kblock1(cv[2], cv[1], kb + 4 < total_kb);
+        }
       }
     }
   } else if (warp == 16) {
@@ -296,9 +364,10 @@ __global__ void __launch_bounds__(kDcnThreads, 1) dcn_fused_kernel(const __grid_
       tc_fence_after();
       const __nv_bfloat16* res = p.res ? static_cast<const __nv_bfloat16*>(p.res) + p.res_coff : nullptr;
       __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out) + p.out_coff;
-      epilogue_tile_direct<BN, __nv_bfloat16, __nv_bfloat16>(tmem_base + as * Cfg::ACC, quarter, lane, t.n, t.p0, t.q0,
-                                                             p.TW, p.P, p.Q, t.nt * BN, p.Cout, p.bias, res,
-                                                             p.res_cstride, out, p.out_cstride, p.slope);
+      if (!HALF || quarter < 2)
+        epilogue_tile_direct<BN, __nv_bfloat16, __nv_bfloat16>(tmem_base + as * Cfg::ACC, quarter, lane, t.n, t.p0, t.q0,
+                                                               p.TW, p.P, p.Q, t.nt * BN, p.Cout, p.bias, res,
+                                                               p.res_cstride, out, p.out_cstride, p.slope);
       tc_fence_before();
       mbar_arrive(&tempty[as]);
     }
@@ -311,10 +380,10 @@ __global__ void __launch_bounds__(kDcnThreads, 1) dcn_fused_kernel(const __grid_
   }
 }
 
-template <int BN, int NSTG>
+template <int BN, int NSTG, bool HALF>
 int launch_t(const ConvGatherParams& p, cudaStream_t stream) {
   using Cfg = DcnCfg<BN, NSTG>;
-  auto kern = dcn_fused_kernel<BN, NSTG>;
+  auto kern = dcn_fused_kernel<BN, NSTG, HALF>;
   static bool configured = false;
   if (!configured) {
     M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
@@ -342,11 +411,38 @@ bool dcn_fused_supported(const ConvGatherParams& p, int BN, int in_dtype, int ou
          static_cast<long>(p.N) * p.H * p.W * p.in_cstride[0] * 2 < (1L << 32);  // 32-bit byte offsets in the table
 }
 
-int launch_dcn_fused(const ConvGatherParams& p, int BN, cudaStream_t stream) {
+int launch_dcn_fused(const ConvGatherParams& p0, int BN, cudaStream_t stream) {
+  ConvGatherParams p = p0;
+  // 64-pixel tiles when they shorten the schedule: waves x tile cost (measured: a half tile costs ~0.7 of a full
+  // one -- the per-k-block barrier / fence work does not shrink), i.e. only when the full tiles cannot fill the device
+  const int sms = persistent_sms();
+  bool half = false;
+  {
+    int best_tw = 8, best_th = 8;
+    long best = -1;
+    const int cands[4][2] = {{8, 8}, {16, 4}, {4, 16}, {32, 2}};
+    for (int i = 0; i < 4; ++i) {
+      const long tiles = static_cast<long>((p.Q + cands[i][0] - 1) / cands[i][0]) * ((p.P + cands[i][1] - 1) / cands[i][1]);
+      if (best < 0 || tiles < best) best = tiles, best_tw = cands[i][0], best_th = cands[i][1];
+    }
+    const long t_full = p.total_tiles, t_half = best * p.N * p.n_tiles;
+    const double cost_full = static_cast<double>((t_full + sms - 1) / sms);
+    const double cost_half = 0.72 * static_cast<double>((t_half + sms - 1) / sms);
+    const char* e = getenv("M3D_DCN_HALF");  // development override: 0 = never, 1 = always
+    half = e != nullptr ? atoi(e) != 0 : cost_half < cost_full;
+    if (half && t_half < (1L << 30)) {
+      p.TW = best_tw, p.TH = best_th;
+      p.tiles_w = (p.Q + best_tw - 1) / best_tw, p.tiles_h = (p.P + best_th - 1) / best_th;
+      p.total_tiles = static_cast<int>(t_half);
+    } else {
+      half = false;
+    }
+  }
   const char* e = getenv("M3D_DCN_STAGES");
   const int nstg = e ? atoi(e) : 2;
-  if (nstg == 3) return BN == 128 ? launch_t<128, 3>(p, stream) : launch_t<256, 3>(p, stream);
-  return BN == 128 ? launch_t<128, 2>(p, stream) : launch_t<256, 2>(p, stream);
+  if (half) return BN == 128 ? launch_t<128, 2, true>(p, stream) : launch_t<256, 2, true>(p, stream);
+  if (nstg == 3) return BN == 128 ? launch_t<128, 3, false>(p, stream) : launch_t<256, 3, false>(p, stream);
+  return BN == 128 ? launch_t<128, 2, false>(p, stream) : launch_t<256, 2, false>(p, stream);
 }
 
 }  // namespace m3d

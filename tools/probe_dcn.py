@@ -54,11 +54,8 @@ def run_case(N, H, W, Cin, Cout, R, legacy, iters=20):
 
 for name, N, H, W, Cin, Cout, R in SHAPES:
     base = None
-    for legacy in (1, 0, -3):
-        if legacy < 0:
-            os.environ["M3D_DCN_STAGES"] = "3"
-        else:
-            os.environ.pop("M3D_DCN_STAGES", None)
+    for legacy in (1, 0, -1):
+        os.environ["M3D_DCN_HALF"] = "1" if legacy < 0 else "0"
         t, out = run_case(N, H, W, Cin, Cout, R, legacy > 0)
         if base is None:
             base = out
