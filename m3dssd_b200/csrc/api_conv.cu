@@ -179,6 +179,8 @@ static int sm_count() {
 
 int launch_conv_simt_f32(const m3d_conv_desc* d, int P, int Q, cudaStream_t stream);
 bool conv_halo_supported(int BN, int out_dtype, bool staged);
+bool conv_halo2_supported(int BN, long m_tiles);
+int launch_conv_halo2(const ConvTmaParams& p, int BN, cudaStream_t stream);
 int launch_conv_halo(const ConvTmaParams& p, int BN, int out_dtype, bool staged, cudaStream_t stream);
 
 static int pick_bn(int cout, int bk, long m_tiles, bool gather, bool split) {
@@ -238,6 +240,7 @@ int persistent_sms() {
   const int all = sm_count();
   return (g_sm_limit > 0 && g_sm_limit < all) ? g_sm_limit : all;
 }
+int reserved_sms() { return sm_count() - persistent_sms(); }
 }  // namespace m3d
 
 extern "C" int m3d_set_sm_limit(int sms) {
@@ -294,7 +297,13 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
   pick_tile(P, Q, 256 / d->stride, &TW, &TH);
   const int tiles_w = (Q + TW - 1) / TW, tiles_h = (P + TH - 1) / TH;
   const long m_tiles = static_cast<long>(tiles_w) * tiles_h * d->N;
-  const int BN = pick_bn(d->Cout, bk, m_tiles * groups, gather, split);
+  int BN = pick_bn(d->Cout, bk, m_tiles * groups, gather, split);
+  // CTA pairs (conv_halo2.cu) share the weights of an N tile between two M tiles: take the wide tile whenever the
+  // pairs still fill most of the device
+  if (!gather && d->R == 3 && d->S == 3 && d->stride == 1 && d->dil == 1 && d->pad == 1 && d->num_inputs == 1 &&
+      groups == 1 && bk == 64 && d->act_dtype == M3D_BF16 && d->out_dtype == M3D_BF16 && d->Cout % 256 == 0 &&
+      conv_halo2_supported(256, m_tiles) && (m_tiles / 2) * (d->Cout / 256) * 5 >= static_cast<long>(sm_count() / 2) * 4)
+    BN = 256;
   const int n_tiles = (d->Cout + BN - 1) / BN;
   const long total_tiles = m_tiles * n_tiles * groups;
   M3D_REQUIRE(total_tiles < (1L << 30), "too many tiles");
@@ -322,9 +331,10 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
                       conv_halo_supported(BN, d->out_dtype == M3D_F32 ? DT_F32 : DT_BF16, staged) &&
                       getenv("M3D_NO_HALO") == nullptr;
     if (halo) {
+      const bool pair = staged && conv_halo2_supported(BN, m_tiles);  // CTA pairs: each CTA loads half of the weight rows
       int rc = make_tmap_nhwc(&p.tmap_a[0], d->in[0], d->N, d->H, d->W, d->in_cstride[0], 64, TW, TH + 2, 1);
       if (rc != M3D_OK) return rc;
-      rc = make_tmap_b_halo(&p.tmap_b, d->weight, d->weight_rows, d->in_c[0] / 64, BN);
+      rc = make_tmap_b_halo(&p.tmap_b, d->weight, d->weight_rows, d->in_c[0] / 64, pair ? BN / 2 : BN);
       if (rc != M3D_OK) return rc;
       p.num_inputs = 1;
       p.chunks[0] = d->in_c[0] / 64;
@@ -338,6 +348,7 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
       p.res = d->res, p.res_cstride = d->res_cstride, p.res_coff = d->res_coff;
       p.slope = d->slope;
       p.total_tiles = static_cast<int>(total_tiles);
+      if (pair) return launch_conv_halo2(p, BN, stream);
       return launch_conv_halo(p, BN, d->out_dtype == M3D_F32 ? DT_F32 : DT_BF16, staged, stream);
     }
     // k-blocks per pipeline stage: enough tensor-pipe clocks per stage (N/2 per k16) to cover the

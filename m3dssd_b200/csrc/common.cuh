@@ -8,6 +8,9 @@ namespace m3d {
 void set_last_error(const char* fmt, ...);
 // SMs the persistent kernels launched from now on may occupy (m3d_set_sm_limit; default: all of the device)
 int persistent_sms();
+// SMs left out by m3d_set_sm_limit (0 when no limit is set): their CTAs may each strand the sibling SM of a TPC,
+// which matters to kernels launched as CTA pairs
+int reserved_sms();
 }
 
 #define M3D_CUDA_OK(expr)                                                                     \

@@ -71,11 +71,14 @@ def main():
     log = open(os.path.join(ROOT, "gpurun_out", "probe_perf.log"), "w")
     for name, N, H, W, Cin, Cout, R, stride in SHAPES:
         gf = 2.0 * N * (H // stride) * (W // stride) * Cin * Cout * R * R / 1e9
-        for dbg in (0, 4, 1, 5, 8, 13):
-            os.environ["M3D_DBG"] = str(dbg)
+        for dbg in (0, 1):
+            if dbg:
+                os.environ.pop("M3D_NO_PAIR", None)
+            else:
+                os.environ["M3D_NO_PAIR"] = "1"
             ksub = dbg
             cold, warm = time_conv(N, H, W, Cin, Cout, R, stride, 0)
-            line = "%-28s dbg=%d  best %7.1f us  median %7.1f us  (%.0f TF/s)" % (name, ksub, cold, warm, gf / cold * 1e-3)
+            line = "%-28s pair=%d  best %7.1f us  median %7.1f us  (%.0f TF/s)" % (name, ksub, cold, warm, gf / cold * 1e-3)
             print(line, flush=True)
             log.write(line + "\n")
     os.environ.pop("M3D_KSUB", None)
