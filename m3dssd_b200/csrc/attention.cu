@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -80,6 +81,64 @@ __global__ void anab_pool_finish_kernel(const float* __restrict__ scratch, int H
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float acc = 0.f;
     for (int k = 0; k < nchunks; ++k) acc += src[k * C + c];
+    acc *= inv;
+    if (c < ck)
+      ktok[(static_cast<long>(n) * T + tok) * ck + c] = acc;
+    else
+      vtok[(static_cast<long>(n) * T + tok) * cv + (c - ck)] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Fast pooling when every pyramid size divides the largest one (S) and S divides H and W (the benchmark shape:
+// 48 x 160, sizes 1/4/8/16): the bins are exact, so every level's bins are unions of the S x S finest regions.
+// Pass 1: block (region, image) reads its pixels ONCE (the general kernels read the map once per level and take
+// a sigmoid per (pixel, channel)), computes the nlev sigmoids per pixel into shared memory and writes the
+// per-level weighted channel sums of the region.  Pass 2: token = fixed-order sum of its regions / bin area.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(320) anab_pool_region_kernel(const float* __restrict__ kvs, int cs, int H, int W,
+                                                               int C, int nlev, int S, float* __restrict__ part) {
+  __shared__ float s_sig[64 * kMaxLevels];
+  const int reg = blockIdx.x, n = blockIdx.y;
+  const int rh = H / S, rw = W / S, npix = rh * rw;  // host: npix <= 64
+  const int y0 = (reg / S) * rh, x0 = (reg % S) * rw;
+  for (int i = threadIdx.x; i < npix * nlev; i += blockDim.x) {
+    const int px = i / nlev, l = i - px * nlev;
+    const int y = y0 + px / rw, x = x0 + px % rw;
+    s_sig[i] = 1.f / (1.f + expf(-__ldg(kvs + ((static_cast<long>(n) * H + y) * W + x) * cs + C + l)));
+  }
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  float acc[kMaxLevels] = {0.f, 0.f, 0.f, 0.f};
+  for (int px = 0; px < npix; ++px) {
+    const int y = y0 + px / rw, x = x0 + px % rw;
+    const float v = __ldg(kvs + ((static_cast<long>(n) * H + y) * W + x) * cs + c);
+#pragma unroll
+    for (int l = 0; l < kMaxLevels; ++l)
+      if (l < nlev) acc[l] = fmaf(v, s_sig[px * nlev + l], acc[l]);
+  }
+  float* dst = part + ((static_cast<long>(n) * S * S + reg) * nlev) * C;
+  for (int l = 0; l < nlev; ++l) dst[l * C + c] = acc[l];
+}
+
+__global__ void anab_pool_region_finish_kernel(const float* __restrict__ part, int H, int W, int ck, int cv,
+                                               const PoolGeom g, int S, int T, float* __restrict__ ktok,
+                                               float* __restrict__ vtok) {
+  const int tok = blockIdx.x, n = blockIdx.y;
+  const int C = ck + cv;
+  int lev = 0;
+  while (lev + 1 < g.nlev && tok >= g.tok0[lev + 1]) ++lev;
+  const int s = g.size[lev];
+  const int b = tok - g.tok0[lev];
+  const int f = S / s;  // finest regions per bin side
+  const int ry0 = (b / s) * f, rx0 = (b % s) * f;
+  const float inv = 1.f / static_cast<float>((H / s) * (W / s));
+  const float* src = part + (static_cast<long>(n) * S * S * g.nlev + lev) * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int ry = ry0; ry < ry0 + f; ++ry)
+      for (int rx = rx0; rx < rx0 + f; ++rx) acc += src[static_cast<long>(ry * S + rx) * g.nlev * C + c];
     acc *= inv;
     if (c < ck)
       ktok[(static_cast<long>(n) * T + tok) * ck + c] = acc;
@@ -180,6 +239,13 @@ __global__ void __launch_bounds__(256) anab_attention_kernel(const TQ* __restric
 
 }  // namespace m3d
 
+namespace m3d {
+bool anab_tc_supported(int ck, int cv, int T, int q_cs, int x_cs, int out_cs);
+int launch_anab_attention_tc(const void* q, int q_cs, const float* ktok, const float* vtok, const void* x, int x_cs,
+                             const float* scale, const float* shift, float slope, void* out, int out_cs, int N, int HW,
+                             int ck, int cv, int T, cudaStream_t stream);
+}  // namespace m3d
+
 using namespace m3d;
 
 static inline cudaStream_t S(m3d_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -225,6 +291,21 @@ extern "C" int m3d_anab_pool(const float* kvs, int kvs_cstride, int N, int H, in
     return M3D_ERR_WORKSPACE;
   }
   float* scratch = static_cast<float*>(workspace);
+  {
+    // exact-bin fast path
+    int SS = 0;
+    for (int l = 0; l < nlev; ++l) SS = sizes[l] > SS ? sizes[l] : SS;
+    bool exact = H % SS == 0 && W % SS == 0 && (H / SS) * (W / SS) <= 64;
+    for (int l = 0; l < nlev; ++l) exact = exact && SS % sizes[l] == 0;
+    const size_t need = static_cast<size_t>(N) * SS * SS * nlev * (ck + cv) * sizeof(float);
+    if (exact && need <= workspace_bytes && getenv("M3D_ANAB_SIMT") == nullptr) {
+      anab_pool_region_kernel<<<dim3(SS * SS, N), 320, 0, S(stream)>>>(kvs, kvs_cstride, H, W, ck + cv, nlev, SS, scratch);
+      M3D_CUDA_OK(cudaGetLastError());
+      anab_pool_region_finish_kernel<<<dim3(T, N), 128, 0, S(stream)>>>(scratch, H, W, ck, cv, g, SS, T, ktok, vtok);
+      M3D_CUDA_OK(cudaGetLastError());
+      return M3D_OK;
+    }
+  }
   dim3 grid(T, g.max_chunks, N);
   anab_pool_partial_kernel<<<grid, 320, 0, S(stream)>>>(kvs, kvs_cstride, H, W, ck, cv, g, scratch);
   M3D_CUDA_OK(cudaGetLastError());
@@ -257,6 +338,10 @@ extern "C" int m3d_anab_attention(const void* q, int q_cstride, const float* kto
                                   void* out, int out_cstride, int N, int HW, int ck, int cv, int T,
                                   m3d_stream_t stream) {
   M3D_REQUIRE(q && ktok && vtok && x && scale && shift && out, "NULL pointer");
+  if (act_dtype == M3D_BF16 && anab_tc_supported(ck, cv, T, q_cstride, x_cstride, out_cstride) &&
+      getenv("M3D_ANAB_SIMT") == nullptr)
+    return launch_anab_attention_tc(q, q_cstride, ktok, vtok, x, x_cstride, scale, shift, slope, out, out_cstride, N, HW,
+                                    ck, cv, T, S(stream));
   if (act_dtype == M3D_BF16)
     return launch_attn<__nv_bfloat16, __nv_bfloat16>(q, q_cstride, ktok, vtok, x, x_cstride, scale, shift, slope, out,
                                                      out_cstride, N, HW, ck, cv, T, S(stream));

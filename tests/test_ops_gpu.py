@@ -150,11 +150,13 @@ def test_layout_round_trip():
     assert torch.equal(back, x)
 
 
+@pytest.mark.parametrize("hw", [(12, 40), (48, 160)])  # uneven adaptive bins / the exact-bin fast pooling path
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_anab_pool_and_attention(dtype):
+def test_anab_pool_and_attention(dtype, hw):
     from m3dssd_b200 import ops
     g = _g(7)
-    B, C, H, W, ck, cv = 2, 128, 12, 40, 168, 128
+    B, C, ck, cv = 2, 128, 168, 128
+    H, W = hw
     sizes = [1, 4, 8, 16]
     T = sum(s * s for s in sizes)
     x = torch.randn(B, C, H, W, generator=g)
