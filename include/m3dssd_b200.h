@@ -198,6 +198,14 @@ int m3d_head_mlp(const void* x, int N, int H, int W, int x_cstride, int x_coff, 
 int m3d_flatten_heads(const float* heads, int heads_cstride, int N, int H, int W, int A,
                       const int* slot_of_output /*host, 11 ints: slot of x,y,w,h,x3d,y3d,z3d,w3d,h3d,l3d,rY3d*/,
                       float* bbox_2d, float* bbox_3d, m3d_stream_t stream);
+/* Post-NMS 3D refinement: the per-box loop of test_kitti_3d with hill_climb / test_projection / project_3d
+ * (lib/rpn_util.py:1801-1852, 652-708, 2015-2050, 921-970; lib/util.py:516-535), float64 like the reference's numpy,
+ * one thread per kept box.  kept: fp32 [B, max_out, row_len >= 13] rows from m3d_gather_kept; p2 / p2_inv: float64
+ * [B, 16] (row-major 4x4, device).  out: float64 [B, max_out, 14] = (class index, alpha, x1, y1, x2, y2, h3d, w3d,
+ * l3d, x3d, y3d, z3d, ry3d, score), the numbers of the KITTI result line; valid[B, max_out] = passed the score cut. */
+int m3d_refine_3d(const float* kept, const int* num_keep, int B, int max_out, int row_len, const double* p2,
+                  const double* p2_inv, float score_thresh, int hill_climbing, double step_r_init, double r_lim,
+                  double* out, int* valid, m3d_stream_t stream);
 /* layout conversion for the NCHW-facing operators */
 int m3d_nchw_to_nhwc(const void* in, int in_dtype, void* out, int out_dtype, int N, int C, int H, int W,
                      int out_cstride, int out_coff, m3d_stream_t stream);

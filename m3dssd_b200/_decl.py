@@ -1,7 +1,7 @@
 """argtypes/restype declarations for the C ABI beyond m3d_conv2d_nhwc."""
 import ctypes as C
 
-vp, i, f, sz, lg = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_long
+vp, i, f, sz, lg, db = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_long, C.c_double
 
 _SIGS = {
     "m3d_dcn_v2_forward": [vp, vp, vp, vp, vp, vp] + [i] * 15 + [vp, sz, vp],
@@ -19,6 +19,7 @@ _SIGS = {
     "m3d_center_align_om": [vp, vp, vp, i, i, i, vp, i, f, f, f, f, f, f, vp, i, lg, vp],
     "m3d_set_sm_limit": [i],
     "m3d_head_mlp": [vp, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, i, i, i, vp, i, i, f, vp],
+    "m3d_refine_3d": [vp, vp, i, i, i, vp, vp, f, i, db, db, vp, vp, vp],
     "m3d_flatten_heads": [vp, i, i, i, i, i, vp, vp, vp, vp],
     "m3d_anab_pool": [vp, i, i, i, i, i, i, i, vp, vp, sz, vp, vp, vp],
     "m3d_anab_attention": [vp, i, vp, vp, vp, i, i, vp, vp, f, vp, i, i, i, i, i, i, vp],

@@ -66,3 +66,38 @@ def im_detect_3d(im, net, rpn_conf, obj, gpu=0, synced=False):
         aboxes[:, 2] = np.clip(aboxes[:, 2], 0, obj.imW - 1)
         aboxes[:, 3] = np.clip(aboxes[:, 3], 0, obj.imH - 1)
     return aboxes
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Post-NMS 3D refinement + KITTI result lines: the loop body of test_kitti_3d
+# (lib/rpn_util.py:1801-1852) with hill_climb (:652-708) on the device, all kept boxes of a batch in one launch.
+# ---------------------------------------------------------------------------------------------------------
+def refine_detections(kept, num_keep, p2, rpn_conf=None, score_thresh=0.75, hill_climbing=None):
+    """kept [B, max_out, >=13] fp32 CUDA rows (x1, y1, x2, y2, score, cls, x3d, y3d, z3d, w3d, h3d, l3d, alpha, ...)
+    as the engine's NMS gather leaves them, num_keep [B] int32 CUDA, p2 [4, 4] or [B, 4, 4].
+    Returns (rows float64 CUDA [B, max_out, 14], valid bool CUDA [B, max_out]); rows = (class index, alpha, x1, y1,
+    x2, y2, h3d, w3d, l3d, x3d, y3d, z3d, ry3d, score), the numbers of the reference's KITTI line.
+    Raises NotImplementedError on CPU tensors (no CPU fallback, like the DCN op)."""
+    from .. import ops
+    if not (torch.is_tensor(kept) and kept.is_cuda):
+        raise NotImplementedError("refine_detections needs CUDA tensors: m3dssd_b200 has no CPU fallback")
+    if hill_climbing is None:
+        hill_climbing = bool(getattr(rpn_conf, "hill_climbing", True)) if rpn_conf is not None else True
+    out, valid = ops.refine_3d(kept.float().contiguous(), num_keep.int().contiguous(), p2, score_thresh=score_thresh,
+                               hill_climbing=hill_climbing)
+    return out, valid.bool()
+
+
+def kitti_result_lines(rows, valid, lbls):
+    """Format one image's refined rows exactly like lib/rpn_util.py:1846-1847."""
+    rows = rows.detach().cpu().numpy() if torch.is_tensor(rows) else np.asarray(rows)
+    valid = valid.detach().cpu().numpy() if torch.is_tensor(valid) else np.asarray(valid)
+    text = ''
+    for r, ok in zip(rows, valid):
+        if not ok:
+            continue
+        cls = lbls[int(r[0])]
+        text += ('{} -1 -1 {:.6f} {:.6f} {:.6f} {:.6f} {:.6f} {:.6f} {:.6f} {:.6f} {:.6f} {:.6f} {:.6f} '
+                 + '{:.6f} {:.6f}\n').format(cls, r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[10], r[11],
+                                             r[12], r[13])
+    return text

@@ -238,6 +238,25 @@ def center_align_om(fg_max, fg_arg, heads, x_coff, y_coff, anchors, feat_stride,
                                     fg_max.numel(), _stream()))
 
 
+def refine_3d(kept, num_keep, p2, score_thresh=0.75, hill_climbing=True, step_r_init=None, r_lim=0.01):
+    """Post-NMS 3D refinement of kept[B, max_out, >=13] (fp32, device) with projection matrices p2 [B, 4, 4] or [4, 4]
+    (any float dtype / device): returns (out float64 [B, max_out, 14], valid int32 [B, max_out]) on the device."""
+    import math
+    B, max_out, row_len = kept.shape
+    p2 = torch.as_tensor(p2, dtype=torch.float64).cpu().reshape(-1, 4, 4)
+    if p2.shape[0] == 1 and B > 1:
+        p2 = p2.expand(B, 4, 4)
+    assert p2.shape[0] == B
+    p2_inv = torch.from_numpy(__import__("numpy").linalg.inv(p2.numpy()))  # the reference inverts with numpy on the host
+    p2d, p2i = p2.contiguous().to(kept.device), p2_inv.contiguous().to(kept.device)
+    out = torch.empty(B, max_out, 14, dtype=torch.float64, device=kept.device)
+    valid = torch.empty(B, max_out, dtype=torch.int32, device=kept.device)
+    step = 0.3 * math.pi if step_r_init is None else float(step_r_init)
+    check(lib().m3d_refine_3d(_p(kept), _p(num_keep), B, max_out, row_len, _p(p2d), _p(p2i), float(score_thresh),
+                              int(bool(hill_climbing)), step, float(r_lim), _p(out), _p(valid), _stream()))
+    return out, valid
+
+
 def set_sm_limit(sms):
     """SMs the persistent kernels launched / captured from now on may use (0 = all)."""
     check(lib().m3d_set_sm_limit(int(sms)))

@@ -80,7 +80,47 @@ def main():
         np.savez_compressed(os.path.join(HERE, "ref_model_%s_96x320.npz" % name), **fix)
         print(name, "fg_frac=%.4f" % fix["fg_frac"], "aboxes", ab.shape,
               {k: v.shape for k, v in fix.items() if hasattr(v, "shape") and v.ndim > 0})
+    hill_climb_golden(ns)
+
+
+def hill_climb_golden(ns):
+    """Post-NMS refinement: the unmodified reference functions (lib/rpn_util.py hill_climb / test_projection /
+    project_3d, lib/util.py convertAlpha2Rot / convertRot2Alpha) driven by the loop body of test_kitti_3d
+    (lib/rpn_util.py:1801-1852) on seeded KITTI-like detections (oracle.hill_climb.synthetic_detections).
+    NOTE: run here under NumPy 2 (NEP 50) the reference keeps float32 in a few scalar expressions that its pinned
+    NumPy 1.x promoted to float64; the float64 oracle therefore matches these vectors to ~2e-6, not bit for bit."""
+    import importlib
+    import math
+    from oracle import hill_climb as HC
+    ru = ns.rpn_util
+    util = importlib.import_module("lib.util")
+    out = {}
+    for seed in (5, 6, 7):
+        rows, p2 = HC.synthetic_detections(64, seed)
+        p2_inv = np.linalg.inv(p2)
+        res = []
+        for i in range(40):
+            box = rows[i]
+            if not box[4] >= 0.75:
+                continue
+            x1, y1, x2, y2 = box[0], box[1], box[2], box[3]
+            width, height = (x2 - x1 + 1), (y2 - y1 + 1)
+            x3d, y3d, z3d, w3d, h3d, l3d, ry3d = box[6], box[7], box[8], box[9], box[10], box[11], box[12]
+            coord3d = np.linalg.inv(p2).dot(np.array([x3d * z3d, y3d * z3d, 1 * z3d, 1]))
+            ry3d = util.convertAlpha2Rot(ry3d, coord3d[2], coord3d[0])
+            z3d, ry3d, _ = ru.hill_climb(p2, p2_inv, np.array([x1, y1, width, height]), x3d, y3d, z3d, w3d, h3d, l3d, ry3d,
+                                         step_r_init=0.3 * math.pi, r_lim=0.01)
+            coord3d = np.linalg.inv(p2).dot(np.array([x3d * z3d, y3d * z3d, 1 * z3d, 1]))
+            alpha = util.convertRot2Alpha(ry3d, coord3d[2], coord3d[0])
+            res.append([box[5] - 1, alpha, x1, y1, x2, y2, h3d, w3d, l3d, coord3d[0], coord3d[1] + h3d / 2, coord3d[2],
+                        ry3d, box[4]])
+        out["refined_%d" % seed] = np.asarray(res, dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "hill_climb.npz"), **out)
+    print("hill_climb", {k: v.shape for k, v in out.items()})
 
 
 if __name__ == "__main__":
-    main()
+    if "--hill-climb-only" in sys.argv:
+        hill_climb_golden(RH.load_reference())
+    else:
+        main()

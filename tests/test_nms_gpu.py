@@ -134,3 +134,49 @@ def test_decode_topk_with_ties():
         assert torch.equal(didx[b].cpu().long(), order)
         assert np.allclose(dets[b].cpu().numpy(), pre.numpy(), rtol=2e-6, atol=1e-4)
         assert int(dnum[b]) == topk
+
+
+@pytest.mark.parametrize("seed", [5, 6, 7, 11])
+def test_refine_3d_vs_oracle(seed):
+    """m3d_refine_3d (post-NMS hill-climb refinement, one thread per box, float64) vs oracle/hill_climb.py and, for
+    the golden seeds, vs the unmodified reference functions (tests/golden/hill_climb.npz)."""
+    import os
+    import torch
+    from m3dssd_b200 import ops
+    from oracle import hill_climb as HC
+    B, max_out = 3, 40
+    kept = np.zeros((B, max_out, 14), dtype=np.float32)
+    nk = np.zeros(B, dtype=np.int32)
+    p2s, refs = [], []
+    for b in range(B):
+        rows, p2 = HC.synthetic_detections(64, seed + 100 * b)
+        if b == 1:  # a different camera and a short list
+            p2 = p2.copy()
+            p2[0, 0] *= 1.1
+            p2[1, 1] *= 1.1
+            rows = rows[:17]
+        if b == 2:  # boxes behind the camera / tiny depth: the `invalid` branch
+            rows = rows.copy()
+            rows[::5, 8] = 0.3
+        n = min(max_out, rows.shape[0])
+        kept[b, :n] = rows[:n]
+        nk[b] = n
+        p2s.append(p2)
+        refs.append(HC.refine_detections(rows[:n], p2, max_out=max_out))
+    out, valid = ops.refine_3d(torch.from_numpy(kept).cuda(), torch.from_numpy(nk).cuda(), np.stack(p2s))
+    out, valid = out.cpu().numpy(), valid.cpu().numpy().astype(bool)
+    for b in range(B):
+        exp_valid = (np.arange(max_out) < nk[b]) & (kept[b, :, 4] >= 0.75)
+        assert np.array_equal(valid[b], exp_valid)
+        got = out[b][valid[b]]
+        assert got.shape == refs[b].shape
+        assert np.allclose(got, refs[b], rtol=1e-9, atol=1e-9), np.abs(got - refs[b]).max()
+        assert np.all(out[b][~valid[b]] == 0)
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hill_climb.npz"))
+    if "refined_%d" % seed in gold:
+        assert np.abs(out[0][valid[0]] - gold["refined_%d" % seed]).max() < 2e-5
+    # no hill climbing: only the alpha <-> rotation round trip and the back-projection
+    out2, valid2 = ops.refine_3d(torch.from_numpy(kept).cuda(), torch.from_numpy(nk).cuda(), np.stack(p2s),
+                                 hill_climbing=False)
+    ref2 = HC.refine_detections(kept[0, :nk[0]], p2s[0], hill_climbing=False, max_out=max_out)
+    assert np.allclose(out2.cpu().numpy()[0][valid2.cpu().numpy()[0].astype(bool)], ref2, rtol=1e-9, atol=1e-9)
