@@ -220,6 +220,71 @@ __global__ void __launch_bounds__(256) upsample_add_kernel(const T* __restrict__
 // ---------------------------------------------------------------------------
 constexpr int SM_PIX = 32;
 
+// K == 4 (the model's 3 classes + background): 16-byte loads / stores, everything in registers.  The tile is
+// staged class-major in shared memory ([K*A][SM_PIX + 1]) so that the NHWC reads (144 contiguous floats per
+// pixel) and the anchor-major writes (16 bytes per (anchor, pixel), pixels contiguous) are both coalesced and
+// the column accesses are bank-conflict free.
+__global__ void __launch_bounds__(256) cls_softmax4_kernel(const float* __restrict__ logits, int lc_stride, int N, int H,
+                                                           int W, int A, float* __restrict__ cls_out,
+                                                           float* __restrict__ prob_out, float* __restrict__ fg_max,
+                                                           int* __restrict__ fg_arg, float* __restrict__ score,
+                                                           unsigned char* __restrict__ cls_pred) {
+  grid_dep_sync();
+  extern __shared__ float s_tile[];  // [4*A][SM_PIX + 1], then fg [A][SM_PIX + 1]
+  constexpr int K = 4, LD = SM_PIX + 1;
+  const int KA = K * A;
+  float* s_fg = s_tile + KA * LD;
+  const int w0 = blockIdx.x * SM_PIX, h = blockIdx.y, n = blockIdx.z;
+  const int npix = min(SM_PIX, W - w0);
+  const float* src = logits + ((static_cast<long>(n) * H + h) * W + w0) * lc_stride;
+  const int c4n = KA >> 2;  // float4 per pixel (host: KA % 4 == 0, lc_stride % 4 == 0)
+  for (int px = threadIdx.x >> 5; px < npix; px += 8) {
+    for (int c4 = threadIdx.x & 31; c4 < c4n; c4 += 32) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + static_cast<long>(px) * lc_stride) + c4);
+      float* d = s_tile + (c4 * 4) * LD + px;
+      d[0] = v.x, d[LD] = v.y, d[2 * LD] = v.z, d[3 * LD] = v.w;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < A * SM_PIX; i += blockDim.x) {
+    const int px = i & (SM_PIX - 1), a = i / SM_PIX;
+    if (px >= npix) continue;
+    const float v0 = s_tile[a * LD + px], v1 = s_tile[(A + a) * LD + px];
+    const float v2 = s_tile[(2 * A + a) * LD + px], v3 = s_tile[(3 * A + a) * LD + px];
+    const float mx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+    const float e0 = expf(v0 - mx), e1 = expf(v1 - mx), e2 = expf(v2 - mx), e3 = expf(v3 - mx);
+    const float sum = ((e0 + e1) + e2) + e3;
+    const float p0 = e0 / sum, p1 = e1 / sum, p2 = e2 / sum, p3 = e3 / sum;
+    const long row = (static_cast<long>(n) * A + a) * H * W + static_cast<long>(h) * W + (w0 + px);
+    *reinterpret_cast<float4*>(cls_out + row * 4) = make_float4(v0, v1, v2, v3);
+    *reinterpret_cast<float4*>(prob_out + row * 4) = make_float4(p0, p1, p2, p3);
+    float best = p1;
+    int bestk = 1;
+    if (p2 > best) best = p2, bestk = 2;
+    if (p3 > best) best = p3, bestk = 3;
+    score[row] = best;
+    cls_pred[row] = static_cast<unsigned char>(bestk);
+    s_fg[a * LD + px] = 1.f - p0;
+  }
+  __syncthreads();
+  if (threadIdx.x < npix) {
+    const int px = threadIdx.x;
+    float best = -1.f;
+    int arg = 0;
+    for (int a = 0; a < A; ++a) {
+      const float f = s_fg[a * LD + px];
+      if (f > best) {  // first maximum wins, like torch.max / topk(k=1)
+        best = f;
+        arg = a;
+      }
+    }
+    const long pix = (static_cast<long>(n) * H + h) * W + w0 + px;
+    fg_max[pix] = best;
+    fg_arg[pix] = arg;
+  }
+}
+
+
 __global__ void __launch_bounds__(256) cls_softmax_kernel(const float* __restrict__ logits, int lc_stride, int N, int H,
                                                           int W, int A, int K, float* __restrict__ cls_out,
                                                           float* __restrict__ prob_out, float* __restrict__ fg_max,
@@ -371,7 +436,7 @@ __global__ void __launch_bounds__(256) flatten_heads_kernel(const float* __restr
     }
   }
   __syncthreads();
-  // thread -> (anchor, pixel) with the pixel fastest: one 16-byte bbox_2d row and one 28-byte bbox_3d row
+  // bbox_2d: thread -> (anchor, pixel), pixel fastest: one 16-byte row each, 512 contiguous bytes per warp
   for (int i = threadIdx.x; i < A * SM_PIX; i += blockDim.x) {
     const int px = i % SM_PIX, a = i / SM_PIX;
     if (px >= npix) continue;
@@ -379,9 +444,18 @@ __global__ void __launch_bounds__(256) flatten_heads_kernel(const float* __restr
     const long row = (static_cast<long>(n) * A + a) * H * W + static_cast<long>(h) * W + (w0 + px);
     *reinterpret_cast<float4*>(bbox_2d + row * 4) =
         make_float4(t[slots.s[0] * A], t[slots.s[1] * A], t[slots.s[2] * A], t[slots.s[3] * A]);
-    float* o3 = bbox_3d + row * 7;
-#pragma unroll
-    for (int j = 0; j < 7; ++j) o3[j] = t[slots.s[4 + j] * A];
+  }
+  // bbox_3d: the npix x 7 floats of one anchor are contiguous in the output: thread -> element, fully coalesced
+  // 4-byte stores (the 28-byte rows written one thread each cost 7 partial-sector stores per row)
+  const int per_a = npix * 7;  // <= 224 < blockDim.x
+  if (threadIdx.x < per_a) {
+    const int e = threadIdx.x;
+    const int px = e / 7, j = e - px * 7;
+    const float* t = s_tile + px * ld + slots.s[4 + j] * A;
+    float* o = bbox_3d + ((static_cast<long>(n) * A) * H * W + static_cast<long>(h) * W + w0) * 7 + e;
+    const long a_stride = static_cast<long>(H) * W * 7;
+#pragma unroll 4
+    for (int a = 0; a < A; ++a) o[a * a_stride] = t[a];
   }
 }
 
@@ -490,9 +564,17 @@ extern "C" int m3d_cls_softmax(const float* logits, int logits_cstride, int N, i
                                m3d_stream_t stream) {
   M3D_REQUIRE(logits && cls_out && prob_out && fg_max && fg_arg && score && cls_pred, "NULL pointer");
   M3D_REQUIRE(K >= 2 && K <= 8 && A >= 1, "K=%d A=%d unsupported", K, A);
+  dim3 grid(cdiv(W, SM_PIX), H, N);
+  if (K == 4 && logits_cstride % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) {
+    const size_t smem4 = static_cast<size_t>(5 * A) * (SM_PIX + 1) * sizeof(float);
+    if (smem4 <= 48 * 1024) {
+      M3D_CUDA_OK(launch_pdl(cls_softmax4_kernel, grid, dim3(256), smem4, S(stream), logits, logits_cstride, N, H, W, A,
+                             cls_out, prob_out, fg_max, fg_arg, score, cls_pred));
+      return M3D_OK;
+    }
+  }
   const size_t smem = static_cast<size_t>(SM_PIX) * (K * A + 1) * sizeof(float);
   M3D_REQUIRE(smem <= 48 * 1024, "K*A too large");
-  dim3 grid(cdiv(W, SM_PIX), H, N);
   M3D_CUDA_OK(launch_pdl(cls_softmax_kernel, dim3(grid), dim3(256), smem, S(stream), logits, logits_cstride, N, H, W, A, K, cls_out, prob_out, fg_max,
                                                      fg_arg, score, cls_pred));
   M3D_CUDA_OK(cudaGetLastError());
