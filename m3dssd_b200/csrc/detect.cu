@@ -9,6 +9,7 @@
 // sweep); here everything stays on the device and is batched over images.
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -25,6 +26,41 @@ constexpr int kMaxTopK = 4096;
 __device__ __forceinline__ uint32_t score_key(float s) {
   uint32_t u = __float_as_uint(s);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // total order for any sign
+}
+
+// Descending scan of a (1 << BITS)-bin histogram in shared memory (all threads of a 1024-thread block): the digit d
+// at which the running count from the top reaches `need`, how many are still needed inside d, and hist[d].
+// Two levels: 32 warp partial sums, then inside the crossing group.
+template <int BITS>
+__device__ void pick_digit(const uint32_t* hist, int need, uint32_t* out_digit, int* out_need, int* out_count) {
+  constexpr int NB = 1 << BITS;
+  constexpr int PER = NB / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ uint32_t s_part[32];
+  uint32_t v = 0;
+  if (warp < 32)
+    for (int i = lane; i < PER; i += 32) v += hist[warp * PER + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0 && warp < 32) s_part[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    int g = 31;
+    for (; g > 0; --g) {
+      if (acc + static_cast<int>(s_part[g]) >= need) break;
+      acc += s_part[g];
+    }
+    int d = g * PER + PER - 1;
+    for (; d > g * PER; --d) {
+      if (acc + static_cast<int>(hist[d]) >= need) break;
+      acc += hist[d];
+    }
+    *out_digit = static_cast<uint32_t>(d);
+    *out_need = need - acc;  // how many still to take from inside digit d
+    *out_count = static_cast<int>(hist[d]);
+  }
+  __syncthreads();
 }
 
 // One histogram pass over the image's scores.  8 elements per thread per trip (two 16-byte loads in
@@ -65,35 +101,7 @@ __device__ void radix_pass(const float* __restrict__ score, int M, uint32_t pref
     if (threadIdx.x < 32) add(live ? score[i] : 0.f, live);
   }
   __syncthreads();
-  // two-level descending scan: 32 warp partial sums, then inside the crossing group
-  {
-    constexpr int PER = NB / 32;
-    const int warp = threadIdx.x >> 5;
-    uint32_t v = 0;
-    for (int i = lane; i < PER; i += 32) v += hist[warp * PER + i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __shared__ uint32_t s_part[32];
-    if (lane == 0) s_part[warp] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int acc = 0;
-      int g = 31;
-      for (; g > 0; --g) {
-        if (acc + static_cast<int>(s_part[g]) >= need) break;
-        acc += s_part[g];
-      }
-      int d = g * PER + PER - 1;
-      for (; d > g * PER; --d) {
-        if (acc + static_cast<int>(hist[d]) >= need) break;
-        acc += hist[d];
-      }
-      *out_digit = static_cast<uint32_t>(d);
-      *out_need = need - acc;  // how many still to take from inside digit d
-      *out_count = static_cast<int>(hist[d]);
-    }
-  }
-  __syncthreads();
+  pick_digit<BITS>(hist, need, out_digit, out_need, out_count);
 }
 
 struct DecodeParams {
@@ -111,13 +119,11 @@ struct DecodeParams {
   int* det_num;  // [N]
 };
 
-__global__ void __launch_bounds__(kSelThreads) topk_decode_kernel(const DecodeParams p) {
-  __shared__ uint32_t hist[2048];
-  __shared__ unsigned long long keys[kMaxTopK];
+// Exact selection by three radix passes + one compaction pass over all M scores (any input).
+__device__ void topk_select_full(const DecodeParams& p, int n, uint32_t* hist, unsigned long long* keys) {
   __shared__ uint32_t s_digit;
   __shared__ int s_need, s_count, s_cnt_gt, s_cnt_eq;
   __shared__ int s_warp_gt[32], s_warp_eq[32];
-  const int n = blockIdx.x;
   const float* score = p.score + static_cast<long>(n) * p.M;
   const int K = min(p.topk, p.M);
 
@@ -202,6 +208,11 @@ __global__ void __launch_bounds__(kSelThreads) topk_decode_kernel(const DecodePa
     }
   }
 
+}
+
+__device__ void topk_sort_decode(const DecodeParams& p, int n, unsigned long long* keys) {
+  const float* score = p.score + static_cast<long>(n) * p.M;
+  const int K = min(p.topk, p.M);
   // ---- bitonic sort, descending on (key, ~index): higher score first, lower index first on ties
   for (int size = 2; size <= kMaxTopK; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -270,6 +281,159 @@ __global__ void __launch_bounds__(kSelThreads) topk_decode_kernel(const DecodePa
   }
 }
 
+__global__ void __launch_bounds__(kSelThreads) topk_decode_kernel(const DecodeParams p) {
+  __shared__ uint32_t hist[2048];
+  __shared__ unsigned long long keys[kMaxTopK];
+  topk_select_full(p, blockIdx.x, hist, keys);
+  topk_sort_decode(p, blockIdx.x, keys);
+}
+
+// ---------------------------------------------------------------- multi-CTA top-K
+// The single-CTA kernel above reads the image's 276 480 scores four times from one SM (0.68 ms for a batch of 8,
+// 8 SMs busy).  Here the two full passes are spread over the device and the rest works on a short candidate list:
+//   1. topk_hist_kernel     (S slices x N images): histogram of the keys' top 11 bits -> global
+//   2. topk_compact_kernel  (S x N): every CTA re-derives the threshold digit d1 from the global histogram and
+//                           appends its keys with top-11 bits >= d1 to the image's candidate list (packed key|~index)
+//   3. topk_finish_kernel   (N): radix passes 2 and 3 over the candidates of digit d1, selection of every key >= T,
+//                           bitonic sort, decode.  Falls back to the full single-CTA selection when the candidate
+//                           list or the tie group at T overflows (pathological score distributions): always exact.
+constexpr int kTopkSlices = 16;
+constexpr int kCandCap = 32768;
+
+__global__ void __launch_bounds__(kSelThreads) topk_hist_kernel(const float* __restrict__ score_all, int M,
+                                                                uint32_t* __restrict__ hist_g) {
+  __shared__ uint32_t hist[2048];
+  const int n = blockIdx.y;
+  const float* score = score_all + static_cast<long>(n) * M;
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const int chunk = (((M + kTopkSlices - 1) / kTopkSlices) + 3) & ~3;
+  const int lo = blockIdx.x * chunk, hi = min(M, lo + chunk);
+  for (int i0 = lo + threadIdx.x * 4; i0 < hi; i0 += blockDim.x * 4) {
+    float v[4];
+    int cnt = min(4, hi - i0);
+    if (cnt == 4 && ((reinterpret_cast<uintptr_t>(score + i0) & 15) == 0)) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(score + i0));
+      v[0] = f.x, v[1] = f.y, v[2] = f.z, v[3] = f.w;
+    } else {
+      for (int e = 0; e < 4; ++e) v[e] = e < cnt ? score[i0 + e] : 0.f;
+    }
+    for (int e = 0; e < cnt; ++e) atomicAdd(&hist[score_key(v[e]) >> 21], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x)
+    if (hist[i]) atomicAdd(&hist_g[n * 2048 + i], hist[i]);
+}
+
+__global__ void __launch_bounds__(kSelThreads) topk_compact_kernel(const float* __restrict__ score_all, int M, int topk,
+                                                                   const uint32_t* __restrict__ hist_g,
+                                                                   uint32_t* __restrict__ count_g,
+                                                                   unsigned long long* __restrict__ cand_g) {
+  __shared__ uint32_t hist[2048];
+  __shared__ uint32_t s_digit;
+  __shared__ int s_need, s_count;
+  const int n = blockIdx.y;
+  const float* score = score_all + static_cast<long>(n) * M;
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = hist_g[n * 2048 + i];
+  __syncthreads();
+  pick_digit<11>(hist, min(topk, M), &s_digit, &s_need, &s_count);
+  const uint32_t d1 = s_digit;
+  const int lane = threadIdx.x & 31;
+  unsigned long long* cand = cand_g + static_cast<long>(n) * kCandCap;
+  const int chunk = (((M + kTopkSlices - 1) / kTopkSlices) + 3) & ~3;
+  const int lo = blockIdx.x * chunk, hi = min(M, lo + chunk);
+  const int span = blockDim.x * 4;
+  for (int base = lo; base < hi; base += span) {  // uniform trip count per block: the ballots need every lane
+    const int i0 = base + threadIdx.x * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    const int cnt = max(0, min(4, hi - i0));
+    if (cnt == 4 && ((reinterpret_cast<uintptr_t>(score + i0) & 15) == 0)) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(score + i0));
+      v[0] = f.x, v[1] = f.y, v[2] = f.z, v[3] = f.w;
+    } else {
+      for (int e = 0; e < cnt; ++e) v[e] = score[i0 + e];
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t k = score_key(v[e]);
+      const bool take = e < cnt && (k >> 21) >= d1;
+      const uint32_t b = __ballot_sync(0xffffffffu, take);
+      if (b) {
+        uint32_t slot = 0;
+        if (lane == 0) slot = atomicAdd(&count_g[n], static_cast<uint32_t>(__popc(b)));
+        slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(b & ((1u << lane) - 1));
+        if (take && slot < kCandCap)
+          cand[slot] = (static_cast<unsigned long long>(k) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(i0 + e));
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kSelThreads) topk_finish_kernel(const DecodeParams p, const uint32_t* __restrict__ hist_g,
+                                                                  const uint32_t* __restrict__ count_g,
+                                                                  const unsigned long long* __restrict__ cand_g) {
+  __shared__ uint32_t hist[2048];
+  __shared__ unsigned long long keys[kMaxTopK];
+  __shared__ uint32_t s_digit;
+  __shared__ int s_need, s_count, s_slots;
+  const int n = blockIdx.x;
+  const int K = min(p.topk, p.M);
+  const uint32_t nc = count_g[n];
+  bool fallback = nc > static_cast<uint32_t>(kCandCap);  // block-uniform
+  if (!fallback) {
+    const unsigned long long* cand = cand_g + static_cast<long>(n) * kCandCap;
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = hist_g[n * 2048 + i];
+    __syncthreads();
+    pick_digit<11>(hist, K, &s_digit, &s_need, &s_count);
+    uint32_t prefix = s_digit << 21, mask = 0x7FFu << 21;
+    int need = s_need;
+    // pass 2: bits [20:10] of the candidates inside digit d1
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
+      const uint32_t k = static_cast<uint32_t>(cand[i] >> 32);
+      if ((k & mask) == prefix) atomicAdd(&hist[(k >> 10) & 0x7FFu], 1u);
+    }
+    __syncthreads();
+    pick_digit<11>(hist, need, &s_digit, &s_need, &s_count);
+    prefix |= s_digit << 10, mask |= 0x7FFu << 10, need = s_need;
+    // pass 3: bits [9:0]
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
+      const uint32_t k = static_cast<uint32_t>(cand[i] >> 32);
+      if ((k & mask) == prefix) atomicAdd(&hist[k & 0x3FFu], 1u);
+    }
+    __syncthreads();
+    pick_digit<10>(hist, need, &s_digit, &s_need, &s_count);
+    const uint32_t T = prefix | s_digit;
+    const int need_eq = s_need, count_eq = s_count;
+    // every key >= T goes to the sort buffer (ties at T included: the sort orders them by index and the first K
+    // rows are the answer); a tie group that does not fit falls back to the ordered full selection
+    fallback = (K - need_eq) + count_eq > kMaxTopK;
+    if (!fallback) {
+      if (threadIdx.x == 0) s_slots = 0;
+      for (int i = threadIdx.x; i < kMaxTopK; i += blockDim.x) keys[i] = 0ull;
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
+        const unsigned long long c = cand[i];
+        if (static_cast<uint32_t>(c >> 32) >= T) keys[atomicAdd(&s_slots, 1)] = c;
+      }
+      __syncthreads();
+    }
+  }
+  if (fallback) topk_select_full(p, n, hist, keys);
+  topk_sort_decode(p, n, keys);
+}
+
+// persistent scratch of the multi-CTA top-K (grow-only; sized by an eager call before graph capture)
+struct TopkWs {
+  uint32_t* hist = nullptr;   // [N][2048] + [N] counts
+  unsigned long long* cand = nullptr;
+  int cap_n = 0, device = -1;
+};
+static TopkWs g_topk;
+
 // -------------------------------------------------------------------- NMS
 // IoU with the +1 pixel convention, in the exact operation order the
 // reference's kernel has when built with nvcc's default -fmad=true
@@ -283,6 +447,16 @@ __device__ __forceinline__ float dev_iou(const float4 a, const float4 b) {
   const float Sa = __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.f), __fadd_rn(__fsub_rn(a.w, a.y), 1.f));
   const float SaSb = __fmaf_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f), Sa);
   return __fdiv_rn(interS, __fsub_rn(SaSb, interS));
+}
+
+// IoU(a, b) > thresh, bit for bit like dev_iou(a, b) > thresh: boxes that do not intersect have interS == 0, hence
+// IoU == +0 (the union is >= 1 pixel) and the comparison is false for any thresh >= 0 -- which skips the IEEE
+// division for the vast majority of pairs (the mask kernel is issue bound on it).
+__device__ __forceinline__ bool iou_above(const float4 a, const float4 b, float thresh) {
+  const float width = fmaxf(__fadd_rn(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 1.f), 0.f);
+  const float height = fmaxf(__fadd_rn(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 1.f), 0.f);
+  if (thresh >= 0.f && (width == 0.f || height == 0.f)) return false;
+  return dev_iou(a, b) > thresh;
 }
 
 // mask[n][i][cb] bit k  <=>  j = cb*64 + k > i  and  IoU(box_i, box_j) > thresh.
@@ -314,8 +488,8 @@ __global__ void __launch_bounds__(128) nms_mask_kernel(const float* __restrict__
     const int i = rb * 64 + r;
     if (i >= nb) break;
     const float4 a = rows[r];
-    const bool s0 = (j0 < nb) && (j0 > i) && (dev_iou(a, c0) > thresh);
-    const bool s1 = (j1 < nb) && (j1 > i) && (dev_iou(a, c1) > thresh);
+    const bool s0 = (j0 < nb) && (j0 > i) && iou_above(a, c0, thresh);
+    const bool s1 = (j1 < nb) && (j1 > i) && iou_above(a, c1, thresh);
     const uint32_t lo = __ballot_sync(0xffffffffu, s0), hi = __ballot_sync(0xffffffffu, s1);
     if (lane == 0)
       mask[(static_cast<long>(n) * max_n + i) * col_blocks + cb] = (static_cast<unsigned long long>(hi) << 32) | lo;
@@ -505,7 +679,31 @@ extern "C" int m3d_decode_topk(const float* score, const unsigned char* cls_pred
   p.M = A * H * W, p.A = A, p.H = H, p.W = W;
   p.feat_stride = feat_stride, p.scale_factor = scale_factor, p.topk = topk;
   p.dets = dets, p.det_idx = det_idx, p.det_num = det_num;
-  topk_decode_kernel<<<batch, kSelThreads, 0, S(stream)>>>(p);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (getenv("M3D_TOPK_SINGLE") == nullptr) {
+    int dev = 0;
+    M3D_CUDA_OK(cudaGetDevice(&dev));
+    if (g_topk.cap_n < batch || g_topk.device != dev) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(st, &cs);
+      M3D_REQUIRE(cs == cudaStreamCaptureStatusNone, "top-K scratch must be sized by an eager call before graph capture");
+      if (g_topk.hist) cudaFree(g_topk.hist);
+      if (g_topk.cand) cudaFree(g_topk.cand);
+      M3D_CUDA_OK(cudaMalloc(&g_topk.hist, static_cast<size_t>(batch) * 2049 * sizeof(uint32_t)));
+      M3D_CUDA_OK(cudaMalloc(&g_topk.cand, static_cast<size_t>(batch) * kCandCap * sizeof(unsigned long long)));
+      g_topk.cap_n = batch, g_topk.device = dev;
+    }
+    uint32_t* count = g_topk.hist + static_cast<size_t>(batch) * 2048;
+    M3D_CUDA_OK(cudaMemsetAsync(g_topk.hist, 0, static_cast<size_t>(batch) * 2049 * sizeof(uint32_t), st));
+    topk_hist_kernel<<<dim3(kTopkSlices, batch), kSelThreads, 0, st>>>(score, p.M, g_topk.hist);
+    M3D_CUDA_OK(cudaGetLastError());
+    topk_compact_kernel<<<dim3(kTopkSlices, batch), kSelThreads, 0, st>>>(score, p.M, topk, g_topk.hist, count, g_topk.cand);
+    M3D_CUDA_OK(cudaGetLastError());
+    topk_finish_kernel<<<batch, kSelThreads, 0, st>>>(p, g_topk.hist, count, g_topk.cand);
+    M3D_CUDA_OK(cudaGetLastError());
+    return M3D_OK;
+  }
+  topk_decode_kernel<<<batch, kSelThreads, 0, st>>>(p);
   M3D_CUDA_OK(cudaGetLastError());
   return M3D_OK;
 }
