@@ -3,8 +3,11 @@
 The forward path has no cross-image dependency (eval-mode BN, per-image align / ANAB / NMS), so the
 only exchange is the one BASELINE.json's config 5 names: an all-gather of the fixed-shape per-image
 detection tensors ([local_batch, topk, 14] fp32 + counts) over NCCL/NVLink, followed by the batched
-NMS over the gathered set.  The reference's equivalent is nn.DataParallel's scatter/replicate/gather
-per iteration (lib/core.py:73-74, scripts/test_rpn_3d.py:50-51); here weights are replicated once.
+NMS over the gathered set.  Every rank holds the gathered set; the NMS of gathered image g runs on
+rank g // local_batch (each image is suppressed exactly once per step instead of world_size times),
+and a second, tiny all-gather ([local_batch, 40, 14] kept rows + counts) leaves the full result on
+every rank.  The reference's equivalent is nn.DataParallel's scatter/replicate/gather per iteration
+(lib/core.py:73-74, scripts/test_rpn_3d.py:50-51); here weights are replicated once.
 """
 import torch
 import torch.distributed as dist
@@ -17,6 +20,11 @@ def shard_range(global_batch, world_size, rank):
     base, rem = divmod(global_batch, world_size)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def nms_slice(global_batch, world_size, rank):
+    """Images of the gathered set whose NMS this rank runs (same contiguous split as shard_range)."""
+    return shard_range(global_batch, world_size, rank)
 
 
 def gather_detections(dets, det_num, group=None):
@@ -42,17 +50,24 @@ class ShardedDetector:
         e = self.engine
         gb = self.world * local_batch
         dev = e.dev
-        self.keep = torch.zeros(gb, e.topk, dtype=torch.int32, device=dev)
         self.num_keep = torch.zeros(gb, dtype=torch.int32, device=dev)
         self.kept = torch.zeros(gb, e.max_out, 14, dtype=torch.float32, device=dev)
-        self.nms_ws = torch.zeros(ops.nms_workspace_bytes(gb, e.topk), dtype=torch.uint8, device=dev)
+        lb = local_batch
+        self.keep_l = torch.zeros(lb, e.topk, dtype=torch.int32, device=dev)
+        self.num_keep_l = torch.zeros(lb, dtype=torch.int32, device=dev)
+        self.kept_l = torch.zeros(lb, e.max_out, 14, dtype=torch.float32, device=dev)
+        self.nms_ws = torch.zeros(ops.nms_workspace_bytes(lb, e.topk), dtype=torch.uint8, device=dev)
         self.launches_per_step = e.launches_per_step("decode") + 3
 
     def _gather_and_nms(self):
         e = self.engine
         dets, num = gather_detections(e.dets, e.det_num)
-        ops.nms_batched(dets, num, float(e.conf.nms_thres), self.nms_ws, self.keep, self.num_keep)
-        ops.gather_kept(dets, self.keep, self.num_keep, e.max_out, self.kept)
+        lo, hi = nms_slice(dets.shape[0], self.world, self.rank)
+        mine, nmine = dets[lo:hi], num[lo:hi]  # this rank's share of the gathered set
+        ops.nms_batched(mine, nmine, float(e.conf.nms_thres), self.nms_ws, self.keep_l, self.num_keep_l)
+        ops.gather_kept(mine, self.keep_l, self.num_keep_l, e.max_out, self.kept_l)
+        dist.all_gather_into_tensor(self.kept, self.kept_l)
+        dist.all_gather_into_tensor(self.num_keep, self.num_keep_l)
 
     def step_pipelined(self, images=None):
         """Asynchronous step (see Engine.detect_pipelined): batch i's tail -- decode, [all-gather,] NMS --
@@ -70,7 +85,5 @@ class ShardedDetector:
         if self.world == 1:
             return e.detect(images)
         e.run(images, "decode")
-        dets, num = gather_detections(e.dets, e.det_num)
-        ops.nms_batched(dets, num, float(e.conf.nms_thres), self.nms_ws, self.keep, self.num_keep)
-        ops.gather_kept(dets, self.keep, self.num_keep, e.max_out, self.kept)
+        self._gather_and_nms()
         return self.kept, self.num_keep
