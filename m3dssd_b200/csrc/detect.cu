@@ -291,20 +291,32 @@ __global__ void __launch_bounds__(kSelThreads) topk_decode_kernel(const DecodePa
 // ---------------------------------------------------------------- multi-CTA top-K
 // The single-CTA kernel above reads the image's 276 480 scores four times from one SM (0.68 ms for a batch of 8,
 // 8 SMs busy).  Here the two full passes are spread over the device and the rest works on a short candidate list:
-//   1. topk_hist_kernel     (S slices x N images): histogram of the keys' top 11 bits -> global
-//   2. topk_compact_kernel  (S x N): every CTA re-derives the threshold digit d1 from the global histogram and
-//                           appends its keys with top-11 bits >= d1 to the image's candidate list (packed key|~index)
-//   3. topk_finish_kernel   (N): radix passes 2 and 3 over the candidates of digit d1, selection of every key >= T,
+//   1. topk_hist_kernel<0>  (S slices x N images): histogram of the keys' top 11 bits -> global
+//      topk_hist_kernel<1>  (S x N): histogram of bits [20:10] of the keys inside the threshold digit d1
+//   2. topk_compact_kernel  (S x N): every CTA re-derives the 22-bit threshold prefix from the global histograms and
+//                           appends its keys >= that prefix to the image's candidate list (packed key|~index): K plus
+//                           at most one 2^-14-wide bin of scores
+//   3. topk_finish_kernel   (N): radix pass 3 over the candidates of that bin, selection of every key >= T,
 //                           bitonic sort, decode.  Falls back to the full single-CTA selection when the candidate
 //                           list or the tie group at T overflows (pathological score distributions): always exact.
 constexpr int kTopkSlices = 16;
 constexpr int kCandCap = 32768;
 
-__global__ void __launch_bounds__(kSelThreads) topk_hist_kernel(const float* __restrict__ score_all, int M,
+template <int LEVEL>
+__global__ void __launch_bounds__(kSelThreads) topk_hist_kernel(const float* __restrict__ score_all, int M, int topk,
                                                                 uint32_t* __restrict__ hist_g) {
   __shared__ uint32_t hist[2048];
+  __shared__ uint32_t s_digit;
+  __shared__ int s_need, s_count;
   const int n = blockIdx.y;
   const float* score = score_all + static_cast<long>(n) * M;
+  uint32_t d1 = 0;
+  if (LEVEL == 1) {  // re-derive the first digit from the finished level-0 histogram
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = hist_g[(n * 2) * 2048 + i];
+    __syncthreads();
+    pick_digit<11>(hist, min(topk, M), &s_digit, &s_need, &s_count);
+    d1 = s_digit;
+  }
   for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
   __syncthreads();
   const int chunk = (((M + kTopkSlices - 1) / kTopkSlices) + 3) & ~3;
@@ -318,11 +330,17 @@ __global__ void __launch_bounds__(kSelThreads) topk_hist_kernel(const float* __r
     } else {
       for (int e = 0; e < 4; ++e) v[e] = e < cnt ? score[i0 + e] : 0.f;
     }
-    for (int e = 0; e < cnt; ++e) atomicAdd(&hist[score_key(v[e]) >> 21], 1u);
+    for (int e = 0; e < cnt; ++e) {
+      const uint32_t k = score_key(v[e]);
+      if (LEVEL == 0)
+        atomicAdd(&hist[k >> 21], 1u);
+      else if ((k >> 21) == d1)
+        atomicAdd(&hist[(k >> 10) & 0x7FFu], 1u);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2048; i += blockDim.x)
-    if (hist[i]) atomicAdd(&hist_g[n * 2048 + i], hist[i]);
+    if (hist[i]) atomicAdd(&hist_g[(n * 2 + LEVEL) * 2048 + i], hist[i]);
 }
 
 __global__ void __launch_bounds__(kSelThreads) topk_compact_kernel(const float* __restrict__ score_all, int M, int topk,
@@ -334,10 +352,16 @@ __global__ void __launch_bounds__(kSelThreads) topk_compact_kernel(const float* 
   __shared__ int s_need, s_count;
   const int n = blockIdx.y;
   const float* score = score_all + static_cast<long>(n) * M;
-  for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = hist_g[n * 2048 + i];
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = hist_g[(n * 2) * 2048 + i];
   __syncthreads();
   pick_digit<11>(hist, min(topk, M), &s_digit, &s_need, &s_count);
   const uint32_t d1 = s_digit;
+  const int need1 = s_need;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = hist_g[(n * 2 + 1) * 2048 + i];
+  __syncthreads();
+  pick_digit<11>(hist, need1, &s_digit, &s_need, &s_count);
+  const uint32_t p22 = (d1 << 11) | s_digit;  // threshold on the keys' top 22 bits
   const int lane = threadIdx.x & 31;
   unsigned long long* cand = cand_g + static_cast<long>(n) * kCandCap;
   const int chunk = (((M + kTopkSlices - 1) / kTopkSlices) + 3) & ~3;
@@ -356,7 +380,7 @@ __global__ void __launch_bounds__(kSelThreads) topk_compact_kernel(const float* 
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const uint32_t k = score_key(v[e]);
-      const bool take = e < cnt && (k >> 21) >= d1;
+      const bool take = e < cnt && (k >> 10) >= p22;
       const uint32_t b = __ballot_sync(0xffffffffu, take);
       if (b) {
         uint32_t slot = 0;
@@ -382,21 +406,18 @@ __global__ void __launch_bounds__(kSelThreads) topk_finish_kernel(const DecodePa
   bool fallback = nc > static_cast<uint32_t>(kCandCap);  // block-uniform
   if (!fallback) {
     const unsigned long long* cand = cand_g + static_cast<long>(n) * kCandCap;
-    for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = hist_g[n * 2048 + i];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = hist_g[(n * 2) * 2048 + i];
     __syncthreads();
     pick_digit<11>(hist, K, &s_digit, &s_need, &s_count);
     uint32_t prefix = s_digit << 21, mask = 0x7FFu << 21;
     int need = s_need;
-    // pass 2: bits [20:10] of the candidates inside digit d1
-    for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
-      const uint32_t k = static_cast<uint32_t>(cand[i] >> 32);
-      if ((k & mask) == prefix) atomicAdd(&hist[(k >> 10) & 0x7FFu], 1u);
-    }
+    // pass 2 was taken device-wide (level-1 histogram)
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = hist_g[(n * 2 + 1) * 2048 + i];
     __syncthreads();
     pick_digit<11>(hist, need, &s_digit, &s_need, &s_count);
     prefix |= s_digit << 10, mask |= 0x7FFu << 10, need = s_need;
+    __syncthreads();
     // pass 3: bits [9:0]
     for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
     __syncthreads();
@@ -428,7 +449,7 @@ __global__ void __launch_bounds__(kSelThreads) topk_finish_kernel(const DecodePa
 
 // persistent scratch of the multi-CTA top-K (grow-only; sized by an eager call before graph capture)
 struct TopkWs {
-  uint32_t* hist = nullptr;   // [N][2048] + [N] counts
+  uint32_t* hist = nullptr;   // [N][2][2048] + [N] counts
   unsigned long long* cand = nullptr;
   int cap_n = 0, device = -1;
 };
@@ -689,13 +710,15 @@ extern "C" int m3d_decode_topk(const float* score, const unsigned char* cls_pred
       M3D_REQUIRE(cs == cudaStreamCaptureStatusNone, "top-K scratch must be sized by an eager call before graph capture");
       if (g_topk.hist) cudaFree(g_topk.hist);
       if (g_topk.cand) cudaFree(g_topk.cand);
-      M3D_CUDA_OK(cudaMalloc(&g_topk.hist, static_cast<size_t>(batch) * 2049 * sizeof(uint32_t)));
+      M3D_CUDA_OK(cudaMalloc(&g_topk.hist, static_cast<size_t>(batch) * 4097 * sizeof(uint32_t)));
       M3D_CUDA_OK(cudaMalloc(&g_topk.cand, static_cast<size_t>(batch) * kCandCap * sizeof(unsigned long long)));
       g_topk.cap_n = batch, g_topk.device = dev;
     }
-    uint32_t* count = g_topk.hist + static_cast<size_t>(batch) * 2048;
-    M3D_CUDA_OK(cudaMemsetAsync(g_topk.hist, 0, static_cast<size_t>(batch) * 2049 * sizeof(uint32_t), st));
-    topk_hist_kernel<<<dim3(kTopkSlices, batch), kSelThreads, 0, st>>>(score, p.M, g_topk.hist);
+    uint32_t* count = g_topk.hist + static_cast<size_t>(batch) * 4096;
+    M3D_CUDA_OK(cudaMemsetAsync(g_topk.hist, 0, static_cast<size_t>(batch) * 4097 * sizeof(uint32_t), st));
+    topk_hist_kernel<0><<<dim3(kTopkSlices, batch), kSelThreads, 0, st>>>(score, p.M, topk, g_topk.hist);
+    M3D_CUDA_OK(cudaGetLastError());
+    topk_hist_kernel<1><<<dim3(kTopkSlices, batch), kSelThreads, 0, st>>>(score, p.M, topk, g_topk.hist);
     M3D_CUDA_OK(cudaGetLastError());
     topk_compact_kernel<<<dim3(kTopkSlices, batch), kSelThreads, 0, st>>>(score, p.M, topk, g_topk.hist, count, g_topk.cand);
     M3D_CUDA_OK(cudaGetLastError());
