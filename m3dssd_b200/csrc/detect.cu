@@ -517,76 +517,97 @@ __global__ void __launch_bounds__(128) nms_mask_kernel(const float* __restrict__
   }
 }
 
-// Greedy sweep (nms_kernel.cu:124-139), one 1024-thread block per image.  For each 64-box block: thread 0
-// resolves the block from its 64 diagonal mask words held in registers (pure ALU, no memory in the
-// dependent chain); then all threads OR the kept rows' mask words into the shared "removed" words of
-// the later blocks: thread -> (word w, row group g of 16), the kept rows come from a shared list so a
-// thread's <= 4 loads are independent and in flight together, and the next block's diagonal words are
-// fetched under the OR phase.  (The previous version walked the kept bits with one dependent L2 load
-// per step: ~10 us per block, 0.5 ms per image.)
+// Greedy sweep (nms_kernel.cu:124-139), one 1024-thread block per image, 256 boxes (4 mask words) per round:
+//   1. the round's 256 x 256 diagonal sub-matrix (256 rows x 4 words) is staged in shared memory (fetched under the
+//      previous round's OR phase);
+//   2. thread 0 resolves the 256 boxes in order from shared memory and registers only -- the dependent chain has
+//      no global memory in it (the first version paid an L2 round trip per kept box: 0.5 ms per image);
+//   3. all threads OR the kept rows' words of the LATER rounds into the shared "removed" words: thread ->
+//      (word, row group), the kept rows come from a shared list, so a thread's loads are independent.
 constexpr int kSweepThreads = 1024;
+constexpr int kSweepRound = 4;  // 64-box blocks per round
 
 __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const unsigned long long* __restrict__ mask,
                                                                    const int* __restrict__ num, int max_n,
                                                                    int col_blocks, int* __restrict__ keep,
                                                                    int* __restrict__ num_keep) {
   __shared__ unsigned long long remv[64];
-  __shared__ unsigned long long diag[64];
-  __shared__ unsigned long long s_keptbits;
+  __shared__ unsigned long long diag[64 * kSweepRound][kSweepRound];
+  __shared__ unsigned long long s_keptbits[kSweepRound];
   __shared__ int s_kept;
-  __shared__ int s_list[64];
+  __shared__ short s_list[64 * kSweepRound];
   const int n = blockIdx.x, tid = threadIdx.x;
   const int nb = num ? num[n] : max_n;
   const unsigned long long* m = mask + static_cast<long>(n) * max_n * col_blocks;
   int* kp = keep + static_cast<long>(n) * max_n;
   const int nblocks = (nb + 63) / 64;
+  const int nrounds = (nblocks + kSweepRound - 1) / kSweepRound;
   if (tid < 64) remv[tid] = 0ull;
   if (tid == 0) s_kept = 0;
-  unsigned long long next_diag = 0ull;
-  if (tid < 64 && tid < nb) next_diag = m[static_cast<long>(tid) * col_blocks];
+  // diagonal words of round 0: thread -> (row, word)
+  const int drow = tid >> 2, dw = tid & 3;  // 256 rows x 4 words = 1024 threads
+  auto load_diag = [&](int round) -> unsigned long long {
+    const int r = round * 64 * kSweepRound + drow, w = round * kSweepRound + dw;
+    return (round < nrounds && r < nb && w < col_blocks) ? m[static_cast<long>(r) * col_blocks + w] : 0ull;
+  };
+  unsigned long long next_diag = load_diag(0);
   __syncthreads();
-  for (int blk = 0; blk < nblocks; ++blk) {
-    if (tid < 64) diag[tid] = next_diag;
+  for (int round = 0; round < nrounds; ++round) {
+    diag[drow][dw] = next_diag;
     __syncthreads();
-    if (tid < 64) {  // next block's diagonal words: independent of this block's outcome
-      const int r = (blk + 1) * 64 + tid;
-      next_diag = (blk + 1 < nblocks && r < nb) ? m[static_cast<long>(r) * col_blocks + blk + 1] : 0ull;
-    }
+    next_diag = load_diag(round + 1);  // independent of this round's outcome
     if (tid == 0) {
-      unsigned long long cur = remv[blk], kept = 0ull;
-      const int lim = min(64, nb - blk * 64);
-#pragma unroll 16
-      for (int b = 0; b < 64; ++b) {  // the shared-memory loads do not depend on `cur`: they issue ahead of the chain
-        const unsigned long long db = diag[b];
-        if (b < lim && !((cur >> b) & 1ull)) {
-          kept |= 1ull << b;
-          cur |= db;
+      unsigned long long cur[kSweepRound];
+#pragma unroll
+      for (int q = 0; q < kSweepRound; ++q) cur[q] = round * kSweepRound + q < 64 ? remv[(round * kSweepRound + q) & 63] : ~0ull;
+#pragma unroll
+      for (int q = 0; q < kSweepRound; ++q) {
+        const int base = (round * kSweepRound + q) * 64;
+        const int lim = min(64, nb - base);
+        unsigned long long kept = 0ull;
+        unsigned long long c = cur[q];
+#pragma unroll 8
+        for (int b = 0; b < 64; ++b) {
+          if (b < lim && !((c >> b) & 1ull)) {
+            kept |= 1ull << b;
+            c |= diag[q * 64 + b][q];
+#pragma unroll
+            for (int q2 = q + 1; q2 < kSweepRound; ++q2) cur[q2] |= diag[q * 64 + b][q2];
+          }
         }
+        s_keptbits[q] = kept;
       }
-      s_keptbits = kept;
     }
     __syncthreads();
-    const unsigned long long kept = s_keptbits;
-    const int base = s_kept;
-    const int nk = __popcll(kept);
-    // kept indices in order: thread b < 64 writes its own slot (global list and the block-local row list)
-    if (tid < 64 && ((kept >> tid) & 1ull)) {
-      const int pos = __popcll(kept & ((1ull << tid) - 1));
-      kp[base + pos] = blk * 64 + tid;
-      s_list[pos] = tid;
+    // kept indices in order: thread (q, b) writes its own slot in the global list and the round-local row list
+    const int base0 = s_kept;
+    int nk = 0;
+    {
+      int before = 0;
+#pragma unroll
+      for (int q = 0; q < kSweepRound; ++q) {
+        const unsigned long long kq = s_keptbits[q];
+        if (tid >= q * 64 && tid < q * 64 + 64 && ((kq >> (tid & 63)) & 1ull)) {
+          const int pos = before + __popcll(kq & ((1ull << (tid & 63)) - 1));
+          kp[base0 + pos] = (round * kSweepRound + q) * 64 + (tid & 63);
+          s_list[pos] = static_cast<short>(q * 64 + (tid & 63));
+        }
+        before += __popcll(kq);
+      }
+      nk = before;
     }
     __syncthreads();
-    // OR kept rows into later words
+    // OR the kept rows into the words of the later rounds
     const int w = tid & 63, g = tid >> 6;
-    if (w > blk && w < col_blocks) {
+    if (w >= (round + 1) * kSweepRound && w < col_blocks) {
       unsigned long long acc = 0ull;
-      const unsigned long long* mrow = m + static_cast<long>(blk) * 64 * col_blocks + w;
+      const unsigned long long* mrow = m + static_cast<long>(round) * 64 * kSweepRound * col_blocks + w;
 #pragma unroll 4
       for (int i = g; i < nk; i += 16) acc |= mrow[static_cast<long>(s_list[i]) * col_blocks];
       if (acc) atomicOr(&remv[w], acc);
     }
     __syncthreads();
-    if (tid == 0) s_kept = base + nk;
+    if (tid == 0) s_kept = base0 + nk;
   }
   __syncthreads();
   if (tid == 0) num_keep[n] = s_kept;
