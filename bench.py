@@ -137,6 +137,17 @@ def run_reference(args):
     return 0
 
 
+def ncu_traffic(kind):
+    """Measured DRAM bytes per launch of this kernel kind (dram__bytes_read.sum + dram__bytes_write.sum from the
+    committed `ncu --set full` capture, profiles/r01c_traffic.json), or None when the kind was not captured."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01c_traffic.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh).get(kind, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        return None
+
+
 def summarize_kernels(prof, peaks, step_ms):
     kinds = {}
     for p in prof:
@@ -313,7 +324,7 @@ def main():
             "peak": peaks["bf16_tflops_sustained"] if tensor_bound else peaks["hbm_gbs"],
             "unit": "TFLOP/s" if tensor_bound else "GB/s",
             "frac": d["tensor_frac"] if tensor_bound else d["hbm_frac"],
-            "traffic": None, "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
+            "traffic": ncu_traffic(dname), "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
             "share_of_step": d["share"], "launches_per_step": d["launches"],
         }
         tot_fl = sum(p["flops"] for p in prof)

@@ -132,7 +132,14 @@ class Engine:
             nbytes += N * P * Q * cout * esz
         if om is not None:
             nbytes += N * P * Q * 3 * k * k * 4
-        kind = "dcn_gather" if om is not None else ("conv_gather" if self.fp32 else "conv_tma")
+        if om is not None:
+            kind = "dcn_fused" if (k == 3 and not self.fp32) else "dcn_gather"  # dcn_fused.cu / conv_gather_kernel
+        elif self.fp32:
+            kind = "conv_gather"
+        elif k == 3 and stride == 1 and pad == 1 and len(inputs) == 1 and inputs[0].c % 64 == 0:
+            kind = "conv3x3"  # conv_halo.cu / conv_halo2.cu (CTA pairs)
+        else:
+            kind = "conv_tma"
         self._add(run, 1, name, kind, flops, nbytes)
         return Act(out, cout, out_coff)
 
