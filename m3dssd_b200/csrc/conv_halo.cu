@@ -31,8 +31,9 @@ struct HaloCfg {
   static constexpr int A_ROWS = 160;                 // (TH + 2) * TW with TH * TW = 128, TH = 8... see host
   static constexpr int A_BYTES = 20 * 1024;          // host guarantees (TH + 2) * TW * 128 <= A_BYTES
   static constexpr int B_BYTES = BN * 128;           // one tap
-  static constexpr int STAGE = A_BYTES + (BRES ? 0 : 3 * B_BYTES);
-  static constexpr int RES_BYTES = BRES ? 9 * B_BYTES : 0;
+  // BRES (Cin = 64): a stage holds the windows of all three kernel columns -> one stage (36 MMAs) per tile
+  static constexpr int STAGE = BRES ? 3 * A_BYTES : A_BYTES + 3 * B_BYTES;
+  static constexpr int RES_BYTES = BRES ? 72 * 1024 : 0;  // 9 * nchunk taps of [BN][64]: BN = 64 x 1 chunk, BN = 32 x <= 2
   static constexpr int EXTRA = (STAGED ? (2 * kSlabBytes + 1024) : 0) + RES_BYTES;
   static constexpr int BUDGET = 225 * 1024 + 512 - EXTRA;
   static constexpr int FIT = BUDGET / STAGE;
@@ -99,16 +100,16 @@ __global__ void __launch_bounds__(STAGED ? 320 : 192, 1) conv_halo_kernel(const 
   grid_dep_sync();
 
   const int nchunk = p.chunks[0];
-  const int n_stages = 3 * nchunk;  // (s, chunk) pairs
+  const int n_stages = BRES ? nchunk : 3 * nchunk;  // (s, chunk) pairs; resident weights: one stage per chunk
   const uint32_t a_bytes = static_cast<uint32_t>((p.TH + 2) * p.TW * 128);
   const uint32_t tap_shift = static_cast<uint32_t>(p.TW * 128) >> 4;  // descriptor units (16 B) per kernel row
 
   if (warp == 0) {
     int stage = 0;
     uint32_t phase = 0;
-    if (BRES && elect_one()) {  // nchunk == 1, n_tiles == 1: the whole weight matrix, once
-      mbar_arrive_expect_tx(bres_bar, 9 * Cfg::B_BYTES);
-      for (int s = 0; s < 3; ++s) tma_load_4d(b_res + s * 3 * Cfg::B_BYTES, &p.tmap_b, bres_bar, 0, 0, s, 0);
+    if (BRES && elect_one()) {  // n_tiles == 1: the whole weight matrix, once, as [s * nchunk + c][r][BN][64]
+      mbar_arrive_expect_tx(bres_bar, 9 * nchunk * Cfg::B_BYTES);
+      for (int i = 0; i < 3 * nchunk; ++i) tma_load_4d(b_res + i * 3 * Cfg::B_BYTES, &p.tmap_b, bres_bar, 0, 0, i, 0);
     }
     __syncwarp();
     HALO_WALK_INIT;
@@ -120,9 +121,16 @@ __global__ void __launch_bounds__(STAGED ? 320 : 192, 1) conv_halo_kernel(const 
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::STAGE;
-          mbar_arrive_expect_tx(&full[stage], ((p.dbg & 1) ? 0 : a_bytes) + (BRES ? 0 : 3 * Cfg::B_BYTES));
-          if (!(p.dbg & 1)) tma_load_4d(sa, &p.tmap_a[0], &full[stage], p.a_coff[0] + c * 64, t.q0 - 1 + s, t.p0 - 1, t.n);
-          if (!BRES) tma_load_4d(sa + Cfg::A_BYTES, &p.tmap_b, &full[stage], 0, brow, s * nchunk + c, 0);
+          if constexpr (BRES) {
+            mbar_arrive_expect_tx(&full[stage], 3 * a_bytes);
+            for (int sc = 0; sc < 3; ++sc)
+              tma_load_4d(sa + sc * Cfg::A_BYTES, &p.tmap_a[0], &full[stage], p.a_coff[0] + st * 64, t.q0 - 1 + sc, t.p0 - 1,
+                          t.n);
+          } else {
+            mbar_arrive_expect_tx(&full[stage], ((p.dbg & 1) ? 0 : a_bytes) + 3 * Cfg::B_BYTES);
+            if (!(p.dbg & 1)) tma_load_4d(sa, &p.tmap_a[0], &full[stage], p.a_coff[0] + c * 64, t.q0 - 1 + s, t.p0 - 1, t.n);
+            tma_load_4d(sa + Cfg::A_BYTES, &p.tmap_b, &full[stage], 0, brow, s * nchunk + c, 0);
+          }
         }
         __syncwarp();
         if (++c == nchunk) c = 0, ++s;
@@ -150,15 +158,29 @@ __global__ void __launch_bounds__(STAGED ? 320 : 192, 1) conv_halo_kernel(const 
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE);
-          const uint64_t da = umma_smem_desc<128>(sa);
-          // resident weights: stage st == kernel column s (nchunk == 1)
-          const uint64_t db = umma_smem_desc<128>(BRES ? smem_u32(b_res) + st * 3 * Cfg::B_BYTES : sa + Cfg::A_BYTES);
+          if constexpr (BRES) {
+            const uint64_t db0 = umma_smem_desc<128>(smem_u32(b_res));
 #pragma unroll
-          for (int r = 0; r < 3; ++r) {
+            for (int sc = 0; sc < 3; ++sc) {
+              const uint64_t da = umma_smem_desc<128>(sa + sc * Cfg::A_BYTES);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (!(p.dbg & 8)) umma_f16(tmem_acc, da + r * tap_shift + 2 * k, db + r * (Cfg::B_BYTES >> 4) + 2 * k, idesc,
-                       (st | r | k) != 0);
+              for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(tmem_acc, da + r * tap_shift + 2 * k,
+                           db0 + (((sc * nchunk + st) * 3 + r) * (Cfg::B_BYTES >> 4)) + 2 * k, idesc, (st | sc | r | k) != 0);
+              }
+            }
+          } else {
+            const uint64_t da = umma_smem_desc<128>(sa);
+            const uint64_t db = umma_smem_desc<128>(sa + Cfg::A_BYTES);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (!(p.dbg & 8)) umma_f16(tmem_acc, da + r * tap_shift + 2 * k, db + r * (Cfg::B_BYTES >> 4) + 2 * k, idesc,
+                                           (st | r | k) != 0);
+            }
           }
           umma_commit(&empty[stage]);
         }
@@ -251,12 +273,15 @@ bool conv_halo_supported(int BN, int out_dtype, bool staged) {
 }
 
 int launch_conv_halo(const ConvTmaParams& p, int BN, int out_dtype, bool staged, cudaStream_t stream) {
+  static const bool bres = !(getenv("M3D_HALO_BRES") && atoi(getenv("M3D_HALO_BRES")) == 0);  // resident-weight variants
   if (staged) {
-    if (BN == 64 && p.chunks[0] == 1 && p.n_tiles == 1) return launch_t<64, __nv_bfloat16, true, true>(p, stream);
+    if (BN == 64 && p.chunks[0] == 1 && p.n_tiles == 1 && bres) return launch_t<64, __nv_bfloat16, true, true>(p, stream);
     if (BN == 64) return launch_t<64, __nv_bfloat16, true>(p, stream);
     if (BN == 128) return launch_t<128, __nv_bfloat16, true>(p, stream);
     return M3D_ERR_UNSUPPORTED;
   }
+  if (BN == 32 && out_dtype != DT_BF16 && p.chunks[0] <= 2 && p.n_tiles == 1 && bres)
+    return launch_t<32, float, false, true>(p, stream);  // offset/mask convs of the Cin <= 128 DCNs
   if (BN == 32)
     return out_dtype == DT_BF16 ? launch_t<32, __nv_bfloat16, false>(p, stream) : launch_t<32, float, false>(p, stream);
   if (BN == 64)

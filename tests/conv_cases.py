@@ -119,6 +119,9 @@ CASES = [
     ("heads_grouped", dict(N=1, H=12, W=40, cins=[256], cout=256, k=1, groups=3)),
     ("heads_grouped_36", dict(N=1, H=12, W=40, cins=[256], cout=36, k=1, groups=4, out_dtype=torch.float32, slope=1.0)),
     ("offsetconv_27_f32", dict(N=1, H=24, W=80, cins=[128], cout=27, out_dtype=torch.float32, slope=1.0)),
+    ("offsetconv_27_c64_f32", dict(N=2, H=13, W=37, cins=[64], cout=27, out_dtype=torch.float32, slope=1.0)),
+    ("offsetconv_27_c256_f32", dict(N=1, H=12, W=40, cins=[256], cout=27, out_dtype=torch.float32, slope=1.0)),
+    ("conv3x3_c64_ragged_res", dict(N=3, H=13, W=37, cins=[64], cout=64, res=True)),
     ("conv7x1ish_5x5", dict(N=1, H=16, W=16, cins=[64], cout=64, k=5)),
     ("gather_plain_bf16", dict(N=1, H=12, W=40, cins=[64], cout=64, force_gather=True)),
     ("gather_plain_s2_bf16", dict(N=1, H=24, W=80, cins=[64], cout=128, stride=2, force_gather=True)),
