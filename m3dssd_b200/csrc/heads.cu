@@ -31,13 +31,17 @@
 namespace m3d {
 
 int make_tmap_nhwc(CUtensorMap* map, const void* base, int N, int H, int W, int C, int bk, int tw, int th, int stride);
+int make_tmap_nhwc_f32(CUtensorMap* map, const void* base, int N, int H, int W, int C, int box_c, int tw, int th);
 int make_tmap_b3d(CUtensorMap* map, const void* base, long rows, long cols, int bk, int box_rows, int ksub);
 void pick_tile(int P, int Q, int max_tw, int* TW, int* TH);
 
 // Phase timeline probe (tools/probe_heads.py): compile with -DM3D_PROBE
 #ifdef M3D_PROBE
+// (stamps go to shared memory and are copied out at the end: a global store per stamp makes the next
+// fence.proxy.async -- a MEMBAR -- of the stamping warp wait an L2 round trip, which delays exactly the slab hand-offs
+// the probe is looking at)
 __device__ long long g_head_dbg[1024];
-#define HDBG(slot) do { if (blockIdx.x == 0 && lane == 0 && li < 6) g_head_dbg[li * 32 + (slot)] = clock64(); } while (0)
+#define HDBG(slot) do { if (blockIdx.x == 0 && lane == 0 && li < 6) s_head_dbg[li * 32 + (slot)] = clock64(); } while (0)
 #else
 #define HDBG(slot) do { } while (0)
 #endif
@@ -53,6 +57,7 @@ struct alignas(64) HeadMlpParams {
   CUtensorMap tmap_w1;  // (64, G*256, K1) box {64, 256, 1}
   CUtensorMap tmap_w2;  // (64, G*256, 4)  box {64, 256, 1}
   CUtensorMap tmap_w3;  // (64, G*R3, 4)   box {64, R3, 4}
+  CUtensorMap tmap_out; // fp32 (C, W, H, N) box {A, TW, TH, 1}: one head's A channels of a pixel tile
   const float *b1, *b2, *b3;
   float* out;
   int out_cstride, out_coff;
@@ -80,11 +85,18 @@ __device__ __forceinline__ HeadTile head_tile(int tile, const HeadMlpParams& p) 
 template <int R3>
 __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_constant__ HeadMlpParams p) {
   extern __shared__ uint8_t smem_raw[];
+#ifdef M3D_PROBE
+  __shared__ long long s_head_dbg[6 * 32];
+  if (threadIdx.x < 6 * 32) s_head_dbg[threadIdx.x] = 0;
+#endif
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sx = smem;                    // K1 k-blocks of X
   uint8_t* sy = smem + 2 * 16384;        // 4 slabs of Y
   uint8_t* sw = smem + 6 * 16384;        // weight ring
-  float* so = reinterpret_cast<float*>(sy);  // [128][R3] fp32 output staging: Y is free between GEMM3 and the next E1
+  // [128][A] fp32 output staging (the TMA store's box, up to 24 KB) over slabs 2-3 of Y, free between GEMM3 and the
+  // moment the next E1 reaches slab 2: the store is not waited for in E3, only (via so_free) before that slab is
+  // rewritten
+  float* so = reinterpret_cast<float*>(sy + 2 * 16384);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * 16384 + kHeadWSlots * kHeadSlotBytes);
   uint64_t* w_full = bars;                      // [kHeadWSlots]
   uint64_t* w_empty = bars + kHeadWSlots;       // [kHeadWSlots]
@@ -97,7 +109,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
   uint64_t* acc3_full = x_full + 6;
   uint64_t* y1_ready = x_full + 7;              // [4], 8 arrivals each
   uint64_t* y2_ready = x_full + 11;             // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 15);
+  uint64_t* so_free = x_full + 15;              // the output TMA store of the previous item has read its staging
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -114,6 +127,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
     mbar_init(acc2_full, 1);
     mbar_init(acc2_empty, kHeadEpiWarps);
     mbar_init(acc3_full, 1);
+    mbar_init(so_free, 1);
     for (int s = 0; s < 4; ++s) {
       mbar_init(&y1_ready[s], kHeadEpiWarps);
       mbar_init(&y2_ready[s], kHeadEpiWarps);
@@ -123,6 +137,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
     prefetch_tmap(&p.tmap_w1);
     prefetch_tmap(&p.tmap_w2);
     prefetch_tmap(&p.tmap_w3);
+    prefetch_tmap(&p.tmap_out);
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
@@ -140,8 +155,11 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
     // ------------------------------------------------------------------ TMA producer
     int slot = 0;
     uint32_t wphase = 0;
+    int li = 0, nload = 0;
     auto load_w = [&](const CUtensorMap* tm, int row, int kb, uint32_t bytes) {
-      mbar_wait(&w_empty[slot], wphase ^ 1);
+      mbar_wait_sleep(&w_empty[slot], wphase ^ 1);
+      if (nload >= 0 && nload < 8) HDBG(24 + nload);
+      ++nload;
       if (elect_one()) {
         mbar_arrive_expect_tx(&w_full[slot], bytes);
         tma_load_3d(sw + slot * kHeadSlotBytes, tm, &w_full[slot], 0, row, kb);
@@ -157,8 +175,9 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
       }
       __syncwarp();
     };
-    for (int it = start, li = 0; it < end; ++it, ++li) {
+    for (int it = start; it < end; ++it, ++li) {
       const int tile = it / p.G, g = it - tile * p.G;
+      nload = li == 0 ? -2 : 0;  // probe: loads of this item in order W2[0..3], W1'[0..1], W3
       if (li == 0) {
         load_x(tile);
         for (int kb = 0; kb < K1; ++kb) load_w(&p.tmap_w1, g * kHeadMid, kb, kHeadSlotBytes);
@@ -166,7 +185,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
       for (int kb = 0; kb < 4; ++kb) load_w(&p.tmap_w2, g * kHeadMid, kb, kHeadSlotBytes);
       if (it + 1 < end) {
         const int ntile = (it + 1) / p.G, ng = (it + 1) - ntile * p.G;
-        mbar_wait(x_empty, li & 1);  // GEMM1 of this item has read X
+        mbar_wait_sleep(x_empty, li & 1);  // GEMM1 of this item has read X
         if (ntile != tile) load_x(ntile);
         for (int kb = 0; kb < K1; ++kb) load_w(&p.tmap_w1, ng * kHeadMid, kb, kHeadSlotBytes);
       }
@@ -185,12 +204,12 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
     };
     auto gemm1 = [&](bool new_x) {
       if (new_x) {
-        mbar_wait(x_full, xcount & 1);
+        mbar_wait_sleep(x_full, xcount & 1);
         ++xcount;
       }
       tc_fence_after();
       for (int kb = 0; kb < K1; ++kb) {
-        mbar_wait(&w_full[slot], wphase);
+        mbar_wait_sleep(&w_full[slot], wphase);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t da = umma_smem_desc<128>(smem_u32(sx + kb * 16384));
@@ -214,11 +233,13 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
       if (li == 0) gemm1(true);
       HDBG(0);
       // GEMM2: acc2 = Y1 . W2^T
-      mbar_wait(acc2_empty, par ^ 1);  // E3 of the previous item has drained acc2 / acc3
+      mbar_wait_sleep(acc2_empty, par ^ 1);  // E3 of the previous item has drained acc2 / acc3
       tc_fence_after();
       for (int kb = 0; kb < 4; ++kb) {
-        mbar_wait(&w_full[slot], wphase);
-        mbar_wait(&y1_ready[kb], par);
+        mbar_wait_sleep(&w_full[slot], wphase);
+        HDBG(16 + kb);
+        mbar_wait_sleep(&y1_ready[kb], par);
+        HDBG(20 + kb);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t da = umma_smem_desc<128>(smem_u32(sy + kb * 16384));
@@ -235,14 +256,14 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
       HDBG(1);
       // GEMM1 of the next item runs under E2 of this one
       if (it + 1 < end) {
-        mbar_wait(acc1_empty, par);  // E1 of this item has drained acc1
+        mbar_wait_sleep(acc1_empty, par);  // E1 of this item has drained acc1
         gemm1((it + 1) / p.G != tile);
       }
       HDBG(2);
       // GEMM3: acc3 = Y2 . W3^T
-      mbar_wait(&w_full[slot], wphase);
+      mbar_wait_sleep(&w_full[slot], wphase);
       for (int kb = 0; kb < 4; ++kb) {
-        mbar_wait(&y2_ready[kb], par);
+        mbar_wait_sleep(&y2_ready[kb], par);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t da = umma_smem_desc<128>(smem_u32(sy + kb * 16384));
@@ -265,15 +286,25 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
     const int quarter = warp & 3;          // TMEM lane quarter this warp may read
     const int part = (warp - 2) >> 2;      // which 16 of a slab's 64 columns
     const int row = quarter * 32 + lane;
-    const int etid = threadIdx.x - 64;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const float slope = p.slope;
-    // acc -> +bias, LeakyReLU, bf16 -> Y; the TMEM load of slab s+1 is in flight while slab s is converted
-    auto drain_to_y = [&](uint32_t acc, const float* bias, uint64_t* ready, uint64_t* acc_empty) {
+    const unsigned long long slope2 = pack_f32x2(p.slope, p.slope);
+    // acc -> +bias, LeakyReLU, bf16 -> Y: every warp converts 16 of the 64 columns of each slab, slab 0 first, so
+    // GEMM2 / GEMM3 start on slab 0 while the rest is drained; the TMEM load of slab s+1 is in flight while slab s
+    // is converted.  (The bias vectors of the item were prefetched into L1 during the previous item: an L2 round
+    // trip per slab used to be exposed here.)
+    auto drain_to_y = [&](uint32_t acc, const float* bias, uint64_t* ready, uint64_t* acc_empty, uint32_t so_par) {
       uint32_t a[2][16];
       tmem_ld16(acc + lane_off + part * 16, a[0]);
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
+        if (s == 2 && acc_empty != nullptr) {  // E1 only: slabs 2-3 hold the output staging of the previous item
+          if (warp == 2 && lane == 0) {        // (the thread that issued the store; nothing outstanding on the first item)
+            tma_store_wait_read<0>();
+            mbar_arrive(so_free);
+          }
+          __syncwarp();
+          mbar_wait(so_free, so_par);
+        }
         tmem_ld_wait();
         if (s < 3) tmem_ld16(acc + lane_off + (s + 1) * 64 + part * 16, a[(s + 1) & 1]);
         const float* bs = bias + s * 64 + part * 16;
@@ -282,15 +313,20 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
         for (int j = 0; j < 2; ++j) {
           const float4 b0 = __ldg(reinterpret_cast<const float4*>(bs + j * 8));
           const float4 b1 = __ldg(reinterpret_cast<const float4*>(bs + j * 8 + 4));
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(a[s & 1][j * 8 + e]);
-          v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w, v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
+          // two channels per instruction (add.f32x2 / mul.f32x2 round like their scalar forms)
+          const unsigned long long bb[4] = {pack_f32x2(b0.x, b0.y), pack_f32x2(b0.z, b0.w), pack_f32x2(b1.x, b1.y),
+                                            pack_f32x2(b1.z, b1.w)};
           uint32_t w[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            __nv_bfloat162 t = __floats2bfloat162_rn(lrelu(v[2 * e], slope), lrelu(v[2 * e + 1], slope));
-            w[e] = *reinterpret_cast<uint32_t*>(&t);
+            const unsigned long long v = add_f32x2(
+                pack_f32x2(__uint_as_float(a[s & 1][j * 8 + 2 * e]), __uint_as_float(a[s & 1][j * 8 + 2 * e + 1])), bb[e]);
+            const unsigned long long t = mul_f32x2(v, slope2);
+            float v0, v1, t0, t1;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(v0), "=f"(v1) : "l"(v));
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(t));
+            __nv_bfloat162 o = __floats2bfloat162_rn(fmaxf(v0, t0), fmaxf(v1, t1));
+            w[e] = *reinterpret_cast<uint32_t*>(&o);
           }
           *reinterpret_cast<uint4*>(slab + swizzled_offset<128>(row, part * 2 + j)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
@@ -304,6 +340,16 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
         if (lane == 0) mbar_arrive(acc_empty);
       }
     };
+    // one 128-byte line of the bias vectors of head `hg` per thread -> L1
+    const int etid = threadIdx.x - 64;
+    auto prefetch_bias = [&](int hg) {
+      const float* a = nullptr;
+      if (etid < 8) a = p.b1 + hg * kHeadMid + etid * 32;
+      else if (etid < 16) a = p.b2 + hg * kHeadMid + (etid - 8) * 32;
+      else if (etid < 16 + (R3 + 31) / 32) a = p.b3 + hg * R3 + (etid - 16) * 32;
+      if (a != nullptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+    };
+    if (start < end) prefetch_bias(start % p.G);
     for (int it = start, li = 0; it < end; ++it, ++li) {
       const uint32_t par = li & 1;
       const int tile = it / p.G, g = it - tile * p.G;
@@ -312,54 +358,58 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
       mbar_wait(acc1_full, par);
       if (warp == 2) HDBG(9);
       tc_fence_after();
-      drain_to_y(tmem_base, p.b1 + g * kHeadMid, y1_ready, acc1_empty);
+      drain_to_y(tmem_base, p.b1 + g * kHeadMid, y1_ready, acc1_empty, par);
       // E2 (acc2_full also means GEMM2 has finished reading Y)
+      if (it + 1 < end) prefetch_bias((it + 1) % p.G);
       if (warp == 2) HDBG(10);
       mbar_wait(acc2_full, par);
       if (warp == 2) HDBG(11);
       tc_fence_after();
-      drain_to_y(tmem_base + kHeadMid, p.b2 + g * kHeadMid, y2_ready, nullptr);
+      drain_to_y(tmem_base + kHeadMid, p.b2 + g * kHeadMid, y2_ready, nullptr, 0);
       // E3: acc3 + b3 -> fp32 staging [128][R3] -> coalesced 16-byte stores (A*4 contiguous bytes per pixel)
       if (warp == 2) HDBG(12);
       mbar_wait(acc3_full, par);
       if (warp == 2) HDBG(13);
       tc_fence_after();
-      if (part * 16 < R3) {
+      const int A = p.A;
+      if (part * 16 < A) {
         uint32_t a[16];
         tmem_ld16(tmem_base + kHeadMid + lane_off + part * 16, a);
         tmem_ld_wait();
         const float* b3 = p.b3 + g * R3 + part * 16;
-        float* dst = so + row * R3 + part * 16;
+        float* dst = so + row * A + part * 16;  // 4 * A-byte rows: A = 36 -> the 16-byte stores of a quarter warp hit distinct banks
 #pragma unroll
         for (int c = 0; c < 16; c += 4) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(b3 + c));
-          *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(a[c]) + b.x, __uint_as_float(a[c + 1]) + b.y,
-                                                            __uint_as_float(a[c + 2]) + b.z, __uint_as_float(a[c + 3]) + b.w);
+          if (part * 16 + c < A) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(b3 + c));
+            *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(a[c]) + b.x, __uint_as_float(a[c + 1]) + b.y,
+                                                              __uint_as_float(a[c + 2]) + b.z, __uint_as_float(a[c + 3]) + b.w);
+          }
         }
+        fence_proxy_async_smem();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc2_empty);
       named_bar_sync(kEpiBarrier, 32 * kHeadEpiWarps);  // staging complete
-      {
-        const HeadTile t = head_tile(tile, p);
-        const int nq = p.A >> 2;  // 16-byte chunks per pixel
-        const int tw_shift = 31 - __clz(p.TW);
-        for (int c = etid; c < 128 * nq; c += 32 * kHeadEpiWarps) {
-          const int r = c / nq, k = c - r * nq;
-          const int pp = t.p0 + (r >> tw_shift), qq = t.q0 + (r & (p.TW - 1));
-          if (pp < p.P && qq < p.Q) {
-            float* dst = p.out + ((static_cast<long>(t.n) * p.P + pp) * p.Q + qq) * p.out_cstride + p.out_coff + g * p.A;
-            *reinterpret_cast<float4*>(dst + 4 * k) = *reinterpret_cast<const float4*>(so + r * R3 + 4 * k);
-          }
+      if (warp == 2) {
+        // one TMA store writes the tile's [TH][TW][A] block (rows beyond the image edge are clipped)
+        if (lane == 0) {  // always the same thread: bulk-store groups are per thread
+          const HeadTile t = head_tile(tile, p);
+          tma_store_4d(&p.tmap_out, so, p.out_coff + g * A, t.q0, t.p0, t.n);
+          tma_store_commit();
         }
+        __syncwarp();
       }
-      named_bar_sync(kEpiBarrier, 32 * kHeadEpiWarps);  // staging free again
       if (warp == 2) HDBG(14);
     }
+    if (warp == 2 && lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
+#ifdef M3D_PROBE
+  if (blockIdx.x == 0 && threadIdx.x < 6 * 32) g_head_dbg[threadIdx.x] = s_head_dbg[threadIdx.x];
+#endif
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -395,6 +445,8 @@ extern "C" int m3d_head_mlp(const void* x, int N, int H, int W, int x_cstride, i
   rc = make_tmap_b3d(&p.tmap_w2, w2, static_cast<long>(G) * kHeadMid, kHeadMid, 64, kHeadMid, 1);
   if (rc != M3D_OK) return rc;
   rc = make_tmap_b3d(&p.tmap_w3, w3, static_cast<long>(G) * rows3, kHeadMid, 64, rows3, 4);
+  if (rc != M3D_OK) return rc;
+  rc = make_tmap_nhwc_f32(&p.tmap_out, out, N, H, W, out_cstride, A, TW, TH);
   if (rc != M3D_OK) return rc;
   p.b1 = b1, p.b2 = b2, p.b3 = b3;
   p.out = out, p.out_cstride = out_cstride, p.out_coff = out_coff;

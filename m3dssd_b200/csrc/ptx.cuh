@@ -35,6 +35,11 @@ __device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, un
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
+__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, unsigned long long b) {
   unsigned long long d;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -118,6 +123,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 8000000000LL) {  // ~4 s at 2 GHz
+      printf("m3dssd_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+// Same, for single warps that wait long next to busy warps on their scheduler (a hot try_wait loop takes issue
+// slots from them: measured ~30 % slower epilogue warps next to a spinning MMA warp): back off between polls.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(32);
+    if (clock64() - t0 > 8000000000LL) {
       printf("m3dssd_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
     }

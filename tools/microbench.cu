@@ -148,6 +148,40 @@ __global__ void __launch_bounds__(64, 1) bench(long long* out) {
   tmem_dealloc<32>(tmem_slot);
 }
 
+// Cost of the generic->async proxy hand-off that every CUDA-core A producer pays per slab / k-block:
+// st.shared.v4 + fence.proxy.async (+ mbarrier arrive), with 1 / 4 / 16 warps running it concurrently.
+__global__ void __launch_bounds__(512, 1) bench_fence(long long* out, int mode) {
+  __shared__ __align__(16) uint4 buf[512 * 2];
+  __shared__ __align__(8) uint64_t bar;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1 << 19);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  uint4 v = make_uint4(threadIdx.x, 1, 2, 3);
+  __syncthreads();
+  long long t0 = clock64();
+  for (int i = 0; i < ITERS; ++i) {
+    v.x += i;
+    buf[threadIdx.x * 2 + (i & 1)] = v;
+    if (mode >= 1) fence_proxy_async_smem();
+    if (mode >= 2) {
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(&bar);
+    }
+    if (mode == 3) {  // 64 independent FMAs after the hand-off (does the fence overlap with math?)
+      float a = __uint_as_float(v.y);
+#pragma unroll
+      for (int k = 0; k < 64; ++k) a = fmaf(a, 1.0001f, 0.5f);
+      v.y = __float_as_uint(a);
+    }
+  }
+  long long t1 = clock64();
+  __syncthreads();
+  const uint4 r = buf[(threadIdx.x * 2 + 3) % (blockDim.x * 2)];  // keep the stores observable
+  if ((threadIdx.x & 31) == 0) out[threadIdx.x >> 5] = t1 - t0 + (v.y + r.x == 77);
+}
+
 int main() {
   long long* d;
   cudaMalloc(&d, 64 * sizeof(long long));
@@ -163,5 +197,13 @@ int main() {
   const char* names[] = {"empty loop", "arrive+wait", "elect+syncwarp", "arrive.expect_tx(0)+wait", "tcgen05.commit+wait",
                          "wait on completed phase", "arrive only", "tc fences", "commit only", "lane0-only arrive+wait"};
   for (int i = 0; i < 10; ++i) printf("%-28s %8.1f clk/iter\n", names[i], double(h[i]) / ITERS);
+  const char* modes[] = {"st.shared.v4 only", "+ fence.proxy.async", "+ syncwarp + arrive", "+ 64 dependent FMAs"};
+  for (int warps = 1; warps <= 16; warps *= 4)
+    for (int mode = 0; mode < 4; ++mode) {
+      for (int rep = 0; rep < 2; ++rep) bench_fence<<<1, 32 * warps>>>(d, mode);  // first launch warms the i-cache
+      if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+      cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+      printf("%2d warps  %-24s %8.1f clk/iter\n", warps, modes[mode], double(h[0]) / ITERS);
+    }
   return 0;
 }

@@ -6,7 +6,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
 import torch
-from m3dssd_b200 import ops, _lib
+from m3dssd_b200 import _lib
+# probe build: nvcc ... -DM3D_PROBE -c m3dssd_b200/csrc/heads.cu -o build/heads_probe.o; link with the other objects
+_lib.LIB_PATH = os.path.join(ROOT, "build", "libm3d_probe.so")
+from m3dssd_b200 import ops
 
 os.environ["M3D_HEAD_DBG"] = "1"
 N, H, W, Cx, G, A, rows3 = 8, 48, 160, 128, 4, 36, 48
@@ -27,6 +30,11 @@ L.m3d_head_debug_read(buf.ctypes.data, buf.size)
 a = buf.reshape(32, 32)
 t0 = a[0, 8]
 names = {0: "G2 start", 1: "G2 issued", 2: "G3 start", 3: "G3 issued", 8: "E1 wait", 9: "E1 go", 10: "E2 wait", 11: "E2 go", 12: "E3 wait", 13: "E3 go", 14: "E3 done"}
+for kb in range(4):
+    names[16 + kb] = "w2[%d] in" % kb       # MMA warp: weight slot of G2 slab kb has landed
+    names[20 + kb] = "y1[%d] rdy" % kb      # MMA warp: Y slab kb written by E1 -> MMAs issued right after
+for i, n in enumerate(["W2[0]", "W2[1]", "W2[2]", "W2[3]", "W1'[0]", "W1'[1]", "W3"]):
+    names[24 + i] = "slot for " + n         # producer: ring slot freed (MMAs that read it have completed)
 for li in range(6):
     ev = sorted((a[li, k] - t0, names[k]) for k in names if a[li, k])
     print("item %d: " % li + "  ".join("%s@%d" % (n, t) for t, n in ev))
