@@ -120,17 +120,19 @@ __device__ __forceinline__ void epilogue_tile_direct(uint32_t tmem_acc, int quar
 
 // ---------------------------------------------------------------- staged
 struct StagedEpilogue {
-  uint8_t* slab[2];    // two 16 KB swizzled staging buffers (1024-byte aligned)
+  // (no arrays indexed at run time here: they would live in local memory and put LDL / STL into the slab loop)
+  uint8_t* stage;      // two 16 KB swizzled staging buffers (1024-byte aligned), buffer b at stage + b * kSlabBytes
   float* bias_s;       // BN floats
   uint64_t* res_bar;   // [2] residual-landed barriers
-  uint32_t res_uses[2];
+  uint32_t res_uses0, res_uses1;
   uint32_t slab_count;  // running slab index: selects the buffer
-  __device__ __forceinline__ void init(uint8_t* stage, float* bias_smem, uint64_t* bars) {
-    slab[0] = stage, slab[1] = stage + kSlabBytes;
+  __device__ __forceinline__ void init(uint8_t* stage_, float* bias_smem, uint64_t* bars) {
+    stage = stage_;
     bias_s = bias_smem, res_bar = bars;
-    res_uses[0] = res_uses[1] = 0;
+    res_uses0 = res_uses1 = 0;
     slab_count = 0;
   }
+  __device__ __forceinline__ uint8_t* slab(int b) const { return stage + b * kSlabBytes; }
 };
 
 // One 128 x BN bf16 tile.  `ep_tid` in [0, 32*NW) numbers the epilogue threads (NW = 4 or 8 warps; with 8 the
@@ -158,22 +160,23 @@ __device__ __forceinline__ void epilogue_tile_staged(StagedEpilogue& st, uint32_
     const int b = st.slab_count & 1;
     tma_store_wait_read<1>();  // the store that last used buffer b (two slabs ago) has drained it
     mbar_arrive_expect_tx(&st.res_bar[b], kSlabBytes);
-    tma_load_4d(st.slab[b], tmap_res, &st.res_bar[b], c_res, q0, p0, n);
+    tma_load_4d(st.slab(b), tmap_res, &st.res_bar[b], c_res, q0, p0, n);
   }
   named_bar_sync(kEpiBarrier, NT);  // bias_s visible
 
 #pragma unroll 1
   for (int s = 0; s < NSLAB; ++s) {
     const int b = st.slab_count & 1;
-    uint8_t* buf = st.slab[b];
+    uint8_t* buf = st.slab(b);
+    const uint32_t buf_s = smem_u32(st.stage) + static_cast<uint32_t>(b) * kSlabBytes;  // shared-space address of buf
     if (has_res) {
       if (leader && s + 1 < NSLAB) {  // prefetch the next residual slab into the other buffer
         tma_store_wait_read<0>();
         mbar_arrive_expect_tx(&st.res_bar[b ^ 1], kSlabBytes);
-        tma_load_4d(st.slab[b ^ 1], tmap_res, &st.res_bar[b ^ 1], c_res + (s + 1) * 64, q0, p0, n);
+        tma_load_4d(st.slab(b ^ 1), tmap_res, &st.res_bar[b ^ 1], c_res + (s + 1) * 64, q0, p0, n);
       }
-      mbar_wait(&st.res_bar[b], st.res_uses[b] & 1);
-      st.res_uses[b]++;
+      mbar_wait(&st.res_bar[b], (b ? st.res_uses1 : st.res_uses0) & 1);
+      if (b) ++st.res_uses1; else ++st.res_uses0;
     } else {
       if (leader) tma_store_wait_read<1>();
       named_bar_sync(kEpiBarrier, NT);  // buffer b is free for everybody
@@ -197,9 +200,9 @@ __device__ __forceinline__ void epilogue_tile_staged(StagedEpilogue& st, uint32_
       const float4 b0 = *reinterpret_cast<const float4*>(st.bias_s + s * 64 + chunk * 8);
       const float4 b1 = *reinterpret_cast<const float4*>(st.bias_s + s * 64 + chunk * 8 + 4);
       v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w, v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
-      uint4* cell = reinterpret_cast<uint4*>(buf + swizzled_offset<128>(row, chunk));
+      const uint32_t cell = buf_s + swizzled_offset<128>(row, chunk);
       if (has_res) {
-        const uint4 u = *cell;
+        const uint4 u = lds128(cell);
         v[0] += __uint_as_float(u.x << 16), v[1] += __uint_as_float(u.x & 0xffff0000u);
         v[2] += __uint_as_float(u.y << 16), v[3] += __uint_as_float(u.y & 0xffff0000u);
         v[4] += __uint_as_float(u.z << 16), v[5] += __uint_as_float(u.z & 0xffff0000u);
@@ -211,7 +214,7 @@ __device__ __forceinline__ void epilogue_tile_staged(StagedEpilogue& st, uint32_
         __nv_bfloat162 t = __floats2bfloat162_rn(lrelu(v[2 * e], slope), lrelu(v[2 * e + 1], slope));
         w[e] = *reinterpret_cast<uint32_t*>(&t);
       }
-      *cell = make_uint4(w[0], w[1], w[2], w[3]);
+      sts128(cell, make_uint4(w[0], w[1], w[2], w[3]));
     }
     fence_proxy_async_smem();
     named_bar_sync(kEpiBarrier, NT);  // slab complete

@@ -109,8 +109,9 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
   uint64_t* acc3_full = x_full + 6;
   uint64_t* y1_ready = x_full + 7;              // [4], 8 arrivals each
   uint64_t* y2_ready = x_full + 11;             // [4]
-  uint64_t* so_free = x_full + 15;              // the output TMA store of the previous item has read its staging
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 16);
+  uint64_t* so_free = x_full + 15;              // the output TMA store of an item has read its staging (TMA warp)
+  uint64_t* so_ready = x_full + 16;             // E3 has staged an item's output (16 epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 17);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
     mbar_init(acc2_empty, kHeadEpiWarps);
     mbar_init(acc3_full, 1);
     mbar_init(so_free, 1);
+    mbar_init(so_ready, kHeadEpiWarps);
     for (int s = 0; s < 4; ++s) {
       mbar_init(&y1_ready[s], kHeadEpiWarps);
       mbar_init(&y2_ready[s], kHeadEpiWarps);
@@ -175,6 +177,21 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
       }
       __syncwarp();
     };
+    // The output tile of an item goes out as ONE TMA store issued here (this warp is mostly idle and always the same
+    // thread issues, bulk groups being per thread): wait for E3's staging, store, and once the store has read the
+    // staging release it to the E1 of the next item.
+    auto store_out = [&](int oit, uint32_t parity) {
+      mbar_wait_sleep(so_ready, parity);
+      if (lane == 0) {
+        const int otile = oit / p.G, og = oit - otile * p.G;
+        const HeadTile t = head_tile(otile, p);
+        tma_store_4d(&p.tmap_out, so, p.out_coff + og * p.A, t.q0, t.p0, t.n);
+        tma_store_commit();
+        tma_store_wait_read<0>();
+        mbar_arrive(so_free);
+      }
+      __syncwarp();
+    };
     for (int it = start; it < end; ++it, ++li) {
       const int tile = it / p.G, g = it - tile * p.G;
       nload = li == 0 ? -2 : 0;  // probe: loads of this item in order W2[0..3], W1'[0..1], W3
@@ -183,6 +200,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
         for (int kb = 0; kb < K1; ++kb) load_w(&p.tmap_w1, g * kHeadMid, kb, kHeadSlotBytes);
       }
       for (int kb = 0; kb < 4; ++kb) load_w(&p.tmap_w2, g * kHeadMid, kb, kHeadSlotBytes);
+      if (li > 0) store_out(it - 1, (li - 1) & 1);  // the previous item's E3 is staging about now
       if (it + 1 < end) {
         const int ntile = (it + 1) / p.G, ng = (it + 1) - ntile * p.G;
         mbar_wait_sleep(x_empty, li & 1);  // GEMM1 of this item has read X
@@ -190,6 +208,10 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
         for (int kb = 0; kb < K1; ++kb) load_w(&p.tmap_w1, ng * kHeadMid, kb, kHeadSlotBytes);
       }
       load_w(&p.tmap_w3, g * R3, 0, 4u * R3 * 128u);
+    }
+    if (end > start) {
+      store_out(end - 1, (end - 1 - start) & 1);
+      if (lane == 0) tma_store_wait_all();
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -292,27 +314,24 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
     // GEMM2 / GEMM3 start on slab 0 while the rest is drained; the TMEM load of slab s+1 is in flight while slab s
     // is converted.  (The bias vectors of the item were prefetched into L1 during the previous item: an L2 round
     // trip per slab used to be exposed here.)
-    auto drain_to_y = [&](uint32_t acc, const float* bias, uint64_t* ready, uint64_t* acc_empty, uint32_t so_par) {
+    auto drain_to_y = [&](uint32_t acc, const float* bias, uint64_t* ready, uint64_t* acc_empty, bool so_wait,
+                          uint32_t so_par) {
       uint32_t a[2][16];
       tmem_ld16(acc + lane_off + part * 16, a[0]);
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
-        if (s == 2 && acc_empty != nullptr) {  // E1 only: slabs 2-3 hold the output staging of the previous item
-          if (warp == 2 && lane == 0) {        // (the thread that issued the store; nothing outstanding on the first item)
-            tma_store_wait_read<0>();
-            mbar_arrive(so_free);
-          }
-          __syncwarp();
-          mbar_wait(so_free, so_par);
-        }
+        // E1 only: slabs 2-3 hold the output staging of the previous item until its TMA store has read it
+        if (s == 2 && so_wait) mbar_wait(so_free, so_par);
+        const float* bs = bias + s * 64 + part * 16;
+        float4 bv[4];  // issued before the TMEM wait: the two latencies overlap
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(bs + j * 4));
         tmem_ld_wait();
         if (s < 3) tmem_ld16(acc + lane_off + (s + 1) * 64 + part * 16, a[(s + 1) & 1]);
-        const float* bs = bias + s * 64 + part * 16;
         uint8_t* slab = sy + s * 16384;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bs + j * 8));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bs + j * 8 + 4));
+          const float4 b0 = bv[2 * j], b1 = bv[2 * j + 1];
           // two channels per instruction (add.f32x2 / mul.f32x2 round like their scalar forms)
           const unsigned long long bb[4] = {pack_f32x2(b0.x, b0.y), pack_f32x2(b0.z, b0.w), pack_f32x2(b1.x, b1.y),
                                             pack_f32x2(b1.z, b1.w)};
@@ -358,30 +377,34 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
       mbar_wait(acc1_full, par);
       if (warp == 2) HDBG(9);
       tc_fence_after();
-      drain_to_y(tmem_base, p.b1 + g * kHeadMid, y1_ready, acc1_empty, par);
+      drain_to_y(tmem_base, p.b1 + g * kHeadMid, y1_ready, acc1_empty, li > 0, (li - 1) & 1);
       // E2 (acc2_full also means GEMM2 has finished reading Y)
       if (it + 1 < end) prefetch_bias((it + 1) % p.G);
       if (warp == 2) HDBG(10);
       mbar_wait(acc2_full, par);
       if (warp == 2) HDBG(11);
       tc_fence_after();
-      drain_to_y(tmem_base + kHeadMid, p.b2 + g * kHeadMid, y2_ready, nullptr, 0);
+      drain_to_y(tmem_base + kHeadMid, p.b2 + g * kHeadMid, y2_ready, nullptr, false, 0);
       // E3: acc3 + b3 -> fp32 staging [128][R3] -> coalesced 16-byte stores (A*4 contiguous bytes per pixel)
+      const int A = p.A;
+      float4 b3v[4];
+      if (part * 16 < R3) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) b3v[c] = __ldg(reinterpret_cast<const float4*>(p.b3 + g * R3 + part * 16 + 4 * c));
+      }
       if (warp == 2) HDBG(12);
       mbar_wait(acc3_full, par);
       if (warp == 2) HDBG(13);
       tc_fence_after();
-      const int A = p.A;
       if (part * 16 < A) {
         uint32_t a[16];
         tmem_ld16(tmem_base + kHeadMid + lane_off + part * 16, a);
         tmem_ld_wait();
-        const float* b3 = p.b3 + g * R3 + part * 16;
         float* dst = so + row * A + part * 16;  // 4 * A-byte rows: A = 36 -> the 16-byte stores of a quarter warp hit distinct banks
 #pragma unroll
         for (int c = 0; c < 16; c += 4) {
           if (part * 16 + c < A) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(b3 + c));
+            const float4 b = b3v[c >> 2];
             *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(a[c]) + b.x, __uint_as_float(a[c + 1]) + b.y,
                                                               __uint_as_float(a[c + 2]) + b.z, __uint_as_float(a[c + 3]) + b.w);
           }
@@ -390,20 +413,12 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc2_empty);
-      named_bar_sync(kEpiBarrier, 32 * kHeadEpiWarps);  // staging complete
-      if (warp == 2) {
-        // one TMA store writes the tile's [TH][TW][A] block (rows beyond the image edge are clipped)
-        if (lane == 0) {  // always the same thread: bulk-store groups are per thread
-          const HeadTile t = head_tile(tile, p);
-          tma_store_4d(&p.tmap_out, so, p.out_coff + g * A, t.q0, t.p0, t.n);
-          tma_store_commit();
-        }
-        __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(acc2_empty);
+        mbar_arrive(so_ready);  // the TMA warp stores the tile
       }
       if (warp == 2) HDBG(14);
     }
-    if (warp == 2 && lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();

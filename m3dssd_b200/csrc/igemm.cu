@@ -271,6 +271,15 @@ __global__ void __launch_bounds__(64 + 32 * conv_epi_warps<STAGED>(), 1)
 constexpr int kGatherBK = 64;
 constexpr int kProducerThreads = 256;
 
+// Phase timeline probe of the gather kernel (tools/probe_stem.py): compile with -DM3D_PROBE.  Stamps go to shared
+// memory (a global store per stamp would stall the stamping warp's next MEMBAR) and are copied out at the end.
+#ifdef M3D_PROBE
+__device__ long long g_gather_dbg[6 * 32];
+#define GDBG(slot) do { if (blockIdx.x == 0 && lane == 0 && local < 6) s_gdbg[local * 32 + (slot)] = clock64(); } while (0)
+#else
+#define GDBG(slot) do { } while (0)
+#endif
+
 template <int BN, bool SPLIT, bool STAGED>
 struct GatherCfg {
   static constexpr int ROW_BYTES = 128;
@@ -322,6 +331,10 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 
 template <int BN, typename InT, typename OutT, bool STAGED>
 __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_constant__ ConvGatherParams p) {
+#ifdef M3D_PROBE
+  __shared__ long long s_gdbg[6 * 32];
+  if (threadIdx.x < 6 * 32) s_gdbg[threadIdx.x] = 0;
+#endif
   constexpr bool SPLIT = sizeof(InT) == 4;
   using Cfg = GatherCfg<BN, SPLIT, STAGED>;
   constexpr int STAGES = Cfg::STAGES;
@@ -387,36 +400,46 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
       // staged once per tile in shared memory with coalesced loads.
       const int th2 = 2 * p.TH + 6, ld = 2 * p.TW + 8;  // TMA box: ld x th2 x 3 fp32, zero outside the image
       const uint32_t img_bytes = static_cast<uint32_t>(3 * th2 * ld * 4);
-      float* s_img2[2] = {om_s, om_s + ((img_bytes + 127) / 128) * 32};  // double-buffered (host checks the fit)
+      // double-buffered (host checks the fit).  The buffers are addressed as offsets from the shared base (an array
+      // of pointers made the loads generic LD.E: long-scoreboard stalls on every window read).
+      const int img_stride = static_cast<int>((img_bytes + 127) / 128) * 32;
       auto load_img = [&](int tl, int buf) {
         const TileCoord tn = decode_tile(tl, p.n_tiles, p.tiles_w, p.tiles_h, p.N, p.TW, p.TH);
         mbar_arrive_expect_tx(&res_bar[buf], img_bytes);
         // x origin 2*q0 - 4 keeps the innermost coordinate 16-byte aligned (window columns start at +1)
-        tma_load_4d(s_img2[buf], &p.tmap_img, &res_bar[buf], 2 * tn.q0 - 4, 2 * tn.p0 - 3, 0, tn.n);
+        tma_load_4d(om_s + buf * img_stride, &p.tmap_img, &res_bar[buf], 2 * tn.q0 - 4, 2 * tn.p0 - 3, 0, tn.n);
       };
       if (pt == 0 && blockIdx.x < p.total_tiles) load_img(blockIdx.x, 0);
       int local = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
         const int buf = local & 1;
         named_bar_sync(1, kProducerThreads);  // the previous tile's readers are done with the other buffer
+        if (warp == 0) GDBG(0);
         if (pt == 0 && tile + gridDim.x < p.total_tiles) load_img(tile + gridDim.x, buf ^ 1);  // next tile's image
         mbar_wait(&res_bar[buf], (local >> 1) & 1);
-        const float* s_img = s_img2[buf];
+        if (warp == 0) GDBG(1);
+        const uint32_t s_img = smem_u32(om_s) + static_cast<uint32_t>(buf * img_stride) * 4u;
         for (int kb = 0; kb < 3; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* a_hi = smem + stage * Cfg::STAGE;
 #pragma unroll
           for (int ii = 0; ii < 4; ++ii) {
             const int row = rbase + 32 * ii;
-            const float* src = s_img + (kb * th2 + 2 * (row >> tw_shift) + j) * ld + 2 * (row & (p.TW - 1)) + 1;
+            // window = floats 1..8 of an 8-byte aligned span: ld.shared 32 + 3 x 64 + 32
+            const uint32_t src =
+                s_img + static_cast<uint32_t>((kb * th2 + 2 * (row >> tw_shift) + j) * ld + 2 * (row & (p.TW - 1))) * 4u;
             float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = src[e];
+            asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(v[0]) : "r"(src));
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+8];" : "=f"(v[1]), "=f"(v[2]) : "r"(src));
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+16];" : "=f"(v[3]), "=f"(v[4]) : "r"(src));
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+24];" : "=f"(v[5]), "=f"(v[6]) : "r"(src));
+            asm volatile("ld.shared.f32 %0, [%1+32];" : "=f"(v[7]) : "r"(src));
             *reinterpret_cast<uint4*>(a_hi + swizzled_offset<128>(row, j)) = pack8(v);
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&full[stage]);
+          if (warp == 0) GDBG(2 + kb);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -728,10 +751,12 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
       mbar_wait(&tempty[as], aphase ^ 1);
+      GDBG(8);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + as * Cfg::ACC;
       for (int kb = 0; kb < total_kb; ++kb) {
         mbar_wait(&full[stage], phase);
+        if (kb < 3) GDBG(9 + kb);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE);
@@ -766,6 +791,7 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
       }
       if (elect_one()) umma_commit(&tfull[as]);
       __syncwarp();
+      GDBG(12);
     }
   } else {
     // --------------------------------------------------------------- epilogue
@@ -779,6 +805,7 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
       mbar_wait(&tfull[as], aphase);
+      if (warp == 10) GDBG(16);
       tc_fence_after();
       if constexpr (STAGED) {
         const int col0 = t.nt * BN;
@@ -796,11 +823,15 @@ __global__ void __launch_bounds__(448, 1) conv_gather_kernel(const __grid_consta
         tc_fence_before();
         mbar_arrive(&tempty[as]);
       }
+      if (warp == 10) GDBG(17);
     }
     if (STAGED && ep_tid == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
+#ifdef M3D_PROBE
+  if (blockIdx.x == 0 && threadIdx.x < 6 * 32) g_gather_dbg[threadIdx.x] = s_gdbg[threadIdx.x];
+#endif
   if (warp == 9) {
     tc_fence_after();
     tmem_dealloc<2 * Cfg::ACC>(tmem_base);
@@ -904,3 +935,9 @@ int launch_conv_gather(const ConvGatherParams& p, int BN, int in_dtype, int out_
 }
 
 }  // namespace m3d
+
+#ifdef M3D_PROBE
+extern "C" int m3d_gather_debug_read(long long* host, int n) {
+  return cudaMemcpyFromSymbol(host, m3d::g_gather_dbg, sizeof(long long) * n) == cudaSuccess ? 0 : -1;
+}
+#endif

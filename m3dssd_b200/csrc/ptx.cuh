@@ -118,14 +118,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug traps (launch fails with an error the host
 // sees) instead of hanging the GPU.
+static __device__ __noinline__ void mbar_timeout_trap() {
+  printf("m3dssd_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) {  // ~4 s at 2 GHz
-      printf("m3dssd_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
+    if (clock64() - t0 > 8000000000LL) mbar_timeout_trap();  // ~4 s at 2 GHz
   }
 }
 
@@ -136,11 +137,19 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     __nanosleep(32);
-    if (clock64() - t0 > 8000000000LL) {
-      printf("m3dssd_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
+    if (clock64() - t0 > 8000000000LL) mbar_timeout_trap();
   }
+}
+
+// Explicit shared-space 16-byte accesses (a buffer picked at run time from an array of pointers makes the compiler
+// fall back to generic LD.E / ST.E, which go through the global-memory scoreboard).
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // ---------------------------------------------------------------------- TMA

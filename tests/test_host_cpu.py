@@ -25,6 +25,26 @@ def test_library_exports_every_declared_symbol():
     assert L.m3d_version() >= 100
 
 
+def test_sass_has_no_generic_or_hot_local_accesses():
+    """Code-generation audit of the built library (cuobjdump, no GPU needed).  A shared-memory buffer chosen at run
+    time through an array of pointers silently compiles to generic LD.E / ST.E (global-memory scoreboard): that cost
+    the stem producer and every staged epilogue before it was found.  No kernel may contain one."""
+    import shutil
+    from m3dssd_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump) or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("cuobjdump or the built library is not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    pat = re.compile(r"^\s+/\*[0-9a-f]{4}\*/\s+(@!?U?P[0-9T] )?(LD\.E|ST\.E|LD |ST )")
+    func, bad = None, {}
+    for line in sass.splitlines():
+        if "Function :" in line:
+            func = line.split("Function :")[1].strip()
+        elif pat.match(line):
+            bad[func] = bad.get(func, 0) + 1
+    assert not bad, "generic loads/stores in: %s" % bad
+
+
 def test_no_cpu_fallback_and_error_surface():
     from m3dssd_b200 import synth
     from m3dssd_b200.model.DCNv2.dcn_v2 import DCN, DCNv2

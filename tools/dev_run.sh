@@ -1,6 +1,5 @@
-# development run on the GPU box (tools/gpurun_retry.sh gpurun_out/x.log 600 'bash tools/dev_run.sh')
-timeout 150 python -m pytest tests/test_ops_gpu.py -m gpu -x -q -k "head" 2>&1 | tail -3
+# development run on the GPU box (tools/gpurun_retry.sh gpurun_out/x.log 900 'bash tools/dev_run.sh')
+timeout 300 python -m pytest tests/test_conv_gpu.py -m gpu -x -q 2>&1 | tail -2
 B='import sys,json; d=json.loads(sys.stdin.read()); print(d["value"], d["e2e"]["value"], d["ms_per_step"])'
 echo "== bench"; timeout 200 python bench.py --steps 30 --warmup 5 2>&1 | tail -1 | python -c "$B"
-timeout 60 python tools/probe_heads.py 2>&1 | tail -3
-timeout 30 ./build/microbench | tail -13
+timeout 60 python tools/probe_stem.py 2>&1 | tail -8
