@@ -222,11 +222,20 @@ static int pick_bn(int cout, int bk, long m_tiles, bool gather, bool split) {
 
 using namespace m3d;
 
+namespace m3d {
+int launch_stem_s2d(const float* image, const void* weight, const float* bias, void* out, int N, int H, int W, float slope,
+                    cudaStream_t stream);
+}
+
 extern "C" int m3d_stem_conv7x7_s2d(const float* image, const void* weight, const float* bias, void* out, int N, int H,
                                     int W, float slope, m3d_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   M3D_REQUIRE(image && weight && bias && out, "NULL pointer");
   M3D_REQUIRE(H % 2 == 0 && W % 4 == 0 && H >= 2 && W >= 4, "space-to-depth stem needs H %% 2 == 0, W %% 4 == 0 (got %dx%d)", H, W);
+  if (getenv("M3D_STEM_LEGACY") == nullptr) {  // dedicated kernel (stem.cu); the shared gather kernel otherwise
+    const int rc = m3d::launch_stem_s2d(image, weight, bias, out, N, H, W, slope, stream);
+    if (rc != M3D_ERR_UNSUPPORTED) return rc;
+  }
   const int P = H / 2, Q = W / 2;
   int TW = 16, TH = 8;
   pick_tile(P, Q, 64, &TW, &TH);  // image tile (2TW+8) x (2TH+6) x 3 fp32 must fit the producer scratch

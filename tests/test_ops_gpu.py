@@ -35,6 +35,29 @@ def test_stem_conv7x7(dtype):
     assert (got - ref).abs().max().item() < tol
 
 
+@pytest.mark.parametrize("shape", [(2, 36, 72), (1, 96, 320), (3, 50, 44)])
+@pytest.mark.parametrize("legacy", [False, True])
+def test_stem_conv7x7_s2d(shape, legacy, monkeypatch):
+    """bf16 trunk stem in 2x2 space-to-depth form (dedicated kernel, and the shared gather kernel it replaced) vs
+    conv2d on the bf16-rounded operands: output channel (ey*2+ex)*16 + c of pixel (Y, X) = channel c at (2Y+ey, 2X+ex)."""
+    from m3dssd_b200 import ops
+    if legacy:
+        monkeypatch.setenv("M3D_STEM_LEGACY", "1")
+    else:
+        monkeypatch.delenv("M3D_STEM_LEGACY", raising=False)
+    N, H, W = shape
+    g = _g(21)
+    x = torch.randn(N, 3, H, W, generator=g)
+    w = torch.randn(16, 3, 7, 7, generator=g) * 0.1
+    b = torch.randn(16, generator=g)
+    wp, bp = ops.pack_stem_s2d(w, b)
+    ref = F.leaky_relu(F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b, padding=3), 0.01)
+    out = torch.full((N, H // 2, W // 2, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.stem_conv7x7_s2d(x.cuda(), wp.cuda(), bp.cuda(), out, 0.01)
+    got = out.float().cpu().reshape(N, H // 2, W // 2, 2, 2, 16).permute(0, 5, 1, 3, 2, 4).reshape(N, 16, H, W)
+    assert (got - ref).abs().max().item() < 2 ** -7 * ref.abs().max().item()
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_maxpool2x2(dtype):
     from m3dssd_b200 import ops
