@@ -135,7 +135,8 @@ int make_tmap_nhwc(CUtensorMap* map, const void* base, int N, int H, int W, int 
 
 // fp32 NHWC tensor as (C, W, H, N); box {box_c, tw, th, 1}, no swizzle (the fused heads' TMA store: box rows are the
 // box_c * 4 contiguous bytes of one pixel, clipped at the image edge).
-int make_tmap_nhwc_f32(CUtensorMap* map, const void* base, int N, int H, int W, int C, int box_c, int tw, int th) {
+int make_tmap_nhwc_f32(CUtensorMap* map, const void* base, int N, int H, int W, int C, int box_c, int tw, int th,
+                       bool swizzle128) {
   auto enc = get_encode();
   M3D_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
@@ -145,8 +146,8 @@ int make_tmap_nhwc_f32(CUtensorMap* map, const void* base, int N, int H, int W, 
   cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th), 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   M3D_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(nhwc f32 N=%d H=%d W=%d C=%d box=%dx%dx%d) failed: %d", N, H, W, C,
               box_c, tw, th, static_cast<int>(r));
   return M3D_OK;
@@ -341,9 +342,19 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
                       BN % 64 == 0 &&
                       d->Cout % 64 == 0 && d->out_cstride % 8 == 0 && d->out_coff % 8 == 0 && d->out_goff % 8 == 0 &&
                       (d->res == nullptr || (d->res_cstride % 8 == 0 && d->res_coff % 8 == 0 && d->res_goff % 8 == 0));
+  // fp32 output of a bf16 1x1 layer with many channels (the class logits): 32-column slabs through the same staging.
+  // A partial last slab is clipped by the TMA store only at the tensor's channel extent.
+  const bool staged_f32 = !gather && d->act_dtype == M3D_BF16 && d->out_dtype == M3D_F32 && bk == 64 && BN == 256 &&
+                          groups == 1 && d->res == nullptr && d->Cout > 64 && d->out_cstride % 4 == 0 &&
+                          d->out_coff % 4 == 0 && (d->Cout % 32 == 0 || d->out_coff + d->Cout == d->out_cstride) &&
+                          !(getenv("M3D_F32_STAGED") && atoi(getenv("M3D_F32_STAGED")) == 0);
   if (!gather) {
     ConvTmaParams p;
     memset(&p, 0, sizeof(p));
+    if (staged_f32) {
+      int rc2 = make_tmap_nhwc_f32(&p.tmap_out, d->out, d->N, P, Q, d->out_cstride, 32, TW, TH, true);
+      if (rc2 != M3D_OK) return rc2;
+    }
     if (staged) {
       int rc2 = make_tmap_nhwc(&p.tmap_out, d->out, d->N, P, Q, d->out_cstride, 64, TW, TH, 1);
       if (rc2 != M3D_OK) return rc2;
@@ -421,7 +432,7 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
     p.res = d->res, p.res_cstride = d->res_cstride, p.res_coff = d->res_coff, p.res_goff = d->res_goff;
     p.slope = d->slope;
     p.total_tiles = static_cast<int>(total_tiles);
-    rc = launch_conv_tma(p, BN, bk, ksub, d->out_dtype, staged, stream);
+    rc = launch_conv_tma(p, BN, bk, ksub, d->out_dtype, staged || staged_f32, stream);
     if (rc == M3D_ERR_UNSUPPORTED) set_last_error("no TMA conv kernel for BN=%d BK=%d", BN, bk);
     return rc;
   }

@@ -226,4 +226,54 @@ __device__ __forceinline__ void epilogue_tile_staged(StagedEpilogue& st, uint32_
   }
 }
 
+// One 128 x BN fp32 tile (bf16 activations, fp32 output: the class logits).  Same staging as above with 32-column
+// slabs (128 rows x 128 bytes, swizzled, one TMA store per slab): a thread writing its row's 576 bytes straight to
+// global memory touches 32 different lines per warp instruction, which made cls.l3 LSU-bound.  No residual.  Slabs
+// past `nvalid` columns are skipped; the last one may be partial only if it ends at the tensor's channel extent
+// (the TMA store clips there) -- the host checks.
+template <int BN, int NW, typename F>
+__device__ __forceinline__ void epilogue_tile_staged_f32(StagedEpilogue& st, uint32_t tmem_acc, int quarter, int lane,
+                                                         int ep_tid, int n, int p0, int q0, const void* tmap_out,
+                                                         int c_out, const float* bias, int nvalid, float slope,
+                                                         F on_tmem_drained) {
+  static_assert(NW == 8, "8 epilogue warps");
+  constexpr int NT = 32 * NW;
+  const int half = ep_tid >> 7;
+  const int row = quarter * 32 + lane;
+  const bool leader = ep_tid == 0;
+  const int nslab = (min(nvalid, BN) + 31) >> 5;
+
+  named_bar_sync(kEpiBarrier, NT);  // previous tile no longer reads bias_s
+  for (int i = ep_tid; i < BN; i += NT) st.bias_s[i] = (bias != nullptr && i < nvalid) ? __ldg(bias + i) : 0.f;
+  named_bar_sync(kEpiBarrier, NT);  // bias_s visible
+
+#pragma unroll 1
+  for (int s = 0; s < nslab; ++s) {
+    const int b = st.slab_count & 1;
+    const uint32_t buf_s = smem_u32(st.stage) + static_cast<uint32_t>(b) * kSlabBytes;
+    uint32_t a[16];
+    tmem_ld16(tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + s * 32 + half * 16, a);
+    if (leader) tma_store_wait_read<1>();  // the store that last used buffer b (two slabs ago) has drained it
+    named_bar_sync(kEpiBarrier, NT);       // buffer b is free for everybody
+    tmem_ld_wait();
+    if (s == nslab - 1) on_tmem_drained();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // chunks of 4 channels
+      const float4 bb = *reinterpret_cast<const float4*>(st.bias_s + s * 32 + half * 16 + j * 4);
+      const float v0 = __uint_as_float(a[4 * j]) + bb.x, v1 = __uint_as_float(a[4 * j + 1]) + bb.y;
+      const float v2 = __uint_as_float(a[4 * j + 2]) + bb.z, v3 = __uint_as_float(a[4 * j + 3]) + bb.w;
+      sts128(buf_s + swizzled_offset<128>(row, half * 4 + j),
+             make_uint4(__float_as_uint(lrelu(v0, slope)), __float_as_uint(lrelu(v1, slope)),
+                        __float_as_uint(lrelu(v2, slope)), __float_as_uint(lrelu(v3, slope))));
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(kEpiBarrier, NT);  // slab complete
+    if (leader) {
+      tma_store_4d(tmap_out, st.slab(b), c_out + s * 32, q0, p0, n);
+      tma_store_commit();
+    }
+    st.slab_count++;
+  }
+}
+
 }  // namespace m3d

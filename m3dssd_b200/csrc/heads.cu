@@ -31,7 +31,8 @@
 namespace m3d {
 
 int make_tmap_nhwc(CUtensorMap* map, const void* base, int N, int H, int W, int C, int bk, int tw, int th, int stride);
-int make_tmap_nhwc_f32(CUtensorMap* map, const void* base, int N, int H, int W, int C, int box_c, int tw, int th);
+int make_tmap_nhwc_f32(CUtensorMap* map, const void* base, int N, int H, int W, int C, int box_c, int tw, int th,
+                       bool swizzle128);
 int make_tmap_b3d(CUtensorMap* map, const void* base, long rows, long cols, int bk, int box_rows, int ksub);
 void pick_tile(int P, int Q, int max_tw, int* TW, int* TH);
 
@@ -461,7 +462,7 @@ extern "C" int m3d_head_mlp(const void* x, int N, int H, int W, int x_cstride, i
   if (rc != M3D_OK) return rc;
   rc = make_tmap_b3d(&p.tmap_w3, w3, static_cast<long>(G) * rows3, kHeadMid, 64, rows3, 4);
   if (rc != M3D_OK) return rc;
-  rc = make_tmap_nhwc_f32(&p.tmap_out, out, N, H, W, out_cstride, A, TW, TH);
+  rc = make_tmap_nhwc_f32(&p.tmap_out, out, N, H, W, out_cstride, A, TW, TH, false);
   if (rc != M3D_OK) return rc;
   p.b1 = b1, p.b2 = b2, p.b3 = b3;
   p.out = out, p.out_cstride = out_cstride, p.out_coff = out_coff;

@@ -226,7 +226,15 @@ __global__ void __launch_bounds__(64 + 32 * conv_epi_warps<STAGED>(), 1)
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const float* bias = p.bias ? p.bias + t.g * p.bias_goff : nullptr;
-      if constexpr (STAGED) {
+      if constexpr (STAGED && sizeof(OutT) == 4) {
+        const int col0 = t.nt * BN;
+        epilogue_tile_staged_f32<BN, NW>(st, tmem_base + as * Cfg::ACC, quarter, lane, ep_tid, t.n, t.p0, t.q0,
+                                         &p.tmap_out, p.out_coff + t.g * p.out_goff + col0, bias ? bias + col0 : nullptr,
+                                         p.Cout - col0, p.slope, [&]() {
+                                           tc_fence_before();
+                                           mbar_arrive(&tempty[as]);
+                                         });
+      } else if constexpr (STAGED) {
         const int col0 = t.nt * BN;
         epilogue_tile_staged<BN, NW>(st, tmem_base + as * Cfg::ACC, quarter, lane, ep_tid, t.n, t.p0, t.q0, &p.tmap_out,
                                  p.out_coff + t.g * p.out_goff + col0, p.res ? &p.tmap_res : nullptr,
@@ -867,6 +875,8 @@ int launch_conv_tma(const ConvTmaParams& p, int BN, int BK, int ksub, int out_dt
 #define M3D_TMA_STAGED(bn, ks)                                                             \
   if (staged && BN == bn && BK == 64 && ksub == ks && out_dtype == DT_BF16)                \
     return launch_tma_t<bn, 64, ks, __nv_bfloat16, true>(p, stream);
+  if (staged && BN == 256 && BK == 64 && ksub == 1 && out_dtype == DT_F32)  // fp32 logits through staging + TMA stores
+    return launch_tma_t<256, 64, 1, float, true>(p, stream);
   if (staged && BN == 64 && BK == 32 && ksub == 1 && out_dtype == DT_BF16)
     return launch_tma_t<64, 32, 1, __nv_bfloat16, true>(p, stream);
   M3D_TMA_STAGED(64, 1)

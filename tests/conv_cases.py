@@ -116,6 +116,8 @@ CASES = [
     ("conv1x1_cout256", dict(N=4, H=24, W=80, cins=[256], cout=256, k=1)),
     ("conv3x3_cout256_big", dict(N=8, H=24, W=80, cins=[256], cout=256)),
     ("head_cout36_f32", dict(N=1, H=12, W=40, cins=[256], cout=36, k=1, out_dtype=torch.float32, slope=1.0)),
+    ("logits_cout144_f32", dict(N=2, H=24, W=80, cins=[256], cout=144, k=1, out_dtype=torch.float32, slope=1.0)),
+    ("logits_cout160_f32_ragged", dict(N=3, H=13, W=37, cins=[128], cout=160, k=1, out_dtype=torch.float32)),
     ("heads_grouped", dict(N=1, H=12, W=40, cins=[256], cout=256, k=1, groups=3)),
     ("heads_grouped_36", dict(N=1, H=12, W=40, cins=[256], cout=36, k=1, groups=4, out_dtype=torch.float32, slope=1.0)),
     ("offsetconv_27_f32", dict(N=1, H=24, W=80, cins=[128], cout=27, out_dtype=torch.float32, slope=1.0)),

@@ -22,7 +22,8 @@ def launches(path):
     ii = hdr.index("ID")
     seq = [(int(r[ii]), short(r[ki]), float(r[vi].replace(",", ""))) for r in rows[1:] if len(r) > vi and r[mi] == "gpu__time_duration.sum"]
     # one step = everything from the last stem launch (first kernel of the plan) onwards
-    starts = [i for i, (_, k, _) in enumerate(seq) if k.startswith("conv_gather_kernel<64,") or k.startswith("stem_conv7x7")]
+    starts = [i for i, (_, k, _) in enumerate(seq)
+              if "stem_s2d_kernel" in k or k.startswith("conv_gather_kernel<64,") or k.startswith("stem_conv7x7")]
     step = seq[starts[-1]:] if starts else seq
     agg = OrderedDict()
     for _, k, v in step:
