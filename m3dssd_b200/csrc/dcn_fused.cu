@@ -26,6 +26,15 @@ namespace m3d {
 namespace {
 
 constexpr int kProd = 512;  // producer threads
+
+// Per-k-block timeline probe (tools/probe_dcn_timeline.py): compile with -DM3D_PROBE.  Block 0, first tile, first 24
+// k-blocks; stamps in shared memory, copied out at kernel end.
+#ifdef M3D_PROBE
+__device__ long long g_dcn_dbg[32 * 8];
+#define DDBG(kbi, slot) do { if (blockIdx.x == 0 && lane == 0 && (kbi) < 32) s_ddbg[(kbi) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define DDBG(kbi, slot) do { } while (0)
+#endif
 constexpr int kDcnThreads = kProd + 6 * 32;
 constexpr int kBK = 64;
 
@@ -94,6 +103,11 @@ __device__ __forceinline__ Entry make_entry(const ConvGatherParams& p, int n, in
 // device gets filled when there are fewer full tiles than SMs (ida_0.proj_1: 30 tiles -> 72).
 template <int BN, int NSTG, bool HALF>
 __global__ void __launch_bounds__(kDcnThreads, 1) dcn_fused_kernel(const __grid_constant__ ConvGatherParams p) {
+#ifdef M3D_PROBE
+  __shared__ long long s_ddbg[32 * 8];
+  if (threadIdx.x < 32 * 8) s_ddbg[threadIdx.x] = 0;
+  int pkb = 0;  // k-blocks seen by this warp role
+#endif
   using Cfg = DcnCfg<BN, NSTG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -144,6 +158,9 @@ __global__ void __launch_bounds__(kDcnThreads, 1) dcn_fused_kernel(const __grid_
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const Tile t = tile_of(tile, p);
+#ifdef M3D_PROBE
+      if (warp == 0 && pkb == 0) DDBG(31, 0);
+#endif
       named_bar_sync(1, kProd);  // previous tile's table readers are done
       if constexpr (!HALF) {
         // thread pt fills row pt/4, taps (pt%4) + 4k: its offset / mask loads are issued together
@@ -200,6 +217,9 @@ __global__ void __launch_bounds__(kDcnThreads, 1) dcn_fused_kernel(const __grid_
         }
       }
       named_bar_sync(1, kProd);
+#ifdef M3D_PROBE
+      if (warp == 0 && pkb == 0) DDBG(31, 1);
+#endif
 
       // unit = (k-block, row half); K is walked chunk-major: k-block -> (chunk, tap).  The corner loads of a unit
       // are issued two units (one k-block) before its blend, into a ring of three register buffers; the bilinear
@@ -254,13 +274,26 @@ __global__ void __launch_bounds__(kDcnThreads, 1) dcn_fused_kernel(const __grid_
       if constexpr (!HALF) {
         // one k-block: its halves sit in buffers A / B; the next k-block's halves are issued into NA / NB
         auto kblock = [&](const uint4 (&A)[4], const uint4 (&B)[4], uint4 (&NA)[4], uint4 (&NB)[4], bool more) {
+#ifdef M3D_PROBE
+          if (warp == 0) DDBG(pkb, 0);
+#endif
           mbar_wait(&empty[stage], phase ^ 1);
+#ifdef M3D_PROBE
+          if (warp == 0) DDBG(pkb, 1);
+#endif
           uint8_t* a_tile = smem + stage * Cfg::STAGE;
           if (more) issue(0, NA);
           blend(0, cur_tap, A, a_tile);
+#ifdef M3D_PROBE
+          if (warp == 0) DDBG(pkb, 2);
+#endif
           if (more) issue(1, NB);  // NB is A's storage when the ring wraps: A has just been consumed
           blend(1, cur_tap, B, a_tile);
           finish_kblock();
+#ifdef M3D_PROBE
+          if (warp == 0) DDBG(pkb, 3);
+          ++pkb;
+#endif
         };
         issue(0, cv[0]);
         issue(1, cv[1]);
@@ -334,6 +367,9 @@ __global__ void __launch_bounds__(kDcnThreads, 1) dcn_fused_kernel(const __grid_
       const uint32_t tmem_acc = tmem_base + as * Cfg::ACC;
       for (int kb = 0; kb < total_kb; ++kb) {
         mbar_wait(&full[stage], phase);
+#ifdef M3D_PROBE
+        DDBG(pkb, 4);
+#endif
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE);
@@ -344,6 +380,10 @@ __global__ void __launch_bounds__(kDcnThreads, 1) dcn_fused_kernel(const __grid_
           umma_commit(&empty[stage]);
         }
         __syncwarp();
+#ifdef M3D_PROBE
+        DDBG(pkb, 5);
+        ++pkb;
+#endif
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -374,6 +414,9 @@ __global__ void __launch_bounds__(kDcnThreads, 1) dcn_fused_kernel(const __grid_
   }
   tc_fence_before();
   __syncthreads();
+#ifdef M3D_PROBE
+  if (blockIdx.x == 0 && threadIdx.x < 32 * 8) g_dcn_dbg[threadIdx.x] = s_ddbg[threadIdx.x];
+#endif
   if (warp == 17) {
     tc_fence_after();
     tmem_dealloc<2 * Cfg::ACC>(tmem_base);
@@ -446,3 +489,9 @@ int launch_dcn_fused(const ConvGatherParams& p0, int BN, cudaStream_t stream) {
 }
 
 }  // namespace m3d
+
+#ifdef M3D_PROBE
+extern "C" int m3d_dcn_debug_read(long long* host, int n) {
+  return cudaMemcpyFromSymbol(host, m3d::g_dcn_dbg, sizeof(long long) * n) == cudaSuccess ? 0 : -1;
+}
+#endif
