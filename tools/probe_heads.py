@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 from m3dssd_b200 import _lib
-# probe build: nvcc ... -DM3D_PROBE -c m3dssd_b200/csrc/heads.cu -o build/heads_probe.o; link with the other objects
+# probe build: tools/build_probe.sh
 _lib.LIB_PATH = os.path.join(ROOT, "build", "libm3d_probe.so")
 from m3dssd_b200 import ops
 
