@@ -1,2 +1,5 @@
-# development run on the GPU box, 4 GPUs
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 4 --steps 30 --warmup 5 2>/dev/null | tail -1 > gpurun_out/r01d_bench_4gpu.json; head -c 260 gpurun_out/r01d_bench_4gpu.json; echo
+# Development run on the GPU box: GPU parity tests + one bench line.
+#   tools/gpurun_retry.sh gpurun_out/x.log 900 'bash tools/dev_run.sh'
+# (edit freely: this is the scratch command file the retry wrapper ships with the snapshot)
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+timeout 300 python bench.py --steps 30 --warmup 5 2>/dev/null | tail -1 | head -c 400; echo
