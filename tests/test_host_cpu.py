@@ -43,6 +43,13 @@ def test_sass_has_no_generic_or_hot_local_accesses():
         elif pat.match(line):
             bad[func] = bad.get(func, 0) + 1
     assert not bad, "generic loads/stores in: %s" % bad
+    # the committed ncu launch list (profiles/) must be a profile of THIS library: every kernel it names exists
+    prof = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r01d_launch_summary.md")
+    funcs = " ".join(l for l in sass.splitlines() if "Function :" in l)
+    names = set(re.findall(r"^\| `(?:unnamed>::)?([A-Za-z0-9_]+)", open(prof).read(), flags=re.M))
+    assert len(names) >= 15, names
+    missing = [n for n in names if n not in funcs]
+    assert not missing, "profiled kernels missing from the library: %s" % missing
 
 
 def test_no_cpu_fallback_and_error_surface():
