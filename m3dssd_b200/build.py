@@ -26,6 +26,9 @@ FLAGS = [
     # devIoU and the bilinear blend must round like the reference's plain fp32
     # expressions: no fast-math anywhere.
 ]
+# Development knob: extra nvcc flags, e.g. M3D_NVCC_EXTRA=-DM3D_HEAD_BIAS_REG (experimental kernel variants that are
+# compiled out of the default build).  Part of the object cache key.
+FLAGS += os.environ.get("M3D_NVCC_EXTRA", "").split()
 
 
 def _sources():
