@@ -62,7 +62,7 @@ int m3d_set_sm_limit(int sms);
  *                       tensor-core accumulators truncate).
  * Weights are packed [rows][K] with K = concat_i (tap-major, channel-minor).
  * ---------------------------------------------------------------------- */
-#define M3D_MAX_CONCAT 4
+#define M3D_MAX_CONCAT 6
 
 typedef struct m3d_conv_desc {
   int act_dtype; /* M3D_BF16 | M3D_F32 */
@@ -148,10 +148,12 @@ int m3d_nms_batched(const float* boxes, int box_stride, const int* num, int batc
 /* Detection decode (lib/rpn_util.py:1444-1521): per image, exact top-`topk` of
  * score (descending, ties by lower index), anchor decode of the selected rows
  * into dets [batch, topk, 14] = x1,y1,x2,y2,score,cls,x3d,y3d,z3d,w3d,h3d,l3d,ry3d,anchor. */
+size_t m3d_decode_topk_workspace(int batch);
 int m3d_decode_topk(const float* score, const unsigned char* cls_pred, const float* bbox_2d, const float* bbox_3d,
                     const float* anchors /*[A,9] device*/, const float* means11 /*host*/, const float* stds11 /*host*/, int batch, int A, int H,
                     int W, float feat_stride, float scale_factor, int topk, float* dets, int* det_idx, int* det_num,
-                    m3d_stream_t stream);
+                    void* workspace /*device, 16-byte aligned, m3d_decode_topk_workspace(batch) bytes, caller-owned*/,
+                    size_t workspace_bytes, m3d_stream_t stream);
 int m3d_gather_kept(const float* dets, int row_len, int batch, int max_n, const int* keep, const int* num_keep,
                     int max_out, float* out, m3d_stream_t stream);
 
@@ -223,9 +225,12 @@ size_t m3d_anab_pool_workspace(int N, int H, int nlev, const int* sizes, int ck,
 int m3d_anab_pool(const float* kvs, int kvs_cstride, int N, int H, int W, int ck, int cv, int nlev,
                   const int* sizes /*host*/, void* workspace, size_t workspace_bytes, float* ktok /*[N,T,ck]*/,
                   float* vtok /*[N,T,cv]*/, m3d_stream_t stream);
+size_t m3d_anab_attention_workspace(int N, int act_dtype);
 int m3d_anab_attention(const void* q, int q_cstride, const float* ktok, const float* vtok, const void* x,
                        int x_cstride, int act_dtype, const float* scale, const float* shift, float slope, void* out,
-                       int out_cstride, int N, int HW, int ck, int cv, int T, m3d_stream_t stream);
+                       int out_cstride, int N, int HW, int ck, int cv, int T,
+                       void* workspace /*device, caller-owned, m3d_anab_attention_workspace(N, act_dtype) bytes*/,
+                       size_t workspace_bytes, m3d_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ _SIGS = {
     "m3d_dcn_v2_backward": [vp] * 10 + [i] * 14 + [vp, sz, vp],
     "m3d_nms": [vp, vp, vp, i, i, f, i],
     "m3d_nms_batched": [vp, i, vp, i, i, f, vp, sz, vp, vp, vp],
-    "m3d_decode_topk": [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, f, f, i, vp, vp, vp, vp],
+    "m3d_decode_topk": [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, f, f, i, vp, vp, vp, vp, sz, vp],
     "m3d_gather_kept": [vp, i, i, i, vp, vp, i, vp, vp],
     "m3d_stem_conv7x7": [vp, vp, vp, vp, i, i, i, i, i, f, vp],
     "m3d_stem_conv7x7_s2d": [vp, vp, vp, vp, i, i, i, f, vp],
@@ -22,7 +22,7 @@ _SIGS = {
     "m3d_refine_3d": [vp, vp, i, i, i, vp, vp, f, i, db, db, vp, vp, vp],
     "m3d_flatten_heads": [vp, i, i, i, i, i, vp, vp, vp, vp],
     "m3d_anab_pool": [vp, i, i, i, i, i, i, i, vp, vp, sz, vp, vp, vp],
-    "m3d_anab_attention": [vp, i, vp, vp, vp, i, i, vp, vp, f, vp, i, i, i, i, i, i, vp],
+    "m3d_anab_attention": [vp, i, vp, vp, vp, i, i, vp, vp, f, vp, i, i, i, i, i, i, vp, sz, vp],
     "m3d_nchw_to_nhwc": [vp, i, vp, i, i, i, i, i, i, i, vp],
     "m3d_nhwc_to_nchw": [vp, i, vp, i, i, i, i, i, i, i, vp],
 }
@@ -31,6 +31,8 @@ _SIZE_FNS = {
     "m3d_dcn_v2_backward_workspace": [i] * 10,
     "m3d_nms_workspace_bytes": [i, i],
     "m3d_anab_pool_workspace": [i, i, i, vp, i, i],
+    "m3d_anab_attention_workspace": [i, i],
+    "m3d_decode_topk_workspace": [i],
 }
 
 

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libm3dssd_b200.so")
 
 M3D_BF16, M3D_F32, M3D_BF16X3 = 0, 1, 2
-MAX_CONCAT = 4
+MAX_CONCAT = 6
 
 
 class M3DError(RuntimeError):

@@ -245,15 +245,13 @@ __global__ void __launch_bounds__(192, 1) anab_attention_tc_kernel(const __grid_
   }
 }
 
-// persistent bf16 token operands (grow-only; allocated outside graph capture by the engine's warm-up run)
-struct TokenWs {
-  __nv_bfloat16* kb = nullptr;
-  __nv_bfloat16* vb = nullptr;
-  int cap_n = 0, device = -1;
-};
-TokenWs g_tok;
-
 }  // namespace
+
+// bf16 token operands (K padded [N][kTP][kCKP], V^T padded [N][kCV][kTK]) live in a CALLER-owned workspace: a
+// process-global buffer would be baked into captured CUDA graphs and freed under them when another engine grows it
+size_t anab_tc_workspace_bytes(int N) {
+  return static_cast<size_t>(N) * (static_cast<size_t>(kTP) * kCKP + static_cast<size_t>(kCV) * kTK) * 2 + 256;
+}
 
 bool anab_tc_supported(int ck, int cv, int T, int q_cs, int x_cs, int out_cs) {
   return ck <= kCKP && cv == kCV && T <= kTP && q_cs % 8 == 0 && x_cs % 8 == 0 && out_cs % 8 == 0;
@@ -261,18 +259,17 @@ bool anab_tc_supported(int ck, int cv, int T, int q_cs, int x_cs, int out_cs) {
 
 int launch_anab_attention_tc(const void* q, int q_cs, const float* ktok, const float* vtok, const void* x, int x_cs,
                              const float* scale, const float* shift, float slope, void* out, int out_cs, int N, int HW,
-                             int ck, int cv, int T, cudaStream_t stream) {
-  int dev = 0;
-  M3D_CUDA_OK(cudaGetDevice(&dev));
-  if (g_tok.cap_n < N || g_tok.device != dev) {
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(stream, &cs);
-    M3D_REQUIRE(cs == cudaStreamCaptureStatusNone, "ANAB token workspace must be sized by an eager call before graph capture");
-    if (g_tok.kb) cudaFree(g_tok.kb);
-    if (g_tok.vb) cudaFree(g_tok.vb);
-    M3D_CUDA_OK(cudaMalloc(&g_tok.kb, static_cast<size_t>(N) * kTP * kCKP * 2));
-    M3D_CUDA_OK(cudaMalloc(&g_tok.vb, static_cast<size_t>(N) * kCV * kTK * 2));
-    g_tok.cap_n = N, g_tok.device = dev;
+                             int ck, int cv, int T, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (workspace == nullptr || workspace_bytes < anab_tc_workspace_bytes(N)) {
+    set_last_error("m3d_anab_attention: workspace of %zu bytes needed (m3d_anab_attention_workspace), got %zu",
+                   anab_tc_workspace_bytes(N), workspace_bytes);
+    return M3D_ERR_WORKSPACE;
+  }
+  struct { __nv_bfloat16 *kb, *vb; } g_tok;
+  {
+    uintptr_t a = (reinterpret_cast<uintptr_t>(workspace) + 127) & ~static_cast<uintptr_t>(127);
+    g_tok.kb = reinterpret_cast<__nv_bfloat16*>(a);
+    g_tok.vb = g_tok.kb + static_cast<size_t>(N) * kTP * kCKP;  // kTP * kCKP * 2 bytes is a multiple of 128
   }
   {
     const int work = kTP * kCKP > kCV * kTK ? kTP * kCKP : kCV * kTK;
@@ -306,11 +303,9 @@ int launch_anab_attention_tc(const void* q, int q_cs, const float* ktok, const f
   p.scale = scale, p.shift = shift, p.slope = slope;
   p.out = static_cast<__nv_bfloat16*>(out), p.out_cs = out_cs;
   p.HW = HW, p.T = T, p.tiles_per_image = (HW + 127) / 128;
-  static bool configured = false;
-  if (!configured) {
+  M3D_ONCE_PER_DEVICE_BEGIN
     M3D_CUDA_OK(cudaFuncSetAttribute(anab_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAnabSmem));
-    configured = true;
-  }
+  M3D_ONCE_PER_DEVICE_END
   M3D_CUDA_OK(launch_pdl(anab_attention_tc_kernel, dim3(p.tiles_per_image * N), dim3(192), kAnabSmem, stream, p));
   return M3D_OK;
 }

@@ -241,9 +241,10 @@ __global__ void __launch_bounds__(256) anab_attention_kernel(const TQ* __restric
 
 namespace m3d {
 bool anab_tc_supported(int ck, int cv, int T, int q_cs, int x_cs, int out_cs);
+size_t anab_tc_workspace_bytes(int N);
 int launch_anab_attention_tc(const void* q, int q_cs, const float* ktok, const float* vtok, const void* x, int x_cs,
                              const float* scale, const float* shift, float slope, void* out, int out_cs, int N, int HW,
-                             int ck, int cv, int T, cudaStream_t stream);
+                             int ck, int cv, int T, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 }  // namespace m3d
 
 using namespace m3d;
@@ -320,11 +321,9 @@ static int launch_attn(const void* q, int q_cs, const float* ktok, const float* 
                        int cv, int T, cudaStream_t st) {
   const size_t smem = sizeof(float) * (static_cast<size_t>(QB) * ck + KCHUNK * (ck + 1) + static_cast<size_t>(QB) * T);
   auto kern = anab_attention_kernel<TQ, TX>;
-  static bool configured = false;
-  if (!configured) {
+  M3D_ONCE_PER_DEVICE_BEGIN
     M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    configured = true;
-  }
+  M3D_ONCE_PER_DEVICE_END
   M3D_REQUIRE(smem <= 160 * 1024, "attention tile does not fit shared memory");
   dim3 grid((HW + QB - 1) / QB, N);
   kern<<<grid, 256, smem, st>>>(static_cast<const TQ*>(q), q_cs, ktok, vtok, static_cast<const TX*>(x), x_cs, scale,
@@ -333,15 +332,19 @@ static int launch_attn(const void* q, int q_cs, const float* ktok, const float* 
   return M3D_OK;
 }
 
+extern "C" size_t m3d_anab_attention_workspace(int N, int act_dtype) {
+  return act_dtype == M3D_BF16 ? anab_tc_workspace_bytes(N) : 0;
+}
+
 extern "C" int m3d_anab_attention(const void* q, int q_cstride, const float* ktok, const float* vtok, const void* x,
                                   int x_cstride, int act_dtype, const float* scale, const float* shift, float slope,
-                                  void* out, int out_cstride, int N, int HW, int ck, int cv, int T,
-                                  m3d_stream_t stream) {
+                                  void* out, int out_cstride, int N, int HW, int ck, int cv, int T, void* workspace,
+                                  size_t workspace_bytes, m3d_stream_t stream) {
   M3D_REQUIRE(q && ktok && vtok && x && scale && shift && out, "NULL pointer");
   if (act_dtype == M3D_BF16 && anab_tc_supported(ck, cv, T, q_cstride, x_cstride, out_cstride) &&
       getenv("M3D_ANAB_SIMT") == nullptr)
     return launch_anab_attention_tc(q, q_cstride, ktok, vtok, x, x_cstride, scale, shift, slope, out, out_cstride, N, HW,
-                                    ck, cv, T, S(stream));
+                                    ck, cv, T, workspace, workspace_bytes, S(stream));
   if (act_dtype == M3D_BF16)
     return launch_attn<__nv_bfloat16, __nv_bfloat16>(q, q_cstride, ktok, vtok, x, x_cstride, scale, shift, slope, out,
                                                      out_cstride, N, HW, ck, cv, T, S(stream));

@@ -30,6 +30,21 @@ int reserved_sms();
     }                                         \
   } while (0)
 
+// Function attributes (cudaFuncSetAttribute) are per DEVICE: remember, per call site and thus per kernel
+// instantiation, on which devices the enclosed statements have already run.  Usage:
+//   M3D_ONCE_PER_DEVICE_BEGIN  M3D_CUDA_OK(cudaFuncSetAttribute(...));  M3D_ONCE_PER_DEVICE_END
+#define M3D_ONCE_PER_DEVICE_BEGIN                                              \
+  {                                                                            \
+    static unsigned long long _m3d_done[4] = {0, 0, 0, 0};                     \
+    int _m3d_dev = 0;                                                          \
+    M3D_CUDA_OK(cudaGetDevice(&_m3d_dev));                                     \
+    _m3d_dev &= 255;                                                           \
+    if (!((_m3d_done[_m3d_dev >> 6] >> (_m3d_dev & 63)) & 1ull)) {
+#define M3D_ONCE_PER_DEVICE_END                                                \
+      _m3d_done[_m3d_dev >> 6] |= 1ull << (_m3d_dev & 63);                     \
+    }                                                                          \
+  }
+
 // Kernel launch with programmatic dependent launch (PDL): the grid may be scheduled while its predecessor
 // in the stream drains (SM by SM), runs its prologue (barrier init, TMEM allocation, descriptor prefetch)
 // and blocks in griddepcontrol.wait until the predecessor has completed and flushed.  Only kernels that

@@ -246,11 +246,9 @@ template <int BN, typename OutT, bool STAGED, bool BRES = false>
 int launch_t(const ConvTmaParams& p, cudaStream_t stream) {
   using Cfg = HaloCfg<BN, STAGED, BRES>;
   auto kern = conv_halo_kernel<BN, OutT, STAGED, BRES>;
-  static bool configured = false;
-  if (!configured) {
+  M3D_ONCE_PER_DEVICE_BEGIN
     M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    configured = true;
-  }
+  M3D_ONCE_PER_DEVICE_END
   const int sms = persistent_sms();
   const int per_sm = (2 * (Cfg::SMEM + 1024) <= 227 * 1024 && 4 * Cfg::ACC <= 512) ? 2 : 1;
   int grid = sms * per_sm;

@@ -280,11 +280,9 @@ template <int BN>
 int launch_t(const ConvTmaParams& p, cudaStream_t stream) {
   using Cfg = Halo2Cfg<BN>;
   auto kern = conv_halo2_kernel<BN>;
-  static bool configured = false;
-  if (!configured) {
+  M3D_ONCE_PER_DEVICE_BEGIN
     M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    configured = true;
-  }
+  M3D_ONCE_PER_DEVICE_END
   const int items = (p.tiles_w * p.tiles_h * p.N / 2) * p.n_tiles;
   // a CTA pair needs both SMs of a TPC: every CTA running on a reserved SM may strand its sibling
   int clusters = (persistent_sms() - reserved_sms()) / 2;

@@ -427,14 +427,12 @@ template <int BN, int NSTG, bool HALF>
 int launch_t(const ConvGatherParams& p, cudaStream_t stream) {
   using Cfg = DcnCfg<BN, NSTG>;
   auto kern = dcn_fused_kernel<BN, NSTG, HALF>;
-  static bool configured = false;
-  if (!configured) {
+  M3D_ONCE_PER_DEVICE_BEGIN
     M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     // what the operand ring does not need goes to L1: the 9 taps of a chunk re-read one input window
     const int pct = (Cfg::SMEM + 2048) * 100 / (228 * 1024) + 1;
     M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct));
-    configured = true;
-  }
+  M3D_ONCE_PER_DEVICE_END
   const int sms = persistent_sms();
   int grid = sms;
   if (grid > p.total_tiles) grid = p.total_tiles;

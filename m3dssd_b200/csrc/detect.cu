@@ -447,13 +447,10 @@ __global__ void __launch_bounds__(kSelThreads) topk_finish_kernel(const DecodePa
   topk_sort_decode(p, n, keys);
 }
 
-// persistent scratch of the multi-CTA top-K (grow-only; sized by an eager call before graph capture)
-struct TopkWs {
-  uint32_t* hist = nullptr;   // [N][2][2048] + [N] counts
-  unsigned long long* cand = nullptr;
-  int cap_n = 0, device = -1;
-};
-static TopkWs g_topk;
+// scratch of the multi-CTA top-K: hist [N][2][2048] + [N] counts, then cand [N][kCandCap].  CALLER-owned (the engine
+// allocates it next to its activations): a process-global buffer would be baked into captured CUDA graphs and freed
+// under them as soon as a second engine with a larger batch resized it.
+static size_t topk_hist_bytes(int batch) { return (static_cast<size_t>(batch) * 4097 * sizeof(uint32_t) + 255) & ~size_t(255); }
 
 // -------------------------------------------------------------------- NMS
 // IoU with the +1 pixel convention, in the exact operation order the
@@ -708,10 +705,15 @@ extern "C" int m3d_nms(int* keep_out, int* num_out, const float* boxes_host, int
   return M3D_OK;
 }
 
+extern "C" size_t m3d_decode_topk_workspace(int batch) {
+  return topk_hist_bytes(batch) + static_cast<size_t>(batch) * kCandCap * sizeof(unsigned long long);
+}
+
 extern "C" int m3d_decode_topk(const float* score, const unsigned char* cls_pred, const float* bbox_2d,
                                const float* bbox_3d, const float* anchors, const float* means11, const float* stds11,
                                int batch, int A, int H, int W, float feat_stride, float scale_factor, int topk,
-                               float* dets, int* det_idx, int* det_num, m3d_stream_t stream) {
+                               float* dets, int* det_idx, int* det_num, void* workspace, size_t workspace_bytes,
+                               m3d_stream_t stream) {
   M3D_REQUIRE(score && cls_pred && bbox_2d && bbox_3d && anchors && means11 && stds11 && dets && det_idx && det_num,
               "NULL pointer");
   M3D_REQUIRE(topk >= 1 && topk <= kMaxTopK, "topk=%d out of range (1..%d)", topk, kMaxTopK);
@@ -723,18 +725,15 @@ extern "C" int m3d_decode_topk(const float* score, const unsigned char* cls_pred
   p.dets = dets, p.det_idx = det_idx, p.det_num = det_num;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (getenv("M3D_TOPK_SINGLE") == nullptr) {
-    int dev = 0;
-    M3D_CUDA_OK(cudaGetDevice(&dev));
-    if (g_topk.cap_n < batch || g_topk.device != dev) {
-      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-      cudaStreamIsCapturing(st, &cs);
-      M3D_REQUIRE(cs == cudaStreamCaptureStatusNone, "top-K scratch must be sized by an eager call before graph capture");
-      if (g_topk.hist) cudaFree(g_topk.hist);
-      if (g_topk.cand) cudaFree(g_topk.cand);
-      M3D_CUDA_OK(cudaMalloc(&g_topk.hist, static_cast<size_t>(batch) * 4097 * sizeof(uint32_t)));
-      M3D_CUDA_OK(cudaMalloc(&g_topk.cand, static_cast<size_t>(batch) * kCandCap * sizeof(unsigned long long)));
-      g_topk.cap_n = batch, g_topk.device = dev;
+    if (workspace == nullptr || workspace_bytes < m3d_decode_topk_workspace(batch) ||
+        (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) {
+      set_last_error("m3d_decode_topk: 16-byte aligned workspace of %zu bytes needed (m3d_decode_topk_workspace), got %zu",
+                     m3d_decode_topk_workspace(batch), workspace_bytes);
+      return M3D_ERR_WORKSPACE;
     }
+    struct { uint32_t* hist; unsigned long long* cand; } g_topk;
+    g_topk.hist = static_cast<uint32_t*>(workspace);
+    g_topk.cand = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + topk_hist_bytes(batch));
     uint32_t* count = g_topk.hist + static_cast<size_t>(batch) * 4096;
     M3D_CUDA_OK(cudaMemsetAsync(g_topk.hist, 0, static_cast<size_t>(batch) * 4097 * sizeof(uint32_t), st));
     topk_hist_kernel<0><<<dim3(kTopkSlices, batch), kSelThreads, 0, st>>>(score, p.M, topk, g_topk.hist);

@@ -613,11 +613,9 @@ extern "C" int m3d_flatten_heads(const float* heads, int heads_cstride, int N, i
   }
   const size_t smem = static_cast<size_t>(SM_PIX) * (11 * A + 1) * sizeof(float);
   M3D_REQUIRE(smem <= 96 * 1024, "A too large");
-  static bool configured = false;
-  if (!configured) {
+  M3D_ONCE_PER_DEVICE_BEGIN
     M3D_CUDA_OK(cudaFuncSetAttribute(flatten_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    configured = true;
-  }
+  M3D_ONCE_PER_DEVICE_END
   dim3 grid(cdiv(W, SM_PIX), H, N);
   M3D_CUDA_OK(launch_pdl(flatten_heads_kernel, dim3(grid), dim3(256), smem, S(stream), heads, heads_cstride, N, H, W, A, slots, bbox_2d, bbox_3d));
   M3D_CUDA_OK(cudaGetLastError());

@@ -505,11 +505,9 @@ extern "C" int m3d_head_mlp(const void* x, int N, int H, int W, int x_cstride, i
   p.total_items = static_cast<int>(items);
   p.slope = slope;
   auto kern = head_mlp_kernel<48>;
-  static bool configured = false;
-  if (!configured) {
+  M3D_ONCE_PER_DEVICE_BEGIN
     M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem));
-    configured = true;
-  }
+  M3D_ONCE_PER_DEVICE_END
   const int sms = persistent_sms();
   int grid = sms;
   if (grid > p.total_items) grid = p.total_items;

@@ -852,11 +852,9 @@ template <int BN, int BK, int KSUB, typename OutT, bool STAGED>
 static int launch_tma_t(const ConvTmaParams& p, cudaStream_t stream) {
   using Cfg = TmaCfg<BN, BK, KSUB, STAGED>;
   auto kern = conv_tma_kernel<BN, BK, KSUB, OutT, STAGED>;
-  static bool configured = false;
-  if (!configured) {
+  M3D_ONCE_PER_DEVICE_BEGIN
     M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    configured = true;
-  }
+  M3D_ONCE_PER_DEVICE_END
   // Two co-resident CTAs per SM when shared memory allows (small tiles).
   const int per_sm = (2 * (Cfg::SMEM + 1024) <= 227 * 1024 && 4 * Cfg::ACC <= 512) ? 2 : 1;
   int grid = persistent_sms() * per_sm;
@@ -905,11 +903,9 @@ template <int BN, typename InT, typename OutT, bool STAGED>
 static int launch_gather_t(const ConvGatherParams& p, cudaStream_t stream) {
   using Cfg = GatherCfg<BN, sizeof(InT) == 4, STAGED>;
   auto kern = conv_gather_kernel<BN, InT, OutT, STAGED>;
-  static bool configured = false;
-  if (!configured) {
+  M3D_ONCE_PER_DEVICE_BEGIN
     M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    configured = true;
-  }
+  M3D_ONCE_PER_DEVICE_END
   int grid = persistent_sms();
   if (grid > p.total_tiles) grid = p.total_tiles;
   M3D_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(448), Cfg::SMEM, stream, p));

@@ -31,7 +31,7 @@
 
 namespace m3d {
 
-constexpr int kMaxConcat = 4;
+constexpr int kMaxConcat = 6;  // dla102: the innermost Root of a 4-level Tree reads 6 tensors
 constexpr int kTileM = 128;
 
 enum : int { DT_BF16 = 0, DT_F32 = 1 };

@@ -262,11 +262,9 @@ int launch_stem_s2d(const float* image, const void* weight, const float* bias, v
   M3D_REQUIRE(tiles < (1L << 30), "too many tiles");
   p.total_tiles = static_cast<int>(tiles);
   p.slope = slope;
-  static bool configured = false;
-  if (!configured) {
+  M3D_ONCE_PER_DEVICE_BEGIN
     M3D_CUDA_OK(cudaFuncSetAttribute(stem_s2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem));
-    configured = true;
-  }
+  M3D_ONCE_PER_DEVICE_END
   int grid = persistent_sms();
   if (grid > p.total_tiles) grid = p.total_tiles;
   M3D_CUDA_OK(launch_pdl(stem_s2d_kernel, dim3(grid), dim3(kStemThreads), kStemSmem, stream, p));

@@ -37,12 +37,14 @@ class Act:
 
 
 def _fold(conv_w, conv_b, bn):
-    w = conv_w.detach().float()
-    b = conv_b.detach().float() if conv_b is not None else torch.zeros(w.shape[0], device=w.device)
+    """Eval-mode BatchNorm folded into (weight, bias), on the HOST (fp32): weight preparation launches no device
+    kernels, so an engine build shows up in a profile as H2D copies only."""
+    w = conv_w.detach().float().cpu()
+    b = conv_b.detach().float().cpu() if conv_b is not None else torch.zeros(w.shape[0])
     if bn is not None:
-        scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+        scale = bn.weight.detach().float().cpu() / torch.sqrt(bn.running_var.detach().float().cpu() + bn.eps)
         w = w * scale.view(-1, 1, 1, 1)
-        b = (b - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+        b = (b - bn.running_mean.detach().float().cpu()) * scale + bn.bias.detach().float().cpu()
     return w, b
 
 
@@ -51,8 +53,10 @@ class Engine:
         assert precision in ("bf16", "bf16x3", "fp32")
         if not torch.cuda.is_available():
             raise RuntimeError("m3dssd_b200.Engine needs a CUDA device: there is no CPU fallback")
-        self.dev = torch.device("cuda", torch.cuda.current_device())
+        pdev = next(net.parameters()).device
+        self.dev = pdev if pdev.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
         self.net = net
+        self._names = {id(m): n for n, m in net.named_modules()}  # module -> state-dict prefix (layer specs)
         self.conf = net.conf
         self.B, self.H, self.W = batch, height, width
         self.fp32 = precision != "bf16"  # fp32 activation storage ("fp32": IEEE FMA; "bf16x3": tensor-core split)
@@ -71,7 +75,7 @@ class Engine:
         self.topk = int(topk or self.conf.nms_topN_pre)
         self.max_out = int(max_out or self.conf.nms_topN_post)
         self.image = torch.zeros(batch, 3, height, width, dtype=torch.float32, device=self.dev)
-        with torch.no_grad():
+        with torch.no_grad(), torch.cuda.device(self.dev):
             self._build()
 
     # ------------------------------------------------------------------ utils
@@ -83,15 +87,22 @@ class Engine:
         self.bufs[name] = t
         return t
 
-    def _add(self, fn, launches=1, name="", kind="misc", flops=0.0, bytes_=0.0):
+    def _add(self, fn, launches=1, name="", kind="misc", flops=0.0, bytes_=0.0, spec=None):
         """Register one step of the plan.  flops / bytes_ are ALGORITHMIC (real channels, every
-        operand read or written once), the numerators of the roofline figures bench.py reports."""
+        operand read or written once), the numerators of the roofline figures bench.py reports.
+        spec: what the step computes in terms of the reference's state-dict keys and the engine's own
+        buffers (inputs / outputs as Act) -- the teacher-forced parity test replays every step's inputs
+        through the oracle and compares with the step's output buffer (tests/test_teacher_forced_gpu.py)."""
         self.ops.append(fn)
-        self.meta.append(dict(name=name, kind=kind, launches=launches, flops=float(flops), bytes=float(bytes_)))
+        self.meta.append(dict(name=name, kind=kind, launches=launches, flops=float(flops), bytes=float(bytes_),
+                              spec=spec))
         self.n_launches += launches
 
+    def _key(self, mod):
+        return self._names[id(mod)] if mod is not None else None
+
     def _conv(self, name, inputs, w, b, bn, k, stride=1, pad=None, slope=0.01, res=None, out=None, out_dtype=None,
-              om=None, sigmoid_mask=False, out_coff=0, out_hw=None):
+              om=None, sigmoid_mask=False, out_coff=0, out_hw=None, keys=None):
         """Register conv(+BN)(+res)(+LeakyReLU) over concatenated NHWC inputs; returns the output Act."""
         pad = k // 2 if pad is None else pad
         wf, bf = _fold(w, b, bn)
@@ -140,12 +151,19 @@ class Engine:
             kind = "conv3x3"  # conv_halo.cu / conv_halo2.cu (CTA pairs)
         else:
             kind = "conv_tma"
-        self._add(run, 1, name, kind, flops, nbytes)
-        return Act(out, cout, out_coff)
+        oact = Act(out, cout, out_coff)
+        spec = None
+        if keys is not None:  # keys = (conv state-dict prefix or list of prefixes, bn prefix or None[, geometry])
+            spec = dict(op="dcn" if om is not None else "conv", inputs=list(inputs), conv=keys[0], bn=keys[1], k=k,
+                        stride=stride, pad=pad, slope=slope, res=res, out=oact, om=om, sigmoid_mask=sigmoid_mask)
+            if len(keys) > 2:
+                spec.update(keys[2])
+        self._add(run, 1, name, kind, flops, nbytes, spec)
+        return oact
 
     def _conv_module(self, name, inputs, conv, bn, slope=0.01, res=None, **kw):
         return self._conv(name, inputs, conv.weight, conv.bias, bn, conv.kernel_size[0], conv.stride[0],
-                          conv.padding[0], slope, res, **kw)
+                          conv.padding[0], slope, res, keys=(self._key(conv), self._key(bn)), **kw)
 
     def _maxpool(self, name, a):
         key = (a.t.data_ptr(), a.coff, a.c)
@@ -159,15 +177,23 @@ class Engine:
         N, H, W, cs = a.t.shape
         out = self._new(name, N, H // 2, W // 2, cs)
         x = a.t
-        self._add(lambda: ops.maxpool2x2(x, out), 1, name, "maxpool", 0, x.numel() * x.element_size() * 1.25)
-        return Act(out, a.c)
+        r = Act(out, a.c)
+        self._add(lambda: ops.maxpool2x2(x, out), 1, name, "maxpool", 0, x.numel() * x.element_size() * 1.25,
+                  dict(op="maxpool", x=a, out=r))
+        return r
 
     # ------------------------------------------------------------- DLA trunk
     def _basic_block(self, name, blk, x, residual):
+        res = residual if residual is not None else x
+        if isinstance(blk, dla.Bottleneck):  # dla102 (model/pose_dla_dcn.py:162-204): 1x1 -> 3x3 (stride) -> 1x1 + residual
+            y = self._conv_module(name + ".conv1", [x], blk.conv1, blk.bn1)
+            y = self._conv_module(name + ".conv2", [y], blk.conv2, blk.bn2)
+            return self._conv_module(name + ".conv3", [y], blk.conv3, blk.bn3, res=res)
         if not isinstance(blk, dla.BasicBlock):
-            raise NotImplementedError("fused engine implements BasicBlock trunks (dla34); got %s" % type(blk).__name__)
+            raise NotImplementedError("fused engine implements BasicBlock / Bottleneck trunks (dla34, dla102); got %s"
+                                      % type(blk).__name__)
         y = self._conv_module(name + ".conv1", [x], blk.conv1, blk.bn1)
-        return self._conv_module(name + ".conv2", [y], blk.conv2, blk.bn2, res=residual if residual is not None else x)
+        return self._conv_module(name + ".conv2", [y], blk.conv2, blk.bn2, res=res)
 
     def _tree(self, name, tree, x, children=None):
         children = [] if children is None else children
@@ -202,9 +228,10 @@ class Engine:
         w, b = w.to(self.dev).contiguous(), b.to(self.dev).contiguous()
         s0 = self._new("stem", B, H, W, self._cpad(c0))
         img = self.image
-        self._add(lambda: ops.stem_conv7x7(img, w, b, s0, 0.01), 1, "stem", "stem", 2.0 * B * H * W * c0 * 147,
-                  B * H * W * (3 * 4 + c0 * s0.element_size()))
         x = Act(s0, c0)
+        stem_spec = dict(op="stem", conv=self._key(base.base_layer[0]), bn=self._key(base.base_layer[1]), out=x)
+        self._add(lambda: ops.stem_conv7x7(img, w, b, s0, 0.01), 1, "stem", "stem", 2.0 * B * H * W * c0 * 147,
+                  B * H * W * (3 * 4 + c0 * s0.element_size()), stem_spec)
         x = self._conv_module("level0", [x], base.level0[0], base.level0[1])
         levels = [x]
         x = self._conv_module("level1", [x], base.level1[0], base.level1[1])
@@ -225,17 +252,22 @@ class Engine:
         wp, bp = wp.to(self.dev), bp.to(self.dev)
         s0 = self._new("stem", B, H // 2, W // 2, 64)
         img = self.image
-        self._add(lambda: ops.stem_conv7x7_s2d(img, wp, bp, s0, 0.01), 1, "stem", "stem_s2d",
-                  2.0 * B * H * W * 16 * 147, B * H * W * (3 * 4 + 16 * 2))
         x = Act(s0, 64, s2d=True)
+        stem_spec = dict(op="stem", conv=self._key(base.base_layer[0]), bn=self._key(base.base_layer[1]), out=x)
+        self._add(lambda: ops.stem_conv7x7_s2d(img, wp, bp, s0, 0.01), 1, "stem", "stem_s2d",
+                  2.0 * B * H * W * 16 * 147, B * H * W * (3 * 4 + 16 * 2), stem_spec)
         w0, b0 = _fold(base.level0[0].weight, None, base.level0[1])
         w0p, b0p = ops.s2d_conv3x3_weight(w0, b0)
-        x = self._conv("level0", [x], w0p, b0p, None, 3, 1, 1, 0.01)
+        # spec geometry = the ORIGINAL layer (3x3 / stride 1 / pad 1 on the un-packed tensor), not the s2d rewrite
+        x = self._conv("level0", [x], w0p, b0p, None, 3, 1, 1, 0.01,
+                       keys=(self._key(base.level0[0]), self._key(base.level0[1]), dict(k=3, stride=1, pad=1)))
         x.s2d = True
+        self.meta[-1]["spec"]["out"] = x
         self._fix_meta("level0", 2.0 * B * H * W * 16 * 144, B * H * W * 16 * 2 * 2)
         levels = [x]
         w1, b1 = _fold(base.level1[0].weight, None, base.level1[1])
-        x = self._conv("level1", [x], ops.s2d_conv3x3_s2_weight(w1), b1, None, 2, 1, 1, 0.01, out_hw=(H // 2, W // 2))
+        x = self._conv("level1", [x], ops.s2d_conv3x3_s2_weight(w1), b1, None, 2, 1, 1, 0.01, out_hw=(H // 2, W // 2),
+                       keys=(self._key(base.level1[0]), self._key(base.level1[1]), dict(k=3, stride=2, pad=1)))
         self._fix_meta("level1", 2.0 * B * (H // 2) * (W // 2) * w1.shape[0] * 144,
                        B * H * W * 16 * 2 + B * (H // 2) * (W // 2) * w1.shape[0] * 2)
         levels.append(x)
@@ -259,7 +291,8 @@ class Engine:
         N, H, W = x.t.shape[:3]
         om = self._new(name + ".om", N, H, W, 32, torch.float32)
         self._conv_module(name + ".offset", [x], dcn.conv_offset_mask, None, slope=1.0, out=om)
-        return self._conv(name, [x], dcn.weight, dcn.bias, m.actf[0], 3, 1, 1, 0.01, om=om, sigmoid_mask=True)
+        return self._conv(name, [x], dcn.weight, dcn.bias, m.actf[0], 3, 1, 1, 0.01, om=om, sigmoid_mask=True,
+                          keys=(self._key(dcn), self._key(m.actf[0])))
 
     def _ida_up(self, name, ida, layers, startp, endp):
         for i in range(startp + 1, endp):
@@ -272,10 +305,12 @@ class Engine:
             u = self._new("%s.up_%d" % (name, k), N, H * f, W * f, cs)
             wt = ops.pack_upsample_weight(up.weight).to(self.dev)
             pt, st = p.t, skip.t
+            ua = Act(u, p.c)
             self._add(lambda pt=pt, wt=wt, st=st, u=u, f=f: ops.upsample_add(pt, wt, st, u, f), 1,
                       "%s.up_%d" % (name, k), "upsample", 2.0 * u.numel() * 4,
-                      (pt.numel() + 2 * u.numel()) * u.element_size())
-            layers[i] = self._deform_conv("%s.node_%d" % (name, k), node, Act(u, p.c))
+                      (pt.numel() + 2 * u.numel()) * u.element_size(),
+                      dict(op="upsample", x=p, skip=skip, up=self._key(up), f=f, out=ua))
+            layers[i] = self._deform_conv("%s.node_%d" % (name, k), node, ua)
 
     def _dla_seg(self):
         seg = self.net.base
@@ -300,7 +335,8 @@ class Engine:
         N, H, W = x.t.shape[:3]
         G = len(names)
         mid = mods[0][0].out_channels
-        if self.fp32:
+        if self.fp32 or not (mid == 256 and A <= 48 and x.c in (64, 128)):
+            # layer by layer: the fp32 parity modes, and head shapes the fused kernel does not cover (dla102: 256 channels)
             for g, m in enumerate(mods):
                 h1 = self._conv_module("%s.%d.l1" % (gname, g), [x], m[0], m[1])
                 h2 = self._conv_module("%s.%d.l2" % (gname, g), [h1], m[3], m[4])
@@ -329,11 +365,12 @@ class Engine:
 
         fl = 2.0 * N * H * W * G * (xc * mid + mid * mid + A * mid)
         by = N * H * W * (xc * 2 + G * A * 4) + G * (xc * mid + mid * mid + A * mid) * 2
-        self._add(run, 1, gname + ".mlp", "head_mlp", fl, by)
+        self._add(run, 1, gname + ".mlp", "head_mlp", fl, by,
+                  dict(op="head_mlp", x=x, heads=[self._key(m) for m in mods], slot0=slot0, out=heads_buf))
 
     def _align(self, name, m, x, om):
         return self._conv(name, [x], m.align.weight, m.align.bias, None, m.align.kernel_size[0], 1, m.align.padding,
-                          1.0, res=x, om=om)
+                          1.0, res=x, om=om, keys=(self._key(m.align), None))
 
     def _anab(self, x):
         """bbox_z3d_gl = ANAB -> BN -> LeakyReLU (model/M3d_inference_align.py:168-173); BN folded into the epilogue."""
@@ -349,22 +386,27 @@ class Engine:
         w = torch.cat([anab.key_conv.weight, anab.value_conv.weight, anab.spatial_conv.weight]).detach()
         ckvs = (ck + cv + len(sizes) + 3) // 4 * 4
         kvs = self._new("anab.kvs", N, H, W, ckvs, torch.float32)
-        self._conv("anab.kvs", [x], w, None, None, 1, 1, 0, 1.0, out=kvs)
+        self._conv("anab.kvs", [x], w, None, None, 1, 1, 0, 1.0, out=kvs,
+                   keys=([self._key(anab.key_conv), self._key(anab.value_conv), self._key(anab.spatial_conv)], None))
         ktok = torch.zeros(N, T, ck, **f32)
         vtok = torch.zeros(N, T, cv, **f32)
         ws = torch.zeros(ops.anab_pool_workspace(N, H, sizes, ck, cv), dtype=torch.uint8, device=self.dev)
         self._add(lambda: ops.anab_pool(kvs, ck, cv, sizes, ktok, vtok, ws), 2, "anab.pool", "anab_pool",
-                  2.0 * N * H * W * (ck + cv) * len(sizes), kvs.numel() * 4)
+                  2.0 * N * H * W * (ck + cv) * len(sizes), kvs.numel() * 4,
+                  dict(op="anab_pool", kvs=kvs, ck=ck, cv=cv, sizes=sizes, ktok=ktok, vtok=vtok))
         scale = (bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)).to(self.dev)
         shift = (bn.bias.detach().float().to(self.dev) - bn.running_mean.detach().float().to(self.dev) * scale)
         scale, shift = scale.contiguous(), shift.contiguous()
         out = self._new("anab.out", N, H, W, x.t.shape[-1])
         qt, xt = q.t, x.t
-        self._add(lambda: ops.anab_attention(qt, ktok, vtok, xt, scale, shift, 0.01, out, ck, cv), 1, "anab.attention",
-                  "anab_attention", 2.0 * N * H * W * T * (ck + cv),
-                  N * H * W * (ck + 2 * cv) * out.element_size() + N * T * (ck + cv) * 4)
-        self.bufs["anab.ktok"], self.bufs["anab.vtok"] = ktok, vtok
-        return Act(out, x.c)
+        aws = ops.anab_attention_workspace(N, xt)  # owned by this engine (baked into its graphs)
+        oa = Act(out, x.c)
+        self._add(lambda: ops.anab_attention(qt, ktok, vtok, xt, scale, shift, 0.01, out, ck, cv, aws), 1,
+                  "anab.attention", "anab_attention", 2.0 * N * H * W * T * (ck + cv),
+                  N * H * W * (ck + 2 * cv) * out.element_size() + N * T * (ck + cv) * 4,
+                  dict(op="anab_attention", q=q, ktok=ktok, vtok=vtok, x=x, bn=self._key(bn), out=oa))
+        self.bufs["anab.ktok"], self.bufs["anab.vtok"], self.bufs["anab.ws"] = ktok, vtok, aws
+        return oa
 
     def _build(self):
         net, conf = self.net, self.conf
@@ -390,7 +432,8 @@ class Engine:
         self.score = torch.zeros(B, M, **f32)
         self.cls_pred = torch.zeros(B, M, dtype=torch.uint8, device=self.dev)
         self._add(lambda: ops.cls_softmax(logits, A, K, self.cls_out, self.prob_out, self.fg_max, self.fg_arg,
-                                          self.score, self.cls_pred), 1, "cls_softmax", "softmax", 0, B * M * K * 4 * 3)
+                                          self.score, self.cls_pred), 1, "cls_softmax", "softmax", 0, B * M * K * 4 * 3,
+                  dict(op="softmax", logits=logits))
         anchors = torch.tensor(np.asarray(conf.anchors), **f32).contiguous()
         self.anchors = anchors
         means = [float(v) for v in np.asarray(conf.bbox_means)[0]]
@@ -402,7 +445,7 @@ class Engine:
             om_s = torch.zeros(B, Hf, Wf, 27, **f32)
             thr = float(net.shape_align.thresh)
             self._add(lambda: ops.shape_align_om(self.fg_max, self.fg_arg, anchors, stride, thr, om_s), 1,
-                      "shape_align.om", "align_om", 0, om_s.numel() * 4)
+                      "shape_align.om", "align_om", 0, om_s.numel() * 4, dict(op="shape_align_om", om=om_s))
             feats = self._align("shape_align", net.shape_align, feat, om_s)
         # --- regression heads (slots follow HEAD_ORDER)
         heads = self._new("heads", B, Hf, Wf, 11 * A, torch.float32)
@@ -415,9 +458,11 @@ class Engine:
             thr = float(net.center_align2d.thresh)
             sx, sy, sx3, sy3 = (HEAD_ORDER.index(n) * A for n in ("bbox_x", "bbox_y", "bbox_x3d", "bbox_y3d"))
             self._add(lambda: ops.center_align_om(self.fg_max, self.fg_arg, heads, sx, sy, anchors, stride, means[0:2],
-                                                  stds[0:2], thr, om2), 1, "center_align2d.om", "align_om", 0, om2.numel() * 4)
+                                                  stds[0:2], thr, om2), 1, "center_align2d.om", "align_om", 0, om2.numel() * 4,
+                      dict(op="center_align_om", om=om2, hx="bbox_x", hy="bbox_y", mean=means[0:2], std=stds[0:2]))
             self._add(lambda: ops.center_align_om(self.fg_max, self.fg_arg, heads, sx3, sy3, anchors, stride,
-                                                  means[4:6], stds[4:6], thr, om3), 1, "center_align3d.om", "align_om", 0, om3.numel() * 4)
+                                                  means[4:6], stds[4:6], thr, om3), 1, "center_align3d.om", "align_om", 0, om3.numel() * 4,
+                      dict(op="center_align_om", om=om3, hx="bbox_x3d", hy="bbox_y3d", mean=means[4:6], std=stds[4:6]))
             f2d = self._align("center_align2d", net.center_align2d, feats, om2)
             f3d = self._align("center_align3d", net.center_align3d, feats, om3)
         self.named["feats_shape"], self.named["feats_align2d"], self.named["feats_align3d"] = feats, f2d, f3d
@@ -431,7 +476,7 @@ class Engine:
         self.bbox_2d = torch.zeros(B, M, 4, **f32)
         self.bbox_3d = torch.zeros(B, M, 7, **f32)
         self._add(lambda: ops.flatten_heads(heads, A, OUT_SLOTS, self.bbox_2d, self.bbox_3d), 1, "flatten_heads",
-                  "flatten", 0, B * M * 11 * 4 * 2)
+                  "flatten", 0, B * M * 11 * 4 * 2, dict(op="flatten"))
         self.n_forward_ops = len(self.ops)
         # --- detection tail
         self.means_t, self.stds_t = means, stds  # host lists (the C ABI takes them by value)
@@ -441,6 +486,7 @@ class Engine:
         self.keep = torch.zeros(B, self.topk, dtype=torch.int32, device=self.dev)
         self.num_keep = torch.zeros(B, dtype=torch.int32, device=self.dev)
         self.nms_ws = torch.zeros(ops.nms_workspace_bytes(B, self.topk), dtype=torch.uint8, device=self.dev)
+        self.topk_ws = ops.decode_topk_workspace(B, self.dev)  # per engine: its pointer is baked into the captured graphs
         self.kept = torch.zeros(B, self.max_out, 14, **f32)
         self.scale_factor = 1.0
         self.feat_size = torch.tensor([Hf, Wf], dtype=torch.float32, device=self.dev)
@@ -453,7 +499,7 @@ class Engine:
     def _run_decode(self):
         ops.decode_topk(self.score, self.cls_pred, self.bbox_2d, self.bbox_3d, self.anchors, self.means_t, self.stds_t,
                         self.A, self.Hf, self.Wf, float(self.conf.feat_stride), self.scale_factor, self.topk, self.dets,
-                        self.det_idx, self.det_num)
+                        self.det_idx, self.det_num, self.topk_ws)
 
     def _run_nms(self):
         ops.nms_batched(self.dets, self.det_num, float(self.conf.nms_thres), self.nms_ws, self.keep, self.num_keep)

@@ -10,6 +10,8 @@ behind the C ABI.  In training mode the modules run one by one under autograd,
 with torch's dense convolutions -- as in the reference -- and the C-ABI DCNv2
 forward/backward for the deformable ones.  There is no CPU path for DCNv2.
 """
+import threading
+
 import numpy as np
 import torch
 from torch import nn
@@ -19,6 +21,7 @@ from .module.attention import ANAB
 from .module.feturealign_mgpu import center_align, shape_align
 from .pose_dla_dcn import DeformConv, DLASeg  # noqa: F401  (DeformConv re-exported like the reference)
 
+_ENGINE_LOCK = threading.Lock()  # module level: an nn.Module attribute would break copy.deepcopy / pickling of the net
 _REG_HEADS = ["bbox_x", "bbox_y", "bbox_w", "bbox_h", "bbox_x3d", "bbox_y3d", "bbox_z3d", "bbox_w3d", "bbox_h3d",
               "bbox_l3d", "bbox_rY3d"]
 
@@ -85,10 +88,19 @@ class RPN(nn.Module):
         """Fused inference engine for a fixed input shape (built on first use, cached)."""
         from ..engine import Engine
         precision = precision or self.precision
-        key = (batch, height, width, precision) + tuple(sorted(kw.items()))
-        if key not in self._engines:
-            self._engines[key] = Engine(self, batch, height, width, precision=precision, **kw)
-        return self._engines[key]
+        dev = next(self.parameters()).device
+        key = (str(dev), batch, height, width, precision) + tuple(sorted(kw.items()))
+        with _ENGINE_LOCK:  # nn.DataParallel replicas share this dict by reference and build from threads
+            if key not in self._engines:
+                self._engines[key] = Engine(self, batch, height, width, precision=precision, **kw)
+            return self._engines[key]
+
+    def engine_supported(self):
+        """The fused engine covers the trunks the reference ships (BasicBlock = dla34, Bottleneck = dla102,
+        model/pose_dla_dcn.py:419-441) with DCNv2 aggregation; anything else runs module by module."""
+        from .pose_dla_dcn import BasicBlock, Bottleneck, Tree
+        blocks = [m.tree1 for m in self.base.base.modules() if isinstance(m, Tree) and m.levels == 1]
+        return bool(self.conf.get("ida_dcnv2", True)) and all(isinstance(b, (BasicBlock, Bottleneck)) for b in blocks)
 
     def invalidate_engines(self):
         """Call after changing parameters (load_state_dict / optimizer step) so weights are re-packed."""
@@ -110,19 +122,24 @@ class RPN(nn.Module):
         kw = {} if max_out is None else dict(max_out=int(max_out))
         eng = self.engine(x.shape[0], x.shape[2], x.shape[3], **kw)
         kept, num = eng.detect(x.float().contiguous(), scale_factor)
-        return kept, num
+        return kept.clone(), num.clone()  # fresh tensors, like any nn.Module (the engine's buffers are reused per call)
 
     # --------------------------------------------------------------- forward
     def forward(self, x):
         if not self.training and x.is_cuda:
-            return self._forward_engine(x)
+            if self.engine_supported():
+                return self._forward_engine(x)
+            with torch.no_grad():
+                return self._forward_modules(x)
         return self._forward_modules(x)
 
     def _forward_engine(self, x):
         B, _, H, W = x.shape
         eng = self.engine(B, H, W)
-        cls, prob, bbox_2d, bbox_3d = eng.forward(x.float().contiguous())
-        feat_size = eng.feat_size
+        # the engine returns views of its persistent buffers (overwritten by the next call); the nn.Module surface
+        # hands out fresh tensors like the reference's forward does
+        cls, prob, bbox_2d, bbox_3d = (t.clone() for t in eng.forward(x.float().contiguous()))
+        feat_size = eng.feat_size.clone()
         if self.feat_size[0] != eng.Hf or self.feat_size[1] != eng.Wf or self.rois.device != x.device:
             self.feat_size = [eng.Hf, eng.Wf]
             self.rois = locate_anchors(self.conf.anchors, self.feat_size, self.feat_stride,

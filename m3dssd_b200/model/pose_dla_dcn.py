@@ -152,9 +152,15 @@ class DLA(nn.Module):
         return y
 
     def load_pretrained_model(self, data="imagenet", name="dla34", hash="ba72cf86"):
-        raise RuntimeError("ImageNet weights are downloaded by the reference (model_zoo.load_url, "
-                           "pose_dla_dcn.py:399-416); there is no network here -- build with pre_train=False "
-                           "and load a checkpoint with load_state_dict")
+        """The reference downloads ImageNet weights here (model_zoo.load_url, pose_dla_dcn.py:399-416) and, as a
+        side effect, registers `self.fc` for good -- so every checkpoint trained with conf.pre_train=True (all the
+        shipped configs) carries base.base.fc.weight / .bias.  There is no network in this environment: the
+        download is skipped with a warning, the `fc` module is registered all the same so those checkpoints load
+        with strict=True; the detector's own checkpoint then overwrites every trunk weight anyway."""
+        import warnings
+        warnings.warn("m3dssd_b200: pre_train requested but ImageNet weights (%s/%s-%s) cannot be downloaded here; "
+                      "the trunk keeps its initialisation until a checkpoint is loaded" % (data, name, hash))
+        self.fc = nn.Conv2d(self.channels[-1], self.num_classes, kernel_size=1, stride=1, padding=0, bias=True)
 
 
 def dla34(pretrained=True, **kwargs):

@@ -289,14 +289,21 @@ def nhwc_to_nchw(x, out, coff=0):
     return out
 
 
+def decode_topk_workspace(batch, device):
+    """Scratch of the multi-CTA top-K for `batch` images: owned by the caller (the engine keeps one per instance)."""
+    return torch.zeros(lib().m3d_decode_topk_workspace(batch), dtype=torch.uint8, device=device)
+
+
 def decode_topk(score, cls_pred, bbox_2d, bbox_3d, anchors, means, stds, A, H, W, feat_stride, scale_factor, topk,
-                dets, det_idx, det_num):
+                dets, det_idx, det_num, workspace=None):
     B = score.shape[0]
+    if workspace is None:
+        workspace = decode_topk_workspace(B, score.device)
     means = (C.c_float * 11)(*[float(v) for v in means])  # host arrays in the C ABI
     stds = (C.c_float * 11)(*[float(v) for v in stds])
     check(lib().m3d_decode_topk(_p(score), _p(cls_pred), _p(bbox_2d), _p(bbox_3d), _p(anchors), means, stds,
                                 B, A, H, W, float(feat_stride), float(scale_factor), topk, _p(dets), _p(det_idx),
-                                _p(det_num), _stream()))
+                                _p(det_num), _p(workspace), workspace.numel(), _stream()))
 
 
 def nms_workspace_bytes(batch, max_n):
@@ -352,11 +359,19 @@ def anab_pool_workspace(N, H, sizes, ck, cv):
     return lib().m3d_anab_pool_workspace(N, H, len(sizes), arr, ck, cv)
 
 
-def anab_attention(q, ktok, vtok, x, scale, shift, slope, out, ck, cv):
+def anab_attention_workspace(N, x):
+    """bf16 token operands of the tensor-core attention kernel (caller-owned; empty in fp32 mode)."""
+    return torch.zeros(max(1, lib().m3d_anab_attention_workspace(N, _dt(x))), dtype=torch.uint8, device=x.device)
+
+
+def anab_attention(q, ktok, vtok, x, scale, shift, slope, out, ck, cv, workspace=None):
     N, H, W, _ = x.shape
     T = ktok.shape[1]
+    if workspace is None:
+        workspace = anab_attention_workspace(N, x)
     check(lib().m3d_anab_attention(_p(q), q.shape[-1], _p(ktok), _p(vtok), _p(x), x.shape[-1], _dt(x), _p(scale),
-                                   _p(shift), float(slope), _p(out), out.shape[-1], N, H * W, ck, cv, T, _stream()))
+                                   _p(shift), float(slope), _p(out), out.shape[-1], N, H * W, ck, cv, T, _p(workspace),
+                                   workspace.numel(), _stream()))
     return out
 
 

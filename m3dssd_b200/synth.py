@@ -87,6 +87,16 @@ def make_conf(attention=None, center_align=True, shape_align=True, back_bone="dl
     return c
 
 
+# Conditioning of the synthetic network (see randomize_weights): with plain He-initialised weights the random net
+# amplifies fp32 round-off 10^2..10^4x between the stem and the boxes (every residual branch as strong as its skip,
+# deformable offsets driven entirely by rough random features, half of the fg probabilities crowding the 0.5 hard
+# mask of the align modules).  Trained detectors are not like that, and neither is this one:
+RES_BRANCH_GAIN = 0.25   # BasicBlock bn2.weight scale: block = skip + 0.25 * branch (zero-gamma-style residuals)
+OFFSET_DATA_SIGMA = 0.5  # px: data-dependent part of every DCN offset; the rest of offset_sigma_px is a fixed per-tap bias
+CLS_LOGIT_GAIN = 3.0     # class logits spread so that few fg probabilities sit near the 0.5 hard-mask threshold
+CENTER_DELTA_GAIN = 0.1  # bbox_x/y/x3d/y3d outputs ~0.1 (they are multiplied by anchor sizes of up to 54 feature px)
+
+
 @torch.no_grad()
 def randomize_weights(model, seed=2, offset_sigma_px=2.0, fg_fraction=0.01, calibrate=True):
     """Deterministic synthetic weights for a reference-shaped RPN (reference modules or ours).
@@ -114,6 +124,8 @@ def randomize_weights(model, seed=2, offset_sigma_px=2.0, fg_fraction=0.01, cali
                 v = torch.rand(t.shape, generator=g) + 0.5
             elif leaf == "weight":
                 v = torch.rand(t.shape, generator=g) + 0.5
+                if name.endswith((".bn2.weight", ".bn3.weight")) and ".tree" in name:
+                    v = v * RES_BRANCH_GAIN
             else:
                 v = torch.randn(t.shape, generator=g) * 0.1
         elif "conv_offset_mask" in name and leaf == "weight":
@@ -129,6 +141,10 @@ def randomize_weights(model, seed=2, offset_sigma_px=2.0, fg_fraction=0.01, cali
         elif t.dim() == 4:
             fan_in = t.shape[1] * t.shape[2] * t.shape[3]
             v = torch.randn(t.shape, generator=g) * math.sqrt(2.0 / fan_in)
+            if name == "cls.6.weight":
+                v = v * CLS_LOGIT_GAIN
+            elif name in ("bbox_x.6.weight", "bbox_y.6.weight", "bbox_x3d.6.weight", "bbox_y3d.6.weight"):
+                v = v * CENTER_DELTA_GAIN
         else:
             v = torch.randn(t.shape, generator=g) * 0.1
         new[name] = v.to(t.dtype)
@@ -183,12 +199,19 @@ def calibrate_statistics(model, seed=2, offset_sigma_px=2.0, fg_fraction=0.01, c
 
     def om_post(name):
         def hook(mod, inp, out):
+            # offsets = fixed per-tap bias pattern + a data-dependent part of sigma OFFSET_DATA_SIGMA (total sigma
+            # ~ offset_sigma_px); mask logits = bias N(0, 0.4^2) + data part of sigma 0.3
             n_off = out.shape[1] // 3 * 2
-            s_off = offset_sigma_px / float(out[:, :n_off].std().clamp_min(1e-9))
-            s_msk = 0.5 / float(out[:, n_off:].std().clamp_min(1e-9))
+            data = out - mod.bias.view(1, -1, 1, 1)
+            sig_d = min(OFFSET_DATA_SIGMA, offset_sigma_px)
+            s_off = sig_d / float(data[:, :n_off].std().clamp_min(1e-9))
+            s_msk = 0.3 / float(data[:, n_off:].std().clamp_min(1e-9))
             scale = torch.cat([torch.full((n_off,), s_off), torch.full((out.shape[1] - n_off,), s_msk)]).double()
             mod.weight.mul_(scale.view(-1, 1, 1, 1))
-            mod.bias.mul_(scale)
+            gb = torch.Generator().manual_seed((hash_name(name) + seed + 7) % (2 ** 31))
+            pat = torch.randn(out.shape[1], generator=gb, dtype=torch.float64)
+            sig_b = math.sqrt(max(offset_sigma_px ** 2 - sig_d ** 2, 0.0))
+            mod.bias.copy_(torch.cat([pat[:n_off] * sig_b, pat[n_off:] * 0.4]))
             fixes[name] = mod
         return hook
 
