@@ -35,6 +35,8 @@ enum {
 enum { M3D_BF16 = 0, M3D_F32 = 1, M3D_BF16X3 = 2 };
 
 const char* m3d_last_error(void);
+/* Name of the kernel instantiation the last m3d_conv2d_nhwc call on this thread dispatched to (measurement aid). */
+const char* m3d_last_kernel(void);
 int m3d_version(void);
 /* Cap the number of SMs the persistent tensor-core kernels launched (or graph-captured) after this call occupy;
  * 0 = the whole device.  The engine leaves one SM per image free while the detection tail of the previous batch
@@ -163,6 +165,12 @@ int m3d_gather_kept(const float* dets, int row_len, int batch, int max_n, const 
 /* DLA.base_layer (model/pose_dla_dcn.py:336-340): 7x7 conv on the NCHW fp32 image, BN folded, LeakyReLU. */
 int m3d_stem_conv7x7(const float* image_nchw, const float* weight /*[16,3,7,7]*/, const float* bias, void* out,
                      int out_dtype, int out_cstride, int N, int H, int W, float slope, m3d_stream_t stream);
+/* Input pipeline on the device (the reference's Normalize + BGR->RGB + HWC->CHW, lib/augmentations.py:44-57,
+ * lib/dataloader.py:942-950): uint8 HWC images [N,H,W,3] as cv2.imread returns them -> fp32 NCHW
+ * out[n][swap_rb ? 2-c : c][h][w] = ((u8 / 255 - mean3[c]) / std3[c]), fp32 IEEE in that order (bit-identical to
+ * numpy).  mean3 / std3 are host arrays indexed by the INPUT channel.  4x less host->device traffic than fp32. */
+int m3d_preprocess_u8(const unsigned char* image_hwc, float* out_nchw, int N, int H, int W, const float* mean3,
+                      const float* std3, int swap_rb, m3d_stream_t stream);
 /* The same layer on the tensor cores, written in 2x2 space-to-depth form: out [N, H/2, W/2, 64] bf16 with
  * channel (dy*2 + dx)*16 + c = stem output channel c at pixel (2Y+dy, 2X+dx).  The 7x7 conv becomes a
  * K = 3*8*8 implicit GEMM (stride-2 8x8 windows of the fp32 NCHW image gathered straight into the

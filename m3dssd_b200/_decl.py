@@ -11,6 +11,7 @@ _SIGS = {
     "m3d_decode_topk": [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, f, f, i, vp, vp, vp, vp, sz, vp],
     "m3d_gather_kept": [vp, i, i, i, vp, vp, i, vp, vp],
     "m3d_stem_conv7x7": [vp, vp, vp, vp, i, i, i, i, i, f, vp],
+    "m3d_preprocess_u8": [vp, vp, i, i, i, vp, vp, i, vp],
     "m3d_stem_conv7x7_s2d": [vp, vp, vp, vp, i, i, i, f, vp],
     "m3d_maxpool2x2_nhwc": [vp, vp, i, i, i, i, i, i, i, vp],
     "m3d_upsample_add_nhwc": [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp],
@@ -48,4 +49,4 @@ def declare(L):
 
 
 def exported_names():
-    return ["m3d_last_error", "m3d_version", "m3d_conv2d_nhwc"] + list(_SIGS) + list(_SIZE_FNS)
+    return ["m3d_last_error", "m3d_last_kernel", "m3d_version", "m3d_conv2d_nhwc"] + list(_SIGS) + list(_SIZE_FNS)

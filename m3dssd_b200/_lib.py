@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libm3dssd_b200.so")
+LIB_PATH = os.environ.get("M3D_LIB") or os.path.join(_HERE, "libm3dssd_b200.so")  # M3D_LIB: development A/B builds
 
 M3D_BF16, M3D_F32, M3D_BF16X3 = 0, 1, 2
 MAX_CONCAT = 6
@@ -57,6 +57,8 @@ def _declare(L):
     L.m3d_last_error.restype = C.c_char_p
     L.m3d_last_error.argtypes = []
     L.m3d_version.restype = C.c_int
+    L.m3d_last_kernel.restype = C.c_char_p
+    L.m3d_last_kernel.argtypes = []
     L.m3d_conv2d_nhwc.restype = C.c_int
     L.m3d_conv2d_nhwc.argtypes = [C.POINTER(ConvDesc), C.c_void_p]
     from . import _decl

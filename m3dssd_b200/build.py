@@ -14,8 +14,11 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(ROOT, "build", "obj")
-LIB = os.path.join(HERE, "libm3dssd_b200.so")
+# Development: M3D_VARIANT=name builds libm3dssd_b200.name.so (own object cache) with M3D_NVCC_EXTRA flags, and
+# M3D_LIB=<path> makes m3dssd_b200._lib load it -- several kernel variants can then be A/B-timed in ONE GPU session.
+VARIANT = os.environ.get("M3D_VARIANT", "")
+OBJ = os.path.join(ROOT, "build", "obj" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(HERE, "libm3dssd_b200%s.so" % ("." + VARIANT if VARIANT else ""))
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -26,7 +29,7 @@ FLAGS = [
     # devIoU and the bilinear blend must round like the reference's plain fp32
     # expressions: no fast-math anywhere.
 ]
-# Development knob: extra nvcc flags, e.g. M3D_NVCC_EXTRA=-DM3D_HEAD_BIAS_REG (experimental kernel variants that are
+# Development knob: extra nvcc flags, e.g. M3D_NVCC_EXTRA=-DM3D_SOME_VARIANT (experimental kernel variants that are
 # compiled out of the default build).  Part of the object cache key.
 FLAGS += os.environ.get("M3D_NVCC_EXTRA", "").split()
 

@@ -22,6 +22,15 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static thread_local char g_last_kernel[128] = "";
+
+void set_last_kernel(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_kernel, sizeof(g_last_kernel), fmt, ap);
+  va_end(ap);
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (fn == nullptr) {
@@ -279,6 +288,7 @@ extern "C" int m3d_set_sm_limit(int sms) {
 }
 
 extern "C" const char* m3d_last_error(void) { return g_last_error; }
+extern "C" const char* m3d_last_kernel(void) { return g_last_kernel; }
 extern "C" int m3d_version(void) { return 100; }
 
 extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
@@ -327,12 +337,8 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
   const int tiles_w = (Q + TW - 1) / TW, tiles_h = (P + TH - 1) / TH;
   const long m_tiles = static_cast<long>(tiles_w) * tiles_h * d->N;
   int BN = pick_bn(d->Cout, bk, m_tiles * groups, gather, split);
-  // CTA pairs (conv_halo2.cu) share the weights of an N tile between two M tiles: take the wide tile whenever the
-  // pairs still fill most of the device
-  if (!gather && d->R == 3 && d->S == 3 && d->stride == 1 && d->dil == 1 && d->pad == 1 && d->num_inputs == 1 &&
-      groups == 1 && bk == 64 && d->act_dtype == M3D_BF16 && d->out_dtype == M3D_BF16 && d->Cout % 256 == 0 &&
-      conv_halo2_supported(256, m_tiles) && (m_tiles / 2) * (d->Cout / 256) * 5 >= static_cast<long>(sm_count() / 2) * 4)
-    BN = 256;
+  // (A 256-wide CTA-pair tile for the level-4 256 -> 256 3x3 convs was built and measured in round 2: 27 us per layer
+  // against 25 us for conv_tma_kernel<256,64,1> on 120 CTAs -- 60 pair items cannot fill 70 clusters -- and removed.)
   const int n_tiles = (d->Cout + BN - 1) / BN;
   const long total_tiles = m_tiles * n_tiles * groups;
   M3D_REQUIRE(total_tiles < (1L << 30), "too many tiles");

@@ -6,6 +6,8 @@
 
 namespace m3d {
 void set_last_error(const char* fmt, ...);
+// name of the kernel instantiation m3d_conv2d_nhwc dispatched to on this thread (bench.py labels its roofline with it)
+void set_last_kernel(const char* fmt, ...);
 // SMs the persistent kernels launched from now on may occupy (m3d_set_sm_limit; default: all of the device)
 int persistent_sms();
 // SMs left out by m3d_set_sm_limit (0 when no limit is set): their CTAs may each strand the sibling SM of a TPC,

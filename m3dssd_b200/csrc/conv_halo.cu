@@ -246,6 +246,7 @@ template <int BN, typename OutT, bool STAGED, bool BRES = false>
 int launch_t(const ConvTmaParams& p, cudaStream_t stream) {
   using Cfg = HaloCfg<BN, STAGED, BRES>;
   auto kern = conv_halo_kernel<BN, OutT, STAGED, BRES>;
+  set_last_kernel("conv_halo_kernel<%d,%s,%d,%d>", BN, sizeof(OutT) == 4 ? "f32" : "bf16", int(STAGED), int(BRES));
   M3D_ONCE_PER_DEVICE_BEGIN
     M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
   M3D_ONCE_PER_DEVICE_END

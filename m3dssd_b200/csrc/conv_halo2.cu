@@ -280,6 +280,7 @@ template <int BN>
 int launch_t(const ConvTmaParams& p, cudaStream_t stream) {
   using Cfg = Halo2Cfg<BN>;
   auto kern = conv_halo2_kernel<BN>;
+  set_last_kernel("conv_halo2_kernel<%d>", BN);
   M3D_ONCE_PER_DEVICE_BEGIN
     M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
   M3D_ONCE_PER_DEVICE_END
@@ -294,14 +295,15 @@ int launch_t(const ConvTmaParams& p, cudaStream_t stream) {
 
 }  // namespace
 
-// staged bf16 3x3 stride-1 convs with BN in {128, 256} and an even number of 128-pixel tiles
+// staged bf16 3x3 stride-1 convs with 128-channel N tiles and an even number of 128-pixel tiles
 bool conv_halo2_supported(int BN, long m_tiles) {
   if (getenv("M3D_NO_PAIR") != nullptr) return false;
-  return (BN == 128 || BN == 256) && m_tiles % 2 == 0;
+  return BN == 128 && m_tiles % 2 == 0;
 }
 
 int launch_conv_halo2(const ConvTmaParams& p, int BN, cudaStream_t stream) {
-  return BN == 128 ? launch_t<128>(p, stream) : launch_t<256>(p, stream);
+  if (BN != 128) return M3D_ERR_UNSUPPORTED;
+  return launch_t<128>(p, stream);
 }
 
 }  // namespace m3d

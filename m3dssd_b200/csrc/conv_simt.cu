@@ -197,6 +197,7 @@ int launch_conv_simt_f32(const m3d_conv_desc* d, int P, int Q, cudaStream_t stre
   p.slope = d->slope;
   const long tiles = static_cast<long>(p.tiles_w) * p.tiles_h * p.N * p.n_tiles;
   M3D_REQUIRE(tiles < (1L << 31), "too many tiles");
+  set_last_kernel("conv_simt_f32_kernel");
   conv_simt_f32_kernel<<<static_cast<unsigned>(tiles), 256, 0, stream>>>(p);
   M3D_CUDA_OK(cudaGetLastError());
   return M3D_OK;

@@ -427,6 +427,7 @@ template <int BN, int NSTG, bool HALF>
 int launch_t(const ConvGatherParams& p, cudaStream_t stream) {
   using Cfg = DcnCfg<BN, NSTG>;
   auto kern = dcn_fused_kernel<BN, NSTG, HALF>;
+  set_last_kernel("dcn_fused_kernel<%d,%d,%d>", BN, NSTG, int(HALF));
   M3D_ONCE_PER_DEVICE_BEGIN
     M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     // what the operand ring does not need goes to L1: the 9 taps of a chunk re-read one input window

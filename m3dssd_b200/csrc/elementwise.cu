@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdint>
 
 #include "common.cuh"
 
@@ -497,11 +498,61 @@ __global__ void nhwc_to_nchw_kernel(const TI* __restrict__ in, TO* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------
+// Input pipeline: the reference's Normalize transform + BGR->RGB + HWC->CHW
+// (lib/augmentations.py:44-57, lib/dataloader.py:942-950) on the device, from the uint8 HWC image cv2.imread
+// returns.  Arithmetic in the reference's order and type (fp32: x / 255, - mean[c], / std[c], with mean/std
+// indexed by the HWC channel BEFORE the swap -- quirk 8 of SURVEY appendix B is preserved), IEEE division, so the
+// result is bit-identical to numpy's.  4 pixels (12 bytes) per thread, one float4 store per plane.
+// ---------------------------------------------------------------------------
+struct Norm3 {
+  float mean[3], stdv[3];
+};
+
+__global__ void __launch_bounds__(256) preprocess_u8_kernel(const unsigned char* __restrict__ img, float* __restrict__ out,
+                                                            long npix4, long HW, Norm3 nm, int swap_rb) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;  // group of 4 pixels inside the batch
+  if (i >= npix4) return;
+  const long pix = i * 4;
+  const long n = pix / HW, p = pix - n * HW;
+  const uint3 raw = *reinterpret_cast<const uint3*>(img + pix * 3);  // 12 bytes: 4 pixels x 3 channels
+  const unsigned int w[3] = {raw.x, raw.y, raw.z};
+  float v[3][4];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    const unsigned int byte = (w[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+    const int c = k % 3, px = k / 3;
+    float x = __fdiv_rn(static_cast<float>(byte), 255.0f);
+    x = __fsub_rn(x, nm.mean[c]);
+    v[c][px] = __fdiv_rn(x, nm.stdv[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int oc = swap_rb ? 2 - c : c;
+    *reinterpret_cast<float4*>(out + (n * 3 + oc) * HW + p) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+  }
+}
+
 }  // namespace m3d
 
 using namespace m3d;
 
 static inline cudaStream_t S(m3d_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" int m3d_preprocess_u8(const unsigned char* image_hwc, float* out_nchw, int N, int H, int W, const float* mean3,
+                                 const float* std3, int swap_rb, m3d_stream_t stream) {
+  M3D_REQUIRE(image_hwc && out_nchw && mean3 && std3, "NULL pointer");
+  const long HW = static_cast<long>(H) * W;
+  M3D_REQUIRE(HW % 4 == 0, "H*W must be a multiple of 4 (got %dx%d)", H, W);
+  M3D_REQUIRE((reinterpret_cast<uintptr_t>(image_hwc) & 3) == 0 && (reinterpret_cast<uintptr_t>(out_nchw) & 15) == 0,
+              "image must be 4-byte aligned, output 16-byte aligned");
+  Norm3 nm;
+  for (int c = 0; c < 3; ++c) nm.mean[c] = mean3[c], nm.stdv[c] = std3[c];
+  const long npix4 = static_cast<long>(N) * HW / 4;
+  preprocess_u8_kernel<<<cdiv(npix4, 256), 256, 0, S(stream)>>>(image_hwc, out_nchw, npix4, HW, nm, swap_rb);
+  M3D_CUDA_OK(cudaGetLastError());
+  return M3D_OK;
+}
 
 extern "C" int m3d_stem_conv7x7(const float* image_nchw, const float* weight, const float* bias, void* out, int out_dtype,
                                 int out_cstride, int N, int H, int W, float slope, m3d_stream_t stream) {

@@ -104,36 +104,6 @@ __device__ __forceinline__ void epilogue_tile_direct(uint32_t tmem_acc, int quar
   const int q = q0 + row % TW;
   const bool pix_ok = (p < P) && (q < Q);
   const long pix = (static_cast<long>(n) * P + p) * Q + q;
-#ifdef M3D_EPI_PIPELINED
-  // Experimental (compiled out of the default build, to be measured): for narrow tiles the chunk loop below is a chain
-  // of exposed latencies (TMEM load, bias loads, residual loads, per 16 columns).  Here the tile's bias is loaded
-  // before the first accumulator wait and the TMEM load of chunk c+1 is in flight while chunk c is written.  Same
-  // arithmetic order (acc + bias, + residual, LeakyReLU).
-  if constexpr (BN <= 64) {
-    constexpr int NCH = BN / 16;
-    const uint32_t tbase = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
-    uint32_t acc[2][16];
-    tmem_ld16(tbase, acc[0]);
-    float bz[BN];
-#pragma unroll
-    for (int i = 0; i < BN; ++i) bz[i] = (bias != nullptr && col_base + i < cout) ? __ldg(bias + col_base + i) : 0.f;
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      tmem_ld_wait();
-      if (c + 1 < NCH) tmem_ld16(tbase + (c + 1) * 16, acc[(c + 1) & 1]);
-      const int col = col_base + c * 16;
-      const int nvalid = cout - col;
-      if (pix_ok && nvalid > 0) {
-        uint32_t a2[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) a2[i] = __float_as_uint(__uint_as_float(acc[c & 1][i]) + bz[c * 16 + i]);
-        epilogue_chunk16<OutT, ResT>(a2, nullptr, res ? res + pix * res_cstride + col : nullptr,
-                                     out + pix * out_cstride + col, nvalid, slope);
-      }
-    }
-    return;
-  }
-#endif
 #pragma unroll 1
   for (int c0 = 0; c0 < BN; c0 += 16) {
     uint32_t acc[16];

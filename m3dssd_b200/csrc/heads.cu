@@ -315,19 +315,15 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
     // GEMM2 / GEMM3 start on slab 0 while the rest is drained; the TMEM load of slab s+1 is in flight while slab s
     // is converted.  (The bias vectors of the item were prefetched into L1 during the previous item: an L2 round
     // trip per slab used to be exposed here.)
-#ifdef M3D_HEAD_BIAS_REG
-    // Experimental (not the default build; to be measured next): the probe timeline shows a slab cadence of
-    // ~500-700 clk for ~60 instructions per warp, i.e. about one L2 round trip per slab, and ncu names
-    // long_scoreboard as the top stall: the per-slab bias loads (read-only path; the prefetch.global.L1 below does not
-    // seem to reach it) are the suspect.  Here each warp keeps its 4 x 16 bias values of the coming drain in lanes
-    // 0-15 of four registers, loaded one epilogue phase ahead, and broadcasts them with shuffles.
+    // Each warp keeps the 4 x 16 bias values of the coming drain in lanes 0-15 of four registers, loaded one epilogue
+    // phase ahead and broadcast with shuffles, instead of four read-only-path loads per slab in the drain itself
+    // (measured round 2: headsA/C 75 -> 72 us, headsB 45.5 -> 43.5 us; the slab cadence is latency-bound).
     float breg[4];
     auto load_bias_regs = [&](const float* bias) {
 #pragma unroll
       for (int s = 0; s < 4; ++s) breg[s] = __ldg(bias + s * 64 + part * 16 + (lane & 15));
     };
     if (start < end) load_bias_regs(p.b1 + (start % p.G) * kHeadMid);
-#endif
     auto drain_to_y = [&](uint32_t acc, const float* bias, uint64_t* ready, uint64_t* acc_empty, bool so_wait,
                           uint32_t so_par) {
       uint32_t a[2][16];
@@ -336,27 +332,17 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
       for (int s = 0; s < 4; ++s) {
         // E1 only: slabs 2-3 hold the output staging of the previous item until its TMA store has read it
         if (s == 2 && so_wait) mbar_wait(so_free, so_par);
-#ifndef M3D_HEAD_BIAS_REG
-        const float* bs = bias + s * 64 + part * 16;
-        float4 bv[4];  // issued before the TMEM wait: the two latencies overlap
-#pragma unroll
-        for (int j = 0; j < 4; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(bs + j * 4));
-#endif
         tmem_ld_wait();
         if (s < 3) tmem_ld16(acc + lane_off + (s + 1) * 64 + part * 16, a[(s + 1) & 1]);
         uint8_t* slab = sy + s * 16384;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-#ifdef M3D_HEAD_BIAS_REG
           // the warp's 16 bias values of this slab live in lanes 0-15 of breg[s] (loaded an epilogue phase ahead)
           float4 b0, b1;
           b0.x = __shfl_sync(0xffffffffu, breg[s], j * 8 + 0), b0.y = __shfl_sync(0xffffffffu, breg[s], j * 8 + 1);
           b0.z = __shfl_sync(0xffffffffu, breg[s], j * 8 + 2), b0.w = __shfl_sync(0xffffffffu, breg[s], j * 8 + 3);
           b1.x = __shfl_sync(0xffffffffu, breg[s], j * 8 + 4), b1.y = __shfl_sync(0xffffffffu, breg[s], j * 8 + 5);
           b1.z = __shfl_sync(0xffffffffu, breg[s], j * 8 + 6), b1.w = __shfl_sync(0xffffffffu, breg[s], j * 8 + 7);
-#else
-          const float4 b0 = bv[2 * j], b1 = bv[2 * j + 1];
-#endif
           // two channels per instruction (add.f32x2 / mul.f32x2 round like their scalar forms)
           const unsigned long long bb[4] = {pack_f32x2(b0.x, b0.y), pack_f32x2(b0.z, b0.w), pack_f32x2(b1.x, b1.y),
                                             pack_f32x2(b1.z, b1.w)};
@@ -403,9 +389,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
       if (warp == 2) HDBG(9);
       tc_fence_after();
       drain_to_y(tmem_base, p.b1 + g * kHeadMid, y1_ready, acc1_empty, li > 0, (li - 1) & 1);
-#ifdef M3D_HEAD_BIAS_REG
       load_bias_regs(p.b2 + g * kHeadMid);  // in flight while GEMM2 finishes
-#endif
       // E2 (acc2_full also means GEMM2 has finished reading Y)
       if (it + 1 < end) prefetch_bias((it + 1) % p.G);
       if (warp == 2) HDBG(10);
@@ -413,9 +397,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_mlp_kernel(const __grid_
       if (warp == 2) HDBG(11);
       tc_fence_after();
       drain_to_y(tmem_base + kHeadMid, p.b2 + g * kHeadMid, y2_ready, nullptr, false, 0);
-#ifdef M3D_HEAD_BIAS_REG
       if (it + 1 < end) load_bias_regs(p.b1 + ((it + 1) % p.G) * kHeadMid);  // in flight during GEMM3 / E3
-#endif
       // E3: acc3 + b3 -> fp32 staging [128][R3] -> coalesced 16-byte stores (A*4 contiguous bytes per pixel)
       const int A = p.A;
       float4 b3v[4];

@@ -852,6 +852,7 @@ template <int BN, int BK, int KSUB, typename OutT, bool STAGED>
 static int launch_tma_t(const ConvTmaParams& p, cudaStream_t stream) {
   using Cfg = TmaCfg<BN, BK, KSUB, STAGED>;
   auto kern = conv_tma_kernel<BN, BK, KSUB, OutT, STAGED>;
+  set_last_kernel("conv_tma_kernel<%d,%d,%d,%s,%d>", BN, BK, KSUB, sizeof(OutT) == 4 ? "f32" : "bf16", int(STAGED));
   M3D_ONCE_PER_DEVICE_BEGIN
     M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
   M3D_ONCE_PER_DEVICE_END
@@ -903,6 +904,7 @@ template <int BN, typename InT, typename OutT, bool STAGED>
 static int launch_gather_t(const ConvGatherParams& p, cudaStream_t stream) {
   using Cfg = GatherCfg<BN, sizeof(InT) == 4, STAGED>;
   auto kern = conv_gather_kernel<BN, InT, OutT, STAGED>;
+  set_last_kernel("conv_gather_kernel<%d,%s,%s,%d>", BN, sizeof(InT) == 4 ? "f32" : "bf16", sizeof(OutT) == 4 ? "f32" : "bf16", int(STAGED));
   M3D_ONCE_PER_DEVICE_BEGIN
     M3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
   M3D_ONCE_PER_DEVICE_END

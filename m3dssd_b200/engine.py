@@ -29,6 +29,13 @@ HEAD_ORDER = ["bbox_x", "bbox_y", "bbox_x3d", "bbox_y3d", "bbox_w", "bbox_h", "b
 OUT_SLOTS = [0, 1, 4, 5, 2, 3, 10, 6, 7, 8, 9]
 
 
+_CONV_KINDS = ("conv3x3", "conv_tma", "conv_gather", "dcn_fused", "dcn_gather")  # ops that go through m3d_conv2d_nhwc
+_KIND_KERNEL = {"stem": "stem_conv7x7_kernel", "stem_s2d": "stem_s2d_kernel", "head_mlp": "head_mlp_kernel<48>",
+                "maxpool": "maxpool2x2_kernel", "upsample": "upsample_add_kernel", "softmax": "cls_softmax4_kernel",
+                "align_om": "align_om_kernel", "flatten": "flatten_heads_kernel", "anab_pool": "anab_pool_region_kernel",
+                "anab_attention": "anab_attention_tc_kernel"}
+
+
 class Act:
     """An NHWC activation: `c` real channels inside a buffer with t.shape[-1] channels per pixel."""
 
@@ -531,8 +538,7 @@ class Engine:
         buffer (None = reuse what is there).  stage: "forward" (network outputs), "decode" (+ top-K
         decode into self.dets) or "detect" (+ batched NMS into self.kept / self.num_keep)."""
         if images is not None:
-            assert tuple(images.shape) == tuple(self.image.shape), (images.shape, self.image.shape)
-            self.image.copy_(images, non_blocking=True)
+            self._set_input(images)
         if not self.use_graph:
             self._run_stage(stage)
             return
@@ -546,6 +552,19 @@ class Engine:
                 self._run_stage(stage)
             self.graph[stage] = g
         self.graph[stage].replay()
+
+    def _set_input(self, images):
+        """fp32 NCHW [B,3,H,W] (already normalised, as the reference's DataLoader yields) is copied into the input
+        buffer; uint8 HWC [B,H,W,3] (what cv2.imread returns) goes through the device-side input pipeline:
+        Normalize + BGR->RGB + HWC->CHW of lib/augmentations.py:44-57 / lib/dataloader.py:942-950, bit-identical."""
+        if images.dtype == torch.uint8:
+            assert tuple(images.shape) == (self.B, self.H, self.W, 3), (images.shape, self.image.shape)
+            mean = self.conf.get("image_means", (0.485, 0.456, 0.406))
+            std = self.conf.get("image_stds", (0.229, 0.224, 0.225))
+            ops.preprocess_u8(images.contiguous(), self.image, mean, std, swap_rb=True)
+            return
+        assert tuple(images.shape) == tuple(self.image.shape), (images.shape, self.image.shape)
+        self.image.copy_(images, non_blocking=True)
 
     def forward(self, images=None):
         """Returns (cls, prob, bbox_2d, bbox_3d): views of the engine's output buffers."""
@@ -613,7 +632,7 @@ class Engine:
             self._pipe_init()
         cur = torch.cuda.current_stream()
         if images is not None:
-            self.image.copy_(images, non_blocking=True)
+            self._set_input(images)
         self._pipe["trunk"]()
         cur.wait_event(self._ev_tail)  # the previous tail has finished reading score / box buffers
         self._pipe["heads"]()
@@ -644,18 +663,22 @@ class Engine:
         self._run_forward()
         torch.cuda.synchronize()
         acc = [0.0] * len(self.ops)
+        kernels = [None] * len(self.ops)
         for _ in range(iters):
             evs = []
             # keep the device busy while the host enqueues the whole step (a ctypes call costs more than most
             # of these kernels run): the events then bracket device time, not launch latency
             torch.cuda._sleep(40_000_000)
-            for op in self.ops:
+            for i, op in enumerate(self.ops):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(st)
                 op()
                 e1.record(st)
                 evs.append((e0, e1))
+                if self.meta[i]["kind"] in _CONV_KINDS:  # which kernel instantiation the C-side dispatch picked
+                    kernels[i] = ops.last_kernel()
             torch.cuda.synchronize()
             for i, (e0, e1) in enumerate(evs):
                 acc[i] += e0.elapsed_time(e1)
-        return [dict(m, ms=acc[i] / iters) for i, m in enumerate(self.meta)]
+        return [dict({k: v for k, v in m.items() if k != "spec"}, ms=acc[i] / iters,
+                     kernel=kernels[i] or _KIND_KERNEL.get(m["kind"], m["kind"])) for i, m in enumerate(self.meta)]

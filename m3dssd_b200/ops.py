@@ -122,6 +122,11 @@ def conv2d_nhwc(inputs, weight, out, *, R, S, stride=1, pad=0, dil=1, Cout=None,
     return out
 
 
+def last_kernel():
+    """Kernel instantiation the last conv2d_nhwc call on this thread dispatched to (e.g. 'conv_halo2_kernel<128>')."""
+    return lib().m3d_last_kernel().decode()
+
+
 # --------------------------------------------------------------------------- other ops
 def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
@@ -134,6 +139,18 @@ def stem_conv7x7(image, weight, bias, out, slope=0.01):
     check(lib().m3d_stem_conv7x7(_p(image), _p(weight), _p(bias), _p(out), _dt(out), out.shape[-1], N, H, W,
                                  float(slope), _stream()))
     return out
+
+
+def preprocess_u8(image_hwc, out_nchw, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), swap_rb=True):
+    """uint8 [N,H,W,3] (cv2 BGR) CUDA tensor -> normalised fp32 NCHW (RGB): the reference's Normalize transform and
+    channel swap (lib/augmentations.py:44-57, lib/dataloader.py:942-950) on the device."""
+    assert image_hwc.dtype == torch.uint8 and image_hwc.is_cuda and image_hwc.is_contiguous() and image_hwc.shape[-1] == 3
+    N, H, W, _ = image_hwc.shape
+    assert tuple(out_nchw.shape) == (N, 3, H, W) and out_nchw.dtype == torch.float32 and out_nchw.is_contiguous()
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    s = (C.c_float * 3)(*[float(v) for v in std])
+    check(lib().m3d_preprocess_u8(_p(image_hwc), _p(out_nchw), N, H, W, m, s, int(bool(swap_rb)), _stream()))
+    return out_nchw
 
 
 def pack_stem_s2d(w, b):

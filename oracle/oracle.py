@@ -119,3 +119,17 @@ def gpu_nms(dets, thresh, device_id=0):
     order = dets[:, 4].argsort()[::-1]
     keep = nms_sorted(dets[order, :], thresh)
     return list(order[keep])
+
+
+def preprocess_u8(im_hwc, mean, std):
+    """The reference's test-time input transform restated (lib/augmentations.py:44-57 Normalize; lib/dataloader.py:942-950
+    BGR->RGB swap and HWC->CHW): uint8 [H,W,3] or [N,H,W,3] -> float32 [.., 3, H, W].  float32 arithmetic in the
+    reference's order; mean / std are applied in the channel order of the INPUT."""
+    im = np.asarray(im_hwc)
+    assert im.dtype == np.uint8 and im.shape[-1] == 3
+    x = im.astype(np.float32)
+    x /= 255.0
+    x -= np.asarray(mean, dtype=np.float32)
+    x /= np.asarray(std, dtype=np.float32)
+    x = x[..., ::-1]  # cv2.COLOR_BGR2RGB
+    return np.ascontiguousarray(np.moveaxis(x, -1, -3)).astype(np.float32)

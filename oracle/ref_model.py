@@ -24,7 +24,9 @@ import torch.nn.functional as F
 
 from . import oracle as O
 
-LEVELS = {"dla34": ([1, 1, 1, 2, 2, 1], [16, 32, 64, 128, 256, 512])}
+# (levels, channels, block, residual_root): model/pose_dla_dcn.py:419-425 (dla34), 435-441 (dla102)
+LEVELS = {"dla34": ([1, 1, 1, 2, 2, 1], [16, 32, 64, 128, 256, 512], "basic", False),
+          "dla102": ([1, 1, 1, 3, 4, 1], [16, 32, 128, 256, 512, 1024], "bottleneck", True)}
 
 
 def _dcn_c(x, offset, mask, w, b, stride, pad):
@@ -69,9 +71,24 @@ class RefModel:
         out = self.bn(self.conv(out, p + ".conv2", 1, 1), p + ".bn2")
         return self.act(out + residual)
 
+    def bottleneck(self, x, p, stride, residual=None):
+        """model/pose_dla_dcn.py:162-204 (expansion 2): 1x1 -> 3x3 (stride) -> 1x1, + residual."""
+        if residual is None:
+            residual = x
+        out = self.act(self.bn(self.conv(x, p + ".conv1"), p + ".bn1"))
+        out = self.act(self.bn(self.conv(out, p + ".conv2", stride, 1), p + ".bn2"))
+        out = self.bn(self.conv(out, p + ".conv3"), p + ".bn3")
+        return self.act(out + residual)
+
+    def block(self, x, p, stride, residual=None):
+        kind = LEVELS[self.conf.back_bone][2]
+        return (self.bottleneck if kind == "bottleneck" else self.basic_block)(x, p, stride, residual)
+
     def root(self, xs, p):
         x = self.bn(self.conv(torch.cat(xs, 1), p + ".conv"), p + ".bn")
-        return self.act(x)  # residual_root is False for dla34
+        if LEVELS[self.conf.back_bone][3]:  # residual_root (dla102), model/pose_dla_dcn.py:262-266
+            x = x + xs[0]
+        return self.act(x)
 
     def tree(self, x, p, levels, cin, cout, stride, level_root, residual=None, children=None):
         children = [] if children is None else children
@@ -80,15 +97,15 @@ class RefModel:
         if level_root:
             children.append(bottom)
         if levels == 1:
-            x1 = self.basic_block(x, p + ".tree1", stride, residual)
-            x2 = self.basic_block(x1, p + ".tree2", 1)
+            x1 = self.block(x, p + ".tree1", stride, residual)
+            x2 = self.block(x1, p + ".tree2", 1)
             return self.root([x2, x1] + children, p + ".root")
         x1 = self.tree(x, p + ".tree1", levels - 1, cin, cout, stride, False, residual)
         children.append(x1)
         return self.tree(x1, p + ".tree2", levels - 1, cout, cout, 1, False, None, children)
 
     def dla(self, x):
-        levels, ch = LEVELS[self.conf.back_bone]
+        levels, ch = LEVELS[self.conf.back_bone][:2]
         p = "base.base"
         x = self.act(self.bn(self.conv(x, p + ".base_layer.0", 1, 3), p + ".base_layer.1"))
         y = []
@@ -147,7 +164,8 @@ class RefModel:
         mask, ind = torch.max(prob, dim=1, keepdim=True)  # topk(k=1); softmax over one element = 1
         return mask, ind, (mask > 0.5).to(prob.dtype)
 
-    def shape_align(self, x, prob):
+    def shape_align_offsets(self, prob):
+        """(offset [B,18,H,W], mask [B,9,H,W]) of shape_align (feturealign_mgpu.py:119-136, 160-172)."""
         stride = self.conf.feat_stride
         aw = (self.anchors[:, 2] - self.anchors[:, 0]) / stride / 3
         ah = (self.anchors[:, 3] - self.anchors[:, 1]) / stride / 3
@@ -157,37 +175,49 @@ class RefModel:
             for j in range(3):
                 offs.append((ah[ind] - 1) * (i - 3 / 2 + 0.5))
                 offs.append((aw[ind] - 1) * (j - 3 / 2 + 0.5))
-        offset = torch.cat(offs, dim=1) * hard
-        y = self.dcn(x, offset, mask.repeat(1, 9, 1, 1), self.sd["shape_align.align.weight"],
-                     self.sd["shape_align.align.bias"], 1, 1)
+        return torch.cat(offs, dim=1) * hard, mask.repeat(1, 9, 1, 1)
+
+    def shape_align(self, x, prob):
+        offset, mask = self.shape_align_offsets(prob)
+        y = self.dcn(x, offset, mask, self.sd["shape_align.align.weight"], self.sd["shape_align.align.bias"], 1, 1)
         return y + x
 
-    def center_align(self, x, bx, by, prob, p, mean, std):
+    def center_align_offsets(self, bx, by, prob, mean, std):
+        """(offset [B,2,H,W] = (dy, dx), mask [B,1,H,W]) of center_align (feturealign_mgpu.py:58-77)."""
         stride = self.conf.feat_stride
         aw = ((self.anchors[:, 2] - self.anchors[:, 0]) / stride).view(1, -1, 1, 1)
         ah = ((self.anchors[:, 3] - self.anchors[:, 1]) / stride).view(1, -1, 1, 1)
         mask, ind, hard = self._top1(prob)
         ox = torch.gather((bx * std[0] + mean[0]) * aw, 1, ind) * hard
         oy = torch.gather((by * std[1] + mean[1]) * ah, 1, ind) * hard
-        offset = torch.cat([oy, ox], dim=1)
+        return torch.cat([oy, ox], dim=1), mask
+
+    def center_align(self, x, bx, by, prob, p, mean, std):
+        offset, mask = self.center_align_offsets(bx, by, prob, mean, std)
         y = self.dcn(x, offset, mask, self.sd[p + ".align.weight"], self.sd[p + ".align.bias"], 1, 0)
         return y + x
+
+    @staticmethod
+    def papa(feats, att, sizes=(1, 4, 8, 16)):
+        """PAPAModule (model/module/attention.py:120-147): attention-weighted pyramid pooling -> [n, c, T]."""
+        n, c = feats.shape[:2]
+        return torch.cat([F.adaptive_avg_pool2d(feats * att[:, i:i + 1], (s, s)).view(n, c, -1)
+                          for i, s in enumerate(sizes)], -1)
+
+    @staticmethod
+    def anab_attend(q, key, value, x):
+        """softmax(Q K) V + x (attention.py:205-214); q [B,HW,ck], key [B,ck,T], value [B,T,cv]."""
+        B, C, H, W = x.shape
+        a = torch.softmax(torch.bmm(q, key), dim=-1)
+        return torch.bmm(a, value).permute(0, 2, 1).reshape(B, C, H, W) + x
 
     def anab(self, x, p):
         B, C, H, W = x.shape
         q = self.conv(x, p + ".query_conv").view(B, -1, H * W).permute(0, 2, 1)
         att = torch.sigmoid(self.conv(x, p + ".spatial_conv"))
-
-        def papa(feats):
-            n, c = feats.shape[:2]
-            return torch.cat([F.adaptive_avg_pool2d(feats * att[:, i:i + 1], (s, s)).view(n, c, -1)
-                              for i, s in enumerate((1, 4, 8, 16))], -1)
-
-        key = papa(self.conv(x, p + ".key_conv"))
-        value = papa(self.conv(x, p + ".value_conv")).permute(0, 2, 1)
-        a = torch.softmax(torch.bmm(q, key), dim=-1)
-        new = torch.bmm(a, value).permute(0, 2, 1).reshape(B, C, H, W)
-        return new + x
+        key = self.papa(self.conv(x, p + ".key_conv"), att)
+        value = self.papa(self.conv(x, p + ".value_conv"), att).permute(0, 2, 1)
+        return self.anab_attend(q, key, value, x)
 
     @staticmethod
     def flatten(t):

@@ -115,6 +115,7 @@ CASES = [
     ("root_concat_4", dict(N=1, H=12, W=40, cins=[128, 128, 64, 128], cout=128, k=1)),
     ("conv1x1_cout256", dict(N=4, H=24, W=80, cins=[256], cout=256, k=1)),
     ("conv3x3_cout256_big", dict(N=8, H=24, W=80, cins=[256], cout=256)),
+    ("conv3x3_cout256_big_res", dict(N=8, H=24, W=80, cins=[256], cout=256, res=True)),  # level4 conv2: pair kernel, BN = 256
     ("head_cout36_f32", dict(N=1, H=12, W=40, cins=[256], cout=36, k=1, out_dtype=torch.float32, slope=1.0)),
     ("logits_cout144_f32", dict(N=2, H=24, W=80, cins=[256], cout=144, k=1, out_dtype=torch.float32, slope=1.0)),
     ("logits_cout160_f32_ragged", dict(N=3, H=13, W=37, cins=[128], cout=160, k=1, out_dtype=torch.float32)),

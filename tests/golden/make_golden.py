@@ -53,6 +53,17 @@ def main():
         out["seed_%d" % n] = np.int32(seed)
     np.savez_compressed(os.path.join(HERE, "nms_py_cpu.npz"), **out)
 
+    # --- input transform: the reference's own Normalize class (lib/augmentations.py:44-57) + its channel swap
+    import importlib
+    aug = importlib.import_module("lib.augmentations")
+    rng = np.random.default_rng(17)
+    im = rng.integers(0, 256, (24, 40, 3), dtype=np.uint8)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]  # scripts/config/kitti_3d_base.py:42-43
+    out, _ = aug.Normalize(mean, std)(im.copy())
+    out = out[:, :, (2, 1, 0)]  # lib/dataloader.py:942-947 (cv2.cvtColor BGR2RGB == this permutation)
+    np.savez_compressed(os.path.join(HERE, "preprocess_u8.npz"), image=im, mean=np.float32(mean), std=np.float32(std),
+                        expected_chw=np.ascontiguousarray(out.transpose(2, 0, 1)).astype(np.float32))
+
     # --- model forward + decode through the unmodified reference modules
     torch.Tensor.cuda = lambda self, *a, **k: self  # im_detect_3d calls .cuda(); stay on CPU
     torch.cuda.FloatTensor = torch.FloatTensor

@@ -1,13 +1,12 @@
 """GPU parity of the fused engine (through the reference-facing nn.Module surface) against the CPU oracle.
 
-Tolerance (north_star: bit-exact NMS keep indices, 1e-3 relative on the fp32 box / score tensors):
-the synthetic random-weight network amplifies ordinary fp32 round-off by 10^2..10^4 between the stem
-and the box outputs (measured on the oracle itself: fp32 vs fp64 evaluation of the SAME reference
-arithmetic differ by ~4e-4 rms at 96x320 and ~1.5e-2 rms at 384x1280, with isolated hard-mask flips).
-So the bars are (a) absolute at the small size -- every score within 1e-3 of the output scale, >= 99.8 %
-of the box regressions within 1e-3, rms < 1.5e-3 -- and (b) self-calibrating at every size: our
-deviation from the EXACT (fp64) evaluation of the reference algorithm must be within 2.5x of the
-deviation the reference's own fp32 arithmetic has from it.
+Tolerance = north_star's, as written: bit-exact NMS keep indices, 1e-3 relative on the fp32 box / score tensors.
+"Relative" is taken against the scale of each output tensor (max |reference|): every score and >= 99.99 % of the
+box regressions must be within 1e-3 of it, rms error < 1e-3, at 96x320 AND at the full 384x1280 resolution.
+(Round 1 needed a self-calibrating bar at full resolution because its He-initialised synthetic network amplified
+fp32 round-off by 10^4; m3dssd_b200/synth.py now builds a well-conditioned network -- oracle fp32 vs fp64 differ by
+5e-5 rms at 384x1280 -- so the bar is absolute.)  The bf16 throughput engine is gated layer by layer with teacher
+forcing in tests/test_teacher_forced_gpu.py and end to end below.
 """
 import numpy as np
 import pytest
@@ -21,6 +20,15 @@ pytestmark = pytest.mark.gpu
 
 def _rms(a, b):
     return float(((a.double() - b.double()).pow(2).mean().sqrt()) / (b.double().pow(2).mean().sqrt() + 1e-30))
+
+
+def _assert_1e3(name, got, ref):
+    scale = ref.abs().max()
+    frac_bad = float(((got - ref).abs() > 1e-3 * scale).float().mean())
+    print("parity %-8s rms %.3e  max %.3e of scale  frac>1e-3 %.2e" % (
+        name, _rms(got, ref), float((got - ref).abs().max() / scale), frac_bad))
+    assert _rms(got, ref) < 1e-3, (name, _rms(got, ref))
+    assert frac_bad <= (0.0 if name in ("cls", "prob") else 1e-4), (name, frac_bad)
 
 
 def _setup(attention, align, crop, batch):
@@ -45,38 +53,38 @@ def test_fp32_engine_vs_oracle_96x320(attention, align):
     assert torch.equal(rois.cpu(), o32[5])
     for name, got, r32, r64 in zip(("cls", "prob", "bbox_2d", "bbox_3d"), (cls, prob, b2, b3), o32, o64):
         got = got.cpu()
-        scale = r32.abs().max()
-        frac_bad = float(((got - r32).abs() > 1e-3 * scale).float().mean())
-        assert _rms(got, r32) < 1.5e-3, (name, _rms(got, r32))
-        assert frac_bad <= (0.0 if name in ("cls", "prob") else 2e-3), (name, frac_bad)
+        _assert_1e3(name, got, r32)
         assert _rms(got, r64) <= 2.5 * _rms(r32, r64) + 1e-6, (name, _rms(got, r64), _rms(r32, r64))
 
 
-def test_fp32_engine_vs_exact_oracle_full_resolution():
-    """384x1280 (BASELINE.json configs[0] geometry): self-calibrating bar only -- see the module docstring."""
-    conf, net, sd, x = _setup(None, True, (384, 1280), 1)
+@pytest.mark.parametrize("attention", [None, "ANAB"])
+def test_fp32_engine_vs_oracle_full_resolution(attention):
+    """384x1280 (BASELINE.json configs[0] geometry), the north_star bar as written: 1e-3 relative, fp32."""
+    conf, net, sd, x = _setup(attention, True, (384, 1280), 1)
     o32 = RM.RefModel(sd, conf, dcn="tv", dtype=torch.float32).forward(x)
-    o64 = RM.RefModel(sd, conf, dcn="tv", dtype=torch.float64).forward(x)
     net = net.cuda().eval()
     eng = net.engine(1, 384, 1280, precision="fp32", use_graph=False)
     outs = eng.forward(x.cuda())
-    for name, got, r32, r64 in zip(("cls", "prob", "bbox_2d", "bbox_3d"), outs, o32, o64):
-        assert _rms(got.cpu(), r64) <= 2.5 * _rms(r32, r64) + 1e-6, (name, _rms(got.cpu(), r64), _rms(r32, r64))
+    for name, got, r32 in zip(("cls", "prob", "bbox_2d", "bbox_3d"), outs, o32):
+        _assert_1e3(name, got.cpu(), r32)
 
 
-def test_bf16_engine_early_layers_and_sanity():
-    """Throughput mode: bf16 activations.  Each layer rounds to 8 mantissa bits (2^-9 relative), which the
-    random network amplifies like any other perturbation, so end-to-end agreement is only statistical;
-    what is asserted is the per-layer error where amplification has not set in yet, finiteness, and
-    that probabilities remain a distribution."""
+def test_bf16_engine_end_to_end_small():
+    """Throughput mode (bf16 activations) end to end at 96x320 through the graph-replayed engine: deviation from the
+    fp32 oracle GATED on the tensors up to the class probabilities (bars of tests/test_teacher_forced_gpu.py, where
+    the layer-by-layer teacher-forced check and the full-size end-to-end gate live), finite outputs, probabilities
+    a distribution."""
+    from test_teacher_forced_gpu import E2E_BARS
     conf, net, sd, x = _setup(None, True, (96, 320), 2)
     oracle = RM.RefModel(sd, conf, dcn="tv")
-    oracle.forward(x)
+    ref = oracle.forward(x)
     net = net.cuda().eval()
     eng = net.engine(2, 96, 320, precision="bf16", use_graph=True)
     cls, prob, b2, b3 = eng.forward(x.cuda())
-    for name, bar in (("level0", 6e-3), ("level1", 8e-3), ("level2", 2e-2)):
-        assert _rms(eng.activation_nchw(name).cpu(), oracle.taps[name]) < bar, name
+    for name in ("level2", "level3", "level4", "level5", "feat"):
+        e = _rms(eng.activation_nchw(name).cpu(), oracle.taps[name])
+        assert e < E2E_BARS["e2e." + name], (name, e)
+    assert _rms(cls.cpu(), ref[0]) < E2E_BARS["e2e.cls"] and _rms(prob.cpu(), ref[1]) < E2E_BARS["e2e.prob"]
     for t in (cls, prob, b2, b3):
         assert torch.isfinite(t).all()
     assert float((prob.sum(dim=2) - 1).abs().max()) < 1e-5

@@ -252,3 +252,17 @@ def test_head_mlp(shape):
         assert (o - ref).abs().mean().item() < 2e-4
     # untouched channels stay untouched
     assert torch.all(got[..., :coff] == 7.0) and torch.all(got[..., coff + G * A:] == 7.0)
+
+
+@pytest.mark.parametrize("shape", [(1, 24, 40), (2, 96, 320), (8, 384, 1280)])
+def test_preprocess_u8_bit_exact_vs_oracle(shape):
+    """Device-side input pipeline (m3d_preprocess_u8) == the reference's Normalize + BGR->RGB + CHW: bit-exact."""
+    from m3dssd_b200 import ops, synth
+    from oracle import oracle as O
+    N, H, W = shape
+    im = synth.make_images_u8(N, (H, W), seed=N)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    out = torch.empty(N, 3, H, W, dtype=torch.float32, device="cuda")
+    ops.preprocess_u8(im.cuda(), out, mean, std, swap_rb=True)
+    ref = O.preprocess_u8(im.numpy(), mean, std)
+    assert np.array_equal(out.cpu().numpy(), ref)

@@ -145,3 +145,11 @@ def test_hill_climb_oracle_vs_reference_golden():
         # the search really moves the rotation: otherwise the comparison is vacuous
         alpha0 = rows[:40][rows[:40, 4] >= 0.75][:, 12]
         assert np.abs(got[:, 1] - alpha0).max() > 0.05
+
+
+def test_preprocess_oracle_vs_reference_normalize_golden():
+    """oracle.preprocess_u8 == the reference's Normalize transform + BGR->RGB + CHW, bit for bit (fixture generated by
+    tests/golden/make_golden.py from the unmodified lib/augmentations.py)."""
+    g = np.load(os.path.join(GOLD, "preprocess_u8.npz"))
+    got = O.preprocess_u8(g["image"], g["mean"], g["std"])
+    assert got.dtype == np.float32 and np.array_equal(got, g["expected_chw"])
