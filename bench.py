@@ -1,20 +1,27 @@
 #!/usr/bin/env python
-"""Benchmark of the M3DSSD dense forward path on B200 (BASELINE.json metric: images/sec @384x1280 bf16).
+"""Benchmark of the M3DSSD dense forward path on B200 (BASELINE.json metric: images/sec @384x1280 bf16,
+1/2/4/8 B200; DCNv2 HBM GB/s & tensor-pipe % vs peak).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--attention ANAB] [--input u8|f32]
 
-One "step" = one pass of the whole hot path over one batch of synthetic KITTI-shaped images on every
-rank: DLA-34 + DLAUp/IDAUp (DCNv2) + shape/centre alignment + heads + softmax + decode/top-3000 +
-(N > 1: NCCL all-gather of the detections) + batched NMS.  Workload = BASELINE.json configs[1]
-(batch-8 384x1280 bf16 inference, DLA-34+DCNv2+align head) per GPU; weak scaling over GPUs.
+One "step" = one pass of the whole hot path over one batch of synthetic KITTI-shaped images on every rank:
+[device-side input normalisation of uint8 images] + DLA-34 + DLAUp/IDAUp (DCNv2) + shape/centre alignment + heads +
+softmax + decode/top-3000 + batched NMS (N > 1: + NCCL all-gather of the detection tensors over NVLink).
+Workload = BASELINE.json configs[1] (batch-8 384x1280 bf16 inference, DLA-34+DCNv2+align head) per GPU, weak scaling;
+`--attention ANAB` = configs[2].
 
-`value`  : images/s with the input batches already resident in HBM (CUDA events, max over ranks).
-`e2e`    : same metric through the public API with HOST (pinned) inputs: H2D copy of every batch and
-           D2H read of the kept detections inside the timed region.
-`roofline`, `kernels`: per-kernel-family device time measured live (CUDA events around every launch of
-           an instrumented pass) against MEASURED_PEAKS.json.
-`cpu_baseline` / `--impl reference`: the reference's PyTorch forward restated for CPU (oracle/ref_model.py,
-           pinned to the unmodified reference modules by tests/golden) on this box's host cores.
+`value`     : images/s, inputs already resident in HBM (CUDA events on the launching stream, max over ranks).
+`e2e`       : same metric through the public API with HOST (pinned) inputs: the H2D copy of every batch and the D2H
+              read of the kept detections are inside the timed region.
+`sustained` : `value` re-measured over >= 2 s of back-to-back steps (clocks sampled through NVML every 5 ms).
+`roofline`  : the top kernel FUNCTION of the step (per-launch CUDA-event times of an instrumented eager pass, summed
+              per kernel instantiation) against MEASURED_PEAKS.json; `dcn` = the DCNv2 kernel's tensor-pipe % and HBM
+              GB/s, as the metric string asks; `kernels` = every kernel function; `step_roofline` = whole step.
+`surface`   : the reference-facing calls timed as the reference's scripts make them (net(im) -> decode -> gpu_nms at
+              batch 1 = lib/rpn_util.py:1427-1555; net.detect at batch 8).
+`cpu_baseline` / `--impl reference`: the reference's PyTorch forward restated for CPU (oracle/ref_model.py, pinned to the
+              unmodified reference modules by tests/golden; the unmodified modules themselves need /root/reference,
+              which does not exist on the GPU box) on this box's host cores.
 """
 import argparse
 import json
@@ -22,6 +29,7 @@ import os
 import statistics
 import subprocess
 import sys
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -30,7 +38,9 @@ sys.path.insert(0, ROOT)
 CROP = (384, 1280)
 LOCAL_BATCH = 8
 WORKLOAD = "batch-8 384x1280 bf16 inference, DLA-34+DCNv2+align head per GPU (BASELINE.json configs[1])"
+WORKLOAD_ANAB = "batch-8 384x1280 bf16 with asymmetric non-local attention enabled per GPU (BASELINE.json configs[2])"
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_traffic.json")  # written by tools/summarize_ncu.py from this round's capture
 
 
 def load_peaks():
@@ -39,37 +49,89 @@ def load_peaks():
         with open(p) as fh:
             d = json.load(fh)
         return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"],
-                    bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
-    return dict(FALLBACK_PEAKS, source="fallback")
+                    bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="MEASURED_PEAKS.json")
+    return dict(FALLBACK_PEAKS, source="fallback (B200_PROFILING.md)")
 
 
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons sampled in-process through NVML every `period` s (a 100 ms nvidia-smi loop
+    misses a 40 ms timed region); falls back to `nvidia-smi -lms 10` when pynvml is unavailable."""
+    BAD = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80}
+    NOTE = {"sw_power_cap": 0x4}
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.proc = None
+    def __init__(self, gpu_index, period=0.005):
+        self.gpu, self.period = gpu_index, period
+        self.samples, self.reasons = [], set()
+        self._stop = threading.Event()
+        self._thr = None
+        self._h = None
+        self._smi = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self._nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self._h = None
+
+    def _loop(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self.samples.append((time.perf_counter(), float(mhz), pw))
+                for name, bit in list(self.BAD.items()) + list(self.NOTE.items()):
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+        self.samples, self.reasons = [], set()
+        self._stop.clear()
+        if self._h is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        else:
+            fields = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                      "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                      "clocks_event_reasons.sw_power_cap")
+            try:
+                self._smi = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + fields,
+                                              "--format=csv,noheader,nounits", "-lms", "10"], stdout=subprocess.PIPE,
+                                             stderr=subprocess.DEVNULL, text=True)
+            except OSError:
+                self._smi = None
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join(timeout=2)
+            self._thr = None
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"], "source": "nvml"}
+            mhz = [s[1] for s in self.samples]
+            return {"sm_mhz": statistics.median(mhz), "sm_min_mhz": min(mhz), "sm_max_mhz": self.max_mhz,
+                    "power_w_max": max(s[2] for s in self.samples), "samples": len(mhz), "period_ms": 1e3 * self.period,
+                    "reasons": sorted(self.reasons), "source": "nvml"}
+        if self._smi is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
+        time.sleep(0.05)
+        self._smi.terminate()
         try:
-            out, _ = self.proc.communicate(timeout=5)
+            out, _ = self._smi.communicate(timeout=5)
         except subprocess.TimeoutExpired:
-            self.proc.kill()
-            out, _ = self.proc.communicate()
+            self._smi.kill()
+            out, _ = self._smi.communicate()
         sm, mx, pw, reasons = [], [], [], set()
         for line in out.splitlines():
             f = [x.strip() for x in line.split(",")]
@@ -85,25 +147,26 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
-                "reasons": sorted(reasons)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "source": "nvidia-smi"}
+        return {"sm_mhz": statistics.median(sm), "sm_min_mhz": min(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
-def cpu_reference(steps, warmup, want_detect=True):
-    """The reference's forward on the host CPU: oracle/ref_model.py (CPU restatement pinned to the
-    unmodified reference modules; DCNv2 = torchvision.ops.deform_conv2d, which the C oracle is pinned
-    against, because the reference has no CPU DCNv2 at all).  One 384x1280 fp32 image per step."""
+def cpu_reference(steps, warmup, batch=1, attention=None, want_detect=True):
+    """The reference's forward on the host CPU: oracle/ref_model.py (the CPU restatement pinned to the unmodified
+    reference modules by tests/golden -- the unmodified modules need /root/reference, absent on the GPU box; DCNv2 =
+    torchvision.ops.deform_conv2d, which the C oracle is pinned against, because the reference has no CPU DCNv2 at
+    all).  `batch` 384x1280 fp32 images per step."""
     import torch
     from m3dssd_b200 import synth
     from m3dssd_b200.model.M3d_inference_align import build
     from oracle import ref_model as RM
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    conf = synth.make_conf(attention=None, center_align=True, shape_align=True, crop_size=CROP)
+    conf = synth.make_conf(attention=attention, center_align=True, shape_align=True, crop_size=CROP)
     sd = synth.randomize_weights(build(conf, "test"))
     model = RM.RefModel(sd, conf, dcn="tv")
-    x = synth.make_images(1, CROP)
+    x = synth.make_images(batch, CROP)
     with torch.no_grad():
         for _ in range(warmup):
             out = model.forward(x)
@@ -111,10 +174,12 @@ def cpu_reference(steps, warmup, want_detect=True):
         for _ in range(steps):
             out = model.forward(x)
             if want_detect:
-                model.detect(out, 0)
+                for b in range(batch):
+                    model.detect(out, b)
         dt = time.perf_counter() - t0
-    return dict(value=steps / dt, unit="images/s", cores=cores, kind="port",
-                sample="%d x (1 image 384x1280 fp32 forward + decode + NMS), torch CPU %d threads" % (steps, cores),
+    return dict(value=batch * steps / dt, unit="images/s", cores=cores, kind="port", batch=batch,
+                sample="%d x (batch %d, 384x1280 fp32 forward + decode + NMS), oracle/ref_model.py restatement of the "
+                       "reference modules (torch CPU, %d threads)" % (steps, batch, cores),
                 ms_per_step=1e3 * dt / steps)
 
 
@@ -122,13 +187,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 2))
-    r = cpu_reference(steps, warmup)
+    steps, warmup = max(1, min(args.steps, 4)), max(1, min(args.warmup, 1))
+    r = cpu_reference(steps, warmup, batch=LOCAL_BATCH, attention=args.attention)
     line = {
         "impl": "reference", "metric": "images_per_sec", "value": r["value"], "unit": "images/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU arm: bounded sample, 1 image per step, fp32"},
+        "config": {"workload": WORKLOAD_ANAB if args.attention else WORKLOAD, "global_batch": LOCAL_BATCH,
+                   "note": "CPU arm: bounded sample (batch 8 per step, few steps), fp32, all host threads"},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -137,35 +203,50 @@ def run_reference(args):
     return 0
 
 
-def ncu_traffic(kind):
-    """Measured DRAM bytes per launch of this kernel kind (dram__bytes_read.sum + dram__bytes_write.sum from the
-    committed `ncu --set full` capture, profiles/r01c_traffic.json), or None when the kind was not captured."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01c_traffic.json")
+def ncu_traffic(kernel, lib_path):
+    """Measured DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over ALL launches of this
+    kernel function in this round's `ncu --set full` capture of one step; profiles/r02_traffic.json written by
+    tools/summarize_ncu.py).  Refused -- None -- when the capture does not know the kernel or the built library no
+    longer contains it (a stale file must not pass as evidence)."""
     try:
-        with open(path) as fh:
-            return json.load(fh).get(kind, {}).get("dram_bytes_per_launch")
+        with open(TRAFFIC_FILE) as fh:
+            table = json.load(fh)
     except (OSError, ValueError):
         return None
+    base = kernel.split("<")[0]
+    rec = table.get(kernel) or table.get(base)
+    if rec is None:
+        return None
+    try:
+        with open(lib_path, "rb") as fh:
+            if base.encode() not in fh.read():
+                return None
+    except OSError:
+        return None
+    return rec
 
 
-def summarize_kernels(prof, peaks, step_ms):
-    kinds = {}
+def summarize_kernels(prof, peaks):
+    ks = {}
     for p in prof:
-        k = kinds.setdefault(p["kind"], dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+        k = ks.setdefault(p["kernel"], dict(ms=0.0, flops=0.0, bytes=0.0, launches=0, ops=0))
         k["ms"] += p["ms"]
         k["flops"] += p["flops"]
         k["bytes"] += p["bytes"]
         k["launches"] += p["launches"]
-    total_ms = sum(k["ms"] for k in kinds.values())
-    pt, ph = peaks["bf16_tflops_sustained"], peaks["hbm_gbs"]
+        k["ops"] += 1
+    total_ms = sum(k["ms"] for k in ks.values())
     out = {}
-    for name, k in kinds.items():
+    for name, k in sorted(ks.items(), key=lambda kv: -kv[1]["ms"]):
         t = k["ms"] * 1e-3
         tf = k["flops"] / t / 1e12 if t > 0 else 0.0
         gb = k["bytes"] / t / 1e9 if t > 0 else 0.0
         out[name] = dict(ms=round(k["ms"], 4), share=round(k["ms"] / total_ms, 4), launches=k["launches"],
-                         tflops=round(tf, 2), hbm_gbs=round(gb, 1), tensor_frac=round(tf / pt, 4),
-                         hbm_frac=round(gb / ph, 4))
+                         tflops=round(tf, 2), hbm_gbs=round(gb, 1),
+                         tensor_frac_burst=round(tf / peaks["bf16_tflops"], 4),
+                         tensor_frac_sustained=round(tf / peaks["bf16_tflops_sustained"], 4),
+                         hbm_frac=round(gb / peaks["hbm_gbs"], 4),
+                         flops_per_launch=k["flops"] / max(1, k["launches"]), bytes_per_launch=k["bytes"] / max(1, k["launches"]))
     return out, total_ms
 
 
@@ -176,20 +257,29 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sustained / surface sub-measurements")
     ap.add_argument("--attention", default=None)
+    ap.add_argument("--input", default="u8", choices=["u8", "f32"],
+                    help="u8: uint8 HWC images normalised on the device (default); f32: pre-normalised fp32 NCHW")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
-    import torch
-    import torch.distributed as dist
-    from m3dssd_b200 import synth
-    from m3dssd_b200.model.M3d_inference_align import build
-    from m3dssd_b200.parallel import ShardedDetector
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        # the two all-gathers of a step move < 11 MB: a handful of NCCL CTAs is plenty, and they must fit into the SMs
+        # the persistent trunk kernels leave free for the detection tail (Engine._pipe_init)
+        os.environ.setdefault("NCCL_MAX_CTAS", "4")
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "4")
+
+    import torch
+    import torch.distributed as dist
+    from m3dssd_b200 import _lib, synth
+    from m3dssd_b200.model.M3d_inference_align import build
+    from m3dssd_b200.parallel import ShardedDetector
+
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
@@ -227,7 +317,10 @@ def main():
     eng = det.engine
 
     NB = 4  # distinct input batches, rotated; activations per step (>1 GB) exceed the 126 MB L2 by themselves
-    host = [synth.make_images(LOCAL_BATCH, CROP, seed=100 * rank + i).pin_memory() for i in range(NB)]
+    if args.input == "u8":
+        host = [synth.make_images_u8(LOCAL_BATCH, CROP, seed=100 * rank + i).pin_memory() for i in range(NB)]
+    else:
+        host = [synth.make_images(LOCAL_BATCH, CROP, seed=100 * rank + i).pin_memory() for i in range(NB)]
     dev = [h.cuda() for h in host]
 
     def barrier():
@@ -235,30 +328,35 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------------------------------------------------- device-resident throughput
+    def allmax(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     def drain():
         torch.cuda.current_stream().wait_event(eng.tail_done)  # the last tail runs on the side stream
 
+    def resident_loop(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            det.step_pipelined(dev[i % NB])
+        drain()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    # ---------------------------------------------------------- device-resident throughput
     for i in range(W):
         det.step_pipelined(dev[i % NB])
     drain()
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        det.step_pipelined(dev[i % NB])
-    drain()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms_total = allmax(resident_loop(K))
     clk = clocks.stop()
-    note("device-resident loop done: %.3f ms/step" % (ms / K))
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    note("device-resident loop done: %.3f ms/step" % (ms_total / K))
     value = world * LOCAL_BATCH * K / (ms_total * 1e-3)
 
     # ---------------------------------------------------------- end to end from host memory
@@ -285,7 +383,7 @@ def main():
                     ready[(i + 1) & 1].record(copy_stream)
             cur.wait_event(ready[s])
             kept, num = det.step_pipelined(stage_bufs[s])
-            consumed[s].record(cur)  # (recorded after the heads; the input buffer is only read by the stem)
+            consumed[s].record(cur)  # (recorded after the heads; the input buffer is only read by the first kernel)
             with torch.cuda.stream(eng.tail_stream):  # D2H of the kept detections right behind their NMS
                 kept_host.copy_(kept, non_blocking=True)
                 num_host.copy_(num, non_blocking=True)
@@ -296,56 +394,101 @@ def main():
     e2e_loop(W)
     barrier()
     note("e2e warm-up done")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
     e2e_loop(K)
     e1.record()
     barrier()
     wall = time.perf_counter() - t0
-    ms_e2e = max(e0.elapsed_time(e1), 0.0)
-    t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * LOCAL_BATCH * K / (float(t.item()) * 1e-3)
-    h2d = LOCAL_BATCH * 3 * CROP[0] * CROP[1] * 4
+    e2e_value = world * LOCAL_BATCH * K / (allmax(max(e0.elapsed_time(e1), 0.0)) * 1e-3)
+    h2d = host[0].numel() * host[0].element_size()
     d2h = kept_host.numel() * 4 + num_host.numel() * 4
 
-    # ---------------------------------------------------------- per-kernel roofline (rank 0)
+    # ---------------------------------------------------------- sustained (>= 2 s) device-resident throughput
+    sustained = None
+    if not args.no_extras:
+        n_sus = max(K, int(2200.0 / (ms_total / K)))
+        clocks.start()
+        ms_sus = allmax(resident_loop(n_sus))
+        clk_sus = clocks.stop()
+        sustained = {"value": world * LOCAL_BATCH * n_sus / (ms_sus * 1e-3), "unit": "images/s", "steps": n_sus,
+                     "seconds": ms_sus * 1e-3, "ms_per_step": ms_sus / n_sus, "clocks": clk_sus}
+        note("sustained loop done")
+
+    # ---------------------------------------------------------- per-kernel roofline + extras (rank 0)
     line = None
     if rank == 0:
         prof = eng.profile(iters=3)
-        kinds, fwd_ms = summarize_kernels(prof, peaks, ms_total / K)
-        dom = max(kinds.items(), key=lambda kv: kv[1]["ms"])
-        dname, d = dom
-        tensor_bound = d["tensor_frac"] >= d["hbm_frac"]
+        kernels, fwd_ms = summarize_kernels(prof, peaks)
+        # the timed region of the headline number lasts K steps: a few tens of ms at full clocks -> the burst peak is
+        # the honest denominator; the >= 2 s loop is judged against the sustained peak.  Both fractions are printed.
+        region_s = ms_total * 1e-3
+        use_burst = region_s < 2.0
+        top_name, top = next(iter(kernels.items()))
+        tensor_bound = top["tensor_frac_burst"] >= top["hbm_frac"]
+        peak_t = peaks["bf16_tflops"] if use_burst else peaks["bf16_tflops_sustained"]
+        traffic = ncu_traffic(top_name, _lib.LIB_PATH)
         roofline = {
-            "kernel": dname, "bound": "tensor" if tensor_bound else "hbm",
-            "achieved": d["tflops"] if tensor_bound else d["hbm_gbs"],
-            "peak": peaks["bf16_tflops_sustained"] if tensor_bound else peaks["hbm_gbs"],
+            "kernel": top_name, "bound": "tensor" if tensor_bound else "hbm",
+            "achieved": top["tflops"] if tensor_bound else top["hbm_gbs"],
+            "peak": peak_t if tensor_bound else peaks["hbm_gbs"],
             "unit": "TFLOP/s" if tensor_bound else "GB/s",
-            "frac": d["tensor_frac"] if tensor_bound else d["hbm_frac"],
-            "traffic": ncu_traffic(dname), "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
-            "share_of_step": d["share"], "launches_per_step": d["launches"],
+            "frac": round(top["tflops"] / peak_t, 4) if tensor_bound else top["hbm_frac"],
+            "frac_burst": top["tensor_frac_burst"], "frac_sustained": top["tensor_frac_sustained"],
+            "hbm_gbs": top["hbm_gbs"], "hbm_frac": top["hbm_frac"],
+            "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+            "traffic_source": (traffic or {}).get("source"),
+            "algorithmic_bytes_per_launch": top["bytes_per_launch"], "algorithmic_flops_per_launch": top["flops_per_launch"],
+            "avg_launch_ms": round(top["ms"] / max(1, top["launches"]), 5),
+            "peak_source": "%s; %s peak because the timed region lasts %.3f s" % (
+                peaks["source"], "burst" if use_burst else "sustained", region_s),
+            "share_of_step": top["share"], "launches_per_step": top["launches"],
         }
+        dcn_rec = None
+        dk = [(n, k) for n, k in kernels.items() if n.startswith("dcn_fused_kernel")]
+        if dk:
+            ms_d = sum(k["ms"] for _, k in dk)
+            fl_d = sum(k["flops_per_launch"] * k["launches"] for _, k in dk)
+            by_d = sum(k["bytes_per_launch"] * k["launches"] for _, k in dk)
+            dcn_rec = {"kernels": [n for n, _ in dk], "launches_per_step": sum(k["launches"] for _, k in dk),
+                       "ms_per_step": round(ms_d, 4), "share_of_step": round(ms_d / fwd_ms, 4),
+                       "tflops": round(fl_d / ms_d / 1e9, 1), "hbm_gbs": round(by_d / ms_d / 1e6, 1),
+                       "tensor_pipe_pct_of_burst_peak": round(100 * fl_d / ms_d / 1e9 / peaks["bf16_tflops"], 2),
+                       "tensor_pipe_pct_of_sustained_peak": round(100 * fl_d / ms_d / 1e9 / peaks["bf16_tflops_sustained"], 2),
+                       "hbm_pct_of_peak": round(100 * by_d / ms_d / 1e6 / peaks["hbm_gbs"], 2)}
+            tr = ncu_traffic(dk[0][0], _lib.LIB_PATH)
+            if tr:
+                dcn_rec["ncu"] = tr
+        for k in kernels.values():
+            k.pop("flops_per_launch"), k.pop("bytes_per_launch")
         tot_fl = sum(p["flops"] for p in prof)
         tot_by = sum(p["bytes"] for p in prof)
         step_s = ms_total / K * 1e-3
         step_roof = {
             "gflop_per_image": round(tot_fl / LOCAL_BATCH / 1e9, 2), "gb_per_image": round(tot_by / LOCAL_BATCH / 1e9, 4),
-            "tensor_frac": round(tot_fl / step_s / 1e12 / peaks["bf16_tflops_sustained"], 4),
+            "tensor_frac_burst": round(tot_fl / step_s / 1e12 / peaks["bf16_tflops"], 4),
+            "tensor_frac_sustained": round(tot_fl / step_s / 1e12 / peaks["bf16_tflops_sustained"], 4),
             "hbm_frac": round(tot_by / step_s / 1e9 / peaks["hbm_gbs"], 4),
             "forward_ms_eager_sum": round(fwd_ms, 3),
         }
+        surface = None
+        if world == 1 and not args.no_extras:
+            surface = time_surface(net, conf, torch, synth)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_reference(steps=4, warmup=1)
-            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            c8 = cpu_reference(steps=1, warmup=1, batch=LOCAL_BATCH, attention=args.attention)
+            c1 = cpu_reference(steps=3, warmup=0, batch=1, attention=args.attention)
+            cpu = {k: c8[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            cpu["batch1"] = {k: c1[k] for k in ("value", "unit", "sample")}
         line = {
             "metric": "images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": world * LOCAL_BATCH, "image": "384x1280",
-                       "backbone": "dla34", "align": True, "attention": args.attention,
+            "config": {"workload": WORKLOAD_ANAB if args.attention else WORKLOAD, "global_batch": world * LOCAL_BATCH,
+                       "image": "384x1280", "backbone": "dla34", "align": True, "attention": args.attention,
+                       "input": ("uint8 HWC images; Normalize + BGR->RGB + CHW (lib/augmentations.py:44-57) on the device, "
+                                 "inside every step" if args.input == "u8" else "pre-normalised fp32 NCHW"),
                        "parallelism": "dp%d (images sharded; all-gather of detections before NMS)" % world,
                        "l2": "4 rotating input batches; per-step activation footprint > 1 GB >> 126 MB L2",
                        "cuda_graph": True,
@@ -354,9 +497,13 @@ def main():
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "wall_s": wall, "pipeline": "H2D of batch i+1 and the detection tail + D2H of batch i overlap the trunk of batch i+1"},
-            "gpu_launches": det.launches_per_step * K,
-            "roofline": roofline, "kernels": kinds, "step_roofline": step_roof,
+            "gpu_launches": (det.launches_per_step + (1 if args.input == "u8" else 0)) * K,
+            "roofline": roofline, "dcn": dcn_rec, "kernels": kernels, "step_roofline": step_roof,
         }
+        if sustained is not None:
+            line["sustained"] = sustained
+        if surface is not None:
+            line["surface"] = surface
         if cpu is not None:
             line["cpu_baseline"] = cpu
     if line is not None:
@@ -369,6 +516,40 @@ def main():
         except Exception as e:  # noqa: BLE001  (the measurement is already printed)
             print("[bench] process-group teardown: %r" % (e,), file=sys.stderr)
     return 0
+
+
+def time_surface(net, conf, torch, synth):
+    """The reference-facing calls, timed the way the reference's scripts make them (host tensors in, numpy out):
+    im_detect_3d(im, net, conf, obj) = net(im) -> decode -> gpu_nms at batch 1 (lib/rpn_util.py:1416-1555), the
+    nn.Module forward net(x) at batch 8, and net.detect(x) at batch 8.  Every call includes its H2D / D2H and the
+    synchronisation the API implies, so the drop-in cost (engine lookup, clone of the outputs, .item() sync) is a number."""
+    import types
+    from m3dssd_b200.lib.rpn_util import im_detect_3d
+    out = {}
+    obj = types.SimpleNamespace(imH=CROP[0], imW=CROP[1], p2=None, scale_factor=1.0)
+    im1 = synth.make_images(1, CROP, seed=7)[0]
+    x8 = synth.make_images(LOCAL_BATCH, CROP, seed=8).pin_memory()
+    net.eval()
+
+    def timeit(fn, n, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n
+
+    t = timeit(lambda: im_detect_3d(im1, net, conf, obj), 20)
+    out["im_detect_3d_batch1"] = {"images_per_s": 1.0 / t, "ms_per_call": 1e3 * t}
+    with torch.no_grad():
+        t = timeit(lambda: [o.shape for o in net(x8.cuda(non_blocking=True))], 20)
+    out["rpn_forward_batch8"] = {"images_per_s": LOCAL_BATCH / t, "ms_per_call": 1e3 * t}
+    t = timeit(lambda: net.detect(x8.cuda(non_blocking=True))[1].cpu(), 20)
+    out["rpn_detect_batch8"] = {"images_per_s": LOCAL_BATCH / t, "ms_per_call": 1e3 * t}
+    out["note"] = "wall clock around host-tensor-in / host-result-out calls, synchronous (no pipelining across calls)"
+    return out
 
 
 if __name__ == "__main__":

@@ -142,6 +142,25 @@ int make_tmap_nhwc(CUtensorMap* map, const void* base, int N, int H, int W, int 
   return M3D_OK;
 }
 
+// bf16 NHWC activation as (C, W, H, N); box {box_c, box_w, box_h, 1}, no swizzle, zero fill outside the tensor:
+// the staged input window of the fused DCN kernel (plain ld.shared addressing: pixel-major, 2 * box_c bytes per pixel).
+int make_tmap_nhwc_plain(CUtensorMap* map, const void* base, int N, int H, int W, int C, int box_c, int box_w, int box_h) {
+  auto enc = get_encode();
+  M3D_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
+                           static_cast<cuuint64_t>(H) * W * C * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  M3D_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(nhwc plain N=%d H=%d W=%d C=%d box=%dx%dx%d) failed: %d", N, H, W,
+              C, box_c, box_w, box_h, static_cast<int>(r));
+  return M3D_OK;
+}
+
 // fp32 NHWC tensor as (C, W, H, N); box {box_c, tw, th, 1}, no swizzle (the fused heads' TMA store: box rows are the
 // box_c * 4 contiguous bytes of one pixel, clipped at the image edge).
 int make_tmap_nhwc_f32(CUtensorMap* map, const void* base, int N, int H, int W, int C, int box_c, int tw, int th,

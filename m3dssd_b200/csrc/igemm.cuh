@@ -91,6 +91,9 @@ struct alignas(64) ConvGatherParams {
   int res_cstride, res_coff;
   float slope;
   int total_tiles;
+  // dcn_fused.cu, staged-window mode: tmap_img is then the bf16 NHWC input as (C, W, H, N) with box
+  // {64, halo_w, halo_h, 1}; the window of a tile starts halo_x / halo_y pixels left of / above it
+  int halo_w, halo_h, halo_x, halo_y;
 };
 
 // Host launchers (igemm.cu).  Return 0 or a negative m3d error code.

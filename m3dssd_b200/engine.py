@@ -522,7 +522,8 @@ class Engine:
             self._run_nms()
 
     def launches_per_step(self, stage="detect"):
-        return self.n_launches + (0, 1, 4)[self._STAGES[stage]]
+        # decode = 2 histogram passes + compaction + finish (m3d_decode_topk); NMS = mask + sweep + gather of the kept rows
+        return self.n_launches + (0, 4, 7)[self._STAGES[stage]]
 
     def activation_nchw(self, name):
         """fp32 NCHW copy of a named intermediate activation (testing aid)."""

@@ -2,11 +2,12 @@
 
 The forward path has no cross-image dependency (eval-mode BN, per-image align / ANAB / NMS), so the
 only exchange is the one BASELINE.json's config 5 names: an all-gather of the fixed-shape per-image
-detection tensors ([local_batch, topk, 14] fp32 + counts) over NCCL/NVLink, followed by the batched
-NMS over the gathered set.  Every rank holds the gathered set; the NMS of gathered image g runs on
-rank g // local_batch (each image is suppressed exactly once per step instead of world_size times),
-and a second, tiny all-gather ([local_batch, 40, 14] kept rows + counts) leaves the full result on
-every rank.  The reference's equivalent is nn.DataParallel's scatter/replicate/gather per iteration
+detection tensors ([local_batch, topk, 14] fp32 + counts) over NCCL/NVLink, and the batched NMS of the
+gathered set.  Every rank ends up holding the gathered set; the NMS of gathered image g runs on rank
+g // local_batch (each image is suppressed exactly once per step instead of world_size times) -- and
+since that rank's share of the gathered set is exactly its own decode output, its NMS does not wait
+for the collective (the gather runs asynchronously beside it).  A second, tiny all-gather
+([local_batch, 40, 14] kept rows + counts) leaves the full result on every rank.  The reference's equivalent is nn.DataParallel's scatter/replicate/gather per iteration
 (lib/core.py:73-74, scripts/test_rpn_3d.py:50-51); here weights are replicated once.
 """
 import torch
@@ -41,7 +42,7 @@ def gather_detections(dets, det_num, group=None):
 
 
 class ShardedDetector:
-    """Per-rank engine + gather + NMS over the gathered detections (config 5)."""
+    """Per-rank engine + all-gather of the detection tensors + NMS (config 5)."""
 
     def __init__(self, net, local_batch, height, width, precision="bf16", use_graph=True):
         self.world = dist.get_world_size() if dist.is_initialized() else 1
@@ -52,22 +53,25 @@ class ShardedDetector:
         dev = e.dev
         self.num_keep = torch.zeros(gb, dtype=torch.int32, device=dev)
         self.kept = torch.zeros(gb, e.max_out, 14, dtype=torch.float32, device=dev)
-        lb = local_batch
-        self.keep_l = torch.zeros(lb, e.topk, dtype=torch.int32, device=dev)
-        self.num_keep_l = torch.zeros(lb, dtype=torch.int32, device=dev)
-        self.kept_l = torch.zeros(lb, e.max_out, 14, dtype=torch.float32, device=dev)
-        self.nms_ws = torch.zeros(ops.nms_workspace_bytes(lb, e.topk), dtype=torch.uint8, device=dev)
-        self.launches_per_step = e.launches_per_step("decode") + 3
+        # the gathered pre-NMS detection set of BASELINE config 5: [world * local_batch, topk, 14] + counts, on every rank
+        self.dets_all = torch.zeros(gb, e.topk, 14, dtype=torch.float32, device=dev)
+        self.det_num_all = torch.zeros(gb, dtype=torch.int32, device=dev)
+        self.launches_per_step = e.launches_per_step("detect")  # our kernels only (NCCL's all-gather kernels not counted)
 
     def _gather_and_nms(self):
+        """Runs on the engine's tail stream after decode.  The all-gather of the detection tensors is issued first,
+        asynchronously (NCCL runs it on its own stream); the NMS of gathered image g belongs to rank g // local_batch,
+        whose share of the gathered set IS its local decode output -- so the suppression starts at once on e.dets
+        instead of waiting for the collective, and only the small all-gather of the kept rows is on the critical path.
+        Both gathers are complete (stream-ordered) when this returns."""
         e = self.engine
-        dets, num = gather_detections(e.dets, e.det_num)
-        lo, hi = nms_slice(dets.shape[0], self.world, self.rank)
-        mine, nmine = dets[lo:hi], num[lo:hi]  # this rank's share of the gathered set
-        ops.nms_batched(mine, nmine, float(e.conf.nms_thres), self.nms_ws, self.keep_l, self.num_keep_l)
-        ops.gather_kept(mine, self.keep_l, self.num_keep_l, e.max_out, self.kept_l)
-        dist.all_gather_into_tensor(self.kept, self.kept_l)
-        dist.all_gather_into_tensor(self.num_keep, self.num_keep_l)
+        w1 = dist.all_gather_into_tensor(self.dets_all, e.dets, async_op=True)
+        w2 = dist.all_gather_into_tensor(self.det_num_all, e.det_num, async_op=True)
+        getattr(e, "_pipe", {}).get("nms", e._run_nms)()  # batched NMS + gather of this rank's images into e.kept / e.num_keep
+        dist.all_gather_into_tensor(self.kept, e.kept)
+        dist.all_gather_into_tensor(self.num_keep, e.num_keep)
+        w1.wait()
+        w2.wait()
 
     def step_pipelined(self, images=None):
         """Asynchronous step (see Engine.detect_pipelined): batch i's tail -- decode, [all-gather,] NMS --

@@ -133,6 +133,12 @@ CASES = [
     ("dcn_bf16_c512_256", dict(N=1, H=12, W=40, cins=[512], cout=256, deform=True, sigmoid_mask=True)),
     ("dcn_bf16_1x1", dict(N=1, H=12, W=40, cins=[128], cout=128, k=1, deform=True, res=False, slope=1.0)),
     ("dcn_bf16_bigoff", dict(N=1, H=12, W=40, cins=[64], cout=64, deform=True, offset_sigma=20.0)),
+    # fused DCN kernel, staged-window mode (dcn_fused.cu, BN = 128): node / proj / shape_align shapes, far offsets that
+    # leave the window (global fallback, entry by entry), image sizes that are not multiples of the tile
+    ("dcn_bf16_c128_node_res", dict(N=2, H=48, W=160, cins=[128], cout=128, deform=True, sigmoid_mask=True, res=True)),
+    ("dcn_bf16_c256_128_proj", dict(N=2, H=24, W=80, cins=[256], cout=128, deform=True, sigmoid_mask=True)),
+    ("dcn_bf16_c128_faroff", dict(N=1, H=24, W=80, cins=[128], cout=128, deform=True, offset_sigma=12.0)),
+    ("dcn_bf16_c128_ragged", dict(N=3, H=13, W=37, cins=[128], cout=128, deform=True, sigmoid_mask=True, offset_sigma=3.0)),
     ("f32_plain_c64", dict(N=1, H=12, W=40, cins=[64], cout=64, dtype=torch.float32)),
     ("f32_plain_s2_res", dict(N=1, H=24, W=80, cins=[64], cout=128, stride=2, dtype=torch.float32)),
     ("f32_concat", dict(N=1, H=12, W=40, cins=[64, 128], cout=64, k=1, dtype=torch.float32)),

@@ -28,8 +28,8 @@ pytestmark = pytest.mark.gpu
 
 # (rms bar, max bar) by layer type; bf16 storage: 2^-9 = 1.95e-3 relative per rounding
 BARS = {
-    "stem": (4e-3, 2e-2), "conv": (4e-3, 2e-2), "conv_f32out": (3e-3, 1.5e-2), "dcn": (6e-3, 3e-2),
-    "upsample": (3e-3, 1e-2), "head_mlp": (1e-2, 5e-2), "anab_pool": (1e-4, 1e-3), "anab_attention": (1e-2, 5e-2),
+    "stem": (4e-3, 2e-2), "conv": (5e-3, 2e-2), "conv_f32out": (3e-3, 1.5e-2), "dcn": (7e-3, 3e-2),
+    "upsample": (3e-3, 1e-2), "head_mlp": (1e-2, 5e-2), "anab_pool": (1e-4, 1e-3), "anab_attention": (1e-2, 1e-1),
 }
 
 

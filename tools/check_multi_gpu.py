@@ -25,6 +25,7 @@ det = ShardedDetector(net, LB, H, W, precision="bf16", use_graph=False)
 kept, num = det.step(images[lo:hi])
 torch.cuda.synchronize()
 kept, num = kept.clone(), num.clone()
+dets_all, det_num_all = det.dets_all.clone(), det.det_num_all.clone()  # the gathered pre-NMS set of config 5
 ref = net.engine(LB, H, W, precision="bf16", use_graph=False)
 ok = True
 for r in range(world):
@@ -32,6 +33,7 @@ for r in range(world):
     k, n = ref.detect(images[a:b])
     torch.cuda.synchronize()
     ok &= bool(torch.equal(n, num[a:b])) and bool(torch.equal(k, kept[a:b]))
+    ok &= bool(torch.equal(ref.dets, dets_all[a:b])) and bool(torch.equal(ref.det_num, det_num_all[a:b]))
 print("rank %d: sharded result == single-engine result on all %d images: %s (kept per image %s)" % (rank, world * LB, ok, num.tolist()), flush=True)
 dist.barrier()
 dist.destroy_process_group()

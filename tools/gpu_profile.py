@@ -22,11 +22,12 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--attention", default=None)
     ap.add_argument("--crop", default="384x1280")
+    ap.add_argument("--offset-sigma", type=float, default=2.0, help="sigma of the synthetic DCN offsets, pixels")
     a = ap.parse_args()
     H, W = [int(v) for v in a.crop.split("x")]
     conf = synth.make_conf(attention=a.attention, crop_size=(H, W))
     net = build(conf, "test")
-    synth.randomize_weights(net)
+    synth.randomize_weights(net, offset_sigma_px=a.offset_sigma)
     net = net.cuda()
     eng = net.engine(a.batch, H, W, precision=a.precision, use_graph=False)
     eng.forward(synth.make_images(a.batch, (H, W)).cuda())

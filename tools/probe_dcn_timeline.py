@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 from m3dssd_b200 import _lib
-_lib.LIB_PATH = os.path.join(ROOT, "build", "libm3d_probe.so")
+_lib.LIB_PATH = os.path.join(ROOT, "m3dssd_b200", "libm3dssd_b200.probe.so")  # M3D_VARIANT=probe M3D_NVCC_EXTRA=-DM3D_PROBE python -m m3dssd_b200.build
 from m3dssd_b200 import ops
 
 N, H, W, Cin, Cout, R = 8, 48, 160, 128, 128, 3
@@ -30,8 +30,10 @@ L.m3d_dcn_debug_read.argtypes = [C.c_void_p, C.c_int]
 L.m3d_dcn_debug_read(buf.ctypes.data, buf.size)
 a = buf.reshape(32, 8)
 t0 = a[31, 0]
-print("table build: %d clk" % (a[31, 1] - a[31, 0]))
+print("table wait at tile start: %d clk" % (a[31, 1] - a[31, 0]))
+print("epilogue of tile 0 (run by producer warp 0 after the first k-block of tile 1): entry %d, accumulator ready +%d, drained +%d clk"
+      % (a[31, 2] - t0, a[31, 3] - a[31, 2], a[31, 4] - a[31, 3]))
 print("kb:  P start  P slot free  P half0 done  P arrived | M full seen  M issued   (clk since tile start)")
-for kb in range(24):
+for kb in range(31):
     r = a[kb]
     print("%2d: %8d %8d %8d %8d | %8d %8d" % ((kb,) + tuple(int(v - t0) if v else -1 for v in r[:6])))
