@@ -112,10 +112,12 @@ int m3d_conv2d_nhwc(const m3d_conv_desc* desc, m3d_stream_t stream);
  * opaque workspace of m3d_dcn_v2_forward_workspace() bytes), shape errors are
  * returned (reference: THError, dcn_v2_cuda.c:33-38), the batch is handled in
  * one launch.  precision: M3D_F32 = reference accuracy (IEEE fp32 FMA), M3D_BF16X3 = 3-part bf16 split on tensor cores,
- * M3D_BF16 = bf16 operands / fp32 accumulate.  deformable_group must be 1.
+ * M3D_BF16 = bf16 operands / fp32 accumulate.  deformable_group > 1 (offset [B, dg*2*kh*kw, Ho, Wo], mask
+ * [B, dg*kh*kw, Ho, Wo], dcn_v2_im2col_cuda.cu:139-149) is evaluated as the sum of the dg single-group operators on
+ * channel slices; C must be a multiple of deformable_group.
  * ---------------------------------------------------------------------- */
 size_t m3d_dcn_v2_forward_workspace(int B, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil,
-                                    int precision);
+                                    int deformable_group, int precision);
 int m3d_dcn_v2_forward(const float* input, const float* weight, const float* bias, const float* offset,
                        const float* mask, float* output, int B, int C, int H, int W, int Cout, int kh, int kw,
                        int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int deformable_group,
@@ -124,8 +126,9 @@ int m3d_dcn_v2_forward(const float* input, const float* weight, const float* bia
 /* DCNv2 backward, reference FFI shape (replaces dcn_v2_cuda_backward, dcn_v2_cuda.h:19-29).  All five
  * gradients are OVERWRITTEN (the reference accumulates into buffers its Python wrapper zero-fills,
  * dcn_v2_func.py:44-48).  fp32; grad_input / grad_weight / grad_bias use float atomics, so -- as in the
- * reference -- the summation order is not reproducible bit for bit.  deformable_group must be 1. */
-size_t m3d_dcn_v2_backward_workspace(int B, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil);
+ * reference -- the summation order is not reproducible bit for bit.  deformable_group >= 1 as in the forward. */
+size_t m3d_dcn_v2_backward_workspace(int B, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil,
+                                     int deformable_group);
 int m3d_dcn_v2_backward(const float* input, const float* weight, const float* offset, const float* mask,
                         const float* grad_output, float* grad_input, float* grad_weight, float* grad_bias,
                         float* grad_offset, float* grad_mask, int B, int C, int H, int W, int Cout, int kh, int kw,

@@ -28,8 +28,8 @@ _SIGS = {
     "m3d_nhwc_to_nchw": [vp, i, vp, i, i, i, i, i, i, i, vp],
 }
 _SIZE_FNS = {
-    "m3d_dcn_v2_forward_workspace": [i] * 11,
-    "m3d_dcn_v2_backward_workspace": [i] * 10,
+    "m3d_dcn_v2_forward_workspace": [i] * 12,
+    "m3d_dcn_v2_backward_workspace": [i] * 11,
     "m3d_nms_workspace_bytes": [i, i],
     "m3d_anab_pool_workspace": [i, i, i, vp, i, i],
     "m3d_anab_attention_workspace": [i, i],

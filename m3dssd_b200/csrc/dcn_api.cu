@@ -5,6 +5,7 @@
 // gather+tcgen05 kernel (igemm.cu) does bias + sampling + contraction.
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include <cstdint>
 
 #include "common.cuh"
@@ -71,17 +72,50 @@ static DcnLayout dcn_layout(int B, int C, int H, int W, int Cout, int kh, int kw
 
 }  // namespace m3d
 
-using namespace m3d;
-
 extern "C" int m3d_nchw_to_nhwc(const void* in, int in_dtype, void* out, int out_dtype, int N, int C, int H, int W,
                                 int out_cstride, int out_coff, m3d_stream_t stream);
 extern "C" int m3d_nhwc_to_nchw(const void* in, int in_dtype, void* out, int out_dtype, int N, int C, int H, int W,
                                 int in_cstride, int in_coff, m3d_stream_t stream);
 
-extern "C" size_t m3d_dcn_v2_forward_workspace(int B, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad,
-                                               int dil, int precision) {
-  return dcn_layout(B, C, H, W, Cout, kh, kw, stride, pad, dil, precision).total;
+namespace m3d {
+// Slices for deformable_group > 1 (dcn_v2_im2col_cuda.cu:139-149: channel c belongs to group c / (C / dg), and group g
+// of sample b reads offset channels [(b*dg + g) * 2*kh*kw, ...) and mask channels [(b*dg + g) * kh*kw, ...)): the
+// operator is the SUM over groups of single-group operators on channel slices, which is how it is evaluated here.
+struct GroupSlices {
+  size_t x, off, msk, w, out, total;
+};
+static inline size_t al256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+GroupSlices group_slices(int B, int Cg, int H, int W, int Cout, int KK, int Ho, int Wo) {
+  GroupSlices g;
+  g.x = align256(static_cast<size_t>(B) * Cg * H * W * 4);
+  g.off = align256(static_cast<size_t>(B) * 2 * KK * Ho * Wo * 4);
+  g.msk = align256(static_cast<size_t>(B) * KK * Ho * Wo * 4);
+  g.w = align256(static_cast<size_t>(Cout) * Cg * KK * 4);
+  g.out = align256(static_cast<size_t>(B) * Cout * Ho * Wo * 4);
+  g.total = g.x + g.off + g.msk + g.w + g.out;
+  return g;
 }
+
+__global__ void add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, long n) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
+    y[i] += x[i];
+}
+
+}  // namespace m3d
+using namespace m3d;
+
+extern "C" size_t m3d_dcn_v2_forward_workspace(int B, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad,
+                                               int dil, int deformable_group, int precision) {
+  const int dg = deformable_group < 1 ? 1 : deformable_group;
+  if (dg == 1) return dcn_layout(B, C, H, W, Cout, kh, kw, stride, pad, dil, precision).total;
+  const DcnLayout L = dcn_layout(B, C / dg, H, W, Cout, kh, kw, stride, pad, dil, precision);
+  return L.total + group_slices(B, C / dg, H, W, Cout, kh * kw, L.Ho, L.Wo).total;
+}
+
+static int dcn_forward_one_group(const float* input, const float* weight, const float* bias, const float* offset,
+                                 const float* mask, float* output, int B, int C, int H, int W, int Cout, int kh, int kw,
+                                 int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int precision,
+                                 void* workspace, size_t workspace_bytes, m3d_stream_t stream_);
 
 extern "C" int m3d_dcn_v2_forward(const float* input, const float* weight, const float* bias, const float* offset,
                                   const float* mask, float* output, int B, int C, int H, int W, int Cout, int kh, int kw,
@@ -89,6 +123,57 @@ extern "C" int m3d_dcn_v2_forward(const float* input, const float* weight, const
                                   int deformable_group, int precision, void* workspace, size_t workspace_bytes,
                                   m3d_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int dg = deformable_group;
+  if (dg == 1)
+    return dcn_forward_one_group(input, weight, bias, offset, mask, output, B, C, H, W, Cout, kh, kw, stride_h, stride_w,
+                                 pad_h, pad_w, dil_h, dil_w, precision, workspace, workspace_bytes, stream_);
+  M3D_REQUIRE(input && weight && offset && mask && output, "NULL tensor pointer");
+  M3D_REQUIRE(dg >= 1 && C % dg == 0, "channels (%d) must be a multiple of deformable_group (%d)", C, dg);
+  const int Cg = C / dg, KK = kh * kw;
+  const DcnLayout L = dcn_layout(B, Cg, H, W, Cout, kh, kw, stride_h, pad_h, dil_h, precision);
+  M3D_REQUIRE(L.Ho >= 1 && L.Wo >= 1, "empty output");
+  const GroupSlices G = group_slices(B, Cg, H, W, Cout, KK, L.Ho, L.Wo);
+  if (workspace == nullptr || workspace_bytes < L.total + G.total) {
+    set_last_error("DCNv2 workspace too small: %zu < %zu", workspace_bytes, L.total + G.total);
+    return M3D_ERR_WORKSPACE;
+  }
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* xg = reinterpret_cast<float*>(ws);
+  float* og = reinterpret_cast<float*>(ws + G.x);
+  float* mg = reinterpret_cast<float*>(ws + G.x + G.off);
+  float* wg = reinterpret_cast<float*>(ws + G.x + G.off + G.msk);
+  float* yg = reinterpret_cast<float*>(ws + G.x + G.off + G.msk + G.w);
+  void* inner = ws + G.total;
+  const size_t hw = static_cast<size_t>(H) * W * 4, howo = static_cast<size_t>(L.Ho) * L.Wo * 4;
+  const long nout = static_cast<long>(B) * Cout * L.Ho * L.Wo;
+  for (int g = 0; g < dg; ++g) {
+    M3D_CUDA_OK(cudaMemcpy2DAsync(xg, Cg * hw, input + static_cast<size_t>(g) * Cg * H * W, C * hw, Cg * hw, B,
+                                  cudaMemcpyDeviceToDevice, stream));
+    M3D_CUDA_OK(cudaMemcpy2DAsync(og, 2 * KK * howo, offset + static_cast<size_t>(g) * 2 * KK * L.Ho * L.Wo,
+                                  dg * 2 * KK * howo, 2 * KK * howo, B, cudaMemcpyDeviceToDevice, stream));
+    M3D_CUDA_OK(cudaMemcpy2DAsync(mg, KK * howo, mask + static_cast<size_t>(g) * KK * L.Ho * L.Wo, dg * KK * howo,
+                                  KK * howo, B, cudaMemcpyDeviceToDevice, stream));
+    M3D_CUDA_OK(cudaMemcpy2DAsync(wg, static_cast<size_t>(Cg) * KK * 4, weight + static_cast<size_t>(g) * Cg * KK,
+                                  static_cast<size_t>(C) * KK * 4, static_cast<size_t>(Cg) * KK * 4, Cout,
+                                  cudaMemcpyDeviceToDevice, stream));
+    const int rc = dcn_forward_one_group(xg, wg, g == 0 ? bias : nullptr, og, mg, g == 0 ? output : yg, B, Cg, H, W, Cout,
+                                         kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, precision, inner,
+                                         workspace_bytes - G.total, stream_);
+    if (rc) return rc;
+    if (g > 0) {
+      add_inplace_kernel<<<static_cast<int>(std::min<long>((nout + 255) / 256, 4096)), 256, 0, stream>>>(output, yg, nout);
+      M3D_CUDA_OK(cudaGetLastError());
+    }
+  }
+  return M3D_OK;
+}
+
+static int dcn_forward_one_group(const float* input, const float* weight, const float* bias, const float* offset,
+                                 const float* mask, float* output, int B, int C, int H, int W, int Cout, int kh, int kw,
+                                 int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int precision,
+                                 void* workspace, size_t workspace_bytes, m3d_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int deformable_group = 1;
   M3D_REQUIRE(input && weight && offset && mask && output, "NULL tensor pointer");
   M3D_REQUIRE(B >= 1 && C >= 1 && H >= 1 && W >= 1 && Cout >= 1 && kh >= 1 && kw >= 1, "bad shape");
   if (deformable_group != 1 || stride_h != stride_w || pad_h != pad_w || dil_h != dil_w || kh * kw > 9) {

@@ -256,10 +256,35 @@ extern "C" int m3d_nchw_to_nhwc(const void* in, int in_dtype, void* out, int out
 extern "C" int m3d_nhwc_to_nchw(const void* in, int in_dtype, void* out, int out_dtype, int N, int C, int H, int W,
                                 int in_cstride, int in_coff, m3d_stream_t stream);
 
-extern "C" size_t m3d_dcn_v2_backward_workspace(int B, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad,
-                                                int dil) {
-  return bwd_layout(B, C, H, W, Cout, kh, kw, stride, pad, dil).total;
+// deformable_group > 1: the operator is a sum over channel groups (see dcn_api.cu), so its backward is the single-group
+// backward of every group on slices: inputs sliced in, input / offset / mask / weight gradients scattered back;
+// grad_bias does not depend on the group.
+struct BwdGroupSlices {
+  size_t x, off, msk, w, gx, goff, gmsk, gw, total;
+};
+static BwdGroupSlices bwd_group_slices(int B, int Cg, int H, int W, int Cout, int KK, int Ho, int Wo) {
+  BwdGroupSlices g;
+  g.x = g.gx = al(static_cast<size_t>(B) * Cg * H * W * 4);
+  g.off = g.goff = al(static_cast<size_t>(B) * 2 * KK * Ho * Wo * 4);
+  g.msk = g.gmsk = al(static_cast<size_t>(B) * KK * Ho * Wo * 4);
+  g.w = g.gw = al(static_cast<size_t>(Cout) * Cg * KK * 4);
+  g.total = 2 * (g.x + g.off + g.msk + g.w);
+  return g;
 }
+
+extern "C" size_t m3d_dcn_v2_backward_workspace(int B, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad,
+                                                int dil, int deformable_group) {
+  const int dg = deformable_group < 1 ? 1 : deformable_group;
+  if (dg == 1) return bwd_layout(B, C, H, W, Cout, kh, kw, stride, pad, dil).total;
+  const BwdLayout L = bwd_layout(B, C / dg, H, W, Cout, kh, kw, stride, pad, dil);
+  return L.total + bwd_group_slices(B, C / dg, H, W, Cout, kh * kw, L.Ho, L.Wo).total;
+}
+
+static int dcn_backward_one_group(const float* input, const float* weight, const float* offset, const float* mask,
+                                  const float* grad_output, float* grad_input, float* grad_weight, float* grad_bias,
+                                  float* grad_offset, float* grad_mask, int B, int C, int H, int W, int Cout, int kh,
+                                  int kw, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                                  void* workspace, size_t workspace_bytes, m3d_stream_t stream_);
 
 extern "C" int m3d_dcn_v2_backward(const float* input, const float* weight, const float* offset, const float* mask,
                                    const float* grad_output, float* grad_input, float* grad_weight, float* grad_bias,
@@ -267,6 +292,62 @@ extern "C" int m3d_dcn_v2_backward(const float* input, const float* weight, cons
                                    int kw, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
                                    int deformable_group, void* workspace, size_t workspace_bytes, m3d_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int dg = deformable_group;
+  if (dg == 1)
+    return dcn_backward_one_group(input, weight, offset, mask, grad_output, grad_input, grad_weight, grad_bias,
+                                  grad_offset, grad_mask, B, C, H, W, Cout, kh, kw, stride_h, stride_w, pad_h, pad_w,
+                                  dil_h, dil_w, workspace, workspace_bytes, stream_);
+  M3D_REQUIRE(input && weight && offset && mask && grad_output && grad_input && grad_weight && grad_bias && grad_offset &&
+                  grad_mask,
+              "NULL tensor pointer");
+  M3D_REQUIRE(dg >= 1 && C % dg == 0, "channels (%d) must be a multiple of deformable_group (%d)", C, dg);
+  const int Cg = C / dg, KK = kh * kw;
+  const BwdLayout L = bwd_layout(B, Cg, H, W, Cout, kh, kw, stride_h, pad_h, dil_h);
+  M3D_REQUIRE(L.Ho >= 1 && L.Wo >= 1, "empty output");
+  const BwdGroupSlices G = bwd_group_slices(B, Cg, H, W, Cout, KK, L.Ho, L.Wo);
+  if (workspace == nullptr || workspace_bytes < L.total + G.total) {
+    set_last_error("DCNv2 backward workspace too small: %zu < %zu", workspace_bytes, L.total + G.total);
+    return M3D_ERR_WORKSPACE;
+  }
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  size_t o = 0;
+  auto take = [&](size_t n) { float* q = reinterpret_cast<float*>(ws + o); o += n; return q; };
+  float *xg = take(G.x), *og = take(G.off), *mg = take(G.msk), *wg = take(G.w);
+  float *gxg = take(G.gx), *gog = take(G.goff), *gmg = take(G.gmsk), *gwg = take(G.gw);
+  void* inner = ws + G.total;
+  const size_t hw = static_cast<size_t>(H) * W * 4, howo = static_cast<size_t>(L.Ho) * L.Wo * 4;
+  const size_t wrow = static_cast<size_t>(Cg) * KK * 4;
+  for (int g = 0; g < dg; ++g) {
+    const size_t xo = static_cast<size_t>(g) * Cg * H * W, oo = static_cast<size_t>(g) * 2 * KK * L.Ho * L.Wo;
+    const size_t mo = static_cast<size_t>(g) * KK * L.Ho * L.Wo, wo = static_cast<size_t>(g) * Cg * KK;
+    M3D_CUDA_OK(cudaMemcpy2DAsync(xg, Cg * hw, input + xo, C * hw, Cg * hw, B, cudaMemcpyDeviceToDevice, stream));
+    M3D_CUDA_OK(cudaMemcpy2DAsync(og, 2 * KK * howo, offset + oo, dg * 2 * KK * howo, 2 * KK * howo, B,
+                                  cudaMemcpyDeviceToDevice, stream));
+    M3D_CUDA_OK(cudaMemcpy2DAsync(mg, KK * howo, mask + mo, dg * KK * howo, KK * howo, B, cudaMemcpyDeviceToDevice, stream));
+    M3D_CUDA_OK(cudaMemcpy2DAsync(wg, wrow, weight + wo, static_cast<size_t>(C) * KK * 4, wrow, Cout,
+                                  cudaMemcpyDeviceToDevice, stream));
+    const int rc = dcn_backward_one_group(xg, wg, og, mg, grad_output, gxg, gwg, grad_bias, gog, gmg, B, Cg, H, W, Cout,
+                                          kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, inner,
+                                          workspace_bytes - G.total, stream_);
+    if (rc) return rc;
+    M3D_CUDA_OK(cudaMemcpy2DAsync(grad_input + xo, C * hw, gxg, Cg * hw, Cg * hw, B, cudaMemcpyDeviceToDevice, stream));
+    M3D_CUDA_OK(cudaMemcpy2DAsync(grad_offset + oo, dg * 2 * KK * howo, gog, 2 * KK * howo, 2 * KK * howo, B,
+                                  cudaMemcpyDeviceToDevice, stream));
+    M3D_CUDA_OK(cudaMemcpy2DAsync(grad_mask + mo, dg * KK * howo, gmg, KK * howo, KK * howo, B, cudaMemcpyDeviceToDevice,
+                                  stream));
+    M3D_CUDA_OK(cudaMemcpy2DAsync(grad_weight + wo, static_cast<size_t>(C) * KK * 4, gwg, wrow, wrow, Cout,
+                                  cudaMemcpyDeviceToDevice, stream));
+  }
+  return M3D_OK;
+}
+
+static int dcn_backward_one_group(const float* input, const float* weight, const float* offset, const float* mask,
+                                  const float* grad_output, float* grad_input, float* grad_weight, float* grad_bias,
+                                  float* grad_offset, float* grad_mask, int B, int C, int H, int W, int Cout, int kh,
+                                  int kw, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                                  void* workspace, size_t workspace_bytes, m3d_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int deformable_group = 1;
   M3D_REQUIRE(input && weight && offset && mask && grad_output && grad_input && grad_weight && grad_bias && grad_offset &&
                   grad_mask,
               "NULL tensor pointer");

@@ -610,6 +610,35 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const unsigned
   if (tid == 0) num_keep[n] = s_kept;
 }
 
+// Greedy sweep for MORE than 4096 boxes per image (the fast kernel above keeps the removed-set in 64 shared words):
+// the reference's host loop (nms_kernel.cu:124-139) on the device, one block per image, the removed-set in global
+// memory.  One block barrier per kept box: slow, exact, and only reached through m3d_nms / m3d_nms_batched with
+// max_n > 4096 (the reference accepts any box count; the engine's top-K is 3000).
+__global__ void __launch_bounds__(256) nms_sweep_generic_kernel(const unsigned long long* __restrict__ mask,
+                                                                const int* __restrict__ num, int max_n, int col_blocks,
+                                                                unsigned long long* __restrict__ remv_all,
+                                                                int* __restrict__ keep, int* __restrict__ num_keep) {
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const int nb = num ? num[n] : max_n;
+  const unsigned long long* m = mask + static_cast<long>(n) * max_n * col_blocks;
+  unsigned long long* remv = remv_all + static_cast<long>(n) * col_blocks;
+  int* kp = keep + static_cast<long>(n) * max_n;
+  for (int w = tid; w < col_blocks; w += blockDim.x) remv[w] = 0ull;
+  __syncthreads();
+  int kept = 0;
+  for (int i = 0; i < nb; ++i) {
+    const bool removed = (remv[i >> 6] >> (i & 63)) & 1ull;  // same value in every thread (written before the barrier)
+    if (!removed) {
+      if (tid == 0) kp[kept] = i;
+      ++kept;
+      const unsigned long long* row = m + static_cast<long>(i) * col_blocks;
+      for (int w = (i >> 6) + tid; w < col_blocks; w += blockDim.x) remv[w] |= row[w];
+      __syncthreads();
+    }
+  }
+  if (tid == 0) num_keep[n] = kept;
+}
+
 __global__ void gather_kept_kernel(const float* __restrict__ dets, int row_len, int max_n, const int* __restrict__ keep,
                                    const int* __restrict__ num_keep, int max_out, float* __restrict__ out) {
   const int n = blockIdx.y;
@@ -628,6 +657,7 @@ struct NmsWorkspace {
   unsigned long long* mask = nullptr;
   int* keep = nullptr;
   int* num_keep = nullptr;
+  unsigned long long* remv = nullptr;  // removed-set of the generic sweep (> 4096 boxes)
   int cap = 0, device = -1;
 };
 static NmsWorkspace g_nms_ws;
@@ -640,7 +670,9 @@ static inline cudaStream_t S(m3d_stream_t s) { return reinterpret_cast<cudaStrea
 
 extern "C" size_t m3d_nms_workspace_bytes(int batch, int max_n) {
   const size_t cb = (max_n + 63) / 64;
-  return static_cast<size_t>(batch) * max_n * cb * sizeof(unsigned long long);
+  // suppression bitmask [batch][max_n][cb] + (more than 4096 boxes per image: generic sweep) removed-set [batch][cb]
+  return static_cast<size_t>(batch) * max_n * cb * sizeof(unsigned long long) +
+         (cb > 64 ? static_cast<size_t>(batch) * cb * sizeof(unsigned long long) : 0);
 }
 
 extern "C" int m3d_nms_batched(const float* boxes, int box_stride, const int* num, int batch, int max_n, float thresh,
@@ -648,7 +680,6 @@ extern "C" int m3d_nms_batched(const float* boxes, int box_stride, const int* nu
   M3D_REQUIRE(boxes && keep && num_keep && workspace, "NULL pointer");
   M3D_REQUIRE(batch >= 1 && max_n >= 1 && box_stride >= 4, "bad geometry");
   const int cb = (max_n + 63) / 64;
-  M3D_REQUIRE(cb <= 64, "at most 4096 boxes per image (got %d)", max_n);
   if (workspace_bytes < m3d_nms_workspace_bytes(batch, max_n)) {
     set_last_error("NMS workspace too small: %zu < %zu", workspace_bytes, m3d_nms_workspace_bytes(batch, max_n));
     return M3D_ERR_WORKSPACE;
@@ -657,7 +688,12 @@ extern "C" int m3d_nms_batched(const float* boxes, int box_stride, const int* nu
   dim3 grid(cb, cb, batch);
   nms_mask_kernel<<<grid, 128, 0, S(stream)>>>(boxes, box_stride, num, max_n, thresh, mask, cb);
   M3D_CUDA_OK(cudaGetLastError());
-  nms_sweep_kernel<<<batch, kSweepThreads, 0, S(stream)>>>(mask, num, max_n, cb, keep, num_keep);
+  if (cb <= 64) {
+    nms_sweep_kernel<<<batch, kSweepThreads, 0, S(stream)>>>(mask, num, max_n, cb, keep, num_keep);
+  } else {
+    unsigned long long* remv = mask + static_cast<size_t>(batch) * max_n * cb;
+    nms_sweep_generic_kernel<<<batch, 256, 0, S(stream)>>>(mask, num, max_n, cb, remv, keep, num_keep);
+  }
   M3D_CUDA_OK(cudaGetLastError());
   return M3D_OK;
 }
@@ -672,14 +708,13 @@ extern "C" int m3d_nms(int* keep_out, int* num_out, const float* boxes_host, int
     return M3D_OK;
   }
   M3D_REQUIRE(boxes_host != nullptr && boxes_dim >= 4, "bad boxes");
-  M3D_REQUIRE(boxes_num <= 4096, "at most 4096 boxes (got %d)", boxes_num);
   int cur = 0;
   M3D_CUDA_OK(cudaGetDevice(&cur));
   if (cur != device_id) M3D_CUDA_OK(cudaSetDevice(device_id));
   std::lock_guard<std::mutex> lock(g_nms_ws.mu);
   NmsWorkspace& ws = g_nms_ws;
   if (ws.device != device_id || ws.cap < boxes_num) {
-    if (ws.boxes) cudaFree(ws.boxes), cudaFree(ws.mask), cudaFree(ws.keep), cudaFree(ws.num_keep);
+    if (ws.boxes) cudaFree(ws.boxes), cudaFree(ws.mask), cudaFree(ws.keep), cudaFree(ws.num_keep), cudaFree(ws.remv);
     ws.cap = std::max(boxes_num, 3072);
     ws.device = device_id;
     const size_t cb = (ws.cap + 63) / 64;
@@ -687,6 +722,7 @@ extern "C" int m3d_nms(int* keep_out, int* num_out, const float* boxes_host, int
     M3D_CUDA_OK(cudaMalloc(&ws.mask, sizeof(unsigned long long) * ws.cap * cb));
     M3D_CUDA_OK(cudaMalloc(&ws.keep, sizeof(int) * ws.cap));
     M3D_CUDA_OK(cudaMalloc(&ws.num_keep, sizeof(int)));
+    M3D_CUDA_OK(cudaMalloc(&ws.remv, sizeof(unsigned long long) * cb));
   }
   M3D_REQUIRE(boxes_dim <= 16, "boxes_dim %d > 16", boxes_dim);
   cudaStream_t st = cudaStreamPerThread;
@@ -695,7 +731,10 @@ extern "C" int m3d_nms(int* keep_out, int* num_out, const float* boxes_host, int
   dim3 grid(cb, cb, 1);
   nms_mask_kernel<<<grid, 128, 0, st>>>(ws.boxes, boxes_dim, nullptr, boxes_num, nms_overlap_thresh, ws.mask, cb);
   M3D_CUDA_OK(cudaGetLastError());
-  nms_sweep_kernel<<<1, kSweepThreads, 0, st>>>(ws.mask, nullptr, boxes_num, cb, ws.keep, ws.num_keep);
+  if (cb <= 64)
+    nms_sweep_kernel<<<1, kSweepThreads, 0, st>>>(ws.mask, nullptr, boxes_num, cb, ws.keep, ws.num_keep);
+  else  // more than 4096 boxes: exact generic sweep (the reference accepts any box count)
+    nms_sweep_generic_kernel<<<1, 256, 0, st>>>(ws.mask, nullptr, boxes_num, cb, ws.remv, ws.keep, ws.num_keep);
   M3D_CUDA_OK(cudaGetLastError());
   M3D_CUDA_OK(cudaMemcpyAsync(num_out, ws.num_keep, sizeof(int), cudaMemcpyDeviceToHost, st));
   M3D_CUDA_OK(cudaStreamSynchronize(st));

@@ -350,7 +350,10 @@ def dcn_v2_forward(input, offset, mask, weight, bias, stride, padding, dilation,
     if tuple(offset.shape) != (B, 2 * deformable_groups * kh * kw, Ho, Wo) or \
             tuple(mask.shape) != (B, deformable_groups * kh * kw, Ho, Wo):
         raise RuntimeError("offset/mask shape does not match the output size %dx%d" % (Ho, Wo))
-    ws_bytes = lib().m3d_dcn_v2_forward_workspace(B, Cin, H, W, Cout, kh, kw, stride, padding, dilation, precision)
+    if Cin % deformable_groups != 0:
+        raise RuntimeError("input channels (%d) must be a multiple of deformable_groups (%d)" % (Cin, deformable_groups))
+    ws_bytes = lib().m3d_dcn_v2_forward_workspace(B, Cin, H, W, Cout, kh, kw, stride, padding, dilation,
+                                                  deformable_groups, precision)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=input.device)
     out = torch.empty(B, Cout, Ho, Wo, dtype=torch.float32, device=input.device)
     args = [t.contiguous().float() for t in (input, weight, bias, offset, mask)]
@@ -401,7 +404,7 @@ def dcn_v2_backward(input, offset, mask, weight, grad_output, stride, padding, d
     gi, go, gm = torch.empty_like(args[0]), torch.empty_like(args[2]), torch.empty_like(args[3])
     gw = torch.empty_like(args[1])
     gb = torch.empty(Cout, dtype=torch.float32, device=input.device)
-    n = lib().m3d_dcn_v2_backward_workspace(B, Cin, H, W, Cout, kh, kw, stride, padding, dilation)
+    n = lib().m3d_dcn_v2_backward_workspace(B, Cin, H, W, Cout, kh, kw, stride, padding, dilation, deformable_groups)
     ws = torch.empty(n, dtype=torch.uint8, device=input.device)
     check(lib().m3d_dcn_v2_backward(*[_p(t) for t in args], _p(gi), _p(gw), _p(gb), _p(go), _p(gm), B, Cin, H, W, Cout,
                                     kh, kw, stride, stride, padding, padding, dilation, dilation, deformable_groups,

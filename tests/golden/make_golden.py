@@ -26,6 +26,8 @@ CONFIGS = {
     "base": dict(attention=None, center_align=False, shape_align=False),
     "align": dict(attention=None, center_align=True, shape_align=True),
     "anab": dict(attention="ANAB", center_align=True, shape_align=True),
+    # the backbone of the reference's shipped configs (scripts/config/kitti_3d_base.py:46): Bottleneck blocks, residual roots
+    "dla102": dict(attention=None, center_align=False, shape_align=False, back_bone="dla102"),
 }
 CROP = (96, 320)
 
@@ -69,6 +71,8 @@ def main():
     torch.cuda.FloatTensor = torch.FloatTensor
     for name, kw in CONFIGS.items():
         conf = ns.EasyDict(synth.make_conf(crop_size=CROP, **kw))
+        if kw.get("back_bone") == "dla102":
+            conf.pre_train = None  # the reference's dla102() downloads ImageNet weights unless this `is None` (pose_dla_dcn.py:439)
         from m3dssd_b200.model.M3d_inference_align import build as our_build
         sd = synth.randomize_weights(our_build(synth.make_conf(crop_size=CROP, **kw), "test"))
         net = ns.rpn.build(conf, "test")  # the unmodified reference modules, fed the same state_dict

@@ -127,3 +127,50 @@ def test_dcn_v2_backward_vs_oracle(shape):
     for name, t, r in zip(("input", "offset", "mask", "weight", "bias"), ts, ref):
         err = np.abs(t.grad.cpu().numpy() - r).max() / max(np.abs(r).max(), 1e-6)
         assert err < 2e-5, (name, err)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 12, 16, 64, 3, 1, 1, 2), (1, 12, 7, 9, 5, 3, 1, 1, 3), (1, 8, 6, 7, 4, 1, 1, 0, 4)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 3e-6), ("bf16x3", 3e-5)])
+def test_dcn_v2_deformable_groups_forward_backward_vs_oracle(shape, precision, tol):
+    """deformable_groups > 1 (the reference's example_dconv uses dg = 2, model/DCNv2/test.py:169-179; index math
+    dcn_v2_im2col_cuda.cu:139-149): forward and all five gradients vs the C oracle."""
+    from m3dssd_b200.model.DCNv2.dcn_v2_func import DCNv2Function
+    B, Cin, H, W, Cout, k, s, p, dg = shape
+    rng = np.random.default_rng(sum(shape) + 7)
+    x = rng.standard_normal((B, Cin, H, W)).astype(np.float32)
+    Ho, Wo = O.dcn_out_shape(H, W, k, k, s, p, 1)
+    off = (rng.standard_normal((B, 2 * dg * k * k, Ho, Wo)) * 2.5).astype(np.float32)
+    m = rng.random((B, dg * k * k, Ho, Wo)).astype(np.float32)
+    w = (rng.standard_normal((Cout, Cin, k, k)) / np.sqrt(Cin * k * k)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    gy = rng.standard_normal((B, Cout, Ho, Wo)).astype(np.float32)
+    ref = O.dcn_v2_forward(x, off, m, w, b, s, p, 1, dg)
+    ts = [torch.from_numpy(a).cuda().requires_grad_(True) for a in (x, off, m, w, b)]
+    out = DCNv2Function(s, p, 1, dg, precision=precision)(*ts)
+    err = np.abs(out.detach().cpu().numpy() - ref).max() / max(np.abs(ref).max(), 1.0)
+    assert out.shape == ref.shape and err < tol, err
+    if precision == "fp32":
+        out.backward(torch.from_numpy(gy).cuda())
+        gref = O.dcn_v2_backward(x, off, m, w, gy, s, p, 1, dg)
+        for name, t, r in zip(("input", "offset", "mask", "weight", "bias"), ts, gref):
+            e = np.abs(t.grad.cpu().numpy() - r).max() / max(np.abs(r).max(), 1e-6)
+            assert e < 2e-5, (name, e)
+
+
+def test_dcn_module_with_two_deformable_groups():
+    """DCN(64, 64, 3, 1, 1, deformable_groups=2) as in the reference's example_dconv: conv_offset_mask has
+    dg * 27 channels; the module output matches the oracle on the module's own offsets / masks."""
+    from m3dssd_b200.model.DCNv2.dcn_v2 import DCN
+    torch.manual_seed(1)
+    dcn = DCN(64, 64, 3, 1, 1, deformable_groups=2).cuda()
+    assert dcn.conv_offset_mask.out_channels == 2 * 27
+    dcn.conv_offset_mask.weight.data.normal_(0, 0.05)
+    dcn.conv_offset_mask.bias.data.normal_(0, 0.2)
+    x = torch.randn(2, 64, 16, 16).cuda()
+    with torch.no_grad():
+        y = dcn(x)
+        om = dcn.conv_offset_mask(x)
+    off, mask = om[:, :36].cpu().numpy(), torch.sigmoid(om[:, 36:]).cpu().numpy()
+    ref = O.dcn_v2_forward(x.cpu().numpy(), off, mask, dcn.weight.detach().cpu().numpy(),
+                           dcn.bias.detach().cpu().numpy(), 1, 1, 1, 2)
+    assert np.abs(y.cpu().numpy() - ref).max() < 3e-6 * max(np.abs(ref).max(), 1)

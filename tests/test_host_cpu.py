@@ -144,3 +144,24 @@ def test_gather_detections_world2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_pre_train_registers_fc_like_the_reference():
+    """conf.pre_train=True (every shipped reference config): the reference's load_pretrained_model registers `fc` on
+    the DLA for good (model/pose_dla_dcn.py:399-416), so its checkpoints carry base.base.fc.*; ours skips the download
+    with a warning and registers the same module, so those checkpoints load with strict=True."""
+    import warnings
+    from m3dssd_b200 import synth
+    from m3dssd_b200.model.M3d_inference_align import build
+    conf = synth.make_conf(crop_size=(96, 320))
+    conf.pre_train = True
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        net = build(conf, "test")
+    assert any("pre_train" in str(x.message) for x in w)
+    sd = net.state_dict()
+    assert tuple(sd["base.base.fc.weight"].shape) == (1000, 512, 1, 1) and tuple(sd["base.base.fc.bias"].shape) == (1000,)
+    conf.pre_train = False
+    plain = build(conf, "test")
+    assert set(sd) - set(plain.state_dict()) == {"base.base.fc.weight", "base.base.fc.bias"}
+    net.load_state_dict(sd, strict=True)

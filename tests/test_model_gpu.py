@@ -31,9 +31,9 @@ def _assert_1e3(name, got, ref):
     assert frac_bad <= (0.0 if name in ("cls", "prob") else 1e-4), (name, frac_bad)
 
 
-def _setup(attention, align, crop, batch):
+def _setup(attention, align, crop, batch, back_bone="dla34"):
     from m3dssd_b200.model.M3d_inference_align import build
-    conf = synth.make_conf(attention=attention, center_align=align, shape_align=align, crop_size=crop)
+    conf = synth.make_conf(attention=attention, center_align=align, shape_align=align, crop_size=crop, back_bone=back_bone)
     net = build(conf, "test")
     sd = synth.randomize_weights(net)
     x = synth.make_images(batch, crop)
@@ -153,3 +153,30 @@ def test_training_mode_forward_backward_runs():
                  "base.ida_up.node_1.conv.bias", "base.base.level2.tree1.conv1.weight"):
         g = dict(net.named_parameters())[name].grad
         assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0, name
+
+
+def test_dla102_runs_through_the_fused_engine():
+    """back_bone='dla102' (the reference's shipped configs, scripts/config/kitti_3d_base.py:46: Bottleneck blocks,
+    residual Roots of up to 6 inputs, 256-channel heads) through net(x): fp32 parity mode at north_star's 1e-3 vs the
+    oracle restatement (pinned to the unmodified reference by tests/golden/ref_model_dla102_96x320.npz), then the bf16
+    engine layer by layer (teacher-forced, tests/test_teacher_forced_gpu.Replay)."""
+    from test_teacher_forced_gpu import BARS, Replay
+    conf, net, sd, x = _setup(None, False, (96, 320), 2, back_bone="dla102")
+    o32 = RM.RefModel(sd, conf, dcn="tv", dtype=torch.float32).forward(x)
+    net = net.cuda().eval()
+    assert net.engine_supported()
+    conf.precision = "fp32"
+    with torch.no_grad():
+        cls, prob, b2, b3, feat_size, rois = net(x.cuda())
+    for name, got, ref in zip(("cls", "prob", "bbox_2d", "bbox_3d"), (cls, prob, b2, b3), o32):
+        _assert_1e3(name, got.cpu(), ref)
+    eng = net.engine(2, 96, 320, precision="bf16", use_graph=False)
+    eng.forward(x.cuda())
+    torch.cuda.synchronize()
+    rows = Replay(eng, sd, conf).run()
+    assert len(rows) > 150  # 3 convs per Bottleneck, 13 heads layer by layer
+    for r in rows:
+        if r["exact"]:
+            assert r["max"] == 0.0, r
+        elif r["kind"] in BARS:
+            assert r["rms"] < BARS[r["kind"]][0] and r["max"] < BARS[r["kind"]][1], r

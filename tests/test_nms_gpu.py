@@ -23,7 +23,7 @@ def _boxes(n, seed, spread=(1200, 350)):
     return np.concatenate([xy, xy + wh, sc[:, None]], 1).astype(np.float32)
 
 
-@pytest.mark.parametrize("n", [0, 1, 2, 63, 64, 65, 127, 500, 3000, 4096])
+@pytest.mark.parametrize("n", [0, 1, 2, 63, 64, 65, 127, 500, 3000, 4096, 4097, 9000])
 def test_gpu_nms_vs_oracle(n):
     from m3dssd_b200.lib.nms.gpu_nms import gpu_nms
     d = _boxes(n, 100 + n) if n else np.zeros((0, 5), np.float32)
@@ -180,3 +180,26 @@ def test_refine_3d_vs_oracle(seed):
                                  hill_climbing=False)
     ref2 = HC.refine_detections(kept[0, :nk[0]], p2s[0], hill_climbing=False, max_out=max_out)
     assert np.allclose(out2.cpu().numpy()[0][valid2.cpu().numpy()[0].astype(bool)], ref2, rtol=1e-9, atol=1e-9)
+
+
+def test_batched_nms_more_than_4096_boxes_per_image():
+    """m3d_nms_batched above the fast sweep's 4096-box limit (generic exact sweep): bit-exact keep lists per image,
+    ragged box counts."""
+    from m3dssd_b200 import ops
+    B, max_n = 2, 5000
+    nums = [5000, 4321]
+    boxes = torch.zeros(B, max_n, 5)
+    exp = []
+    for b in range(B):
+        d = _boxes(nums[b], 40 + b, spread=(900, 300))
+        sd = np.ascontiguousarray(d[d[:, 4].argsort()[::-1]])
+        boxes[b, :nums[b]] = torch.from_numpy(sd)
+        exp.append(O.nms_sorted(sd, 0.4))
+    ws = torch.zeros(ops.nms_workspace_bytes(B, max_n), dtype=torch.uint8, device="cuda")
+    keep = torch.zeros(B, max_n, dtype=torch.int32, device="cuda")
+    nk = torch.zeros(B, dtype=torch.int32, device="cuda")
+    ops.nms_batched(boxes.cuda(), torch.tensor(nums, dtype=torch.int32, device="cuda"), 0.4, ws, keep, nk)
+    torch.cuda.synchronize()
+    for b in range(B):
+        n = int(nk[b])
+        assert n == len(exp[b]) and np.array_equal(keep[b, :n].cpu().numpy(), np.asarray(exp[b]))

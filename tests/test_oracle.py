@@ -95,6 +95,7 @@ def test_nms_mask_consistent_with_sweep():
     ("base", dict(attention=None, center_align=False, shape_align=False)),
     ("align", dict(attention=None, center_align=True, shape_align=True)),
     ("anab", dict(attention="ANAB", center_align=True, shape_align=True)),
+    ("dla102", dict(attention=None, center_align=False, shape_align=False, back_bone="dla102")),
 ])
 def test_model_restatement_vs_reference_golden(name, kw):
     """oracle/ref_model.py reproduces the unmodified reference modules' outputs (fixtures)."""

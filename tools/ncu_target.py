@@ -19,7 +19,7 @@ ap.add_argument("--ops", default="", help="comma-separated engine op names: prof
 a = ap.parse_args()
 conf = synth.make_conf(attention=a.attention, crop_size=(384, 1280))
 net = build(conf, "test")
-synth.randomize_weights(net, calibrate=False)
+synth.randomize_weights(net)
 net = net.cuda()
 eng = net.engine(a.batch, 384, 1280, precision="bf16", use_graph=False)
 x = synth.make_images(a.batch, (384, 1280)).cuda()
