@@ -250,6 +250,108 @@ def summarize_kernels(prof, peaks):
     return out, total_ms
 
 
+def run_train(args):
+    """BASELINE.json configs[3]: kitti_3d_base train step (forward + backward + SGD) on a synthetic KITTI batch, one
+    B200: batch 4 (scripts/config/kitti_3d_base.py:89), 384x1280, no align / attention, DLA-34 (substituted for the
+    config's dla102, as SURVEY 8d prescribes), SGD lr 0.004 / momentum 0.9 / weight decay 5e-4 (:21-24).  The loss is
+    m3dssd_b200.train.surrogate_loss (cross-entropy + smooth-L1 with the structure of RPN_3D_loss_smp; the reference's
+    per-image target matching is out of scope).  Beside it: the same step through torch's own
+    convolutions (cuDNN), fp32 as the reference runs it and bf16 autocast."""
+    import torch
+    from m3dssd_b200 import ops, synth, train
+    from m3dssd_b200.model.M3d_inference_align import build
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    B, W_, K = 4, max(3, args.warmup), args.steps
+    conf = synth.make_conf(attention=None, center_align=False, shape_align=False, crop_size=CROP, batch_size=B)
+    net = build(conf, "train")
+    sd = synth.randomize_weights(net)
+    NB = 4
+    host = [synth.make_images(B, CROP, seed=100 * rank + i).pin_memory() for i in range(NB)]
+    dev = [h.cuda() for h in host]
+    labels, t2, t3 = train.surrogate_targets(conf, B, "cuda")
+
+    def timed(step, n, from_host=False):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(n):
+            x = host[i % NB].cuda(non_blocking=True) if from_host else dev[i % NB]
+            loss = step(x, labels, t2, t3)
+            if from_host:
+                loss.item()  # the reference reads the loss every iteration (train_rpn_3d.py:208)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    # ---- torch / cuDNN arms (the reference's way), before cuDNN is switched off for the native path
+    baselines = {}
+    for name, autocast in (("torch_cudnn_fp32", False), ("torch_cudnn_bf16_autocast", True)):
+        ref = build(conf, "train").cuda()
+        ref.load_state_dict(sd)
+        st = train.TrainStep(ref, conf, native=False)
+
+        def step(x, labels, t2, t3, st=st, autocast=autocast):
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                st.net.train()
+                cls, prob, b2, b3, _ = st.net(x)
+                loss = train.surrogate_loss(cls, b2, b3, labels, t2, t3)
+            st.opt.zero_grad(set_to_none=True)
+            loss.backward()
+            st.opt.step()
+            return loss
+
+        timed(step, 3)
+        ms = timed(step, max(5, K // 2))
+        baselines[name] = {"images_per_s": B * max(5, K // 2) / (ms * 1e-3), "ms_per_step": ms / max(5, K // 2)}
+        del ref, st
+        torch.cuda.empty_cache()
+
+    net = net.cuda()
+    eager = train.TrainStep(net, conf, native=True)
+    timed(eager, 3)
+    ms_eager = timed(eager, max(5, K // 2))
+    baselines["native_eager"] = {"images_per_s": B * max(5, K // 2) / (ms_eager * 1e-3), "ms_per_step": ms_eager / max(5, K // 2)}
+    step = train.TrainStep(net, conf, native=True, graph=True, warmup=0)  # the whole iteration as one CUDA graph
+    step.opt = eager.opt
+    timed(step, W_)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    n0 = ops.LAUNCHES
+    timed(eager, 1)
+    launches = (ops.LAUNCHES - n0) * K  # C-ABI kernels of one iteration (counted on an eager pass) x K graph replays
+    ms = timed(step, K)
+    clk = clocks.stop()
+    ms_e2e = timed(step, K, from_host=True)
+    if rank != 0:
+        return 0
+    h2d = host[0].numel() * 4
+    line = {
+        "metric": "images_per_sec", "value": world * B * K / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": K,
+        "warmup": W_, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "kitti_3d_base train step (fwd+bwd+SGD) on a synthetic KITTI batch, batch 4 384x1280, "
+                               "DLA-34 substituted for dla102 (BASELINE.json configs[3])",
+                   "global_batch": world * B, "precision": "bf16 activations / fp32 master weights, statistics, optimizer",
+                   "loss": "surrogate (cross-entropy + smooth-L1, m3dssd_b200.train.surrogate_loss)",
+                   "optimizer": "SGD lr 0.004 momentum 0.9 weight_decay 5e-4",
+                   "native": "every nn.Conv2d forward / dgrad / wgrad and DCNv2 forward / backward through the C ABI; "
+                             "BatchNorm, activations, pooling, loss, SGD = torch elementwise kernels; cuDNN disabled; the whole "
+                             "iteration replayed as one CUDA graph",
+                   "multi_gpu": "replicas only (config 4 is single-GPU; no gradient all-reduce)" if world > 1 else None},
+        "clocks": clk,
+        "e2e": {"value": world * B * K / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "train": {"native": {"images_per_s": B * K / (ms * 1e-3), "ms_per_step": ms / K}, **baselines},
+    }
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -259,11 +361,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the sustained / surface sub-measurements")
     ap.add_argument("--attention", default=None)
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer: BASELINE configs[1] / [2] (default); train: configs[3], the kitti_3d_base train step")
     ap.add_argument("--input", default="u8", choices=["u8", "f32"],
                     help="u8: uint8 HWC images normalised on the device (default); f32: pre-normalised fp32 NCHW")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.mode == "train":
+        return run_train(args)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

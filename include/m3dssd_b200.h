@@ -136,6 +136,19 @@ int m3d_dcn_v2_backward(const float* input, const float* weight, const float* of
                         void* workspace, size_t workspace_bytes, m3d_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * Training path (BASELINE config 4; scripts/train_rpn_3d.py:204-218 runs loss.backward() through cuDNN): weight
+ * gradient of a convolution on the tensor cores,
+ *     dW[co][ci][r][s] = sum_{n,p,q} gy[n,p,q,co] * x[n, p*stride - pad + r*dil, q*stride - pad + s*dil, ci],
+ * x / gy bf16 NHWC (channel strides multiples of 8), dW fp32 in torch's [Cout][Cin][R][S] layout, fp32 accumulation,
+ * deterministic (split-K partials reduced in a fixed order).  The input gradient of a convolution is itself a
+ * convolution (m3d_conv2d_nhwc on gy with the flipped, transposed weights).
+ * ---------------------------------------------------------------------- */
+size_t m3d_conv2d_wgrad_workspace(int N, int P, int Q, int Cin, int Cout, int R, int S);
+int m3d_conv2d_wgrad(const void* x, int x_cstride, int x_coff, const void* gy, int gy_cstride, int gy_coff, float* dw,
+                     int N, int H, int W, int Cin, int P, int Q, int Cout, int R, int S, int stride, int pad, int dil,
+                     void* workspace, size_t workspace_bytes, m3d_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * gpu_nms.  m3d_nms is the drop-in for `_nms` (lib/nms/gpu_nms.hpp:1-2): HOST
  * pointers, boxes [n, boxes_dim] already sorted by score, keep_out receives the
  * kept row indices; synchronous.  The +1 pixel IoU convention and the strict

@@ -37,7 +37,10 @@ class _DCNv2Op(Function):
         stride, padding, dilation, dg = ctx.cfg
         gi, go, gm, gw, gb = ops.dcn_v2_backward(input, offset, mask, weight, grad_output.contiguous(), stride, padding,
                                                  dilation, dg)
-        return gi, go, gm, gw, gb, None, None, None, None, None
+        # (the C ABI computes in fp32; autograd wants each gradient in its tensor's dtype: the mixed-precision training
+        #  path feeds bf16 activations)
+        return (gi.to(input.dtype), go.to(offset.dtype), gm.to(mask.dtype), gw.to(weight.dtype), gb.to(bias.dtype),
+                None, None, None, None, None)
 
 
 class DCNv2Function(object):

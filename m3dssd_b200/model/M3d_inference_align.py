@@ -81,6 +81,7 @@ class RPN(nn.Module):
         for name in ("bbox_w3d", "bbox_h3d", "bbox_l3d", "bbox_rY3d"):
             setattr(self, name, _head(ch, mid, A))
         self.softmax = nn.Softmax(dim=1)
+        self._feat_size_cache = {}
         self._engines = {}
 
     # ---------------------------------------------------------------- engine
@@ -151,7 +152,7 @@ class RPN(nn.Module):
         A, K = self.num_anchors, self.num_classes
         x = self.base(x)
         Hf, Wf = x.shape[2:]
-        cls = self.cls(x).view(B, K, Hf * A, Wf)
+        cls = self.cls(x).contiguous().view(B, K, Hf * A, Wf)  # (contiguous: the native training path is channels_last)
         prob = self.softmax(cls)
         fg_prob = (1 - prob.detach()[:, 0]).view(B, A, Hf, Wf)
         feats = self.shape_align(x, fg_prob) if self.shape_align is not None else x
@@ -172,7 +173,10 @@ class RPN(nn.Module):
         flat = {n: flatten_tensor(t.reshape(B, 1, Hf * A, Wf)) for n, t in out.items()}
         bbox_2d = torch.cat([flat[n] for n in _REG_HEADS[:4]], dim=2)
         bbox_3d = torch.cat([flat[n] for n in _REG_HEADS[4:]], dim=2)
-        feat_size = torch.tensor([Hf, Wf], dtype=torch.float, device=x.device)
+        key = (Hf, Wf, str(x.device))  # cached: a host->device copy per call would also break CUDA-graph capture
+        if key not in self._feat_size_cache:
+            self._feat_size_cache[key] = torch.tensor([Hf, Wf], dtype=torch.float, device=x.device)
+        feat_size = self._feat_size_cache[key]
         cls, prob = flatten_tensor(cls), flatten_tensor(prob)
         if self.training:
             return cls, prob, bbox_2d, bbox_3d, feat_size

@@ -7,6 +7,14 @@ from . import _lib
 from ._lib import ConvDesc, M3D_BF16, M3D_BF16X3, M3D_F32, check, lib
 
 
+LAUNCHES = 0  # kernels launched through the C ABI by this process (bench.py's gpu_launches claim for the training step)
+
+
+def _count(n):
+    global LAUNCHES
+    LAUNCHES += n
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -119,6 +127,7 @@ def conv2d_nhwc(inputs, weight, out, *, R, S, stride=1, pad=0, dil=1, Cout=None,
     d.sigmoid_mask = int(sigmoid_mask)
     d.force_gather = int(force_gather)
     check(lib().m3d_conv2d_nhwc(C.byref(d), _stream()))
+    _count(1)
     return out
 
 
@@ -360,6 +369,7 @@ def dcn_v2_forward(input, offset, mask, weight, bias, stride, padding, dilation,
     check(lib().m3d_dcn_v2_forward(_p(args[0]), _p(args[1]), _p(args[2]), _p(args[3]), _p(args[4]), _p(out), B, Cin, H,
                                    W, Cout, kh, kw, stride, stride, padding, padding, dilation, dilation,
                                    deformable_groups, precision, _p(ws), ws_bytes, _stream()))
+    _count(6 * deformable_groups)  # 3 layout conversions in, weight pack, fused gather + GEMM, layout conversion out
     return out
 
 
@@ -409,4 +419,20 @@ def dcn_v2_backward(input, offset, mask, weight, grad_output, stride, padding, d
     check(lib().m3d_dcn_v2_backward(*[_p(t) for t in args], _p(gi), _p(gw), _p(gb), _p(go), _p(gm), B, Cin, H, W, Cout,
                                     kh, kw, stride, stride, padding, padding, dilation, dilation, deformable_groups,
                                     _p(ws), n, _stream()))
+    _count(12 * deformable_groups)  # layout conversions, W^T dY GEMM, coordinate / input gradient kernels, dW, bias, repack
     return gi, go, gm, gw, gb
+
+
+def conv2d_wgrad(x, gy, Cin, Cout, R, S, stride=1, pad=0, dil=1, x_coff=0, gy_coff=0):
+    """Weight gradient of a convolution (training path): x [N,H,W,Cx] and gy [N,P,Q,Cy] bf16 NHWC CUDA tensors (channel
+    strides multiples of 8; channels [x_coff, x_coff+Cin) / [gy_coff, gy_coff+Cout) are used) -> dW fp32 [Cout,Cin,R,S]."""
+    assert x.dtype == torch.bfloat16 and gy.dtype == torch.bfloat16 and x.is_contiguous() and gy.is_contiguous()
+    N, H, W, cx = x.shape
+    _, P, Q, cy = gy.shape
+    dw = torch.empty(Cout, Cin, R, S, dtype=torch.float32, device=x.device)
+    n = lib().m3d_conv2d_wgrad_workspace(N, P, Q, Cin, Cout, R, S)
+    ws = torch.empty(n, dtype=torch.uint8, device=x.device)
+    check(lib().m3d_conv2d_wgrad(_p(x), cx, x_coff, _p(gy), cy, gy_coff, _p(dw), N, H, W, Cin, P, Q, Cout, R, S, stride, pad,
+                                 dil, _p(ws), n, _stream()))
+    _count(2)  # wgrad + slice reduction
+    return dw

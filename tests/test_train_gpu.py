@@ -1,0 +1,115 @@
+"""GPU parity of the training-path kernels (BASELINE config 4) against torch CPU autograd (the reference's training
+loop differentiates nn.Conv2d through torch / cuDNN: scripts/train_rpn_3d.py:204-218)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("case", [
+    dict(N=2, H=24, W=80, Cin=128, Cout=128, k=3, stride=1, pad=1),
+    dict(N=4, H=48, W=160, Cin=128, Cout=128, k=3, stride=1, pad=1),
+    dict(N=2, H=24, W=80, Cin=64, Cout=128, k=3, stride=2, pad=1),
+    dict(N=1, H=12, W=40, Cin=256, Cout=512, k=1, stride=1, pad=0),
+    dict(N=2, H=13, W=37, Cin=64, Cout=64, k=3, stride=1, pad=1),      # ragged: patches cross the image edge
+    dict(N=1, H=32, W=64, Cin=16, Cout=32, k=3, stride=2, pad=1),      # channel padding by TMA zero fill
+    dict(N=1, H=24, W=80, Cin=128, Cout=27, k=3, stride=1, pad=1, cy=32),  # offset/mask conv: 27 of 32 channels
+    dict(N=2, H=24, W=80, Cin=448, Cout=128, k=1, stride=1, pad=0),    # Root conv over a concatenation
+])
+def test_conv2d_wgrad_vs_torch(case):
+    from m3dssd_b200 import ops
+    N, H, W, Cin, Cout, k, stride, pad = (case[n] for n in ("N", "H", "W", "Cin", "Cout", "k", "stride", "pad"))
+    g = torch.Generator().manual_seed(Cin + Cout + H)
+    x = torch.randn(N, Cin, H, W, generator=g).bfloat16().float()
+    P, Q = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    gy = torch.randn(N, Cout, P, Q, generator=g).bfloat16().float()
+    ref = torch.nn.grad.conv2d_weight(x.double(), (Cout, Cin, k, k), gy.double(), stride=stride, padding=pad).float()
+    cy = case.get("cy", Cout)
+    gy_d = torch.zeros(N, P, Q, cy, dtype=torch.bfloat16, device="cuda")
+    gy_d[..., :Cout] = _nhwc(gy).bfloat16().cuda()
+    dw = ops.conv2d_wgrad(_nhwc(x).bfloat16().cuda(), gy_d, Cin, Cout, k, k, stride, pad)
+    err = (dw.cpu() - ref).abs().max().item() / ref.abs().max().item()
+    assert dw.shape == ref.shape and err < 2e-5, err  # exact bf16 products, fp32 accumulation over up to 30720 pixels
+
+
+@pytest.mark.parametrize("case", [
+    dict(N=2, H=24, W=80, Cin=128, Cout=128, k=3, stride=1, pad=1),
+    dict(N=2, H=24, W=80, Cin=64, Cout=128, k=3, stride=2, pad=1),
+    dict(N=1, H=25, W=81, Cin=32, Cout=64, k=3, stride=2, pad=1),     # odd size: the strided gradient needs the extra row
+    dict(N=2, H=12, W=40, Cin=256, Cout=36, k=1, stride=1, pad=0),     # head predictor, 36 of 40 channels
+    dict(N=1, H=24, W=80, Cin=128, Cout=27, k=3, stride=1, pad=1),     # offset / mask predictor
+    dict(N=1, H=32, W=64, Cin=3, Cout=16, k=7, stride=1, pad=3),       # stem (no input gradient needed, but check it)
+])
+def test_native_conv_autograd_vs_torch(case):
+    """_ConvFn (forward, dgrad, wgrad, bias gradient through the C ABI) vs torch CPU autograd on the same bf16-rounded
+    operands: forward / input gradient within bf16 output rounding, weight / bias gradients to fp32 accumulation noise."""
+    from m3dssd_b200.train import _ConvFn
+    N, H, W, Cin, Cout, k, stride, pad = (case[n] for n in ("N", "H", "W", "Cin", "Cout", "k", "stride", "pad"))
+    g = torch.Generator().manual_seed(7 * Cin + Cout)
+    x = torch.randn(N, Cin, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).bfloat16().float()
+    b = torch.randn(Cout, generator=g)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, br, stride=stride, padding=pad)
+    gy = torch.randn(yr.shape, generator=g).bfloat16().float()
+    yr.backward(gy)
+    xd = x.cuda().bfloat16().requires_grad_(True)
+    wd, bd = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    yd = _ConvFn.apply(xd, wd, bd, stride, pad)
+    yd.backward(gy.cuda().bfloat16())
+
+    def rel(a, r):
+        return (a.float().cpu() - r).abs().max().item() / r.abs().max().item()
+
+    assert yd.shape == yr.shape and rel(yd.detach(), yr.detach()) < 2 ** -7
+    assert rel(xd.grad, xr.grad) < 2 ** -7
+    assert rel(wd.grad, wr.grad) < 3e-5 and rel(bd.grad, br.grad) < 1e-5
+
+
+def test_native_train_step_learns_and_calls_no_cudnn():
+    """BASELINE config 4 at test size: kitti_3d_base (no align, no attention), DLA-34, batch 2, 96x320.  The native
+    step (C-ABI convolutions in both directions, DCNv2 forward / backward; bf16 activations, fp32 master weights) must
+    (a) produce parameter gradients as close to torch's fp32 autograd as torch's OWN bf16 mixed precision (autocast)
+    gets on the same graph -- measured: cosine 0.89 at the stem .. 0.999 at the heads for both, the train-mode
+    BatchNorms of a batch-2 network amplify bf16 rounding -- (b) reduce the loss over a few SGD steps, (c) leave cuDNN
+    disabled."""
+    from m3dssd_b200 import synth, train
+    from m3dssd_b200.model.M3d_inference_align import build
+    conf = synth.make_conf(attention=None, center_align=False, shape_align=False, crop_size=(96, 320), batch_size=2)
+    net = build(conf, "train")
+    sd = synth.randomize_weights(net)
+    x = synth.make_images(2, (96, 320)).cuda()
+    labels, t2, t3 = train.surrogate_targets(conf, 2, "cuda", fg_per_image=60)
+
+    def grads(model, autocast=False):
+        model.train()
+        model.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            cls, prob, b2, b3, _ = model(x)
+        train.surrogate_loss(cls, b2, b3, labels, t2, t3).backward()
+        return {n: p.grad.float().flatten().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    def cos(a, b):
+        return float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30))
+
+    ref = build(conf, "train").cuda()  # the same module graph with torch's convolutions
+    ref.load_state_dict(sd)
+    g32, g16 = grads(ref), grads(ref, autocast=True)
+    net = net.cuda()
+    step = train.TrainStep(net, conf, lr=0.002)
+    assert torch.backends.cudnn.enabled is False
+    gn = grads(net)
+    assert set(gn) == set(g32)
+    for name in ("base.base.base_layer.0.weight", "base.base.level2.tree1.conv1.weight",
+                 "base.base.level4.tree2.root.conv.weight", "base.dla_up.ida_1.node_1.conv.weight",
+                 "base.ida_up.proj_1.conv.conv_offset_mask.weight", "cls.0.weight", "bbox_z3d.6.weight"):
+        c_native, c_autocast = cos(gn[name], g32[name]), cos(g16[name], g32[name])
+        assert torch.isfinite(gn[name]).all() and c_native > c_autocast - 0.03 and c_native > 0.8, (name, c_native, c_autocast)
+    assert cos(gn["bbox_z3d.6.weight"], g32["bbox_z3d.6.weight"]) > 0.995
+    losses = [float(step(x, labels, t2, t3).detach()) for _ in range(8)]
+    assert losses[-1] < losses[0], losses
