@@ -5,7 +5,7 @@ vp, i, f, sz, lg, db = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_long, C.c
 
 _SIGS = {
     "m3d_dcn_v2_forward": [vp, vp, vp, vp, vp, vp] + [i] * 15 + [vp, sz, vp],
-    "m3d_dcn_v2_backward": [vp] * 10 + [i] * 14 + [vp, sz, vp],
+    "m3d_dcn_v2_backward": [vp] * 10 + [i] * 15 + [vp, sz, vp],
     "m3d_nms": [vp, vp, vp, i, i, f, i],
     "m3d_nms_batched": [vp, i, vp, i, i, f, vp, sz, vp, vp, vp],
     "m3d_decode_topk": [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, f, f, i, vp, vp, vp, vp, sz, vp],

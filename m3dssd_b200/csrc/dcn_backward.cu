@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <cstdint>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace m3d {
@@ -222,6 +224,24 @@ __global__ void pack_wt_kernel(const float* __restrict__ w, float* __restrict__ 
   }
 }
 
+// the same matrix as three bf16 parts (hi + mid + lo = 24 mantissa bits) for the tensor-core (bf16x3) GEMM
+__global__ void pack_wt_split_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                     __nv_bfloat16* __restrict__ mid, __nv_bfloat16* __restrict__ lo, int Cout, int C, int KK,
+                                     int CoutP) {
+  const long total = static_cast<long>(KK) * C * CoutP;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(i % CoutP);
+    const long k = i / CoutP;
+    const int c = static_cast<int>(k % C), t = static_cast<int>(k / C);
+    const float v = co < Cout ? w[(static_cast<long>(co) * C + c) * KK + t] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    hi[i] = h, mid[i] = m, lo[i] = __float2bfloat16_rn(r1 - __bfloat162float(m));
+  }
+}
+
 static inline size_t al(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 struct BwdLayout {
@@ -234,13 +254,13 @@ static BwdLayout bwd_layout(int B, int C, int H, int W, int Cout, int kh, int kw
   L.Ho = (H + 2 * pad - (dil * (kh - 1) + 1)) / stride + 1;
   L.Wo = (W + 2 * pad - (dil * (kw - 1) + 1)) / stride + 1;
   L.KK = kh * kw, L.K = C * L.KK;
-  L.CoutP = (Cout + 15) / 16 * 16;
+  L.CoutP = (Cout + 63) / 64 * 64;  // k-block of the tensor-core (bf16x3) W^T dY GEMM
   const size_t npo = static_cast<size_t>(B) * L.Ho * L.Wo;
   L.x = al(static_cast<size_t>(B) * H * W * C * 4);
   L.om = al(npo * 3 * L.KK * 4);
   L.gy = al(npo * L.CoutP * 4);
   L.gcol = al(npo * L.K * 4);
-  L.wt = al(static_cast<size_t>(L.K) * L.CoutP * 4);
+  L.wt = al(static_cast<size_t>(L.K) * L.CoutP * 6);  // fp32, or three bf16 parts
   L.gx = L.x;
   L.gw = al(static_cast<size_t>(Cout) * L.K * 4);
   L.total = L.x + L.om + L.gy + L.gcol + L.wt + L.gx + L.gw;
@@ -284,19 +304,21 @@ static int dcn_backward_one_group(const float* input, const float* weight, const
                                   const float* grad_output, float* grad_input, float* grad_weight, float* grad_bias,
                                   float* grad_offset, float* grad_mask, int B, int C, int H, int W, int Cout, int kh,
                                   int kw, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
-                                  void* workspace, size_t workspace_bytes, m3d_stream_t stream_);
+                                  int precision, void* workspace, size_t workspace_bytes, m3d_stream_t stream_);
 
 extern "C" int m3d_dcn_v2_backward(const float* input, const float* weight, const float* offset, const float* mask,
                                    const float* grad_output, float* grad_input, float* grad_weight, float* grad_bias,
                                    float* grad_offset, float* grad_mask, int B, int C, int H, int W, int Cout, int kh,
                                    int kw, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
-                                   int deformable_group, void* workspace, size_t workspace_bytes, m3d_stream_t stream_) {
+                                   int deformable_group, int precision, void* workspace, size_t workspace_bytes,
+                                   m3d_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3D_REQUIRE(precision == M3D_F32 || precision == M3D_BF16X3, "backward precision must be M3D_F32 or M3D_BF16X3");
   const int dg = deformable_group;
   if (dg == 1)
     return dcn_backward_one_group(input, weight, offset, mask, grad_output, grad_input, grad_weight, grad_bias,
                                   grad_offset, grad_mask, B, C, H, W, Cout, kh, kw, stride_h, stride_w, pad_h, pad_w,
-                                  dil_h, dil_w, workspace, workspace_bytes, stream_);
+                                  dil_h, dil_w, precision, workspace, workspace_bytes, stream_);
   M3D_REQUIRE(input && weight && offset && mask && grad_output && grad_input && grad_weight && grad_bias && grad_offset &&
                   grad_mask,
               "NULL tensor pointer");
@@ -327,7 +349,7 @@ extern "C" int m3d_dcn_v2_backward(const float* input, const float* weight, cons
     M3D_CUDA_OK(cudaMemcpy2DAsync(wg, wrow, weight + wo, static_cast<size_t>(C) * KK * 4, wrow, Cout,
                                   cudaMemcpyDeviceToDevice, stream));
     const int rc = dcn_backward_one_group(xg, wg, og, mg, grad_output, gxg, gwg, grad_bias, gog, gmg, B, Cg, H, W, Cout,
-                                          kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, inner,
+                                          kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, precision, inner,
                                           workspace_bytes - G.total, stream_);
     if (rc) return rc;
     M3D_CUDA_OK(cudaMemcpy2DAsync(grad_input + xo, C * hw, gxg, Cg * hw, Cg * hw, B, cudaMemcpyDeviceToDevice, stream));
@@ -345,7 +367,7 @@ static int dcn_backward_one_group(const float* input, const float* weight, const
                                   const float* grad_output, float* grad_input, float* grad_weight, float* grad_bias,
                                   float* grad_offset, float* grad_mask, int B, int C, int H, int W, int Cout, int kh,
                                   int kw, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
-                                  void* workspace, size_t workspace_bytes, m3d_stream_t stream_) {
+                                  int precision, void* workspace, size_t workspace_bytes, m3d_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int deformable_group = 1;
   M3D_REQUIRE(input && weight && offset && mask && grad_output && grad_input && grad_weight && grad_bias && grad_offset &&
@@ -385,8 +407,13 @@ static int dcn_backward_one_group(const float* input, const float* weight, const
   M3D_CUDA_OK(cudaMemsetAsync(grad_bias, 0, sizeof(float) * Cout, stream));
   {
     const long total = static_cast<long>(L.K) * L.CoutP;
-    pack_wt_kernel<<<static_cast<int>(std::min<long>((total + 255) / 256, 4096)), 256, 0, stream>>>(weight, wt, Cout, C,
-                                                                                                   L.KK, L.CoutP);
+    const int grid = static_cast<int>(std::min<long>((total + 255) / 256, 4096));
+    if (precision == M3D_F32) {
+      pack_wt_kernel<<<grid, 256, 0, stream>>>(weight, wt, Cout, C, L.KK, L.CoutP);
+    } else {
+      __nv_bfloat16* w3 = reinterpret_cast<__nv_bfloat16*>(wt);
+      pack_wt_split_kernel<<<grid, 256, 0, stream>>>(weight, w3, w3 + total, w3 + 2 * total, Cout, C, L.KK, L.CoutP);
+    }
     M3D_CUDA_OK(cudaGetLastError());
   }
   // gcol[pix][k] = sum_co Wt[k][co] * gy[pix][co]  : a 1x1 "convolution" with K output channels
@@ -397,7 +424,14 @@ static int dcn_backward_one_group(const float* input, const float* weight, const
   d.N = B, d.H = L.Ho, d.W = L.Wo;
   d.R = 1, d.S = 1, d.stride = 1, d.pad = 0, d.dil = 1;
   d.Cout = L.K, d.groups = 1;
-  d.weight_f32 = wt, d.weight_rows = L.K;
+  if (precision == M3D_F32) {  // IEEE fp32 FMA on the CUDA cores (reference accuracy)
+    d.weight_f32 = wt;
+  } else {  // 3-part bf16 split on the tensor cores (~3e-6 relative)
+    const long total = static_cast<long>(L.K) * L.CoutP;
+    const __nv_bfloat16* w3 = reinterpret_cast<const __nv_bfloat16*>(wt);
+    d.weight = w3, d.weight_mid = w3 + total, d.weight_lo = w3 + 2 * total;
+  }
+  d.weight_rows = L.K;
   d.out = gcol, d.out_cstride = L.K;
   d.slope = 1.0f;
   rc = m3d_conv2d_nhwc(&d, stream_);

@@ -32,7 +32,10 @@ class DCNv2(nn.Module):
             self.bias.zero_()
 
     def _op(self):
-        return DCNv2Function(self.stride, self.padding, self.dilation, self.deformable_groups)
+        # `precision` (None = dcn_v2_func.default_precision = "fp32"): set per module, e.g. by the mixed-precision
+        # training path (m3dssd_b200.train.enable)
+        return DCNv2Function(self.stride, self.padding, self.dilation, self.deformable_groups,
+                             precision=getattr(self, "precision", None))
 
     def forward(self, input, offset, mask):
         return self._op()(input, offset, mask, self.weight, self.bias)

@@ -24,7 +24,7 @@ class _DCNv2Op(Function):
     def forward(ctx, input, offset, mask, weight, bias, stride, padding, dilation, deformable_groups, precision):
         if not input.is_cuda:
             raise NotImplementedError  # same contract as the reference (dcn_v2_func.py:23-24): no CPU path
-        ctx.cfg = (stride, padding, dilation, deformable_groups)
+        ctx.cfg = (stride, padding, dilation, deformable_groups, _PRECISION[precision])
         ctx.save_for_backward(input, offset, mask, weight, bias)
         return ops.dcn_v2_forward(input, offset, mask, weight, bias, stride, padding, dilation, deformable_groups,
                                   _PRECISION[precision])
@@ -34,9 +34,9 @@ class _DCNv2Op(Function):
         if not grad_output.is_cuda:
             raise NotImplementedError
         input, offset, mask, weight, bias = ctx.saved_tensors
-        stride, padding, dilation, dg = ctx.cfg
+        stride, padding, dilation, dg, prec = ctx.cfg
         gi, go, gm, gw, gb = ops.dcn_v2_backward(input, offset, mask, weight, grad_output.contiguous(), stride, padding,
-                                                 dilation, dg)
+                                                 dilation, dg, precision=prec)
         # (the C ABI computes in fp32; autograd wants each gradient in its tensor's dtype: the mixed-precision training
         #  path feeds bf16 activations)
         return (gi.to(input.dtype), go.to(offset.dtype), gm.to(mask.dtype), gw.to(weight.dtype), gb.to(bias.dtype),

@@ -405,7 +405,8 @@ def anab_attention(q, ktok, vtok, x, scale, shift, slope, out, ck, cv, workspace
     return out
 
 
-def dcn_v2_backward(input, offset, mask, weight, grad_output, stride, padding, dilation, deformable_groups):
+def dcn_v2_backward(input, offset, mask, weight, grad_output, stride, padding, dilation, deformable_groups,
+                    precision=M3D_F32):
     """DCNv2Function.backward (model/DCNv2/dcn_v2_func.py:40-62): returns (grad_input, grad_offset, grad_mask,
     grad_weight, grad_bias), fp32 NCHW CUDA tensors."""
     B, Cin, H, W = input.shape
@@ -418,7 +419,7 @@ def dcn_v2_backward(input, offset, mask, weight, grad_output, stride, padding, d
     ws = torch.empty(n, dtype=torch.uint8, device=input.device)
     check(lib().m3d_dcn_v2_backward(*[_p(t) for t in args], _p(gi), _p(gw), _p(gb), _p(go), _p(gm), B, Cin, H, W, Cout,
                                     kh, kw, stride, stride, padding, padding, dilation, dilation, deformable_groups,
-                                    _p(ws), n, _stream()))
+                                    M3D_F32 if precision == M3D_F32 else M3D_BF16X3, _p(ws), n, _stream()))
     _count(12 * deformable_groups)  # layout conversions, W^T dY GEMM, coordinate / input gradient kernels, dW, bias, repack
     return gi, go, gm, gw, gb
 

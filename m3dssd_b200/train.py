@@ -127,12 +127,15 @@ def _upsample_forward(self, x):
     return nn.ConvTranspose2d.forward(self, x)
 
 
-def enable(net):
+def enable(net, dcn_precision="bf16x3"):
     """Route every nn.Conv2d / depthwise nn.ConvTranspose2d of `net` through the native kernels while it is in training
     mode (eval mode keeps using the fused engine).  Returns the number of patched modules."""
     import types
     n = 0
+    from .model.DCNv2.dcn_v2 import DCNv2
     for m in net.modules():
+        if isinstance(m, DCNv2):
+            m.precision = dcn_precision  # tensor-core arithmetic for the deformable layers of the training graph
         if type(m) is nn.Conv2d:
             m.forward = types.MethodType(_conv_forward, m)
             n += 1

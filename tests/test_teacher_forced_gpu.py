@@ -30,7 +30,7 @@ pytestmark = pytest.mark.gpu
 BARS = {
     # conv_linear = the Trees' `project` (1x1 conv + BN only): its BatchNorm removes the large common mean of the
     # post-activation input, so the same absolute rounding error is a larger fraction of what is left
-    "stem": (4e-3, 2e-2), "conv": (5e-3, 2e-2), "conv_linear": (1e-2, 3e-2), "conv_f32out": (3e-3, 1.5e-2), "dcn": (7e-3, 3e-2),
+    "stem": (4e-3, 2e-2), "conv": (7e-3, 2e-2), "conv_linear": (1e-2, 3e-2), "conv_f32out": (3e-3, 1.5e-2), "dcn": (7e-3, 3e-2),
     "upsample": (3e-3, 1e-2), "head_mlp": (1e-2, 5e-2), "anab_pool": (1e-4, 1e-3), "anab_attention": (1e-2, 1e-1),
 }
 

@@ -1,1 +1,1 @@
-timeout 900 python bench.py --mode train --steps 10 --warmup 3 2>&1 | tail -3 | cut -c1-3000
+timeout 600 python -m pytest tests/test_model_gpu.py -m gpu -q -x -k dla102 2>&1 | grep -E "AssertionError|assert |Error" | head -8
