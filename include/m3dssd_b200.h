@@ -149,6 +149,11 @@ int m3d_conv2d_wgrad(const void* x, int x_cstride, int x_coff, const void* gy, i
                      int N, int H, int W, int Cin, int P, int Q, int Cout, int R, int S, int stride, int pad, int dil,
                      void* workspace, size_t workspace_bytes, m3d_stream_t stream);
 
+/* Bias gradient: out[c] = sum over the npix pixels of x[pix][coff + c] (bf16 NHWC, fp32 sums, deterministic). */
+size_t m3d_channel_sum_workspace(int C);
+int m3d_channel_sum(const void* x, long npix, int C, int cstride, int coff, float* out, void* workspace,
+                    size_t workspace_bytes, m3d_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * gpu_nms.  m3d_nms is the drop-in for `_nms` (lib/nms/gpu_nms.hpp:1-2): HOST
  * pointers, boxes [n, boxes_dim] already sorted by score, keep_out receives the

@@ -12,6 +12,7 @@ _SIGS = {
     "m3d_gather_kept": [vp, i, i, i, vp, vp, i, vp, vp],
     "m3d_stem_conv7x7": [vp, vp, vp, vp, i, i, i, i, i, f, vp],
     "m3d_conv2d_wgrad": [vp, i, i, vp, i, i, vp] + [i] * 12 + [vp, sz, vp],
+    "m3d_channel_sum": [vp, lg, i, i, i, vp, vp, sz, vp],
     "m3d_preprocess_u8": [vp, vp, i, i, i, vp, vp, i, vp],
     "m3d_stem_conv7x7_s2d": [vp, vp, vp, vp, i, i, i, f, vp],
     "m3d_maxpool2x2_nhwc": [vp, vp, i, i, i, i, i, i, i, vp],
@@ -36,6 +37,7 @@ _SIZE_FNS = {
     "m3d_anab_attention_workspace": [i, i],
     "m3d_decode_topk_workspace": [i],
     "m3d_conv2d_wgrad_workspace": [i] * 7,
+    "m3d_channel_sum_workspace": [i],
 }
 
 

@@ -253,7 +253,79 @@ WgradPlan plan(int N, int P, int Q, int Cin, int Cout, int R, int S) {
 }  // namespace
 }  // namespace m3d
 
+namespace m3d {
+namespace {
+// Bias gradient of a convolution = per-channel sum of the output gradient (bf16 NHWC -> fp32[C]).  Two passes, fixed
+// order (deterministic): blocks of 256 threads sum 8 channels x their slab of pixels, then the slabs are added.
+constexpr int kSumSlabs = 64;
+__global__ void __launch_bounds__(256) channel_sum_partial_kernel(const __nv_bfloat16* __restrict__ x, long npix, int C,
+                                                                  int cstride, int coff, float* __restrict__ partial) {
+  __shared__ float red[32][65];
+  const int cgrp = blockIdx.x, slab = blockIdx.y;     // 64 channels per block column
+  const int lane8 = threadIdx.x & 7, rlane = threadIdx.x >> 3;  // 8 threads x 8 channels, 32 row lanes
+  const int c0 = cgrp * 64 + lane8 * 8;
+  const long per = (npix + gridDim.y - 1) / gridDim.y;
+  const long r0 = slab * per, r1 = min(npix, r0 + per);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const bool vec = c0 + 8 <= C && ((cstride | coff) & 7) == 0;
+  for (long r = r0 + rlane; r < r1; r += 32) {
+    const __nv_bfloat16* px = x + r * cstride + coff + c0;
+    if (vec) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(px));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[2 * i] += __uint_as_float(w[i] << 16);
+        acc[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (c0 + i < C) acc[i] += __bfloat162float(px[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[rlane][lane8 * 8 + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) s += red[r][threadIdx.x];
+    const int c = cgrp * 64 + threadIdx.x;
+    if (c < C) partial[static_cast<long>(slab) * C + c] = s;
+  }
+}
+__global__ void channel_sum_final_kernel(const float* __restrict__ partial, int nslab, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int i = 0; i < nslab; ++i) s += partial[static_cast<long>(i) * C + c];
+  out[c] = s;
+}
+}  // namespace
+}  // namespace m3d
+
 using namespace m3d;
+
+extern "C" size_t m3d_channel_sum_workspace(int C) { return static_cast<size_t>(kSumSlabs) * C * sizeof(float); }
+
+extern "C" int m3d_channel_sum(const void* x, long npix, int C, int cstride, int coff, float* out, void* workspace,
+                               size_t workspace_bytes, m3d_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3D_REQUIRE(x && out && workspace && npix >= 1 && C >= 1 && cstride >= C, "bad arguments");
+  if (workspace_bytes < m3d_channel_sum_workspace(C)) {
+    set_last_error("channel-sum workspace too small");
+    return M3D_ERR_WORKSPACE;
+  }
+  float* partial = static_cast<float*>(workspace);
+  const int slabs = static_cast<int>(std::min<long>(kSumSlabs, (npix + 255) / 256));
+  dim3 grid((C + 63) / 64, slabs);
+  channel_sum_partial_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), npix, C, cstride, coff, partial);
+  M3D_CUDA_OK(cudaGetLastError());
+  channel_sum_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>(partial, slabs, C, out);
+  M3D_CUDA_OK(cudaGetLastError());
+  return M3D_OK;
+}
 
 extern "C" size_t m3d_conv2d_wgrad_workspace(int N, int P, int Q, int Cin, int Cout, int R, int S) {
   return plan(N, P, Q, Cin, Cout, R, S).partial_bytes + 256;

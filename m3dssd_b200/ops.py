@@ -437,3 +437,16 @@ def conv2d_wgrad(x, gy, Cin, Cout, R, S, stride=1, pad=0, dil=1, x_coff=0, gy_co
                                  dil, _p(ws), n, _stream()))
     _count(2)  # wgrad + slice reduction
     return dw
+
+
+def channel_sum(x_nhwc, C, coff=0):
+    """Per-channel sum over all pixels of a bf16 NHWC tensor -> fp32 [C] (the bias gradient of a convolution)."""
+    assert x_nhwc.dtype == torch.bfloat16 and x_nhwc.is_contiguous()
+    cs = x_nhwc.shape[-1]
+    npix = x_nhwc.numel() // cs
+    out = torch.empty(C, dtype=torch.float32, device=x_nhwc.device)
+    n = lib().m3d_channel_sum_workspace(C)
+    ws = torch.empty(n, dtype=torch.uint8, device=x_nhwc.device)
+    check(lib().m3d_channel_sum(_p(x_nhwc), npix, C, cs, coff, _p(out), _p(ws), n, _stream()))
+    _count(2)
+    return out

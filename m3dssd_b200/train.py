@@ -79,7 +79,7 @@ class _ConvFn(Function):
         gyn, _ = _pad_channels(_cl(gy).permute(0, 2, 3, 1), 16)
         P, Q, cop = gyn.shape[1], gyn.shape[2], gyn.shape[3]
         dw = ops.conv2d_wgrad(xn, gyn, ci, co, k, k, stride, pad) if ctx.needs_input_grad[1] else None
-        db = gy.sum(dim=(0, 2, 3), dtype=torch.float32) if has_bias and ctx.needs_input_grad[2] else None
+        db = ops.channel_sum(gyn, co) if has_bias and ctx.needs_input_grad[2] else None
         dx = None
         if ctx.needs_input_grad[0]:
             # dx = conv(U, flip(w)^T, pad k-1-pad), U = gy with stride-1 zeros inserted, sized so that the result is H x W

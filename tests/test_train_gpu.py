@@ -113,3 +113,15 @@ def test_native_train_step_learns_and_calls_no_cudnn():
     assert cos(gn["bbox_z3d.6.weight"], g32["bbox_z3d.6.weight"]) > 0.995
     losses = [float(step(x, labels, t2, t3).detach()) for _ in range(8)]
     assert losses[-1] < losses[0], losses
+
+
+@pytest.mark.parametrize("shape", [(4, 48, 160, 128), (2, 13, 37, 27), (1, 96, 320, 16), (1, 5, 7, 144)])
+def test_channel_sum_vs_torch(shape):
+    from m3dssd_b200 import ops
+    N, H, W, C = shape
+    cs = (C + 7) // 8 * 8
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(N, H, W, cs, generator=g).bfloat16()
+    got = ops.channel_sum(x.cuda(), C)
+    ref = x.double()[..., :C].sum(dim=(0, 1, 2))
+    assert (got.cpu().double() - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())

@@ -1,3 +1,4 @@
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 30 --warmup 5 > gpurun_out/r02_bench_8gpu.json 2> gpurun_out/r02_bench_8gpu.err; python -c "
-import json
-d=json.load(open('gpurun_out/r02_bench_8gpu.json')); print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d.get('sustained',{}).get('value'), d['clocks'])"; tail -2 gpurun_out/r02_bench_8gpu.err
+timeout 600 python -m pytest tests/test_train_gpu.py -m gpu -q -x 2>&1 | tail -4
+timeout 900 python bench.py --mode train --steps 10 --warmup 3 2>/dev/null | tail -1 | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches']); print(json.dumps(d['train']))"
