@@ -242,11 +242,26 @@ __global__ void pack_wt_split_kernel(const float* __restrict__ w, __nv_bfloat16*
   }
 }
 
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long n) {
+  for (long i = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) * 4; i < n;
+       i += static_cast<long>(gridDim.x) * blockDim.x * 4) {
+    if (i + 4 <= n) {
+      const float4 v = *reinterpret_cast<const float4*>(in + i);
+      __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&a), o.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(out + i) = o;
+    } else {
+      for (long j = i; j < n; ++j) out[j] = __float2bfloat16_rn(in[j]);
+    }
+  }
+}
+
 static inline size_t al(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 struct BwdLayout {
   int Ho, Wo, KK, K, CoutP;
-  size_t x, om, gy, gcol, wt, gx, gw, total;
+  size_t x, om, gy, gcol, wt, gx, gw, colb, gyb, wg, total;  // colb / gyb / wg: bf16 copies + wgrad workspace (M3D_BF16)
 };
 
 static BwdLayout bwd_layout(int B, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil) {
@@ -263,7 +278,10 @@ static BwdLayout bwd_layout(int B, int C, int H, int W, int Cout, int kh, int kw
   L.wt = al(static_cast<size_t>(L.K) * L.CoutP * 6);  // fp32, or three bf16 parts
   L.gx = L.x;
   L.gw = al(static_cast<size_t>(Cout) * L.K * 4);
-  L.total = L.x + L.om + L.gy + L.gcol + L.wt + L.gx + L.gw;
+  L.colb = al(npo * L.K * 2);
+  L.gyb = al(npo * L.CoutP * 2);
+  L.wg = al(m3d_conv2d_wgrad_workspace(B, L.Ho, L.Wo, L.K, Cout, 1, 1)) + al(m3d_channel_sum_workspace(Cout));
+  L.total = L.x + L.om + L.gy + L.gcol + L.wt + L.gx + L.gw + L.colb + L.gyb + L.wg;
   return L;
 }
 
@@ -313,7 +331,8 @@ extern "C" int m3d_dcn_v2_backward(const float* input, const float* weight, cons
                                    int deformable_group, int precision, void* workspace, size_t workspace_bytes,
                                    m3d_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  M3D_REQUIRE(precision == M3D_F32 || precision == M3D_BF16X3, "backward precision must be M3D_F32 or M3D_BF16X3");
+  M3D_REQUIRE(precision == M3D_F32 || precision == M3D_BF16X3 || precision == M3D_BF16,
+              "backward precision must be M3D_F32, M3D_BF16X3 or M3D_BF16");
   const int dg = deformable_group;
   if (dg == 1)
     return dcn_backward_one_group(input, weight, offset, mask, grad_output, grad_input, grad_weight, grad_bias,
@@ -391,6 +410,9 @@ static int dcn_backward_one_group(const float* input, const float* weight, const
   float* wt = reinterpret_cast<float*>(ws + L.x + L.om + L.gy + L.gcol);
   float* gx = reinterpret_cast<float*>(ws + L.x + L.om + L.gy + L.gcol + L.wt);
   float* gw = reinterpret_cast<float*>(ws + L.x + L.om + L.gy + L.gcol + L.wt + L.gx);
+  __nv_bfloat16* colb = reinterpret_cast<__nv_bfloat16*>(ws + L.x + L.om + L.gy + L.gcol + L.wt + L.gx + L.gw);
+  __nv_bfloat16* gyb = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(colb) + L.colb);
+  uint8_t* wg_ws = reinterpret_cast<uint8_t*>(gyb) + L.gyb;
   const long npo = static_cast<long>(B) * L.Ho * L.Wo;
 
   int rc = m3d_nchw_to_nhwc(input, M3D_F32, x, M3D_F32, B, C, H, W, C, 0, stream_);
@@ -410,7 +432,7 @@ static int dcn_backward_one_group(const float* input, const float* weight, const
     const int grid = static_cast<int>(std::min<long>((total + 255) / 256, 4096));
     if (precision == M3D_F32) {
       pack_wt_kernel<<<grid, 256, 0, stream>>>(weight, wt, Cout, C, L.KK, L.CoutP);
-    } else {
+    } else {  // (M3D_BF16 uses the high part only)
       __nv_bfloat16* w3 = reinterpret_cast<__nv_bfloat16*>(wt);
       pack_wt_split_kernel<<<grid, 256, 0, stream>>>(weight, w3, w3 + total, w3 + 2 * total, Cout, C, L.KK, L.CoutP);
     }
@@ -424,7 +446,14 @@ static int dcn_backward_one_group(const float* input, const float* weight, const
   d.N = B, d.H = L.Ho, d.W = L.Wo;
   d.R = 1, d.S = 1, d.stride = 1, d.pad = 0, d.dil = 1;
   d.Cout = L.K, d.groups = 1;
-  if (precision == M3D_F32) {  // IEEE fp32 FMA on the CUDA cores (reference accuracy)
+  if (precision == M3D_BF16) {  // bf16 operands (the training throughput mode): gy rounded to bf16 once, used twice
+    const long n = npo * L.CoutP;
+    f32_to_bf16_kernel<<<static_cast<int>(std::min<long>((n / 4 + 255) / 256, 4096)), 256, 0, stream>>>(gy, gyb, n);
+    M3D_CUDA_OK(cudaGetLastError());
+    d.act_dtype = M3D_BF16;
+    d.in[0] = gyb;
+    d.weight = reinterpret_cast<const __nv_bfloat16*>(wt);
+  } else if (precision == M3D_F32) {  // IEEE fp32 FMA on the CUDA cores (reference accuracy)
     d.weight_f32 = wt;
   } else {  // 3-part bf16 split on the tensor cores (~3e-6 relative)
     const long total = static_cast<long>(L.K) * L.CoutP;
@@ -446,7 +475,23 @@ static int dcn_backward_one_group(const float* input, const float* weight, const
   M3D_CUDA_OK(cudaGetLastError());
   dcn_bwd_input_kernel<<<blocks, 256, 0, stream>>>(g, x, om, gcol, gx);  // gcol becomes col
   M3D_CUDA_OK(cudaGetLastError());
-  {
+  if (precision == M3D_BF16 && L.K % 8 == 0) {  // (K = C * kh * kw not a multiple of 8: TMA strides, SIMT path below)
+    // dW = gy^T col on the tensor cores (wgrad.cu: the sampled columns are the "input" of a 1x1 convolution with K
+    // channels), bias gradient by the deterministic channel sum -- no atomics in this mode except the input scatter
+    const long n = npo * L.K;
+    f32_to_bf16_kernel<<<static_cast<int>(std::min<long>((n / 4 + 255) / 256, 8192)), 256, 0, stream>>>(gcol, colb, n);
+    M3D_CUDA_OK(cudaGetLastError());
+    const size_t wsz = m3d_conv2d_wgrad_workspace(B, L.Ho, L.Wo, L.K, Cout, 1, 1);
+    rc = m3d_conv2d_wgrad(colb, L.K, 0, gyb, L.CoutP, 0, gw, B, L.Ho, L.Wo, L.K, L.Ho, L.Wo, Cout, 1, 1, 1, 0, 1, wg_ws, wsz,
+                          stream_);
+    if (rc) return rc;
+    rc = m3d_channel_sum(gyb, npo, Cout, L.CoutP, 0, grad_bias, wg_ws + al(wsz), m3d_channel_sum_workspace(Cout), stream_);
+    if (rc) return rc;
+    const long total = static_cast<long>(Cout) * L.K;
+    repack_weight_grad_kernel<<<static_cast<int>(std::min<long>((total + 255) / 256, 4096)), 256, 0, stream>>>(
+        gw, grad_weight, Cout, C, L.KK);
+    M3D_CUDA_OK(cudaGetLastError());
+  } else {
     const int split = static_cast<int>(std::max<long>(1, std::min<long>(64, npo / 2048)));
     const long per = ((npo + split - 1) / split + 15) / 16 * 16;
     dim3 grid((L.K + 63) / 64, (Cout + 63) / 64, split);

@@ -419,7 +419,7 @@ def dcn_v2_backward(input, offset, mask, weight, grad_output, stride, padding, d
     ws = torch.empty(n, dtype=torch.uint8, device=input.device)
     check(lib().m3d_dcn_v2_backward(*[_p(t) for t in args], _p(gi), _p(gw), _p(gb), _p(go), _p(gm), B, Cin, H, W, Cout,
                                     kh, kw, stride, stride, padding, padding, dilation, dilation, deformable_groups,
-                                    M3D_F32 if precision == M3D_F32 else M3D_BF16X3, _p(ws), n, _stream()))
+                                    precision, _p(ws), n, _stream()))
     _count(12 * deformable_groups)  # layout conversions, W^T dY GEMM, coordinate / input gradient kernels, dW, bias, repack
     return gi, go, gm, gw, gb
 

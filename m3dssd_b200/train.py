@@ -127,7 +127,7 @@ def _upsample_forward(self, x):
     return nn.ConvTranspose2d.forward(self, x)
 
 
-def enable(net, dcn_precision="bf16x3"):
+def enable(net, dcn_precision="bf16"):
     """Route every nn.Conv2d / depthwise nn.ConvTranspose2d of `net` through the native kernels while it is in training
     mode (eval mode keeps using the fused engine).  Returns the number of patched modules."""
     import types
