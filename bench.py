@@ -265,6 +265,21 @@ def run_train(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
+    ddp = world > 1
+    if ddp:
+        # multi-GPU training = the reference's data parallelism (lib/core.py:73-83 wraps the net in nn.DataParallel) done
+        # the one-process-per-GPU way: gradients all-reduced over NCCL, bucketed and overlapped with the backward pass
+        import torch.distributed as dist
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)  # NCCL prints its banner on stdout
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.all_reduce(torch.zeros(1, device="cuda"))
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     B, W_, K = 4, max(3, args.warmup), args.steps
     conf = synth.make_conf(attention=None, center_align=False, shape_align=False, crop_size=CROP, batch_size=B)
     net = build(conf, "train")
@@ -289,7 +304,7 @@ def run_train(args):
 
     # ---- torch / cuDNN arms (the reference's way), before cuDNN is switched off for the native path
     baselines = {}
-    for name, autocast in (("torch_cudnn_fp32", False), ("torch_cudnn_bf16_autocast", True)):
+    for name, autocast in (() if ddp else (("torch_cudnn_fp32", False), ("torch_cudnn_bf16_autocast", True))):
         ref = build(conf, "train").cuda()
         ref.load_state_dict(sd)
         st = train.TrainStep(ref, conf, native=False)
@@ -311,6 +326,29 @@ def run_train(args):
         torch.cuda.empty_cache()
 
     net = net.cuda()
+    if ddp:
+        train.enable(net)
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], gradient_as_bucket_view=True)
+        eager = train.TrainStep(model, conf, native=False)  # (already enabled; TrainStep drives the DDP wrapper)
+        timed(eager, W_)
+        dist.barrier()
+        ms = timed(eager, K)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        if rank == 0:
+            print(json.dumps({
+                "metric": "images_per_sec", "value": world * B * K / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
+                "steps": K, "warmup": W_, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "kitti_3d_base train step (fwd+bwd+SGD), batch 4 384x1280 per GPU, DLA-34 "
+                                       "(BASELINE.json configs[3] extended to N GPUs, SURVEY 8f rank 2)",
+                           "global_batch": world * B, "parallelism": "ddp%d: NCCL gradient all-reduce overlapped with "
+                           "the backward pass (torch DistributedDataParallel buckets); eager (no CUDA graph)" % world},
+                "e2e": None, "gpu_launches": None}))
+        dist.barrier()
+        dist.destroy_process_group()
+        return 0
     eager = train.TrainStep(net, conf, native=True)
     timed(eager, 3)
     ms_eager = timed(eager, max(5, K // 2))

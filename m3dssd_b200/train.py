@@ -96,6 +96,43 @@ class _ConvFn(Function):
         return dx, dw, db, None, None
 
 
+class _DCNFn(Function):
+    """DCNv2 in the training graph on the NHWC / bf16 tensors themselves: forward = the fused deformable kernel
+    (m3d_conv2d_nhwc with offsets / mask: bilinear gather + tcgen05 GEMM, no NCHW round trip), backward =
+    m3d_dcn_v2_backward in its bf16 tensor-core mode.  `mask` is the modulation after the sigmoid, as DCNv2.forward
+    receives it (model/DCNv2/dcn_v2.py:39-41)."""
+
+    @staticmethod
+    def forward(ctx, x, offset, mask, weight, bias, stride, pad):
+        co, ci, k, _ = weight.shape
+        xn = _cl(x).permute(0, 2, 3, 1)
+        om = torch.cat([offset, mask], dim=1).permute(0, 2, 3, 1).float().contiguous()  # [N, P, Q, 3 k^2]
+        N, P, Q, _ = om.shape
+        out = torch.empty(N, P, Q, co, dtype=torch.bfloat16, device=x.device)
+        ops.conv2d_nhwc([(xn, 0, ci)], _pack(weight.detach(), ci), out, R=k, S=k, stride=stride, pad=pad, Cout=co,
+                        bias=bias.detach().float().contiguous(), slope=1.0, om=om, sigmoid_mask=False)
+        ctx.save_for_backward(x, offset, mask, weight, bias)
+        ctx.cfg = (stride, pad)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        from ._lib import M3D_BF16
+        x, offset, mask, weight, bias = ctx.saved_tensors
+        stride, pad = ctx.cfg
+        gi, go, gm, gw, gb = ops.dcn_v2_backward(x, offset, mask, weight, gy, stride, pad, 1, 1, precision=M3D_BF16)
+        return gi.to(x.dtype), go.to(offset.dtype), gm.to(mask.dtype), gw, gb, None, None
+
+
+def _dcn_op(self):
+    """Replacement of DCNv2._op for modules in the native training graph."""
+    ok = (self.training and self.dilation == 1 and self.deformable_groups == 1 and self.in_channels % 64 == 0 and
+          self.out_channels % 8 == 0 and self.kernel_size == (3, 3))
+    if not ok:
+        return type(self)._op(self)
+    return lambda x, offset, mask, weight, bias: _DCNFn.apply(x, offset, mask, weight, bias, self.stride, self.padding)
+
+
 class _UpsampleFn:
     """IDAUp.up_i: depthwise ConvTranspose2d(2f, stride f, pad f // 2, groups = C, no bias) (model/pose_dla_dcn.py:536-539)
     as k*k strided slice-accumulates (differentiable torch indexing; 0.03 GFLOP per image in the whole network)."""
@@ -136,6 +173,7 @@ def enable(net, dcn_precision="bf16"):
     for m in net.modules():
         if isinstance(m, DCNv2):
             m.precision = dcn_precision  # tensor-core arithmetic for the deformable layers of the training graph
+            m._op = types.MethodType(_dcn_op, m)
         if type(m) is nn.Conv2d:
             m.forward = types.MethodType(_conv_forward, m)
             n += 1
