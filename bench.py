@@ -328,7 +328,8 @@ def run_train(args):
     net = net.cuda()
     if ddp:
         train.enable(net)
-        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], gradient_as_bucket_view=True)
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], gradient_as_bucket_view=True,
+                                                          find_unused_parameters=True)  # nested Trees own a `project` their forward never uses
         eager = train.TrainStep(model, conf, native=False)  # (already enabled; TrainStep drives the DDP wrapper)
         timed(eager, W_)
         dist.barrier()
