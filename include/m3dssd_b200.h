@@ -135,7 +135,8 @@ int m3d_dcn_v2_backward(const float* input, const float* weight, const float* of
                         int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int deformable_group,
                         int precision /* M3D_F32: GEMMs on the CUDA cores in IEEE fp32; M3D_BF16X3: W^T dY on the tensor cores (3-part
                                          split); M3D_BF16: W^T dY and dW (m3d_conv2d_wgrad on the sampled columns) on
-                                         the tensor cores with bf16 operands, deterministic bias gradient */,
+                                         the tensor cores with bf16 operands; every gradient deterministic (fixed-point col2im
+                                         accumulation, ordered split-K and channel sums) */,
                         void* workspace, size_t workspace_bytes, m3d_stream_t stream);
 
 /* ------------------------------------------------------------------------

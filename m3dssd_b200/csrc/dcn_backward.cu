@@ -96,8 +96,14 @@ __global__ void dcn_bwd_coord_kernel(const BwdGeom g, const float* __restrict__ 
 
 // d input (NHWC, zero-initialised): scatter w_corner * gcol * m to the four corners.
 // Also rewrites gcol in place with the forward column value (sampled * m) for the dW GEMM.
+// FIXED: the scatter accumulates in 64-bit FIXED POINT (2^-32 resolution): integer addition is associative, so the
+// result does not depend on the order in which the atomics land -- a deterministic col2im (the reference's float
+// atomicAdd, dcn_v2_im2col_cuda.cu:182-231, is not reproducible run to run).
+constexpr float kFixScale = 4294967296.f;  // 2^32
+template <bool FIXED>
 __global__ void dcn_bwd_input_kernel(const BwdGeom g, const float* __restrict__ x, const float* __restrict__ om,
-                                     float* __restrict__ gcol, float* __restrict__ grad_x) {
+                                     float* __restrict__ gcol, float* __restrict__ grad_x,
+                                     unsigned long long* __restrict__ grad_x_fix) {
   const int lane = threadIdx.x & 31;
   const long wid = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
   const long total = static_cast<long>(g.B) * g.Ho * g.Wo * g.KK;
@@ -126,7 +132,12 @@ __global__ void dcn_bwd_input_kernel(const BwdGeom g, const float* __restrict__ 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (s.ok[k]) {
-        if (wgt[k] != 0.f) atomicAdd(grad_x + off[k] + c, wgt[k] * top);
+        if (wgt[k] != 0.f) {
+          if constexpr (FIXED)
+            atomicAdd(grad_x_fix + off[k] + c, static_cast<unsigned long long>(__float2ll_rn(wgt[k] * top * kFixScale)));
+          else
+            atomicAdd(grad_x + off[k] + c, wgt[k] * top);
+        }
         val += wgt[k] * x[off[k] + c];
       }
     }
@@ -242,6 +253,11 @@ __global__ void pack_wt_split_kernel(const float* __restrict__ w, __nv_bfloat16*
   }
 }
 
+__global__ void fixed_to_f32_kernel(const unsigned long long* __restrict__ in, float* __restrict__ out, long n) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
+    out[i] = static_cast<float>(static_cast<double>(static_cast<long long>(in[i])) * (1.0 / 4294967296.0));
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long n) {
   for (long i = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) * 4; i < n;
        i += static_cast<long>(gridDim.x) * blockDim.x * 4) {
@@ -261,7 +277,8 @@ static inline size_t al(size_t x) { return (x + 255) & ~static_cast<size_t>(255)
 
 struct BwdLayout {
   int Ho, Wo, KK, K, CoutP;
-  size_t x, om, gy, gcol, wt, gx, gw, colb, gyb, wg, total;  // colb / gyb / wg: bf16 copies + wgrad workspace (M3D_BF16)
+  size_t x, om, gy, gcol, wt, gx, gw, colb, gyb, wg, gx64, total;  // colb / gyb / wg / gx64: M3D_BF16 mode (bf16 copies,
+                                                                   // wgrad workspace, fixed-point input-gradient accumulator)
 };
 
 static BwdLayout bwd_layout(int B, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil) {
@@ -281,7 +298,8 @@ static BwdLayout bwd_layout(int B, int C, int H, int W, int Cout, int kh, int kw
   L.colb = al(npo * L.K * 2);
   L.gyb = al(npo * L.CoutP * 2);
   L.wg = al(m3d_conv2d_wgrad_workspace(B, L.Ho, L.Wo, L.K, Cout, 1, 1)) + al(m3d_channel_sum_workspace(Cout));
-  L.total = L.x + L.om + L.gy + L.gcol + L.wt + L.gx + L.gw + L.colb + L.gyb + L.wg;
+  L.gx64 = al(static_cast<size_t>(B) * H * W * C * 8);
+  L.total = L.x + L.om + L.gy + L.gcol + L.wt + L.gx + L.gw + L.colb + L.gyb + L.wg + L.gx64;
   return L;
 }
 
@@ -413,6 +431,7 @@ static int dcn_backward_one_group(const float* input, const float* weight, const
   __nv_bfloat16* colb = reinterpret_cast<__nv_bfloat16*>(ws + L.x + L.om + L.gy + L.gcol + L.wt + L.gx + L.gw);
   __nv_bfloat16* gyb = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(colb) + L.colb);
   uint8_t* wg_ws = reinterpret_cast<uint8_t*>(gyb) + L.gyb;
+  unsigned long long* gx64 = reinterpret_cast<unsigned long long*>(wg_ws + L.wg);
   const long npo = static_cast<long>(B) * L.Ho * L.Wo;
 
   int rc = m3d_nchw_to_nhwc(input, M3D_F32, x, M3D_F32, B, C, H, W, C, 0, stream_);
@@ -473,7 +492,15 @@ static int dcn_backward_one_group(const float* input, const float* weight, const
   const int blocks = static_cast<int>((warps * 32 + 255) / 256);
   dcn_bwd_coord_kernel<<<blocks, 256, 0, stream>>>(g, x, om, gcol, grad_offset, grad_mask);
   M3D_CUDA_OK(cudaGetLastError());
-  dcn_bwd_input_kernel<<<blocks, 256, 0, stream>>>(g, x, om, gcol, gx);  // gcol becomes col
+  if (precision == M3D_BF16) {  // deterministic: fixed-point accumulation, then one conversion pass
+    const long nx = static_cast<long>(B) * H * W * C;
+    M3D_CUDA_OK(cudaMemsetAsync(gx64, 0, static_cast<size_t>(nx) * 8, stream));
+    dcn_bwd_input_kernel<true><<<blocks, 256, 0, stream>>>(g, x, om, gcol, gx, gx64);  // gcol becomes col
+    M3D_CUDA_OK(cudaGetLastError());
+    fixed_to_f32_kernel<<<static_cast<int>(std::min<long>((nx + 255) / 256, 8192)), 256, 0, stream>>>(gx64, gx, nx);
+  } else {
+    dcn_bwd_input_kernel<false><<<blocks, 256, 0, stream>>>(g, x, om, gcol, gx, nullptr);  // gcol becomes col
+  }
   M3D_CUDA_OK(cudaGetLastError());
   if (precision == M3D_BF16 && L.K % 8 == 0) {  // (K = C * kh * kw not a multiple of 8: TMA strides, SIMT path below)
     // dW = gy^T col on the tensor cores (wgrad.cu: the sampled columns are the "input" of a 1x1 convolution with K

@@ -175,3 +175,20 @@ def test_dcn_module_with_two_deformable_groups():
     ref = O.dcn_v2_forward(x.cpu().numpy(), off, mask, dcn.weight.detach().cpu().numpy(),
                            dcn.bias.detach().cpu().numpy(), 1, 1, 1, 2)
     assert np.abs(y.cpu().numpy() - ref).max() < 3e-6 * max(np.abs(ref).max(), 1)
+
+
+def test_dcn_v2_backward_bf16_mode_is_deterministic():
+    """M3D_BF16 backward (the training mode): fixed-point col2im accumulation, ordered split-K wgrad and channel sums ->
+    two runs give bit-identical gradients (the reference's float atomicAdd col2im does not)."""
+    from m3dssd_b200 import ops
+    from m3dssd_b200._lib import M3D_BF16
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 64, 24, 40, generator=g).cuda()
+    off = (torch.randn(2, 18, 24, 40, generator=g) * 2.5).cuda()
+    m = torch.rand(2, 9, 24, 40, generator=g).cuda()
+    w = (torch.randn(64, 64, 3, 3, generator=g) / 24).cuda()
+    gy = torch.randn(2, 64, 24, 40, generator=g).cuda()
+    a = ops.dcn_v2_backward(x, off, m, w, gy, 1, 1, 1, 1, precision=M3D_BF16)
+    b = ops.dcn_v2_backward(x, off, m, w, gy, 1, 1, 1, 1, precision=M3D_BF16)
+    for name, ta, tb in zip(("input", "offset", "mask", "weight", "bias"), a, b):
+        assert torch.equal(ta, tb), name
