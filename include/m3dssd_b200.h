@@ -209,6 +209,11 @@ int m3d_maxpool2x2_nhwc(const void* in, void* out, int dtype, int N, int H, int 
 int m3d_upsample_add_nhwc(const void* x, const float* weight /*tap-major [(2f)^2, C]*/, const void* skip, void* out, int dtype,
                           int N, int H, int W, int C, int f, int x_cstride, int skip_cstride, int out_cstride,
                           m3d_stream_t stream);
+/* Backward of the same up-sampling (training path; bf16 NHWC, dense channels): gx = depthwise strided conv of gy with the
+ * weights, gw [(2f)^2, C] fp32 (tap-major) = per-tap correlation of gy with x. */
+size_t m3d_upsample_backward_workspace(int C, int f);
+int m3d_upsample_backward(const void* gy, const void* x, const float* weight, void* gx, float* gw, int N, int H, int W,
+                          int C, int f, void* workspace, size_t workspace_bytes, m3d_stream_t stream);
 /* softmax over classes + fg prob + top-1 anchor + score/class (model/M3d_inference_align.py:229-234). */
 int m3d_cls_softmax(const float* logits, int logits_cstride, int N, int H, int W, int A, int K, float* cls_out,
                     float* prob_out, float* fg_max, int* fg_arg, float* score, unsigned char* cls_pred,

@@ -17,6 +17,7 @@ _SIGS = {
     "m3d_stem_conv7x7_s2d": [vp, vp, vp, vp, i, i, i, f, vp],
     "m3d_maxpool2x2_nhwc": [vp, vp, i, i, i, i, i, i, i, vp],
     "m3d_upsample_add_nhwc": [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp],
+    "m3d_upsample_backward": [vp, vp, vp, vp, vp, i, i, i, i, i, vp, sz, vp],
     "m3d_cls_softmax": [vp, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp],
     "m3d_shape_align_om": [vp, vp, vp, i, f, f, vp, lg, vp],
     "m3d_center_align_om": [vp, vp, vp, i, i, i, vp, i, f, f, f, f, f, f, vp, i, lg, vp],
@@ -38,6 +39,7 @@ _SIZE_FNS = {
     "m3d_decode_topk_workspace": [i],
     "m3d_conv2d_wgrad_workspace": [i] * 7,
     "m3d_channel_sum_workspace": [i],
+    "m3d_upsample_backward_workspace": [i, i],
 }
 
 

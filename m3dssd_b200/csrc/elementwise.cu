@@ -533,11 +533,113 @@ __global__ void __launch_bounds__(256) preprocess_u8_kernel(const unsigned char*
   }
 }
 
+// ---------------------------------------------------------------------------
+// Backward of the depthwise ConvTranspose2d(2f, stride f, pad f/2) up-sampling (training path), bf16 NHWC:
+//   gx[n,iy,ix,c]   = sum_{ky,kx} gy[n, iy*f - pad + ky, ix*f - pad + kx, c] * w[ky,kx,c]
+//   gw[ky,kx,c]     = sum_{n,iy,ix} gy[n, iy*f - pad + ky, ix*f - pad + kx, c] * x[n,iy,ix,c]
+// One thread = one input pixel x 8 channels; the weight gradient is reduced per block in shared memory in 64-bit FIXED
+// POINT (integer atomics: the order of arrival does not change the sum) and written as per-block partials
+// [blocks][k*k][C], added in block order by a second kernel: deterministic end to end.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upsample_bwd_kernel(const __nv_bfloat16* __restrict__ gy,
+                                                           const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
+                                                           __nv_bfloat16* __restrict__ gx, float* __restrict__ gw_partial,
+                                                           int N, int H, int W, int C, int f) {
+  extern __shared__ unsigned long long s_gw[];  // [k*k][C], fixed point 2^-32
+  const int k = 2 * f, pad = f / 2, kk = k * k;
+  const int Ho = H * f, Wo = W * f, cv = C / 8;
+  for (int i = threadIdx.x; i < kk * C; i += blockDim.x) s_gw[i] = 0ull;
+  __syncthreads();
+  const long total = static_cast<long>(N) * H * W * cv;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % cv) * 8;
+    long pix = idx / cv;
+    const int ix = static_cast<int>(pix % W);
+    pix /= W;
+    const int iy = static_cast<int>(pix % H), n = static_cast<int>(pix / H);
+    float xv[8], acc[8];
+    {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<long>(n) * H + iy) * W + ix) * C + c));
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) xv[2 * q] = __uint_as_float(w4[q] << 16), xv[2 * q + 1] = __uint_as_float(w4[q] & 0xffff0000u);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    for (int ky = 0; ky < k; ++ky) {
+      const int oy = iy * f - pad + ky;
+      if (oy < 0 || oy >= Ho) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int ox = ix * f - pad + kx;
+        if (ox < 0 || ox >= Wo) continue;
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(gy + ((static_cast<long>(n) * Ho + oy) * Wo + ox) * C + c));
+        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+        const float* wp = wt + (ky * k + kx) * C + c;
+        unsigned long long* gp = s_gw + (ky * k + kx) * C + c;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float g0 = __uint_as_float(w4[q] << 16), g1 = __uint_as_float(w4[q] & 0xffff0000u);
+          acc[2 * q] += g0 * __ldg(wp + 2 * q);
+          acc[2 * q + 1] += g1 * __ldg(wp + 2 * q + 1);
+          atomicAdd(gp + 2 * q, static_cast<unsigned long long>(__float2ll_rn(g0 * xv[2 * q] * 4294967296.f)));
+          atomicAdd(gp + 2 * q + 1, static_cast<unsigned long long>(__float2ll_rn(g1 * xv[2 * q + 1] * 4294967296.f)));
+        }
+      }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      __nv_bfloat162 b2 = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
+      o[q] = *reinterpret_cast<uint32_t*>(&b2);
+    }
+    *reinterpret_cast<uint4*>(gx + ((static_cast<long>(n) * H + iy) * W + ix) * C + c) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kk * C; i += blockDim.x)
+    gw_partial[static_cast<long>(blockIdx.x) * kk * C + i] =
+        static_cast<float>(static_cast<double>(static_cast<long long>(s_gw[i])) * (1.0 / 4294967296.0));
+}
+
+__global__ void upsample_bwd_reduce_kernel(const float* __restrict__ partial, int nblocks, int n, float* __restrict__ gw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += partial[static_cast<long>(b) * n + i];
+  gw[i] = s;
+}
+
 }  // namespace m3d
 
 using namespace m3d;
 
 static inline cudaStream_t S(m3d_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kUpBwdBlocks = 296;
+extern "C" size_t m3d_upsample_backward_workspace(int C, int f) {
+  return static_cast<size_t>(kUpBwdBlocks) * 4 * f * f * C * sizeof(float);
+}
+
+extern "C" int m3d_upsample_backward(const void* gy, const void* x, const float* weight, void* gx, float* gw, int N, int H,
+                                     int W, int C, int f, void* workspace, size_t workspace_bytes, m3d_stream_t stream) {
+  M3D_REQUIRE(gy && x && weight && gx && gw && workspace, "NULL pointer");
+  M3D_REQUIRE(C % 8 == 0 && f >= 1 && f <= 4, "C must be a multiple of 8, f in 1..4");
+  const int kk = 4 * f * f;
+  const size_t smem = static_cast<size_t>(kk) * C * sizeof(unsigned long long);
+  M3D_REQUIRE(smem <= 48 * 1024, "k*k*C too large for the shared weight-gradient tile");
+  if (workspace_bytes < m3d_upsample_backward_workspace(C, f)) {
+    set_last_error("upsample backward workspace too small");
+    return M3D_ERR_WORKSPACE;
+  }
+  float* partial = static_cast<float*>(workspace);
+  upsample_bwd_kernel<<<kUpBwdBlocks, 256, smem, S(stream)>>>(static_cast<const __nv_bfloat16*>(gy),
+                                                               static_cast<const __nv_bfloat16*>(x), weight,
+                                                               static_cast<__nv_bfloat16*>(gx), partial, N, H, W, C, f);
+  M3D_CUDA_OK(cudaGetLastError());
+  upsample_bwd_reduce_kernel<<<(kk * C + 255) / 256, 256, 0, S(stream)>>>(partial, kUpBwdBlocks, kk * C, gw);
+  M3D_CUDA_OK(cudaGetLastError());
+  return M3D_OK;
+}
 
 extern "C" int m3d_preprocess_u8(const unsigned char* image_hwc, float* out_nchw, int N, int H, int W, const float* mean3,
                                  const float* std3, int swap_rb, m3d_stream_t stream) {

@@ -450,3 +450,17 @@ def channel_sum(x_nhwc, C, coff=0):
     check(lib().m3d_channel_sum(_p(x_nhwc), npix, C, cs, coff, _p(out), _p(ws), n, _stream()))
     _count(2)
     return out
+
+
+def upsample_backward(gy, x, weight, f):
+    """Backward of upsample_add without the skip (training path): gy [N,H*f,W*f,C], x [N,H,W,C] bf16 NHWC dense,
+    weight tap-major [(2f)^2, C] fp32 -> (gx bf16 [N,H,W,C], gw fp32 [(2f)^2, C])."""
+    N, H, W, Cc = x.shape
+    assert gy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and gy.is_contiguous() and x.is_contiguous()
+    gx = torch.empty_like(x)
+    gw = torch.empty(4 * f * f, Cc, dtype=torch.float32, device=x.device)
+    n = lib().m3d_upsample_backward_workspace(Cc, f)
+    ws = torch.empty(n, dtype=torch.uint8, device=x.device)
+    check(lib().m3d_upsample_backward(_p(gy), _p(x), _p(weight), _p(gx), _p(gw), N, H, W, Cc, f, _p(ws), n, _stream()))
+    _count(2)
+    return gx, gw

@@ -12,8 +12,8 @@ training mode, through the C ABI in both directions:
 and the deformable layers through m3d_dcn_v2_forward / m3d_dcn_v2_backward (model/DCNv2/dcn_v2_func.py).  Activations are
 bf16 in channels_last (= NHWC) storage, so torch's elementwise / BatchNorm / pooling kernels and the C-ABI kernels share
 buffers without layout copies; master weights, BatchNorm statistics, gradients of the parameters and the optimizer
-state stay fp32 (mixed precision).  The depthwise ConvTranspose2d up-sampling of IDAUp (0.03 GFLOP) is expressed as 16
-strided slice-accumulates.  No cuDNN / cuBLAS convolution is called: `enable(net)` also switches cuDNN off for the
+state stay fp32 (mixed precision).  The depthwise ConvTranspose2d up-sampling of IDAUp runs through m3d_upsample_add_nhwc /
+m3d_upsample_backward.  No cuDNN / cuBLAS convolution is called: `enable(net)` also switches cuDNN off for the
 process so that a stray nn.functional.conv2d cannot silently fall back to it.
 """
 import torch
@@ -133,21 +133,28 @@ def _dcn_op(self):
     return lambda x, offset, mask, weight, bias: _DCNFn.apply(x, offset, mask, weight, bias, self.stride, self.padding)
 
 
-class _UpsampleFn:
-    """IDAUp.up_i: depthwise ConvTranspose2d(2f, stride f, pad f // 2, groups = C, no bias) (model/pose_dla_dcn.py:536-539)
-    as k*k strided slice-accumulates (differentiable torch indexing; 0.03 GFLOP per image in the whole network)."""
+class _UpsampleFn(Function):
+    """IDAUp.up_i: depthwise ConvTranspose2d(2f, stride f, pad f // 2, groups = C, no bias) (model/pose_dla_dcn.py:536-539):
+    forward m3d_upsample_add_nhwc (no skip), backward m3d_upsample_backward (input gradient = depthwise strided
+    correlation, weight gradient reduced deterministically)."""
 
     @staticmethod
-    def apply(x, weight, f):
-        N, C, H, W = x.shape
-        k, p = 2 * f, f // 2
-        full = torch.zeros(N, C, (H - 1) * f + k, (W - 1) * f + k, dtype=x.dtype, device=x.device)
-        full = full.contiguous(memory_format=torch.channels_last)
-        w = weight.to(x.dtype)
-        for ky in range(k):
-            for kx in range(k):
-                full[:, :, ky:ky + (H - 1) * f + 1:f, kx:kx + (W - 1) * f + 1:f] += x * w[:, 0, ky, kx].view(1, C, 1, 1)
-        return full[:, :, p:p + H * f, p:p + W * f]
+    def forward(ctx, x, weight, f):
+        xn = _cl(x).permute(0, 2, 3, 1)
+        N, H, W, C = xn.shape
+        wt = ops.pack_upsample_weight(weight)  # tap-major [(2f)^2, C] fp32
+        out = torch.empty(N, H * f, W * f, C, dtype=torch.bfloat16, device=x.device)
+        ops.upsample_add(xn, wt, None, out, f)
+        ctx.save_for_backward(xn, wt)
+        ctx.f = f
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xn, wt = ctx.saved_tensors
+        gx, gw = ops.upsample_backward(_cl(gy).permute(0, 2, 3, 1).contiguous(), xn, wt, ctx.f)
+        k = 2 * ctx.f
+        return gx.permute(0, 3, 1, 2), gw.t().reshape(-1, 1, k, k).contiguous(), None
 
 
 def _conv_forward(self, x):

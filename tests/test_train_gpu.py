@@ -125,3 +125,26 @@ def test_channel_sum_vs_torch(shape):
     got = ops.channel_sum(x.cuda(), C)
     ref = x.double()[..., :C].sum(dim=(0, 1, 2))
     assert (got.cpu().double() - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("shape", [(2, 128, 12, 20, 2), (1, 256, 6, 10, 2), (2, 64, 5, 7, 2)])
+def test_upsample_autograd_vs_torch(shape):
+    """_UpsampleFn (IDAUp's depthwise ConvTranspose2d through m3d_upsample_add_nhwc / m3d_upsample_backward) vs torch CPU."""
+    from m3dssd_b200.train import _UpsampleFn
+    N, C, H, W, f = shape
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(N, C, H, W, generator=g).bfloat16().float()
+    w = torch.rand(C, 1, 2 * f, 2 * f, generator=g)
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yr = F.conv_transpose2d(xr, wr, None, stride=f, padding=f // 2, groups=C)
+    gy = torch.randn(yr.shape, generator=g).bfloat16().float()
+    yr.backward(gy)
+    xd, wd = x.cuda().bfloat16().requires_grad_(True), w.cuda().requires_grad_(True)
+    yd = _UpsampleFn.apply(xd, wd, f)
+    yd.backward(gy.cuda().bfloat16())
+
+    def rel(a, r):
+        return (a.float().cpu() - r).abs().max().item() / r.abs().max().item()
+
+    assert yd.shape == yr.shape and rel(yd.detach(), yr.detach()) < 2 ** -7
+    assert rel(xd.grad, xr.grad) < 2 ** -7 and rel(wd.grad, wr.grad) < 1e-4
