@@ -181,6 +181,16 @@ int m3d_decode_topk(const float* score, const unsigned char* cls_pred, const flo
                     int W, float feat_stride, float scale_factor, int topk, float* dets, int* det_idx, int* det_num,
                     void* workspace /*device, 16-byte aligned, m3d_decode_topk_workspace(batch) bytes, caller-owned*/,
                     size_t workspace_bytes, m3d_stream_t stream);
+/* Same selection and decode with the regression outputs read where the heads wrote them: the NHWC buffer
+ * [batch, H, W, heads_cstride] in which output j (x,y,w,h,x3d,y3d,z3d,w3d,h3d,l3d,rY3d) of anchor a at a pixel is
+ * channel slot_of_output[j] * A + a.  Only the <= topk selected rows are read, so the detection path never
+ * materialises the reference's flattened bbox_2d / bbox_3d (lib/rpn_util.py:892-901): results are bit-identical to
+ * m3d_flatten_heads followed by m3d_decode_topk. */
+int m3d_decode_topk_heads(const float* score, const unsigned char* cls_pred, const float* heads, int heads_cstride,
+                          const int* slot_of_output /*host [11]*/, const float* anchors, const float* means11,
+                          const float* stds11, int batch, int A, int H, int W, float feat_stride, float scale_factor,
+                          int topk, float* dets, int* det_idx, int* det_num, void* workspace, size_t workspace_bytes,
+                          m3d_stream_t stream);
 int m3d_gather_kept(const float* dets, int row_len, int batch, int max_n, const int* keep, const int* num_keep,
                     int max_out, float* out, m3d_stream_t stream);
 

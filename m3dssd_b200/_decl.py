@@ -9,6 +9,7 @@ _SIGS = {
     "m3d_nms": [vp, vp, vp, i, i, f, i],
     "m3d_nms_batched": [vp, i, vp, i, i, f, vp, sz, vp, vp, vp],
     "m3d_decode_topk": [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, f, f, i, vp, vp, vp, vp, sz, vp],
+    "m3d_decode_topk_heads": [vp, vp, vp, i, vp, vp, vp, vp, i, i, i, i, f, f, i, vp, vp, vp, vp, sz, vp],
     "m3d_gather_kept": [vp, i, i, i, vp, vp, i, vp, vp],
     "m3d_stem_conv7x7": [vp, vp, vp, vp, i, i, i, i, i, f, vp],
     "m3d_conv2d_wgrad": [vp, i, i, vp, i, i, vp] + [i] * 12 + [vp, sz, vp],

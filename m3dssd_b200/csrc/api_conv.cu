@@ -227,7 +227,7 @@ static int sm_count() {
 
 int launch_conv_simt_f32(const m3d_conv_desc* d, int P, int Q, cudaStream_t stream);
 bool conv_halo_supported(int BN, int out_dtype, bool staged);
-bool conv_halo2_supported(int BN, long m_tiles);
+bool conv_halo2_supported(int BN, long m_tiles, int cout);
 int launch_conv_halo2(const ConvTmaParams& p, int BN, cudaStream_t stream);
 int launch_conv_halo(const ConvTmaParams& p, int BN, int out_dtype, bool staged, cudaStream_t stream);
 
@@ -395,7 +395,7 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
                       conv_halo_supported(BN, d->out_dtype == M3D_F32 ? DT_F32 : DT_BF16, staged) &&
                       getenv("M3D_NO_HALO") == nullptr;
     if (halo) {
-      const bool pair = staged && conv_halo2_supported(BN, m_tiles);  // CTA pairs: each CTA loads half of the weight rows
+      const bool pair = staged && conv_halo2_supported(BN, m_tiles, d->Cout);  // CTA pairs: each CTA loads half of the weight rows
       int rc = make_tmap_nhwc(&p.tmap_a[0], d->in[0], d->N, d->H, d->W, d->in_cstride[0], 64, TW, TH + 2, 1);
       if (rc != M3D_OK) return rc;
       rc = make_tmap_b_halo(&p.tmap_b, d->weight, d->weight_rows, d->in_c[0] / 64, pair ? BN / 2 : BN);

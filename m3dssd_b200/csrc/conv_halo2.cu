@@ -20,6 +20,11 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#ifdef M3D_PROBE
+// epilogue stamps of the leader CTA's first epilogue thread: rows 32.. (8 slots per tile, two rows of the table)
+namespace m3d { __device__ long long g_h2_epi[64]; __device__ int g_h2_epi_row; }
+#define EPI_STAMP(slot) do { if (blockIdx.x == 0 && threadIdx.x == 64 && m3d::g_h2_epi_row < 7) m3d::g_h2_epi[m3d::g_h2_epi_row * 8 + (slot)] = clock64(); } while (0)
+#endif
 #include "epilogue.cuh"
 #include "igemm.cuh"
 #include "ptx.cuh"
@@ -38,7 +43,8 @@ struct Halo2Cfg {
   static constexpr int A_BYTES = 20 * 1024;
   static constexpr int BH_BYTES = (BN / 2) * 128;  // this CTA's half of one tap's weight tile
   static constexpr int STAGE = A_BYTES + 3 * BH_BYTES;
-  static constexpr int EXTRA = 2 * kSlabBytes + 1024;
+  static constexpr int BIAS_FLOATS = 1024;  // every bias of the layer lives in shared memory (host gate: Cout <= 1024)
+  static constexpr int EXTRA = 2 * kSlabBytes + BIAS_FLOATS * 4;
   static constexpr int BUDGET = 225 * 1024 + 512 - EXTRA;
   static constexpr int FIT = BUDGET / STAGE;
   static constexpr int STAGES = FIT >= 4 ? 4 : FIT;
@@ -114,11 +120,27 @@ struct H2Tile {
   int nt, n, p0, q0;
 };
 
+// Timeline probe (tools/probe_halo2.py): compile with -DM3D_PROBE.  Cluster 0, leader CTA; rows = pipeline stages
+// (first 40) / items; stamps in shared memory, copied out at kernel end.
+#ifdef M3D_PROBE
+__device__ long long g_h2_dbg[64 * 4];
+#define H2DBG(row, slot) do { if (blockIdx.x == 0 && lane == 0 && (row) < 64) s_dbg[(row) * 4 + (slot)] = clock64(); } while (0)
+#else
+#define H2DBG(row, slot) do { } while (0)
+#endif
+
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
     conv_halo2_kernel(const __grid_constant__ ConvTmaParams p) {
   using Cfg = Halo2Cfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
+#ifdef M3D_PROBE
+  __shared__ long long s_dbg[64 * 4];
+  if (blockIdx.x == 0 && threadIdx.x == 64) g_h2_epi_row = 0;
+  if (threadIdx.x < 64 * 4) s_dbg[threadIdx.x] = 0;
+  int prow = 0;
+  const long long t_entry = clock64();
+#endif
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_out = smem + STAGES * Cfg::STAGE;
@@ -127,8 +149,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = tfull + 2;
-  uint64_t* res_bar = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
+  uint64_t* ready = tempty + 2;  // per epilogue group: residual slab landed / slab buffer free
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -143,7 +165,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);          // multicast commit
       mbar_init(&tempty[s], 2 * kNW);   // one arrival per epilogue warp of both CTAs
-      mbar_init(&res_bar[s], 1);
+      mbar_init(&ready[s], 1);
     }
     fence_barrier_init();
     prefetch_tmap(&p.tmap_a[0]);
@@ -156,7 +178,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
   cluster_sync_all();  // both CTAs' barriers are initialised before anything signals across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#ifdef M3D_PROBE
+  const long long t_setup = clock64();
+#endif
   grid_dep_sync();
+#ifdef M3D_PROBE
+  if (blockIdx.x == 0 && threadIdx.x == 0) s_dbg[47 * 4] = t_entry, s_dbg[47 * 4 + 1] = t_setup, s_dbg[47 * 4 + 2] = clock64();
+#endif
 
   const int nchunk = p.chunks[0];
   const int n_stages = 3 * nchunk;
@@ -215,11 +243,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
       for (int it = first; it < last; ++it, ++local) {
         const int as = local & 1;
         const uint32_t aphase = (local >> 1) & 1;
+        H2DBG(48 + local, 0);
         mbar_wait(&tempty[as], aphase ^ 1);
+        H2DBG(48 + local, 1);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + as * Cfg::ACC;
         for (int st = 0; st < n_stages; ++st) {
+          H2DBG(prow, 0);
           mbar_wait(&full[stage], phase);
+          H2DBG(prow, 1);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE);
@@ -235,6 +267,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
             umma2_commit_mc(&empty[stage]);
           }
           __syncwarp();
+#ifdef M3D_PROBE
+          H2DBG(prow, 2);
+          ++prow;
+#endif
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -245,30 +281,56 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
       }
     }
   } else {
+    // two independent groups of 4 warps, each draining half of the tile's columns (epilogue.cuh, "grouped")
     const int quarter = warp & 3;
     const int ep_tid = threadIdx.x - 64;
-    StagedEpilogue st;
-    st.init(stage_out, reinterpret_cast<float*>(stage_out + 2 * kSlabBytes), res_bar);
+    const int group = ep_tid >> 7, gtid = ep_tid & 127;
+    float* bias_s = reinterpret_cast<float*>(stage_out + 2 * kSlabBytes);
+    const int nb = p.n_tiles * BN;
+    for (int i = ep_tid; i < nb; i += 32 * kNW) bias_s[i] = (p.bias != nullptr && i < p.Cout) ? __ldg(p.bias + i) : 0.f;
+    named_bar_sync(kEpiBarrier + 2, 32 * kNW);
+    GroupedEpilogue st;
+    st.init(stage_out + group * kSlabBytes, bias_s, &ready[group]);
+    const void* tmap_res = p.res ? &p.tmap_res : nullptr;
+    auto epi_tile = [&](int it) {
+      const H2Tile t = item_tile(it);
+      return EpiTile{t.n, t.p0, t.q0, t.nt * BN};
+    };
+    EpiTile cur = epi_tile(first);
+    if (first < last) epilogue_grouped_begin<BN>(st, gtid, group, cur, tmap_res, p.res_coff);
     int local = 0;
     for (int it = first; it < last; ++it, ++local) {
-      const H2Tile t = item_tile(it);
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
+      EpiTile nxt = cur;
+      if (it + 1 < last) nxt = epi_tile(it + 1);
+      if (warp == 2) H2DBG(48 + local, 2);
       mbar_wait(&tfull[as], aphase);
+      if (warp == 2) H2DBG(48 + local, 3);
       tc_fence_after();
-      const int col0 = t.nt * BN;
-      epilogue_tile_staged<BN, kNW>(st, tmem_base + as * Cfg::ACC, quarter, lane, ep_tid, t.n, t.p0, t.q0, &p.tmap_out,
-                                    p.out_coff + col0, p.res ? &p.tmap_res : nullptr, p.res_coff + col0,
-                                    p.bias ? p.bias + col0 : nullptr, p.Cout - col0, p.slope, [&]() {
-                                      tc_fence_before();
-                                      __syncwarp();
-                                      if (lane == 0) mbar_arrive_leader(&tempty[as]);
-                                    });
+      epilogue_tile_grouped<BN>(st, tmem_base + as * Cfg::ACC, quarter, lane, gtid, group, cur,
+                                it + 1 < last ? &nxt : nullptr, &p.tmap_out, p.out_coff, tmap_res, p.res_coff, p.slope,
+                                [&]() {
+                                  tc_fence_before();
+                                  __syncwarp();
+                                  if (lane == 0) mbar_arrive_leader(&tempty[as]);
+                                });
+      cur = nxt;
+#ifdef M3D_PROBE
+      EPI_STAMP(6);
+      if (blockIdx.x == 0 && threadIdx.x == 64) ++g_h2_epi_row;
+#endif
     }
-    if (ep_tid == 0) tma_store_wait_all();
+    if (gtid == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
+#ifdef M3D_PROBE
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) s_dbg[47 * 4 + 3] = clock64();
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x < 64 * 4) g_h2_dbg[threadIdx.x] = s_dbg[threadIdx.x];
+#endif
   cluster_sync_all();  // the peer may still be signalling / reading this CTA's shared memory and TMEM
   if (warp == 1) {
     tc_fence_after();
@@ -296,9 +358,9 @@ int launch_t(const ConvTmaParams& p, cudaStream_t stream) {
 }  // namespace
 
 // staged bf16 3x3 stride-1 convs with 128-channel N tiles and an even number of 128-pixel tiles
-bool conv_halo2_supported(int BN, long m_tiles) {
+bool conv_halo2_supported(int BN, long m_tiles, int cout) {
   if (getenv("M3D_NO_PAIR") != nullptr) return false;
-  return BN == 128 && m_tiles % 2 == 0;
+  return BN == 128 && m_tiles % 2 == 0 && (cout + BN - 1) / BN * BN <= Halo2Cfg<128>::BIAS_FLOATS;
 }
 
 int launch_conv_halo2(const ConvTmaParams& p, int BN, cudaStream_t stream) {
@@ -307,3 +369,12 @@ int launch_conv_halo2(const ConvTmaParams& p, int BN, cudaStream_t stream) {
 }
 
 }  // namespace m3d
+
+#ifdef M3D_PROBE
+extern "C" int m3d_halo2_debug_read(long long* host, int n) {
+  return cudaMemcpyFromSymbol(host, m3d::g_h2_dbg, sizeof(long long) * n) == cudaSuccess ? 0 : -1;
+}
+extern "C" int m3d_halo2_epi_read(long long* host) {
+  return cudaMemcpyFromSymbol(host, m3d::g_h2_epi, sizeof(long long) * 64) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -109,6 +109,9 @@ struct DecodeParams {
   const unsigned char* cls;   // [N, M]
   const float* bbox_2d;       // [N, M, 4]
   const float* bbox_3d;       // [N, M, 7]
+  const float* heads;         // or (bbox_2d == nullptr): the NHWC head buffer [N, H, W, heads_cstride], column of output
+  int heads_cstride;          //   j of anchor a = slot[j] * A + a (j: x,y,w,h,x3d,y3d,z3d,w3d,h3d,l3d,rY3d)
+  int slot[11];
   const float* anchors;       // [A, 9]
   float means[11], stds[11];
   int M, A, H, W;
@@ -251,8 +254,17 @@ __device__ void topk_sort_decode(const DecodeParams& p, int n, unsigned long lon
     const float ry2 = static_cast<float>(static_cast<double>(h) * p.feat_stride + static_cast<double>(an[3]));
     const float widths = rx2 - rx1 + 1.0f, heights = ry2 - ry1 + 1.0f;
     const float ctr_x = rx1 + 0.5f * widths, ctr_y = ry1 + 0.5f * heights;
-    const float* b2 = p.bbox_2d + (static_cast<long>(n) * p.M + idx) * 4;
-    const float* b3 = p.bbox_3d + (static_cast<long>(n) * p.M + idx) * 7;
+    float b2[4], b3[7];
+    if (p.bbox_2d != nullptr) {
+      const float* s2 = p.bbox_2d + (static_cast<long>(n) * p.M + idx) * 4;
+      const float* s3 = p.bbox_3d + (static_cast<long>(n) * p.M + idx) * 7;
+      for (int j = 0; j < 4; ++j) b2[j] = s2[j];
+      for (int j = 0; j < 7; ++j) b3[j] = s3[j];
+    } else {  // the same values, before flatten_tensor (lib/rpn_util.py:892-901) moved them
+      const float* hp = p.heads + ((static_cast<long>(n) * p.H + h) * p.W + w) * p.heads_cstride + a;
+      for (int j = 0; j < 4; ++j) b2[j] = hp[p.slot[j] * p.A];
+      for (int j = 0; j < 7; ++j) b3[j] = hp[p.slot[4 + j] * p.A];
+    }
     float t3[7];
     for (int j = 0; j < 7; ++j) t3[j] = b3[j] * p.stds[4 + j] + p.means[4 + j];
     const float x3d = t3[0] * widths + ctr_x;
@@ -748,16 +760,17 @@ extern "C" size_t m3d_decode_topk_workspace(int batch) {
   return topk_hist_bytes(batch) + static_cast<size_t>(batch) * kCandCap * sizeof(unsigned long long);
 }
 
-extern "C" int m3d_decode_topk(const float* score, const unsigned char* cls_pred, const float* bbox_2d,
-                               const float* bbox_3d, const float* anchors, const float* means11, const float* stds11,
-                               int batch, int A, int H, int W, float feat_stride, float scale_factor, int topk,
-                               float* dets, int* det_idx, int* det_num, void* workspace, size_t workspace_bytes,
-                               m3d_stream_t stream) {
-  M3D_REQUIRE(score && cls_pred && bbox_2d && bbox_3d && anchors && means11 && stds11 && dets && det_idx && det_num,
-              "NULL pointer");
+static int decode_topk_impl(const float* score, const unsigned char* cls_pred, const float* bbox_2d,
+                            const float* bbox_3d, const float* heads, int heads_cstride, const int* slot_of_output,
+                            const float* anchors, const float* means11, const float* stds11, int batch, int A, int H,
+                            int W, float feat_stride, float scale_factor, int topk, float* dets, int* det_idx,
+                            int* det_num, void* workspace, size_t workspace_bytes, m3d_stream_t stream) {
+  M3D_REQUIRE(score && cls_pred && anchors && means11 && stds11 && dets && det_idx && det_num, "NULL pointer");
   M3D_REQUIRE(topk >= 1 && topk <= kMaxTopK, "topk=%d out of range (1..%d)", topk, kMaxTopK);
   DecodeParams p;
   p.score = score, p.cls = cls_pred, p.bbox_2d = bbox_2d, p.bbox_3d = bbox_3d, p.anchors = anchors;
+  p.heads = heads, p.heads_cstride = heads_cstride;
+  for (int i = 0; i < 11; ++i) p.slot[i] = slot_of_output ? slot_of_output[i] : 0;
   for (int i = 0; i < 11; ++i) p.means[i] = means11[i], p.stds[i] = stds11[i];
   p.M = A * H * W, p.A = A, p.H = H, p.W = W;
   p.feat_stride = feat_stride, p.scale_factor = scale_factor, p.topk = topk;
@@ -788,6 +801,30 @@ extern "C" int m3d_decode_topk(const float* score, const unsigned char* cls_pred
   topk_decode_kernel<<<batch, kSelThreads, 0, st>>>(p);
   M3D_CUDA_OK(cudaGetLastError());
   return M3D_OK;
+}
+
+extern "C" int m3d_decode_topk(const float* score, const unsigned char* cls_pred, const float* bbox_2d,
+                               const float* bbox_3d, const float* anchors, const float* means11, const float* stds11,
+                               int batch, int A, int H, int W, float feat_stride, float scale_factor, int topk,
+                               float* dets, int* det_idx, int* det_num, void* workspace, size_t workspace_bytes,
+                               m3d_stream_t stream) {
+  M3D_REQUIRE(bbox_2d && bbox_3d, "NULL pointer");
+  return decode_topk_impl(score, cls_pred, bbox_2d, bbox_3d, nullptr, 0, nullptr, anchors, means11, stds11, batch, A, H, W,
+                          feat_stride, scale_factor, topk, dets, det_idx, det_num, workspace, workspace_bytes, stream);
+}
+
+extern "C" int m3d_decode_topk_heads(const float* score, const unsigned char* cls_pred, const float* heads,
+                                     int heads_cstride, const int* slot_of_output, const float* anchors,
+                                     const float* means11, const float* stds11, int batch, int A, int H, int W,
+                                     float feat_stride, float scale_factor, int topk, float* dets, int* det_idx,
+                                     int* det_num, void* workspace, size_t workspace_bytes, m3d_stream_t stream) {
+  M3D_REQUIRE(heads && slot_of_output, "NULL pointer");
+  for (int i = 0; i < 11; ++i)
+    M3D_REQUIRE(slot_of_output[i] >= 0 && (slot_of_output[i] + 1) * A <= heads_cstride, "head slot %d outside the buffer",
+                slot_of_output[i]);
+  return decode_topk_impl(score, cls_pred, nullptr, nullptr, heads, heads_cstride, slot_of_output, anchors, means11, stds11,
+                          batch, A, H, W, feat_stride, scale_factor, topk, dets, det_idx, det_num, workspace,
+                          workspace_bytes, stream);
 }
 
 extern "C" int m3d_gather_kept(const float* dets, int row_len, int batch, int max_n, const int* keep, const int* num_keep,

@@ -226,6 +226,127 @@ __device__ __forceinline__ void epilogue_tile_staged(StagedEpilogue& st, uint32_
   }
 }
 
+// ---------------------------------------------------------------- grouped
+// Same job as epilogue_tile_staged with the serial chain taken apart (timeline probe, round 2: the staged drain of a
+// 128 x 128 tile held its accumulator for ~5.5 k clocks and took 6.8 k in all -- bias __ldg, residual TMA issued only
+// after the accumulator was complete, two slabs in lock step -- against 4.6 k clocks of MMAs per tile).  Here
+//  * the 8 epilogue warps are two independent groups of 4; group g owns columns [g*BN/2, (g+1)*BN/2) of the tile, one
+//    16 KB slab buffer, one `ready` mbarrier and one named barrier: no cross-group synchronisation;
+//  * a thread pulls all 64 columns of its row of a slab out of TMEM at once, so a 128-column accumulator is released
+//    a few hundred clocks after it completed;
+//  * the residual slab of the NEXT tile is TMA-loaded into the group's buffer as soon as the store of the current
+//    one has read it, i.e. a whole tile time before it is needed; without a residual the leader just arrives;
+//  * the layer's biases are copied to shared memory once per kernel.
+struct EpiTile {
+  int n, p0, q0, col0;  // image, first tile row / column, first output channel of the BN-wide tile
+};
+#ifndef EPI_STAMP  // timeline probe hook (conv_halo2.cu defines it under -DM3D_PROBE)
+#define EPI_STAMP(slot) do { } while (0)
+#endif
+
+struct GroupedEpilogue {
+  uint8_t* buf;         // this group's slab (1024-byte aligned)
+  const float* bias_s;  // every bias of the layer (zero padded to n_tiles * BN)
+  uint64_t* ready;      // residual landed / buffer free
+  uint32_t uses;
+  __device__ __forceinline__ void init(uint8_t* buf_, const float* bias_smem, uint64_t* ready_) {
+    buf = buf_, bias_s = bias_smem, ready = ready_;
+    uses = 0;
+  }
+};
+
+// column offset (inside the BN tile) of slab k of group g
+template <int BN>
+__device__ __forceinline__ int grouped_col(int group, int k) {
+  return group * (BN / 2) + k * 64;
+}
+
+// Before the first tile: the group leader (gtid == 0) fetches the first residual slab / declares the buffer free.
+template <int BN>
+__device__ __forceinline__ void epilogue_grouped_begin(GroupedEpilogue& st, int gtid, int group, const EpiTile& t,
+                                                       const void* tmap_res, int res_coff) {
+  if (gtid != 0) return;
+  if (tmap_res != nullptr) {
+    mbar_arrive_expect_tx(st.ready, kSlabBytes);
+    tma_load_4d(st.buf, tmap_res, st.ready, res_coff + t.col0 + grouped_col<BN>(group, 0), t.q0, t.p0, t.n);
+  } else {
+    mbar_arrive(st.ready);
+  }
+}
+
+template <int BN, typename F>
+__device__ __forceinline__ void epilogue_tile_grouped(GroupedEpilogue& st, uint32_t tmem_acc, int quarter, int lane,
+                                                      int gtid, int group, const EpiTile& t, const EpiTile* next,
+                                                      const void* tmap_out, int out_coff, const void* tmap_res,
+                                                      int res_coff, float slope, F on_tmem_drained) {
+  static_assert(BN % 128 == 0, "two groups of whole 64-channel slabs");
+  constexpr int NS = BN / 128;  // slabs per group
+  const int row = quarter * 32 + lane;
+  const bool has_res = tmap_res != nullptr;
+  const uint32_t buf_s = smem_u32(st.buf);
+#pragma unroll 1
+  for (int k = 0; k < NS; ++k) {
+    const int c = grouped_col<BN>(group, k);
+    uint32_t a[64];
+    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + c;
+    tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(a));
+    tmem_ld32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(a + 32));
+    tmem_ld_wait();
+    EPI_STAMP(0);
+    if (k == NS - 1) on_tmem_drained();
+    mbar_wait(st.ready, st.uses & 1);
+    EPI_STAMP(1);
+    ++st.uses;
+    const float* bias = st.bias_s + t.col0 + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // chunks of 8 channels
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(a[j * 8 + e]);
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + j * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias + j * 8 + 4);
+      v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w, v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
+      const uint32_t cell = buf_s + swizzled_offset<128>(row, j);
+      if (has_res) {
+        const uint4 u = lds128(cell);
+        v[0] += __uint_as_float(u.x << 16), v[1] += __uint_as_float(u.x & 0xffff0000u);
+        v[2] += __uint_as_float(u.y << 16), v[3] += __uint_as_float(u.y & 0xffff0000u);
+        v[4] += __uint_as_float(u.z << 16), v[5] += __uint_as_float(u.z & 0xffff0000u);
+        v[6] += __uint_as_float(u.w << 16), v[7] += __uint_as_float(u.w & 0xffff0000u);
+      }
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(lrelu(v[2 * e], slope), lrelu(v[2 * e + 1], slope));
+        w[e] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      sts128(cell, make_uint4(w[0], w[1], w[2], w[3]));
+    }
+    EPI_STAMP(2);
+    fence_proxy_async_smem();
+    EPI_STAMP(3);
+    named_bar_sync(kEpiBarrier + group, 128);  // slab complete
+    EPI_STAMP(4);
+    if (gtid == 0) {
+      tma_store_4d(tmap_out, st.buf, out_coff + t.col0 + c, t.q0, t.p0, t.n);
+      tma_store_commit();
+      const bool same = k + 1 < NS;
+      if (same || next != nullptr) {
+        tma_store_wait_read<0>();  // the buffer has left
+        EPI_STAMP(5);
+        if (has_res) {
+          const EpiTile& u = same ? t : *next;
+          mbar_arrive_expect_tx(st.ready, kSlabBytes);
+          tma_load_4d(st.buf, tmap_res, st.ready, res_coff + u.col0 + grouped_col<BN>(group, same ? k + 1 : 0), u.q0,
+                      u.p0, u.n);
+        } else {
+          mbar_arrive(st.ready);
+        }
+      }
+    }
+  }
+}
+
 // One 128 x BN fp32 tile (bf16 activations, fp32 output: the class logits).  Same staging as above with 32-column
 // slabs (128 rows x 128 bytes, swizzled, one TMA store per slab): a thread writing its row's 576 bytes straight to
 // global memory touches 32 different lines per warp instruction, which made cls.l3 LSU-bound.  No residual.  Slabs

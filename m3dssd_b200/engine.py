@@ -482,6 +482,9 @@ class Engine:
         self._head_group("headsZ", ["bbox_z3d"], fz, heads)
         self.bbox_2d = torch.zeros(B, M, 4, **f32)
         self.bbox_3d = torch.zeros(B, M, 7, **f32)
+        # the reference's flattened outputs (lib/rpn_util.py:892-901): part of "forward" (what RPN.forward returns) only;
+        # the detection stages decode their <= topk rows straight from `heads` (m3d_decode_topk_heads)
+        self.n_detect_ops = len(self.ops)
         self._add(lambda: ops.flatten_heads(heads, A, OUT_SLOTS, self.bbox_2d, self.bbox_3d), 1, "flatten_heads",
                   "flatten", 0, B * M * 11 * 4 * 2, dict(op="flatten"))
         self.n_forward_ops = len(self.ops)
@@ -499,14 +502,14 @@ class Engine:
         self.feat_size = torch.tensor([Hf, Wf], dtype=torch.float32, device=self.dev)
 
     # ------------------------------------------------------------------- run
-    def _run_forward(self):
-        for op in self.ops:
+    def _run_forward(self, flatten=True):
+        for op in (self.ops if flatten else self.ops[:self.n_detect_ops]):
             op()
 
     def _run_decode(self):
-        ops.decode_topk(self.score, self.cls_pred, self.bbox_2d, self.bbox_3d, self.anchors, self.means_t, self.stds_t,
-                        self.A, self.Hf, self.Wf, float(self.conf.feat_stride), self.scale_factor, self.topk, self.dets,
-                        self.det_idx, self.det_num, self.topk_ws)
+        ops.decode_topk_heads(self.score, self.cls_pred, self.heads, OUT_SLOTS, self.anchors, self.means_t, self.stds_t,
+                              self.A, self.Hf, self.Wf, float(self.conf.feat_stride), self.scale_factor, self.topk,
+                              self.dets, self.det_idx, self.det_num, self.topk_ws)
 
     def _run_nms(self):
         ops.nms_batched(self.dets, self.det_num, float(self.conf.nms_thres), self.nms_ws, self.keep, self.num_keep)
@@ -515,7 +518,8 @@ class Engine:
     _STAGES = {"forward": 0, "decode": 1, "detect": 2}
 
     def _run_stage(self, stage):
-        self._run_forward()
+        # bbox_2d / bbox_3d (the flattened copies) are refreshed by "forward" only
+        self._run_forward(flatten=self._STAGES[stage] == 0)
         if self._STAGES[stage] >= 1:
             self._run_decode()
         if self._STAGES[stage] >= 2:
@@ -523,7 +527,8 @@ class Engine:
 
     def launches_per_step(self, stage="detect"):
         # decode = 2 histogram passes + compaction + finish (m3d_decode_topk); NMS = mask + sweep + gather of the kept rows
-        return self.n_launches + (0, 4, 7)[self._STAGES[stage]]
+        st = self._STAGES[stage]
+        return self.n_launches - (1 if st >= 1 else 0) + (0, 4, 7)[st]  # the detection stages skip flatten_heads
 
     def activation_nchw(self, name):
         """fp32 NCHW copy of a named intermediate activation (testing aid)."""
@@ -567,6 +572,12 @@ class Engine:
         assert tuple(images.shape) == tuple(self.image.shape), (images.shape, self.image.shape)
         self.image.copy_(images, non_blocking=True)
 
+    def flatten_outputs(self):
+        """Refresh self.bbox_2d / self.bbox_3d (the reference's flattened box tensors) from the head buffer after a
+        "decode" / "detect" / pipelined step, which do not write them.  Returns (bbox_2d, bbox_3d)."""
+        self.ops[self.n_detect_ops]()
+        return self.bbox_2d, self.bbox_3d
+
     def forward(self, images=None):
         """Returns (cls, prob, bbox_2d, bbox_3d): views of the engine's output buffers."""
         self.run(images, "forward")
@@ -604,7 +615,7 @@ class Engine:
                 op()
 
         def heads():
-            for op in self.ops[self.n_trunk_ops:]:
+            for op in self.ops[self.n_trunk_ops:self.n_detect_ops]:
                 op()
 
         if self.use_graph:

@@ -332,6 +332,22 @@ def decode_topk(score, cls_pred, bbox_2d, bbox_3d, anchors, means, stds, A, H, W
                                 _p(det_num), _p(workspace), workspace.numel(), _stream()))
 
 
+def decode_topk_heads(score, cls_pred, heads, slots, anchors, means, stds, A, H, W, feat_stride, scale_factor, topk,
+                      dets, det_idx, det_num, workspace=None):
+    """decode_topk with the regression outputs read from the NHWC head buffer [B,H,W,>=11*A] (output j of anchor a =
+    channel slots[j]*A + a): the detection path skips flatten_heads; same results bit for bit."""
+    B = score.shape[0]
+    assert heads.dtype == torch.float32 and heads.is_contiguous() and tuple(heads.shape[:3]) == (B, H, W)
+    if workspace is None:
+        workspace = decode_topk_workspace(B, score.device)
+    means = (C.c_float * 11)(*[float(v) for v in means])
+    stds = (C.c_float * 11)(*[float(v) for v in stds])
+    sl = (C.c_int * 11)(*[int(v) for v in slots])
+    check(lib().m3d_decode_topk_heads(_p(score), _p(cls_pred), _p(heads), heads.shape[-1], sl, _p(anchors), means, stds,
+                                      B, A, H, W, float(feat_stride), float(scale_factor), topk, _p(dets), _p(det_idx),
+                                      _p(det_num), _p(workspace), workspace.numel(), _stream()))
+
+
 def nms_workspace_bytes(batch, max_n):
     return lib().m3d_nms_workspace_bytes(batch, max_n)
 

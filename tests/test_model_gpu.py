@@ -97,6 +97,7 @@ def test_detection_tail_matches_oracle_on_engine_outputs():
     net = net.cuda().eval()
     eng = net.engine(2, 96, 320, precision="fp32", use_graph=False, max_out=3000)
     kept, num = eng.detect(x.cuda())
+    eng.flatten_outputs()  # the detect stage decodes from the head buffer and leaves bbox_2d / bbox_3d alone
     torch.cuda.synchronize()
     outs = [t.cpu() for t in (eng.cls_out, eng.prob_out, eng.bbox_2d, eng.bbox_3d)]
     oracle = RM.RefModel(sd, conf, dcn="tv")

@@ -134,6 +134,17 @@ def test_decode_topk_with_ties():
         assert torch.equal(didx[b].cpu().long(), order)
         assert np.allclose(dets[b].cpu().numpy(), pre.numpy(), rtol=2e-6, atol=1e-4)
         assert int(dnum[b]) == topk
+    # the same rows decoded from the NHWC head buffer (what the detection stages do): bit-identical
+    slots = [3, 7, 0, 9, 1, 10, 4, 2, 8, 5, 6]  # any permutation: output j lives in slot slots[j]
+    heads = torch.zeros(B, H, W, 11 * A + 4)
+    flat = torch.cat([b2, b3], dim=2).view(B, A, H, W, 11)  # row = (a*H + h)*W + w
+    for j in range(11):
+        heads[..., slots[j] * A:(slots[j] + 1) * A] = flat[..., j].permute(0, 2, 3, 1)
+    dets2, didx2, dnum2 = torch.zeros_like(dets), torch.zeros_like(didx), torch.zeros_like(dnum)
+    ops.decode_topk_heads(score.contiguous().cuda(), cls_pred.contiguous().cuda(), heads.cuda(), slots,
+                          torch.tensor(conf.anchors).cuda(), conf.bbox_means[0], conf.bbox_stds[0], A, H, W, 8.0, 1.0, topk,
+                          dets2, didx2, dnum2)
+    assert torch.equal(dets2, dets) and torch.equal(didx2, didx) and torch.equal(dnum2, dnum)
 
 
 @pytest.mark.parametrize("seed", [5, 6, 7, 11])

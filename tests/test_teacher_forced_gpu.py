@@ -29,8 +29,10 @@ pytestmark = pytest.mark.gpu
 # (rms bar, max bar) by layer type; bf16 storage: 2^-9 = 1.95e-3 relative per rounding
 BARS = {
     # conv_linear = the Trees' `project` (1x1 conv + BN only): its BatchNorm removes the large common mean of the
-    # post-activation input, so the same absolute rounding error is a larger fraction of what is left
-    "stem": (4e-3, 2e-2), "conv": (7e-3, 2e-2), "conv_linear": (1e-2, 3e-2), "conv_f32out": (3e-3, 1.5e-2), "dcn": (7e-3, 3e-2),
+    # post-activation input, so the same absolute rounding error (bf16 weights: 2^-9 per product, growing with
+    # sqrt(Cin)) is a larger fraction of what is left: measured 5-7e-3 for dla34, up to 1.15e-2 for dla102's
+    # 512/1024-channel projects.  A wiring error shows up as O(1), not as a few 1e-3.
+    "stem": (4e-3, 2e-2), "conv": (7e-3, 2e-2), "conv_linear": (1.5e-2, 4e-2), "conv_f32out": (3e-3, 1.5e-2), "dcn": (7e-3, 3e-2),
     "upsample": (3e-3, 1e-2), "head_mlp": (1e-2, 5e-2), "anab_pool": (1e-4, 1e-3), "anab_attention": (1e-2, 1e-1),
 }
 
@@ -246,6 +248,7 @@ def test_bf16_engine_teacher_forced_at_baseline_config(attention):
     net = net.cuda().eval()
     eng = net.engine(B, crop[0], crop[1], precision="bf16", use_graph=True, max_out=3000)
     eng.detect(x.cuda())  # the graph-replayed path, exactly what bench.py runs
+    eng.flatten_outputs()  # (the detect stage decodes from the head buffer; bbox_2d / bbox_3d belong to "forward")
     torch.cuda.synchronize()
     rep = Replay(eng, sd, conf)
     rows = rep.run()
