@@ -224,10 +224,16 @@ int m3d_upsample_add_nhwc(const void* x, const float* weight /*tap-major [(2f)^2
 size_t m3d_upsample_backward_workspace(int C, int f);
 int m3d_upsample_backward(const void* gy, const void* x, const float* weight, void* gx, float* gw, int N, int H, int W,
                           int C, int f, void* workspace, size_t workspace_bytes, m3d_stream_t stream);
-/* softmax over classes + fg prob + top-1 anchor + score/class (model/M3d_inference_align.py:229-234). */
+/* softmax over classes + fg prob + top-1 anchor + score/class (model/M3d_inference_align.py:229-234).
+ * cls_out / prob_out (the flattened copies RPN.forward returns) may both be NULL: the detection path does not read them. */
 int m3d_cls_softmax(const float* logits, int logits_cstride, int N, int H, int W, int A, int K, float* cls_out,
                     float* prob_out, float* fg_max, int* fg_arg, float* score, unsigned char* cls_pred,
                     m3d_stream_t stream);
+/* The same with m3d_shape_align_om folded into the per-pixel tail (one launch less; identical values). */
+int m3d_cls_softmax_shape_om(const float* logits, int logits_cstride, int N, int H, int W, int A, int K, float* cls_out,
+                             float* prob_out, float* fg_max, int* fg_arg, float* score, unsigned char* cls_pred,
+                             const float* anchors, int anchor_ld, float feat_stride, float thresh,
+                             float* shape_om /*[N*H*W,27]*/, m3d_stream_t stream);
 /* shape_align / center_align offset builders (model/module/feturealign_mgpu.py:119-136,58-77). */
 int m3d_shape_align_om(const float* fg_max, const int* fg_arg, const float* anchors, int anchor_ld, float feat_stride,
                        float thresh, float* om /*[npix,27]*/, long npix, m3d_stream_t stream);
@@ -235,6 +241,12 @@ int m3d_center_align_om(const float* fg_max, const int* fg_arg, const float* hea
                         int y_coff, const float* anchors, int anchor_ld, float feat_stride, float mean_x, float mean_y,
                         float std_x, float std_y, float thresh, float* om, int om_cstride, long npix,
                         m3d_stream_t stream);
+/* Both centre alignments of a pixel in one launch: xy_coff4 = {x_coff, y_coff} of om_a then of om_b, mean4 / std4 =
+ * {mean_x, mean_y} / {std_x, std_y} likewise (host arrays).  Same values as two m3d_center_align_om calls. */
+int m3d_center_align_om2(const float* fg_max, const int* fg_arg, const float* heads, int heads_cstride,
+                         const int* xy_coff4, const float* mean4, const float* std4, const float* anchors, int anchor_ld,
+                         float feat_stride, float thresh, float* om_a, float* om_b, int om_cstride, long npix,
+                         m3d_stream_t stream);
 /* G three-layer 1x1 regression heads that share the input x, fused in one kernel (conv1x1 + BN + LeakyReLU,
  * conv1x1 + BN + LeakyReLU, conv1x1: model/M3d_inference_align.py:66-210, 236-277; BatchNorm folded into w/b).
  * x: bf16 NHWC [N,H,W,x_cstride], channels [x_coff, x_coff+Cx), Cx in {64,128}.  w1: bf16 [G*256][Cx],

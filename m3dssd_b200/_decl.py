@@ -20,6 +20,8 @@ _SIGS = {
     "m3d_upsample_add_nhwc": [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp],
     "m3d_upsample_backward": [vp, vp, vp, vp, vp, i, i, i, i, i, vp, sz, vp],
     "m3d_cls_softmax": [vp, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp],
+    "m3d_cls_softmax_shape_om": [vp, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, i, f, f, vp, vp],
+    "m3d_center_align_om2": [vp, vp, vp, i, vp, vp, vp, vp, i, f, f, vp, vp, i, lg, vp],
     "m3d_shape_align_om": [vp, vp, vp, i, f, f, vp, lg, vp],
     "m3d_center_align_om": [vp, vp, vp, i, i, i, vp, i, f, f, f, f, f, f, vp, i, lg, vp],
     "m3d_set_sm_limit": [i],

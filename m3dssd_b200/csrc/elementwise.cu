@@ -225,11 +225,15 @@ constexpr int SM_PIX = 32;
 // staged class-major in shared memory ([K*A][SM_PIX + 1]) so that the NHWC reads (144 contiguous floats per
 // pixel) and the anchor-major writes (16 bytes per (anchor, pixel), pixels contiguous) are both coalesced and
 // the column accesses are bank-conflict free.
+__device__ __forceinline__ void shape_align_om_pixel(float fg, int a, const float* __restrict__ anchors, int anchor_ld,
+                                                     float feat_stride, float thresh, float* __restrict__ om, long i);
 __global__ void __launch_bounds__(256) cls_softmax4_kernel(const float* __restrict__ logits, int lc_stride, int N, int H,
                                                            int W, int A, float* __restrict__ cls_out,
                                                            float* __restrict__ prob_out, float* __restrict__ fg_max,
                                                            int* __restrict__ fg_arg, float* __restrict__ score,
-                                                           unsigned char* __restrict__ cls_pred) {
+                                                           unsigned char* __restrict__ cls_pred,
+                                                           const float* __restrict__ anchors, int anchor_ld,
+                                                           float feat_stride, float thresh, float* __restrict__ shape_om) {
   grid_dep_sync();
   extern __shared__ float s_tile[];  // [4*A][SM_PIX + 1], then fg [A][SM_PIX + 1]
   constexpr int K = 4, LD = SM_PIX + 1;
@@ -257,8 +261,10 @@ __global__ void __launch_bounds__(256) cls_softmax4_kernel(const float* __restri
     const float sum = ((e0 + e1) + e2) + e3;
     const float p0 = e0 / sum, p1 = e1 / sum, p2 = e2 / sum, p3 = e3 / sum;
     const long row = (static_cast<long>(n) * A + a) * H * W + static_cast<long>(h) * W + (w0 + px);
-    *reinterpret_cast<float4*>(cls_out + row * 4) = make_float4(v0, v1, v2, v3);
-    *reinterpret_cast<float4*>(prob_out + row * 4) = make_float4(p0, p1, p2, p3);
+    if (cls_out != nullptr) {  // (NULL: the detection stages only need score / class / fg below)
+      *reinterpret_cast<float4*>(cls_out + row * 4) = make_float4(v0, v1, v2, v3);
+      *reinterpret_cast<float4*>(prob_out + row * 4) = make_float4(p0, p1, p2, p3);
+    }
     float best = p1;
     int bestk = 1;
     if (p2 > best) best = p2, bestk = 2;
@@ -282,6 +288,7 @@ __global__ void __launch_bounds__(256) cls_softmax4_kernel(const float* __restri
     const long pix = (static_cast<long>(n) * H + h) * W + w0 + px;
     fg_max[pix] = best;
     fg_arg[pix] = arg;
+    if (shape_om != nullptr) shape_align_om_pixel(best, arg, anchors, anchor_ld, feat_stride, thresh, shape_om, pix);
   }
 }
 
@@ -323,8 +330,7 @@ __global__ void __launch_bounds__(256) cls_softmax_kernel(const float* __restric
     int bestk = 1;
     for (int k = 0; k < K; ++k) {
       const float p = e[k] / sum;
-      cls_out[row * K + k] = v[k];
-      prob_out[row * K + k] = p;
+      if (cls_out != nullptr) cls_out[row * K + k] = v[k], prob_out[row * K + k] = p;
       if (k >= 1 && p > best) {
         best = p;
         bestk = k;
@@ -358,14 +364,20 @@ __global__ void __launch_bounds__(256) cls_softmax_kernel(const float* __restric
 // for the top-1 anchor, zeroed where fg <= thresh; modulation mask = fg.
 // om layout: [N,H,W,27] = 18 offsets (dh, dw per tap) + 9 masks.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ void shape_align_om_pixel(float fg, int a, const float* __restrict__ anchors, int anchor_ld,
+                                                     float feat_stride, float thresh, float* __restrict__ om, long i);
+
 __global__ void shape_align_om_kernel(const float* __restrict__ fg_max, const int* __restrict__ fg_arg,
                                       const float* __restrict__ anchors, int anchor_ld, float feat_stride, float thresh,
                                       float* __restrict__ om, long npix) {
   grid_dep_sync();  // PDL: launched while the previous kernel drains
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (i >= npix) return;
-  const float fg = fg_max[i];
-  const int a = fg_arg[i];
+  shape_align_om_pixel(fg_max[i], fg_arg[i], anchors, anchor_ld, feat_stride, thresh, om, i);
+}
+
+__device__ __forceinline__ void shape_align_om_pixel(float fg, int a, const float* __restrict__ anchors, int anchor_ld,
+                                                     float feat_stride, float thresh, float* __restrict__ om, long i) {
   const float hard = fg > thresh ? 1.f : 0.f;
   const float aw = anchors[a * anchor_ld + 2] - anchors[a * anchor_ld + 0];
   const float ah = anchors[a * anchor_ld + 3] - anchors[a * anchor_ld + 1];
@@ -384,6 +396,17 @@ __global__ void shape_align_om_kernel(const float* __restrict__ fg_max, const in
 // center_align offsets (feturealign_mgpu.py:58-77): the 1x1 DCNv2 samples at
 // (dy, dx) = ((by*std_y + mean_y) * ah/stride, (bx*std_x + mean_x) * aw/stride)
 // of the top-1 anchor, zeroed where fg <= thresh; mask = fg.  om: [N,H,W,3].
+struct CenterAlignSet {
+  int x_coff, y_coff;
+  float mean_x, mean_y, std_x, std_y;
+  float* om;
+};
+__device__ __forceinline__ void center_align_om_pixel(float fg, int a, const float* __restrict__ heads, int heads_cstride,
+                                                      int x_coff, int y_coff, const float* __restrict__ anchors,
+                                                      int anchor_ld, float feat_stride, float mean_x, float mean_y,
+                                                      float std_x, float std_y, float thresh, float* __restrict__ om,
+                                                      int om_cstride, long i);
+
 __global__ void center_align_om_kernel(const float* __restrict__ fg_max, const int* __restrict__ fg_arg,
                                        const float* __restrict__ heads, int heads_cstride, int x_coff, int y_coff,
                                        const float* __restrict__ anchors, int anchor_ld, float feat_stride,
@@ -392,8 +415,31 @@ __global__ void center_align_om_kernel(const float* __restrict__ fg_max, const i
   grid_dep_sync();  // PDL: launched while the previous kernel drains
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (i >= npix) return;
+  center_align_om_pixel(fg_max[i], fg_arg[i], heads, heads_cstride, x_coff, y_coff, anchors, anchor_ld, feat_stride, mean_x,
+                        mean_y, std_x, std_y, thresh, om, om_cstride, i);
+}
+
+// both centre alignments (2D and 3D centres) of a pixel in one launch
+__global__ void center_align_om2_kernel(const float* __restrict__ fg_max, const int* __restrict__ fg_arg,
+                                        const float* __restrict__ heads, int heads_cstride, const CenterAlignSet s0,
+                                        const CenterAlignSet s1, const float* __restrict__ anchors, int anchor_ld,
+                                        float feat_stride, float thresh, int om_cstride, long npix) {
+  grid_dep_sync();
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (i >= npix) return;
   const float fg = fg_max[i];
   const int a = fg_arg[i];
+  center_align_om_pixel(fg, a, heads, heads_cstride, s0.x_coff, s0.y_coff, anchors, anchor_ld, feat_stride, s0.mean_x,
+                        s0.mean_y, s0.std_x, s0.std_y, thresh, s0.om, om_cstride, i);
+  center_align_om_pixel(fg, a, heads, heads_cstride, s1.x_coff, s1.y_coff, anchors, anchor_ld, feat_stride, s1.mean_x,
+                        s1.mean_y, s1.std_x, s1.std_y, thresh, s1.om, om_cstride, i);
+}
+
+__device__ __forceinline__ void center_align_om_pixel(float fg, int a, const float* __restrict__ heads, int heads_cstride,
+                                                      int x_coff, int y_coff, const float* __restrict__ anchors,
+                                                      int anchor_ld, float feat_stride, float mean_x, float mean_y,
+                                                      float std_x, float std_y, float thresh, float* __restrict__ om,
+                                                      int om_cstride, long i) {
   const float hard = fg > thresh ? 1.f : 0.f;
   const float aw = (anchors[a * anchor_ld + 2] - anchors[a * anchor_ld + 0]) / feat_stride;
   const float ah = (anchors[a * anchor_ld + 3] - anchors[a * anchor_ld + 1]) / feat_stride;
@@ -712,17 +758,20 @@ extern "C" int m3d_upsample_add_nhwc(const void* x, const float* weight, const v
   return M3D_OK;
 }
 
-extern "C" int m3d_cls_softmax(const float* logits, int logits_cstride, int N, int H, int W, int A, int K, float* cls_out,
-                               float* prob_out, float* fg_max, int* fg_arg, float* score, unsigned char* cls_pred,
-                               m3d_stream_t stream) {
-  M3D_REQUIRE(logits && cls_out && prob_out && fg_max && fg_arg && score && cls_pred, "NULL pointer");
+static int cls_softmax_impl(const float* logits, int logits_cstride, int N, int H, int W, int A, int K, float* cls_out,
+                            float* prob_out, float* fg_max, int* fg_arg, float* score, unsigned char* cls_pred,
+                            const float* anchors, int anchor_ld, float feat_stride, float thresh, float* shape_om,
+                            m3d_stream_t stream) {
+  M3D_REQUIRE(logits && fg_max && fg_arg && score && cls_pred, "NULL pointer");
+  M3D_REQUIRE((cls_out == nullptr) == (prob_out == nullptr), "cls_out and prob_out: both or neither");
   M3D_REQUIRE(K >= 2 && K <= 8 && A >= 1, "K=%d A=%d unsupported", K, A);
   dim3 grid(cdiv(W, SM_PIX), H, N);
   if (K == 4 && logits_cstride % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) {
     const size_t smem4 = static_cast<size_t>(5 * A) * (SM_PIX + 1) * sizeof(float);
     if (smem4 <= 48 * 1024) {
       M3D_CUDA_OK(launch_pdl(cls_softmax4_kernel, grid, dim3(256), smem4, S(stream), logits, logits_cstride, N, H, W, A,
-                             cls_out, prob_out, fg_max, fg_arg, score, cls_pred));
+                             cls_out, prob_out, fg_max, fg_arg, score, cls_pred, anchors, anchor_ld, feat_stride, thresh,
+                             shape_om));
       return M3D_OK;
     }
   }
@@ -731,7 +780,26 @@ extern "C" int m3d_cls_softmax(const float* logits, int logits_cstride, int N, i
   M3D_CUDA_OK(launch_pdl(cls_softmax_kernel, dim3(grid), dim3(256), smem, S(stream), logits, logits_cstride, N, H, W, A, K, cls_out, prob_out, fg_max,
                                                      fg_arg, score, cls_pred));
   M3D_CUDA_OK(cudaGetLastError());
+  if (shape_om != nullptr)
+    return m3d_shape_align_om(fg_max, fg_arg, anchors, anchor_ld, feat_stride, thresh, shape_om,
+                              static_cast<long>(N) * H * W, stream);
   return M3D_OK;
+}
+
+extern "C" int m3d_cls_softmax(const float* logits, int logits_cstride, int N, int H, int W, int A, int K, float* cls_out,
+                               float* prob_out, float* fg_max, int* fg_arg, float* score, unsigned char* cls_pred,
+                               m3d_stream_t stream) {
+  return cls_softmax_impl(logits, logits_cstride, N, H, W, A, K, cls_out, prob_out, fg_max, fg_arg, score, cls_pred, nullptr,
+                          0, 0.f, 0.f, nullptr, stream);
+}
+
+extern "C" int m3d_cls_softmax_shape_om(const float* logits, int logits_cstride, int N, int H, int W, int A, int K,
+                                        float* cls_out, float* prob_out, float* fg_max, int* fg_arg, float* score,
+                                        unsigned char* cls_pred, const float* anchors, int anchor_ld, float feat_stride,
+                                        float thresh, float* shape_om, m3d_stream_t stream) {
+  M3D_REQUIRE(anchors && shape_om, "NULL pointer");
+  return cls_softmax_impl(logits, logits_cstride, N, H, W, A, K, cls_out, prob_out, fg_max, fg_arg, score, cls_pred, anchors,
+                          anchor_ld, feat_stride, thresh, shape_om, stream);
 }
 
 extern "C" int m3d_shape_align_om(const float* fg_max, const int* fg_arg, const float* anchors, int anchor_ld,
@@ -753,6 +821,19 @@ extern "C" int m3d_center_align_om(const float* fg_max, const int* fg_arg, const
                                                                  anchors, anchor_ld, feat_stride, mean_x, mean_y, std_x,
                                                                  std_y, thresh, om, om_cstride, npix));
   M3D_CUDA_OK(cudaGetLastError());
+  return M3D_OK;
+}
+
+extern "C" int m3d_center_align_om2(const float* fg_max, const int* fg_arg, const float* heads, int heads_cstride,
+                                    const int* xy_coff4, const float* mean4, const float* std4, const float* anchors,
+                                    int anchor_ld, float feat_stride, float thresh, float* om_a, float* om_b,
+                                    int om_cstride, long npix, m3d_stream_t stream) {
+  M3D_REQUIRE(fg_max && fg_arg && heads && anchors && om_a && om_b && xy_coff4 && mean4 && std4, "NULL pointer");
+  M3D_REQUIRE(om_cstride >= 3, "om_cstride=%d", om_cstride);
+  CenterAlignSet s0{xy_coff4[0], xy_coff4[1], mean4[0], mean4[1], std4[0], std4[1], om_a};
+  CenterAlignSet s1{xy_coff4[2], xy_coff4[3], mean4[2], mean4[3], std4[2], std4[3], om_b};
+  M3D_CUDA_OK(launch_pdl(center_align_om2_kernel, dim3(cdiv(npix, 256)), dim3(256), 0, S(stream), fg_max, fg_arg, heads,
+                         heads_cstride, s0, s1, anchors, anchor_ld, feat_stride, thresh, om_cstride, npix));
   return M3D_OK;
 }
 

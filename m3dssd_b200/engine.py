@@ -75,6 +75,7 @@ class Engine:
         self._pool_cache = {}
         self.named = {}  # name -> Act of notable intermediate activations (parity checks)
         self.n_launches = 0
+        self.detect_alt = {}  # op index -> cheaper callable used by the detection stages
         self.use_graph = use_graph
         self.graph = None
         self.A = net.num_anchors
@@ -441,6 +442,10 @@ class Engine:
         self._add(lambda: ops.cls_softmax(logits, A, K, self.cls_out, self.prob_out, self.fg_max, self.fg_arg,
                                           self.score, self.cls_pred), 1, "cls_softmax", "softmax", 0, B * M * K * 4 * 3,
                   dict(op="softmax", logits=logits))
+        # detection stages: same kernel without the flattened cls / prob copies (70 MB of stores nobody reads there)
+        i_softmax = len(self.ops) - 1
+        self.detect_alt[i_softmax] = lambda: ops.cls_softmax(logits, A, K, None, None, self.fg_max, self.fg_arg,
+                                                             self.score, self.cls_pred)
         anchors = torch.tensor(np.asarray(conf.anchors), **f32).contiguous()
         self.anchors = anchors
         means = [float(v) for v in np.asarray(conf.bbox_means)[0]]
@@ -450,9 +455,13 @@ class Engine:
         feats = feat
         if net.shape_align is not None:
             om_s = torch.zeros(B, Hf, Wf, 27, **f32)
-            thr = float(net.shape_align.thresh)
-            self._add(lambda: ops.shape_align_om(self.fg_max, self.fg_arg, anchors, stride, thr, om_s), 1,
+            thr_s = float(net.shape_align.thresh)
+            self._add(lambda: ops.shape_align_om(self.fg_max, self.fg_arg, anchors, stride, thr_s, om_s), 1,
                       "shape_align.om", "align_om", 0, om_s.numel() * 4, dict(op="shape_align_om", om=om_s))
+            # detection stages: the offset builder rides in the softmax kernel's per-pixel tail
+            self.detect_alt[i_softmax] = lambda: ops.cls_softmax_shape_om(logits, A, K, None, None, self.fg_max, self.fg_arg,
+                                                                          self.score, self.cls_pred, anchors, stride, thr_s, om_s)
+            self.detect_alt[len(self.ops) - 1] = None
             feats = self._align("shape_align", net.shape_align, feat, om_s)
         # --- regression heads (slots follow HEAD_ORDER)
         heads = self._new("heads", B, Hf, Wf, 11 * A, torch.float32)
@@ -470,6 +479,11 @@ class Engine:
             self._add(lambda: ops.center_align_om(self.fg_max, self.fg_arg, heads, sx3, sy3, anchors, stride,
                                                   means[4:6], stds[4:6], thr, om3), 1, "center_align3d.om", "align_om", 0, om3.numel() * 4,
                       dict(op="center_align_om", om=om3, hx="bbox_x3d", hy="bbox_y3d", mean=means[4:6], std=stds[4:6]))
+            # detection stages: one launch builds both
+            self.detect_alt[len(self.ops) - 2] = lambda: ops.center_align_om2(
+                self.fg_max, self.fg_arg, heads, (sx, sy, sx3, sy3), anchors, stride, means[0:2] + means[4:6],
+                stds[0:2] + stds[4:6], thr, om2, om3)
+            self.detect_alt[len(self.ops) - 1] = None
             f2d = self._align("center_align2d", net.center_align2d, feats, om2)
             f3d = self._align("center_align3d", net.center_align3d, feats, om3)
         self.named["feats_shape"], self.named["feats_align2d"], self.named["feats_align3d"] = feats, f2d, f3d
@@ -502,8 +516,14 @@ class Engine:
         self.feat_size = torch.tensor([Hf, Wf], dtype=torch.float32, device=self.dev)
 
     # ------------------------------------------------------------------- run
+    def _detect_ops(self):
+        """The op list of the detection stages: no flattened copies of the network outputs (cls / prob / bbox_2d /
+        bbox_3d are RPN.forward's return values; decode reads score, class and the head buffer)."""
+        alt = [self.detect_alt.get(i, op) for i, op in enumerate(self.ops[:self.n_detect_ops])]
+        return [op for op in alt if op is not None]  # None: folded into a neighbour's kernel
+
     def _run_forward(self, flatten=True):
-        for op in (self.ops if flatten else self.ops[:self.n_detect_ops]):
+        for op in (self.ops if flatten else self._detect_ops()):
             op()
 
     def _run_decode(self):
@@ -528,7 +548,8 @@ class Engine:
     def launches_per_step(self, stage="detect"):
         # decode = 2 histogram passes + compaction + finish (m3d_decode_topk); NMS = mask + sweep + gather of the kept rows
         st = self._STAGES[stage]
-        return self.n_launches - (1 if st >= 1 else 0) + (0, 4, 7)[st]  # the detection stages skip flatten_heads
+        folded = 1 + sum(1 for v in self.detect_alt.values() if v is None)  # flatten_heads + launches folded into neighbours
+        return self.n_launches - (folded if st >= 1 else 0) + (0, 4, 7)[st]
 
     def activation_nchw(self, name):
         """fp32 NCHW copy of a named intermediate activation (testing aid)."""
@@ -573,10 +594,11 @@ class Engine:
         self.image.copy_(images, non_blocking=True)
 
     def flatten_outputs(self):
-        """Refresh self.bbox_2d / self.bbox_3d (the reference's flattened box tensors) from the head buffer after a
-        "decode" / "detect" / pipelined step, which do not write them.  Returns (bbox_2d, bbox_3d)."""
+        """Refresh the reference's flattened network outputs (cls, prob, bbox_2d, bbox_3d) from the logits / head
+        buffers after a "decode" / "detect" / pipelined step, which do not write them.  Returns the four tensors."""
+        self.ops[min(self.detect_alt)]()  # the full softmax (flattened cls / prob copies)
         self.ops[self.n_detect_ops]()
-        return self.bbox_2d, self.bbox_3d
+        return self.cls_out, self.prob_out, self.bbox_2d, self.bbox_3d
 
     def forward(self, images=None):
         """Returns (cls, prob, bbox_2d, bbox_3d): views of the engine's output buffers."""
@@ -615,7 +637,7 @@ class Engine:
                 op()
 
         def heads():
-            for op in self.ops[self.n_trunk_ops:self.n_detect_ops]:
+            for op in self._detect_ops()[self.n_trunk_ops:]:
                 op()
 
         if self.use_graph:

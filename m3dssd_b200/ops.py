@@ -252,6 +252,23 @@ def cls_softmax(logits, A, K, cls_out, prob_out, fg_max, fg_arg, score, cls_pred
                                 _p(score), _p(cls_pred), _stream()))
 
 
+def cls_softmax_shape_om(logits, A, K, cls_out, prob_out, fg_max, fg_arg, score, cls_pred, anchors, feat_stride, thresh, om):
+    """cls_softmax + shape_align_om in one launch (identical values)."""
+    N, H, W, cs = logits.shape
+    check(lib().m3d_cls_softmax_shape_om(_p(logits), cs, N, H, W, A, K, _p(cls_out), _p(prob_out), _p(fg_max), _p(fg_arg),
+                                         _p(score), _p(cls_pred), _p(anchors), anchors.shape[1], float(feat_stride),
+                                         float(thresh), _p(om), _stream()))
+
+
+def center_align_om2(fg_max, fg_arg, heads, coffs4, anchors, feat_stride, mean4, std4, thresh, om_a, om_b):
+    """The 2D- and 3D-centre offset builders in one launch (identical values to two center_align_om calls)."""
+    assert om_a.shape == om_b.shape
+    check(lib().m3d_center_align_om2(_p(fg_max), _p(fg_arg), _p(heads), heads.shape[-1], (C.c_int * 4)(*[int(v) for v in coffs4]),
+                                     (C.c_float * 4)(*[float(v) for v in mean4]), (C.c_float * 4)(*[float(v) for v in std4]),
+                                     _p(anchors), anchors.shape[1], float(feat_stride), float(thresh), _p(om_a), _p(om_b),
+                                     om_a.shape[-1], fg_max.numel(), _stream()))
+
+
 def shape_align_om(fg_max, fg_arg, anchors, feat_stride, thresh, om):
     check(lib().m3d_shape_align_om(_p(fg_max), _p(fg_arg), _p(anchors), anchors.shape[1], float(feat_stride),
                                    float(thresh), _p(om), fg_max.numel(), _stream()))

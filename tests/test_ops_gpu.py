@@ -160,6 +160,44 @@ def test_align_offset_builders():
     om = torch.zeros(B, H, W, 4, **f32)
     ops.center_align_om(fg_max, fg_arg, _nhwc(heads), 0, A, anchors.cuda(), 8.0, mean, std, 0.5, om)
     assert (_nchw(om)[:, :3] - ref).abs().max().item() < 1e-5
+    # the two-in-one launch of the detection stages: same bits as two calls
+    mean3, std3 = [0.3, 0.05], [0.9, 1.1]
+    om_b = torch.zeros(B, H, W, 4, **f32)
+    ops.center_align_om(fg_max, fg_arg, _nhwc(heads), 2 * A, 3 * A, anchors.cuda(), 8.0, mean3, std3, 0.5, om_b)
+    o2a, o2b = torch.zeros_like(om), torch.zeros_like(om)
+    ops.center_align_om2(fg_max, fg_arg, _nhwc(heads), (0, A, 2 * A, 3 * A), anchors.cuda(), 8.0, mean + mean3, std + std3,
+                         0.5, o2a, o2b)
+    assert torch.equal(o2a, om) and torch.equal(o2b, om_b)
+
+
+def test_softmax_detect_variants():
+    """The detection stages' softmax (no flattened cls / prob copies, shape_align offsets built in its tail) writes the
+    same score / class / fg / om bits as cls_softmax + shape_align_om."""
+    from m3dssd_b200 import ops, synth
+    g = _g(14)
+    B, A, K, H, W = 2, 36, 4, 5, 41
+    logits = _nhwc(torch.randn(B, K * A, H, W, generator=g) * 2)
+    anchors = torch.tensor(synth.make_conf().anchors).cuda()
+    M = A * H * W
+    f32 = dict(dtype=torch.float32, device="cuda")
+
+    def bufs():
+        return (torch.zeros(B, H, W, **f32), torch.zeros(B, H, W, dtype=torch.int32, device="cuda"), torch.zeros(B, M, **f32),
+                torch.zeros(B, M, dtype=torch.uint8, device="cuda"))
+    fm, fa, sc, cp = bufs()
+    cls_o, prob_o = torch.zeros(B, M, K, **f32), torch.zeros(B, M, K, **f32)
+    ops.cls_softmax(logits, A, K, cls_o, prob_o, fm, fa, sc, cp)
+    om = torch.zeros(B, H, W, 27, **f32)
+    ops.shape_align_om(fm, fa, anchors, 8.0, 0.5, om)
+    for fused in (False, True):
+        fm2, fa2, sc2, cp2 = bufs()
+        om2 = torch.zeros_like(om)
+        if fused:
+            ops.cls_softmax_shape_om(logits, A, K, None, None, fm2, fa2, sc2, cp2, anchors, 8.0, 0.5, om2)
+            assert torch.equal(om2, om)
+        else:
+            ops.cls_softmax(logits, A, K, None, None, fm2, fa2, sc2, cp2)
+        assert torch.equal(fm2, fm) and torch.equal(fa2, fa) and torch.equal(sc2, sc) and torch.equal(cp2, cp)
 
 
 def test_layout_round_trip():
