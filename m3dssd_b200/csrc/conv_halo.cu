@@ -59,6 +59,9 @@ template <int BN, typename OutT, bool STAGED, bool BRES>
 __global__ void __launch_bounds__(STAGED ? 320 : 192, 1) conv_halo_kernel(const __grid_constant__ ConvTmaParams p) {
   using Cfg = HaloCfg<BN, STAGED, BRES>;
   constexpr int NW = STAGED ? 8 : 4;  // epilogue warps (see conv_tma_kernel)
+  // one-slab tiles: the two 4-warp groups take alternate tiles whole (epilogue.cuh, "grouped", SPLIT = false) -- the
+  // serial drain of a 64-column tile (~2.8 k clocks: barriers, residual TMA, store) was longer than its 36 MMAs
+  constexpr bool ALT = STAGED && BN == 64;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(STAGED ? 320 : 192, 1) conv_halo_kernel(const 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], NW);  // one arrival per epilogue warp
+      mbar_init(&tempty[s], ALT ? 4 : NW);  // one arrival per epilogue warp that drains this accumulator stage
       mbar_init(&res_bar[s], 1);
     }
     mbar_init(bres_bar, 1);
@@ -193,7 +196,46 @@ __global__ void __launch_bounds__(STAGED ? 320 : 192, 1) conv_halo_kernel(const 
       if (elect_one()) umma_commit(&tfull[as]);
       __syncwarp();
     }
-  } else {
+  } else if constexpr (ALT) {
+    const int quarter = warp & 3;
+    const int ep_tid = threadIdx.x - 64;
+    const int group = ep_tid >> 7, gtid = ep_tid & 127;
+    float* bias_s = reinterpret_cast<float*>(stage_out + 2 * kSlabBytes);  // 256 floats (host: n_tiles * BN <= 256)
+    for (int i = ep_tid; i < p.n_tiles * BN; i += 32 * NW) bias_s[i] = (p.bias != nullptr && i < p.Cout) ? __ldg(p.bias + i) : 0.f;
+    named_bar_sync(kEpiBarrier + 2, 32 * NW);
+    GroupedEpilogue st;
+    st.init(stage_out + group * kSlabBytes, bias_s, &res_bar[group]);
+    const void* tmap_res = p.res ? &p.tmap_res : nullptr;
+    HALO_WALK_INIT;
+    int tile = tw_.first;
+    if (group == 1) {
+      ++tile;
+      HALO_WALK_NEXT;
+    }
+    auto epi_tile = [&]() {
+      const HTile t = htile(tw_, p);
+      return EpiTile{t.n, t.p0, t.q0, t.nt * BN};
+    };
+    EpiTile cur = epi_tile();
+    if (tile < tw_.last) epilogue_grouped_begin<BN, false>(st, gtid, group, cur, tmap_res, p.res_coff);
+    for (int local = group; tile < tw_.last; tile += 2, local += 2) {
+      HALO_WALK_NEXT;
+      HALO_WALK_NEXT;
+      const EpiTile nxt = epi_tile();  // this group's next tile (coordinates only meaningful when it exists)
+      const uint32_t aphase = (local >> 1) & 1;
+      mbar_wait(&tfull[group], aphase);
+      tc_fence_after();
+      epilogue_tile_grouped<BN, false>(st, tmem_base + group * Cfg::ACC, quarter, lane, gtid, group, cur,
+                                       tile + 2 < tw_.last ? &nxt : nullptr, &p.tmap_out, p.out_coff, tmap_res, p.res_coff,
+                                       p.slope, [&]() {
+                                         tc_fence_before();
+                                         __syncwarp();
+                                         if (lane == 0) mbar_arrive(&tempty[group]);
+                                       });
+      cur = nxt;
+    }
+    if (gtid == 0) tma_store_wait_all();
+  }  else {
     const int quarter = warp & 3;
     const int ep_tid = threadIdx.x - 64;
     StagedEpilogue st;
@@ -274,6 +316,7 @@ bool conv_halo_supported(int BN, int out_dtype, bool staged) {
 int launch_conv_halo(const ConvTmaParams& p, int BN, int out_dtype, bool staged, cudaStream_t stream) {
   static const bool bres = !(getenv("M3D_HALO_BRES") && atoi(getenv("M3D_HALO_BRES")) == 0);  // resident-weight variants
   if (staged) {
+    if (BN == 64 && p.n_tiles * 64 > 256) return M3D_ERR_UNSUPPORTED;  // bias area of the alternate-tile epilogue
     if (BN == 64 && p.chunks[0] == 1 && p.n_tiles == 1 && bres) return launch_t<64, __nv_bfloat16, true, true>(p, stream);
     if (BN == 64) return launch_t<64, __nv_bfloat16, true>(p, stream);
     if (BN == 128) return launch_t<128, __nv_bfloat16, true>(p, stream);

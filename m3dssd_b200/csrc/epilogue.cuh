@@ -237,6 +237,9 @@ __device__ __forceinline__ void epilogue_tile_staged(StagedEpilogue& st, uint32_
 //  * the residual slab of the NEXT tile is TMA-loaded into the group's buffer as soon as the store of the current
 //    one has read it, i.e. a whole tile time before it is needed; without a residual the leader just arrives;
 //  * the layer's biases are copied to shared memory once per kernel.
+// SPLIT = true: the two groups share every tile (columns halved; BN = 128, 256: conv_halo2.cu).  SPLIT = false: the
+// groups take alternate tiles whole (BN = 64, one slab per tile: conv_halo.cu) -- group g then always drains
+// accumulator stage g, and `next` is the group's next tile, two tiles ahead.
 struct EpiTile {
   int n, p0, q0, col0;  // image, first tile row / column, first output channel of the BN-wide tile
 };
@@ -256,37 +259,37 @@ struct GroupedEpilogue {
 };
 
 // column offset (inside the BN tile) of slab k of group g
-template <int BN>
+template <int BN, bool SPLIT = true>
 __device__ __forceinline__ int grouped_col(int group, int k) {
-  return group * (BN / 2) + k * 64;
+  return (SPLIT ? group * (BN / 2) : 0) + k * 64;
 }
 
 // Before the first tile: the group leader (gtid == 0) fetches the first residual slab / declares the buffer free.
-template <int BN>
+template <int BN, bool SPLIT = true>
 __device__ __forceinline__ void epilogue_grouped_begin(GroupedEpilogue& st, int gtid, int group, const EpiTile& t,
                                                        const void* tmap_res, int res_coff) {
   if (gtid != 0) return;
   if (tmap_res != nullptr) {
     mbar_arrive_expect_tx(st.ready, kSlabBytes);
-    tma_load_4d(st.buf, tmap_res, st.ready, res_coff + t.col0 + grouped_col<BN>(group, 0), t.q0, t.p0, t.n);
+    tma_load_4d(st.buf, tmap_res, st.ready, res_coff + t.col0 + grouped_col<BN, SPLIT>(group, 0), t.q0, t.p0, t.n);
   } else {
     mbar_arrive(st.ready);
   }
 }
 
-template <int BN, typename F>
+template <int BN, bool SPLIT = true, typename F>
 __device__ __forceinline__ void epilogue_tile_grouped(GroupedEpilogue& st, uint32_t tmem_acc, int quarter, int lane,
                                                       int gtid, int group, const EpiTile& t, const EpiTile* next,
                                                       const void* tmap_out, int out_coff, const void* tmap_res,
                                                       int res_coff, float slope, F on_tmem_drained) {
-  static_assert(BN % 128 == 0, "two groups of whole 64-channel slabs");
-  constexpr int NS = BN / 128;  // slabs per group
+  static_assert(BN % (SPLIT ? 128 : 64) == 0, "groups work on whole 64-channel slabs");
+  constexpr int NS = SPLIT ? BN / 128 : BN / 64;  // slabs per group and tile
   const int row = quarter * 32 + lane;
   const bool has_res = tmap_res != nullptr;
   const uint32_t buf_s = smem_u32(st.buf);
 #pragma unroll 1
   for (int k = 0; k < NS; ++k) {
-    const int c = grouped_col<BN>(group, k);
+    const int c = grouped_col<BN, SPLIT>(group, k);
     uint32_t a[64];
     const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + c;
     tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(a));
@@ -337,7 +340,7 @@ __device__ __forceinline__ void epilogue_tile_grouped(GroupedEpilogue& st, uint3
         if (has_res) {
           const EpiTile& u = same ? t : *next;
           mbar_arrive_expect_tx(st.ready, kSlabBytes);
-          tma_load_4d(st.buf, tmap_res, st.ready, res_coff + u.col0 + grouped_col<BN>(group, same ? k + 1 : 0), u.q0,
+          tma_load_4d(st.buf, tmap_res, st.ready, res_coff + u.col0 + grouped_col<BN, SPLIT>(group, same ? k + 1 : 0), u.q0,
                       u.p0, u.n);
         } else {
           mbar_arrive(st.ready);
