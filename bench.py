@@ -254,8 +254,9 @@ def run_train(args):
     """BASELINE.json configs[3]: kitti_3d_base train step (forward + backward + SGD) on a synthetic KITTI batch, one
     B200: batch 4 (scripts/config/kitti_3d_base.py:89), 384x1280, no align / attention, DLA-34 (substituted for the
     config's dla102, as SURVEY 8d prescribes), SGD lr 0.004 / momentum 0.9 / weight decay 5e-4 (:21-24).  The loss is
-    m3dssd_b200.train.surrogate_loss (cross-entropy + smooth-L1 with the structure of RPN_3D_loss_smp; the reference's
-    per-image target matching is out of scope).  Beside it: the same step through torch's own
+    the reference's RPN_3D_loss_smp in its static-shape device form (m3dssd_b200.lib.loss.rpn_3d, golden-pinned to the
+    unmodified reference class) on synthetic targets in the dataloader's layout; target matching itself (lib/rpn_util.py:
+    430-650, done by the reference's dataloader workers) is out of scope.  Beside it: the same step through torch's own
     convolutions (cuDNN), fp32 as the reference runs it and bf16 autocast."""
     import torch
     from m3dssd_b200 import ops, synth, train
@@ -287,7 +288,16 @@ def run_train(args):
     NB = 4
     host = [synth.make_images(B, CROP, seed=100 * rank + i).pin_memory() for i in range(NB)]
     dev = [h.cuda() for h in host]
-    labels, t2, t3 = train.surrogate_targets(conf, B, "cuda")
+    if args.train_loss == "rpn3d":
+        # the reference's loss (lib/loss/rpn_3d.py:659-1360; kitti_3d_base hyper-parameters) in its static-shape form,
+        # on targets laid out as the reference's dataloader does (~300 foreground anchors per image)
+        from m3dssd_b200.lib.loss.rpn_3d import RPN_3D_loss_smp
+        synth.loss_conf(conf)
+        criterion = RPN_3D_loss_smp(conf).cuda()
+        targets = (train.targets_to(synth.make_targets(conf, B, seed=rank), "cuda"),)
+    else:
+        criterion = None
+        targets = train.surrogate_targets(conf, B, "cuda")
 
     def timed(step, n, from_host=False):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -295,7 +305,7 @@ def run_train(args):
         e0.record()
         for i in range(n):
             x = host[i % NB].cuda(non_blocking=True) if from_host else dev[i % NB]
-            loss = step(x, labels, t2, t3)
+            loss = step(x, *targets)
             if from_host:
                 loss.item()  # the reference reads the loss every iteration (train_rpn_3d.py:208)
         e1.record()
@@ -309,11 +319,11 @@ def run_train(args):
         ref.load_state_dict(sd)
         st = train.TrainStep(ref, conf, native=False)
 
-        def step(x, labels, t2, t3, st=st, autocast=autocast):
+        def step(x, *tg, st=st, autocast=autocast):
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
                 st.net.train()
-                cls, prob, b2, b3, _ = st.net(x)
-                loss = train.surrogate_loss(cls, b2, b3, labels, t2, t3)
+                cls, prob, b2, b3, fs = st.net(x)
+                loss = criterion(cls, prob, b2, b3, tg[0], fs)[0] if criterion is not None else train.surrogate_loss(cls, b2, b3, *tg)
             st.opt.zero_grad(set_to_none=True)
             loss.backward()
             st.opt.step()
@@ -330,7 +340,7 @@ def run_train(args):
         train.enable(net)
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], gradient_as_bucket_view=True,
                                                           find_unused_parameters=True)  # nested Trees own a `project` their forward never uses
-        eager = train.TrainStep(model, conf, native=False)  # (already enabled; TrainStep drives the DDP wrapper)
+        eager = train.TrainStep(model, conf, native=False, criterion=criterion)  # (already enabled; TrainStep drives the DDP wrapper)
         timed(eager, W_)
         dist.barrier()
         ms = timed(eager, K)
@@ -350,11 +360,11 @@ def run_train(args):
         dist.barrier()
         dist.destroy_process_group()
         return 0
-    eager = train.TrainStep(net, conf, native=True)
+    eager = train.TrainStep(net, conf, native=True, criterion=criterion)
     timed(eager, 3)
     ms_eager = timed(eager, max(5, K // 2))
     baselines["native_eager"] = {"images_per_s": B * max(5, K // 2) / (ms_eager * 1e-3), "ms_per_step": ms_eager / max(5, K // 2)}
-    step = train.TrainStep(net, conf, native=True, graph=True, warmup=0)  # the whole iteration as one CUDA graph
+    step = train.TrainStep(net, conf, native=True, graph=True, warmup=0, criterion=criterion)  # the whole iteration as one CUDA graph
     step.opt = eager.opt
     timed(step, W_)
     clocks = ClockSampler(local_rank)
@@ -375,7 +385,10 @@ def run_train(args):
         "config": {"workload": "kitti_3d_base train step (fwd+bwd+SGD) on a synthetic KITTI batch, batch 4 384x1280, "
                                "DLA-34 substituted for dla102 (BASELINE.json configs[3])",
                    "global_batch": world * B, "precision": "bf16 activations / fp32 master weights, statistics, optimizer",
-                   "loss": "surrogate (cross-entropy + smooth-L1, m3dssd_b200.train.surrogate_loss)",
+                   "loss": ("RPN_3D_loss_smp (lib/loss/rpn_3d.py:659-1360, kitti_3d_base hyper-parameters: OHEM sampling, weighted "
+                            "cross-entropy, smooth-L1 3D, IoU loss) in its static-shape device form, m3dssd_b200.lib.loss.rpn_3d"
+                            if criterion is not None else
+                            "surrogate (cross-entropy + smooth-L1, m3dssd_b200.train.surrogate_loss)"),
                    "optimizer": "SGD lr 0.004 momentum 0.9 weight_decay 5e-4",
                    "native": "every nn.Conv2d forward / dgrad / wgrad and DCNv2 forward / backward through the C ABI; "
                              "BatchNorm, activations, pooling, loss, SGD = torch elementwise kernels; cuDNN disabled; the whole "
@@ -402,6 +415,8 @@ def main():
     ap.add_argument("--attention", default=None)
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer: BASELINE configs[1] / [2] (default); train: configs[3], the kitti_3d_base train step")
+    ap.add_argument("--train-loss", default="rpn3d", choices=["rpn3d", "surrogate"],
+                    help="--mode train: the reference's RPN_3D_loss_smp (static-shape device form) or the round-2a surrogate")
     ap.add_argument("--input", default="u8", choices=["u8", "f32"],
                     help="u8: uint8 HWC images normalised on the device (default); f32: pre-normalised fp32 NCHW")
     args = ap.parse_args()

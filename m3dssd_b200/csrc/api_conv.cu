@@ -230,6 +230,7 @@ bool conv_halo_supported(int BN, int out_dtype, bool staged);
 bool conv_halo2_supported(int BN, long m_tiles, int cout);
 int launch_conv_halo2(const ConvTmaParams& p, int BN, cudaStream_t stream);
 int launch_conv_halo(const ConvTmaParams& p, int BN, int out_dtype, bool staged, cudaStream_t stream);
+bool conv_halo_unified(int BN, int out_dtype, bool staged, int nchunk, int n_tiles);
 
 static int pick_bn(int cout, int bk, long m_tiles, bool gather, bool split) {
   if (bk == 16) return cout <= 16 ? 16 : 32;
@@ -376,6 +377,18 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
   if (!gather) {
     ConvTmaParams p;
     memset(&p, 0, sizeof(p));
+    // 3x3 stride-1 convs: one (TH+2)-row window per kernel column serves its three taps (conv_halo.cu)
+    const bool halo = d->R == 3 && d->S == 3 && d->stride == 1 && d->dil == 1 && d->pad == 1 && d->num_inputs == 1 &&
+                      groups == 1 && bk == 64 && d->out_h <= 0 && d->out_w <= 0 && TW <= 16 &&
+                      d->in_cstride[0] % 8 == 0 && d->in_coff[0] % 8 == 0 &&
+                      conv_halo_supported(BN, d->out_dtype == M3D_F32 ? DT_F32 : DT_BF16, staged) &&
+                      getenv("M3D_NO_HALO") == nullptr;
+    // resident-weight variants read all nine taps from one (TH+2) x (TW+2) window: 16 x 8 pixel tiles
+    const bool uni = halo && conv_halo_unified(BN, d->out_dtype == M3D_F32 ? DT_F32 : DT_BF16, staged, d->in_c[0] / 64, n_tiles);
+    if (uni) TW = 8, TH = 16;
+    const int tiles_w = (Q + TW - 1) / TW, tiles_h = (P + TH - 1) / TH;  // (shadow the estimates above)
+    const long m_tiles = static_cast<long>(tiles_w) * tiles_h * d->N;
+    const long total_tiles = m_tiles * n_tiles * groups;
     if (staged_f32) {
       int rc2 = make_tmap_nhwc_f32(&p.tmap_out, d->out, d->N, P, Q, d->out_cstride, 32, TW, TH, true);
       if (rc2 != M3D_OK) return rc2;
@@ -388,15 +401,9 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
         if (rc2 != M3D_OK) return rc2;
       }
     }
-    // 3x3 stride-1 convs: one (TH+2)-row window per kernel column serves its three taps (conv_halo.cu)
-    const bool halo = d->R == 3 && d->S == 3 && d->stride == 1 && d->dil == 1 && d->pad == 1 && d->num_inputs == 1 &&
-                      groups == 1 && bk == 64 && d->out_h <= 0 && d->out_w <= 0 && TW <= 16 &&
-                      d->in_cstride[0] % 8 == 0 && d->in_coff[0] % 8 == 0 &&
-                      conv_halo_supported(BN, d->out_dtype == M3D_F32 ? DT_F32 : DT_BF16, staged) &&
-                      getenv("M3D_NO_HALO") == nullptr;
     if (halo) {
       const bool pair = staged && conv_halo2_supported(BN, m_tiles, d->Cout);  // CTA pairs: each CTA loads half of the weight rows
-      int rc = make_tmap_nhwc(&p.tmap_a[0], d->in[0], d->N, d->H, d->W, d->in_cstride[0], 64, TW, TH + 2, 1);
+      int rc = make_tmap_nhwc(&p.tmap_a[0], d->in[0], d->N, d->H, d->W, d->in_cstride[0], 64, uni ? TW + 2 : TW, TH + 2, 1);
       if (rc != M3D_OK) return rc;
       rc = make_tmap_b_halo(&p.tmap_b, d->weight, d->weight_rows, d->in_c[0] / 64, pair ? BN / 2 : BN);
       if (rc != M3D_OK) return rc;

@@ -8,6 +8,12 @@
 // swizzle atoms: the UMMA descriptor just starts r * TW * 128 bytes later.  A traffic drops 3 * TH / (TH + 2)
 // = 2.4x (TH = 8); the stage's three weight k-blocks arrive as one 4-D TMA box.  12 MMAs per stage also
 // amortise the barrier hand-shakes.  Same warp roles / TMEM double buffering / epilogues as conv_tma_kernel.
+//
+// Resident-weight variants (BRES: Cin <= 128 and one N tile -- level0 / level2, the offset/mask convs) go one step
+// further: the tile is TH x TW = 16 x 8, ONE TMA box of (TH+2) x (TW+2) = 18 x 10 pixels per 64-channel chunk holds
+// every tap, and tap (r, s) of tile row g starts at window row (g + r) * 10 + s: an A descriptor with start
+// (r * 10 + s) * 128 bytes and 1280 bytes between 8-row groups (umma_smem_desc_sbo: the swizzle is a function of the
+// absolute address, so neither needs 1024-byte alignment).  A bytes per tile and chunk: 3 x 20 KB -> 22.5 KB.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -32,7 +38,8 @@ struct HaloCfg {
   static constexpr int A_BYTES = 20 * 1024;          // host guarantees (TH + 2) * TW * 128 <= A_BYTES
   static constexpr int B_BYTES = BN * 128;           // one tap
   // BRES (Cin = 64): a stage holds the windows of all three kernel columns -> one stage (36 MMAs) per tile
-  static constexpr int STAGE = BRES ? 3 * A_BYTES : A_BYTES + 3 * B_BYTES;
+  static constexpr int WIN_BYTES = 23 * 1024;        // BRES: (16 + 2) x (8 + 2) pixels x 128 B = 23 040, rounded up
+  static constexpr int STAGE = BRES ? WIN_BYTES : A_BYTES + 3 * B_BYTES;
   static constexpr int RES_BYTES = BRES ? 72 * 1024 : 0;  // 9 * nchunk taps of [BN][64]: BN = 64 x 1 chunk, BN = 32 x <= 2
   static constexpr int EXTRA = (STAGED ? (2 * kSlabBytes + 1024) : 0) + RES_BYTES;
   static constexpr int BUDGET = 225 * 1024 + 512 - EXTRA;
@@ -104,8 +111,8 @@ __global__ void __launch_bounds__(STAGED ? 320 : 192, 1) conv_halo_kernel(const 
 
   const int nchunk = p.chunks[0];
   const int n_stages = BRES ? nchunk : 3 * nchunk;  // (s, chunk) pairs; resident weights: one stage per chunk
-  const uint32_t a_bytes = static_cast<uint32_t>((p.TH + 2) * p.TW * 128);
-  const uint32_t tap_shift = static_cast<uint32_t>(p.TW * 128) >> 4;  // descriptor units (16 B) per kernel row
+  const uint32_t a_bytes = static_cast<uint32_t>((p.TH + 2) * (BRES ? p.TW + 2 : p.TW) * 128);
+  const uint32_t tap_shift = static_cast<uint32_t>((BRES ? p.TW + 2 : p.TW) * 128) >> 4;  // descriptor units (16 B) per kernel row
 
   if (warp == 0) {
     int stage = 0;
@@ -124,11 +131,9 @@ __global__ void __launch_bounds__(STAGED ? 320 : 192, 1) conv_halo_kernel(const 
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::STAGE;
-          if constexpr (BRES) {
-            mbar_arrive_expect_tx(&full[stage], 3 * a_bytes);
-            for (int sc = 0; sc < 3; ++sc)
-              tma_load_4d(sa + sc * Cfg::A_BYTES, &p.tmap_a[0], &full[stage], p.a_coff[0] + st * 64, t.q0 - 1 + sc, t.p0 - 1,
-                          t.n);
+          if constexpr (BRES) {  // the whole (TH+2) x (TW+2) window of this chunk
+            mbar_arrive_expect_tx(&full[stage], a_bytes);
+            tma_load_4d(sa, &p.tmap_a[0], &full[stage], p.a_coff[0] + st * 64, t.q0 - 1, t.p0 - 1, t.n);
           } else {
             mbar_arrive_expect_tx(&full[stage], ((p.dbg & 1) ? 0 : a_bytes) + 3 * Cfg::B_BYTES);
             if (!(p.dbg & 1)) tma_load_4d(sa, &p.tmap_a[0], &full[stage], p.a_coff[0] + c * 64, t.q0 - 1 + s, t.p0 - 1, t.n);
@@ -165,7 +170,8 @@ __global__ void __launch_bounds__(STAGED ? 320 : 192, 1) conv_halo_kernel(const 
             const uint64_t db0 = umma_smem_desc<128>(smem_u32(b_res));
 #pragma unroll
             for (int sc = 0; sc < 3; ++sc) {
-              const uint64_t da = umma_smem_desc<128>(sa + sc * Cfg::A_BYTES);
+              // tile row g of tap (r, sc) = window rows (g + r) * (TW + 2) + sc ...: 8-row groups (TW + 2) * 128 B apart
+              const uint64_t da = umma_smem_desc_sbo(sa + sc * 128, tap_shift << 4);
 #pragma unroll
               for (int r = 0; r < 3; ++r) {
 #pragma unroll
@@ -308,22 +314,31 @@ int launch_t(const ConvTmaParams& p, cudaStream_t stream) {
 // three kernel rows of one (s, chunk) as consecutive [bn][64] tiles.
 int make_tmap_b_halo(CUtensorMap* map, const void* base, long rows, int nchunk, int bn);
 
+// Will launch_conv_halo pick a resident-weight (unified-window, 16 x 8 pixel tiles) variant for this layer?
+bool conv_halo_unified(int BN, int out_dtype, bool staged, int nchunk, int n_tiles) {
+  static const bool bres = !(getenv("M3D_HALO_BRES") && atoi(getenv("M3D_HALO_BRES")) == 0);
+  if (!bres || n_tiles != 1) return false;
+  if (staged) return BN == 64 && nchunk == 1;
+  return BN == 32 && out_dtype != DT_BF16 && nchunk <= 2;
+}
+
 bool conv_halo_supported(int BN, int out_dtype, bool staged) {
   if (staged) return out_dtype == DT_BF16 && (BN == 64 || BN == 128);
   return BN == 32 || BN == 64;
 }
 
 int launch_conv_halo(const ConvTmaParams& p, int BN, int out_dtype, bool staged, cudaStream_t stream) {
-  static const bool bres = !(getenv("M3D_HALO_BRES") && atoi(getenv("M3D_HALO_BRES")) == 0);  // resident-weight variants
+  // resident-weight variants: the host (api_conv.cu) asked conv_halo_unified() too and built 16 x 8 tiles + window map
+  const bool bres = conv_halo_unified(BN, out_dtype, staged, p.chunks[0], p.n_tiles);
+  if (bres && (p.TW != 8 || p.TH != 16)) return M3D_ERR_UNSUPPORTED;
   if (staged) {
     if (BN == 64 && p.n_tiles * 64 > 256) return M3D_ERR_UNSUPPORTED;  // bias area of the alternate-tile epilogue
-    if (BN == 64 && p.chunks[0] == 1 && p.n_tiles == 1 && bres) return launch_t<64, __nv_bfloat16, true, true>(p, stream);
+    if (BN == 64 && bres) return launch_t<64, __nv_bfloat16, true, true>(p, stream);
     if (BN == 64) return launch_t<64, __nv_bfloat16, true>(p, stream);
     if (BN == 128) return launch_t<128, __nv_bfloat16, true>(p, stream);
     return M3D_ERR_UNSUPPORTED;
   }
-  if (BN == 32 && out_dtype != DT_BF16 && p.chunks[0] <= 2 && p.n_tiles == 1 && bres)
-    return launch_t<32, float, false, true>(p, stream);  // offset/mask convs of the Cin <= 128 DCNs
+  if (BN == 32 && bres) return launch_t<32, float, false, true>(p, stream);  // offset/mask convs of the Cin <= 128 DCNs
   if (BN == 32)
     return out_dtype == DT_BF16 ? launch_t<32, __nv_bfloat16, false>(p, stream) : launch_t<32, float, false>(p, stream);
   if (BN == 64)

@@ -285,6 +285,15 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
          (static_cast<uint64_t>(1) << 46) | (layout << 61);
 }
 
+// The same for 128-byte rows with an arbitrary distance between 8-row groups and any 128-byte aligned start.
+// Measured (tools/microbench_desc.cu): with the base-offset field left 0 the tensor core applies the 128B swizzle to
+// ABSOLUTE shared-memory address bits, exactly as TMA writes it, so 8-row groups may start on any 128-byte row and
+// `sbo_bytes` need not be a multiple of 1024 -- a 3x3 conv can address all nine taps inside ONE pixel window.
+__device__ __forceinline__ uint64_t umma_smem_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  return static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4) | (static_cast<uint64_t>(1) << 16) |
+         (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);
+}
+
 // Byte offset of 16-byte chunk `chunk` of row `row` inside a swizzled K-major
 // tile (tile base aligned to 8*ROW_BYTES): the chunk index is XORed with the
 // row index modulo the number of chunks per span (TMA and tcgen05 agree).

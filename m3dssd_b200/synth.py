@@ -266,3 +266,51 @@ def make_images_u8(batch, crop_size=(384, 1280), seed=0):
 def make_images(batch, crop_size=(384, 1280), seed=0):
     g = torch.Generator().manual_seed(seed)
     return torch.randn(batch, 3, crop_size[0], crop_size[1], generator=g)
+
+
+def loss_conf(conf):
+    """The loss hyper-parameters of scripts/config/kitti_3d_base.py:89-142 on top of make_conf()."""
+    conf.box_samples, conf.fg_fraction = 0.20, 0.20
+    conf.bg_thresh_lo, conf.bg_thresh_hi, conf.fg_thresh, conf.ign_thresh, conf.best_thresh = 0, 0.5, 0.5, 0.5, 0.35
+    conf.hard_negatives, conf.focal_loss = True, 0
+    conf.cls_2d_lambda, conf.iou_2d_lambda, conf.bbox_2d_lambda, conf.bbox_3d_lambda = 1, 1, 0, 1
+    conf.bbox_3d_proj_lambda, conf.bbox_3d_iou_lambda = 0.0, 0
+    conf.min_gt_vis, conf.min_gt_h, conf.max_gt_h = 0.65, 0, 10e10
+    return conf
+
+
+def make_targets(conf, batch, feat_hw=None, seed=0, fg_per_image=300, ign_fraction=0.05, empty_images=(), box_sigma=0.1):
+    """Synthetic training targets in the reference's `imobjs` layout (lib/dataloader.py:959-982):
+    labels_fg / labels_bg / labels_ign [B, M] bool, labels [B, M] int64 (0 background, 1..3 classes, 3000 ignored),
+    bbox_2d [B, M, 4], bbox_3d [B, M, 7] regression targets, meta.rois [B, M, 5], meta.any_val [B], meta.p2 [B, 4, 4].
+    Images listed in `empty_images` have no foreground and no ignored anchors (the loss's all-background branch)."""
+    from .lib.rpn_util import locate_anchors
+    g = torch.Generator().manual_seed(seed)
+    A = conf.anchors.shape[0]
+    if feat_hw is None:
+        feat_hw = (conf.crop_size[0] // conf.feat_stride, conf.crop_size[1] // conf.feat_stride)
+    Hf, Wf = feat_hw
+    M = A * Hf * Wf
+    labels = torch.zeros(batch, M, dtype=torch.long)
+    fg = torch.zeros(batch, M, dtype=torch.bool)
+    ign = torch.zeros(batch, M, dtype=torch.bool)
+    for b in range(batch):
+        if b in empty_images:
+            continue
+        perm = torch.randperm(M, generator=g)
+        nf = min(fg_per_image, M // 8)
+        ni = int(M * ign_fraction)
+        fg[b, perm[:nf]] = True
+        ign[b, perm[nf:nf + ni]] = True
+        labels[b, perm[:nf]] = torch.randint(1, len(conf.lbls) + 1, (nf,), generator=g)
+        labels[b, perm[nf:nf + ni]] = 3000
+    bg = ~fg & ~ign
+    rois = torch.from_numpy(locate_anchors(conf.anchors, (Hf, Wf), conf.feat_stride)).float()
+    p2 = torch.eye(4).repeat(batch, 1, 1)
+    p2[:, 0, 0] = p2[:, 1, 1] = 721.5
+    p2[:, 0, 2], p2[:, 1, 2] = 609.5, 172.8
+    return {
+        "labels_fg": fg, "labels_bg": bg, "labels_ign": ign, "labels": labels,
+        "bbox_2d": torch.randn(batch, M, 4, generator=g) * box_sigma, "bbox_3d": torch.randn(batch, M, 7, generator=g) * 0.3,
+        "meta": {"rois": rois.unsqueeze(0).repeat(batch, 1, 1), "any_val": torch.ones(batch, dtype=torch.bool), "p2": p2},
+    }

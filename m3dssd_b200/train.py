@@ -230,37 +230,67 @@ class TrainStep:
     is then bound by the device, not by Python / ctypes / dispatcher time (measured: 65 ms of host time per eager step
     against 44 ms of device time).  Inputs are copied into static buffers; the returned loss is a static tensor."""
 
-    def __init__(self, net, conf, lr=0.004, momentum=0.9, weight_decay=0.0005, native=True, graph=False, warmup=3):
+    def __init__(self, net, conf, lr=0.004, momentum=0.9, weight_decay=0.0005, native=True, graph=False, warmup=3,
+                 criterion=None):
+        """criterion: None = surrogate_loss(cls, bbox_2d, bbox_3d, labels, t2, t3) on the three target tensors passed to
+        __call__; or an RPN_3D_loss_smp instance (m3dssd_b200.lib.loss.rpn_3d: the reference's loss with static shapes),
+        __call__ then takes the reference's `imobjs` target dict (tensors on the device)."""
         self.net, self.conf = net, conf
         if native:
             enable(net)
         self.opt = torch.optim.SGD(net.parameters(), lr=lr, momentum=momentum, weight_decay=weight_decay)
         self.use_graph, self.warmup = graph, warmup
+        self.criterion = criterion
         self._n, self._graph, self._static = 0, None, None
 
-    def _iteration(self, images, labels, t2, t3):
+    def _iteration(self, images, *targets):
         self.net.train()
         cls, prob, bbox_2d, bbox_3d, feat_size = self.net(images)
-        loss = surrogate_loss(cls, bbox_2d, bbox_3d, labels, t2, t3)
+        if self.criterion is not None:
+            loss, self.stats = self.criterion(cls, prob, bbox_2d, bbox_3d, targets[0], feat_size)
+        else:
+            loss = surrogate_loss(cls, bbox_2d, bbox_3d, *targets)
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
         self.opt.step()
         return loss
 
-    def __call__(self, images, labels, t2, t3):
+    @staticmethod
+    def _tensors(obj):
+        """The tensors of a (nested dict of) target(s), in a fixed order."""
+        if isinstance(obj, dict):
+            return [t for k in sorted(obj) for t in TrainStep._tensors(obj[k])]
+        return [obj]
+
+    @staticmethod
+    def _clone(obj):
+        if isinstance(obj, dict):
+            return {k: TrainStep._clone(v) for k, v in obj.items()}
+        return obj.clone()
+
+    def __call__(self, images, *targets):
         if not self.use_graph:
-            return self._iteration(images, labels, t2, t3)
+            return self._iteration(images, *targets)
         if self._graph is None:
             if self._n < self.warmup:
                 self._n += 1
-                return self._iteration(images, labels, t2, t3)
-            self._static = [t.clone() for t in (images, labels, t2, t3)]
+                return self._iteration(images, *targets)
+            self._static = [images.clone()] + [self._clone(t) for t in targets]
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._loss = self._iteration(*self._static)
             self._graph = g
-        for dst, src in zip(self._static, (images, labels, t2, t3)):
-            dst.copy_(src, non_blocking=True)
+        self._static[0].copy_(images, non_blocking=True)
+        dsts = [t for tgt in self._static[1:] for t in self._tensors(tgt)]
+        srcs = [t for tgt in targets for t in self._tensors(tgt)]
+        for dst, src in zip(dsts, srcs):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
         self._graph.replay()
         return self._loss
+
+
+def targets_to(imobjs, device):
+    """The reference's target dict (synth.make_targets / lib/dataloader.py:959-982) with every tensor on `device`."""
+    return {k: (targets_to(v, device) if isinstance(v, dict) else v.to(device)) for k, v in imobjs.items()}

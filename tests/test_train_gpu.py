@@ -1,5 +1,6 @@
 """GPU parity of the training-path kernels (BASELINE config 4) against torch CPU autograd (the reference's training
 loop differentiates nn.Conv2d through torch / cuDNN: scripts/train_rpn_3d.py:204-218)."""
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -113,6 +114,29 @@ def test_native_train_step_learns_and_calls_no_cudnn():
     assert cos(gn["bbox_z3d.6.weight"], g32["bbox_z3d.6.weight"]) > 0.995
     losses = [float(step(x, labels, t2, t3).detach()) for _ in range(8)]
     assert losses[-1] < losses[0], losses
+
+
+def test_train_step_with_reference_loss_as_one_cuda_graph():
+    """scripts/train_rpn_3d.py:196-218 with the reference's own criterion (RPN_3D_loss_smp, static-shape form, pinned to
+    the unmodified class by tests/test_loss.py): native forward / backward, loss and SGD captured as ONE CUDA graph --
+    the reference's loss synchronises with the host a dozen times per image -- and the loss goes down."""
+    from m3dssd_b200 import synth, train
+    from m3dssd_b200.lib.loss.rpn_3d import RPN_3D_loss_smp
+    from m3dssd_b200.model.M3d_inference_align import build
+    conf = synth.loss_conf(synth.make_conf(attention=None, center_align=False, shape_align=False, crop_size=(96, 320),
+                                           batch_size=2))
+    net = build(conf, "train")
+    synth.randomize_weights(net)
+    net = net.cuda()
+    x = synth.make_images(2, (96, 320)).cuda()
+    tar = train.targets_to(synth.make_targets(conf, 2, fg_per_image=60), "cuda")
+    crit = RPN_3D_loss_smp(conf).cuda()
+    step = train.TrainStep(net, conf, lr=0.002, graph=True, warmup=2, criterion=crit)
+    losses = [float(step(x, tar).detach()) for _ in range(10)]
+    assert step._graph is not None and all(np.isfinite(losses)), losses
+    assert losses[-1] < losses[0], losses
+    names = {(s["group"], s["name"]) for s in step.stats}
+    assert {("loss", "cls"), ("loss", "bbox3d"), ("loss", "iou"), ("acc", "iou"), ("misc", "z")} <= names
 
 
 @pytest.mark.parametrize("shape", [(4, 48, 160, 128), (2, 13, 37, 27), (1, 96, 320, 16), (1, 5, 7, 144)])

@@ -18,6 +18,8 @@ SHAPES = [
     ("level5 3x3 512->512 +res", 8, 12, 40, 512, 512, 3, 1, True),
     ("level5 3x3 512->512", 8, 12, 40, 512, 512, 3, 1, False),
     ("level2 3x3 64->64 +res", 8, 96, 320, 64, 64, 3, 1, True),
+    ("level0 3x3 64->64 s2d", 8, 192, 640, 64, 64, 3, 1, False),
+    ("offset 3x3 128->27 f32", 8, 48, 160, 128, 27, 3, 1, False),
     ("level3 3x3 s2 64->128", 8, 96, 320, 64, 128, 3, 2, False),
     ("level4 3x3 s2 128->256", 8, 48, 160, 128, 256, 3, 2, False),
     ("root 1x1 256->128", 8, 48, 160, 256, 128, 1, 1, False),
@@ -34,14 +36,20 @@ for name, N, H, W, Cin, Cout, R, stride, has_res in SHAPES:
     P, Q = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
     xs = [torch.randn(N, H, W, Cin, device="cuda", generator=g).to(torch.bfloat16) for _ in range(SETS)]
     rs = [torch.randn(N, P, Q, Cout, device="cuda", generator=g).to(torch.bfloat16) for _ in range(SETS)] if has_res else None
-    outs = [torch.empty(N, P, Q, Cout, device="cuda", dtype=torch.bfloat16) for _ in range(SETS)]
+    f32out = "f32" in name
+    outs = [torch.empty(N, P, Q, 32 if f32out else Cout, device="cuda", dtype=torch.float32 if f32out else torch.bfloat16)
+            for _ in range(SETS)]
     w = torch.randn(Cout, Cin, R, R, device="cuda", generator=g) / (Cin * R * R) ** 0.5
     wp, _ = ops.pack_conv_weight(w.cpu())
+    if f32out:  # weight rows padded to the N tile
+        wpad = torch.zeros(32, wp.shape[1], dtype=wp.dtype)
+        wpad[:Cout] = wp
+        wp = wpad
     wp = wp.cuda()
     b = torch.randn(Cout, device="cuda", generator=g)
 
     def run(i):
-        ops.conv2d_nhwc([xs[i]], wp, outs[i], R=R, S=R, stride=stride, pad=pad, Cout=Cout, bias=b, slope=0.01,
+        ops.conv2d_nhwc([xs[i]], wp, outs[i], R=R, S=R, stride=stride, pad=pad, Cout=Cout, bias=b, slope=1.0 if f32out else 0.01,
                         res=rs[i] if has_res else None)
     for i in range(SETS):
         run(i)
@@ -50,8 +58,8 @@ for name, N, H, W, Cin, Cout, R, stride, has_res in SHAPES:
     ref = F.conv2d(xs[0].float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), b, stride=stride, padding=pad)
     if has_res:
         ref = ref + rs[0].float().permute(0, 3, 1, 2)
-    ref = F.leaky_relu(ref, 0.01).permute(0, 2, 3, 1)
-    err = (outs[0].float() - ref).abs().max().item() / ref.abs().max().item()
+    ref = (ref if f32out else F.leaky_relu(ref, 0.01)).permute(0, 2, 3, 1)
+    err = (outs[0][..., :Cout].float() - ref).abs().max().item() / ref.abs().max().item()
     # replay through a CUDA graph: the eager ctypes call costs ~20 us of host time, more than most of these kernels
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
