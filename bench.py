@@ -284,7 +284,9 @@ def run_train(args):
     B, W_, K = 4, max(3, args.warmup), args.steps
     conf = synth.make_conf(attention=None, center_align=False, shape_align=False, crop_size=CROP, batch_size=B)
     net = build(conf, "train")
-    sd = synth.randomize_weights(net)
+    synth.randomize_weights(net)
+    synth.condition_for_training(net)  # (finite IoU loss: see there)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
     NB = 4
     host = [synth.make_images(B, CROP, seed=100 * rank + i).pin_memory() for i in range(NB)]
     dev = [h.cuda() for h in host]

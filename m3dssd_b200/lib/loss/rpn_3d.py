@@ -14,7 +14,8 @@ forward / backward passes (m3dssd_b200.train.TrainStep).  Same constructor, forw
 (lib/dataloader.py:959-982).  Differences, all outside the shipped configs (scripts/config/*.py): `focal_loss` and
 `bbox_2d_lambda` follow the formulas the reference intends (its own code paths for them reference undefined names);
 `hard_negatives=False` draws its random subset with torch.rand keys, not torch.randperm (same distribution, different
-stream); stats whose presence depends on the data in the reference (`acc fg`, `bbox3d`, ...) are always present.
+stream); stats whose presence depends on the data in the reference (`acc fg`, `bbox3d`, ...) are always present and
+their values are detached (the reference's keep the whole autograd graph of the iteration alive until the next one).
 """
 import math
 
@@ -128,7 +129,7 @@ class RPN_3D_loss_smp(nn.Module):
         for name, m in (("fg", (labels > 0) & valid), ("bg", (labels == 0) & valid)):
             if self.cls_2d_lambda:
                 acc = ((cls_pred == labels) & m).sum().float() / m.sum().clamp(min=1).float()
-                stats.append({"name": name, "val": acc, "format": "{:0.2f}", "group": "acc"})
+                stats.append({"name": name, "val": (acc).detach(), "format": "{:0.2f}", "group": "acc"})
 
         # ---- box weighting (rpn_3d.py:1110-1175)
         fg_cnt, bg_cnt = fg_mask.sum().float(), bg_mask.sum().float()
@@ -149,7 +150,7 @@ class RPN_3D_loss_smp(nn.Module):
             loss_cls = torch.where(active, loss_cls, torch.zeros_like(loss_cls)).sum() / active.sum().clamp(min=1).float()
             loss_cls = loss_cls * self.cls_2d_lambda
             loss = loss + loss_cls
-            stats.append({"name": "cls", "val": loss_cls, "format": "{:0.4f}", "group": "loss"})
+            stats.append({"name": "cls", "val": (loss_cls).detach(), "format": "{:0.4f}", "group": "loss"})
 
         # ---- regression losses over the sampled foreground anchors (rpn_3d.py:1198-1353)
         fgf = fg_mask.float()
@@ -162,7 +163,7 @@ class RPN_3D_loss_smp(nn.Module):
             l2 = F.smooth_l1_loss(bbox_2d, t2, reduction="none")
             bbox_2d_loss = sum(fg_mean(l2[..., j]) for j in range(4)) * self.bbox_2d_lambda
             loss = loss + bbox_2d_loss
-            stats.append({"name": "bbox2d", "val": bbox_2d_loss, "format": "{:0.4f}", "group": "loss"})
+            stats.append({"name": "bbox2d", "val": (bbox_2d_loss).detach(), "format": "{:0.4f}", "group": "loss"})
         if self.bbox_3d_lambda:
             l3 = F.smooth_l1_loss(bbox_3d, t3, reduction="none")
             # the reference adds x, y, z first and then (w + h + l + ry): same association here
@@ -170,7 +171,7 @@ class RPN_3D_loss_smp(nn.Module):
             bbox_3d_loss = bbox_3d_loss + (fg_mean(l3[..., 3]) + fg_mean(l3[..., 4]) + fg_mean(l3[..., 5]) + fg_mean(l3[..., 6]))
             bbox_3d_loss = bbox_3d_loss * self.bbox_3d_lambda
             loss = loss + bbox_3d_loss
-            stats.append({"name": "bbox3d", "val": bbox_3d_loss, "format": "{:0.4f}", "group": "loss"})
+            stats.append({"name": "bbox3d", "val": (bbox_3d_loss).detach(), "format": "{:0.4f}", "group": "loss"})
 
         # depth / rotation error in absolute units (rpn_3d.py:786-806, 1056-1066)
         src = anchors[rois[:, 4].long()]
@@ -191,6 +192,6 @@ class RPN_3D_loss_smp(nn.Module):
             # (anchors outside the sample take IoU 1 -> log 0: no value, no gradient, no 0 * inf)
             iou_loss = fg_mean(-torch.log(torch.where(fg_mask, ious, torch.ones_like(ious)))) * self.iou_2d_lambda
             loss = loss + iou_loss
-            stats.append({"name": "iou", "val": iou_loss, "format": "{:0.4f}", "group": "loss"})
-        stats.append({"name": "ttloss", "val": loss, "format": "{:0.4f}", "group": "loss"})
+            stats.append({"name": "iou", "val": (iou_loss).detach(), "format": "{:0.4f}", "group": "loss"})
+        stats.append({"name": "ttloss", "val": (loss).detach(), "format": "{:0.4f}", "group": "loss"})
         return loss, stats

@@ -314,3 +314,18 @@ def make_targets(conf, batch, feat_hw=None, seed=0, fg_per_image=300, ign_fracti
         "bbox_2d": torch.randn(batch, M, 4, generator=g) * box_sigma, "bbox_3d": torch.randn(batch, M, 7, generator=g) * 0.3,
         "meta": {"rois": rois.unsqueeze(0).repeat(batch, 1, 1), "any_val": torch.ones(batch, dtype=torch.bool), "p2": p2},
     }
+
+
+@torch.no_grad()
+def condition_for_training(net, box_gain=0.05, center_gain=0.3):
+    """Training-mode conditioning of the synthetic network: RPN_3D_loss_smp's IoU term is -log(IoU) with no epsilon
+    (lib/loss/rpn_3d.py:1338), so ONE sampled foreground anchor whose decoded box misses its target makes the loss inf --
+    a freshly initialised bbox_w / bbox_h head (log-size deltas ~ N(0, 2^2)) does that at once, in the reference as
+    here.  Scale the last layers of the 2D box heads so every decoded box overlaps its target, as in a network a few
+    hundred iterations into training.  Not used by the inference goldens."""
+    for name, gain in (("bbox_w", box_gain), ("bbox_h", box_gain), ("bbox_x", center_gain), ("bbox_y", center_gain)):
+        last = getattr(net, name)[-1]
+        last.weight.mul_(gain)
+        if last.bias is not None:
+            last.bias.mul_(gain)
+    return net

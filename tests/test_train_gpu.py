@@ -127,6 +127,7 @@ def test_train_step_with_reference_loss_as_one_cuda_graph():
                                            batch_size=2))
     net = build(conf, "train")
     synth.randomize_weights(net)
+    synth.condition_for_training(net)
     net = net.cuda()
     x = synth.make_images(2, (96, 320)).cuda()
     tar = train.targets_to(synth.make_targets(conf, 2, fg_per_image=60), "cuda")

@@ -1,2 +1,3 @@
-echo "=== new (unified window)"; timeout 300 python tools/probe_conv_perf.py level2 level0 offset
-echo "=== old (3 column windows)"; M3D_LIB=$PWD/m3dssd_b200/libm3dssd_b200.old.so timeout 300 python tools/probe_conv_perf.py level2 level0 offset
+timeout 900 python -m pytest tests/test_loss.py tests/test_train_gpu.py -m gpu -x -q 2>&1 | tail -3
+timeout 900 python bench.py --mode train --steps 10 --warmup 3 2>gpurun_out/r02_train.err | tail -1 > gpurun_out/r02_bench_train.json; python -c "
+import json; d=json.load(open('gpurun_out/r02_bench_train.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches']); print(json.dumps(d['train']))"
