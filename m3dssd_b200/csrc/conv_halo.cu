@@ -154,6 +154,8 @@ __global__ void __launch_bounds__(STAGED ? 320 : 192, 1) conv_halo_kernel(const 
     uint32_t phase = 0;
     int local = 0;
     if (BRES) mbar_wait(bres_bar, 0);
+    const uint64_t db_res = umma_smem_desc<128>(smem_u32(b_res));                        // BRES: resident weights
+    const uint32_t sc_stride = static_cast<uint32_t>(nchunk) * 3 * (Cfg::B_BYTES >> 4);  // one kernel column of them
     HALO_WALK_INIT;
     for (int tile = tw_.first; tile < tw_.last; ++tile, ++local) {
       const int as = local & 1;
@@ -164,34 +166,48 @@ __global__ void __launch_bounds__(STAGED ? 320 : 192, 1) conv_halo_kernel(const 
       for (int st = 0; st < n_stages; ++st) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE);
-          if constexpr (BRES) {
-            const uint64_t db0 = umma_smem_desc<128>(smem_u32(b_res));
+        // Descriptor bases are computed HERE, in warp-uniform code, so they live in uniform registers and the elected
+        // thread spends ~3 instructions per MMA (two 64-bit immediate adds + the MMA).  Computed inside the elected
+        // branch they cost ~11 (IMAD / IADD3 / R2UR per operand): a lone thread then needs ~70 clocks per MMA while
+        // an N = 64 MMA occupies the tensor pipe for 32 -- level0 / level2 ran at 2.5 k clocks per 36-MMA tile.
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE);
+        if constexpr (BRES) {
+          constexpr uint32_t kTap = ((8 + 2) * 128) >> 4;  // descriptor units per kernel row of the 18 x 10 window
+          constexpr uint32_t kB16 = Cfg::B_BYTES >> 4;
+          const uint64_t da0 = umma_smem_desc_sbo(sa, kTap << 4);
+          const uint64_t db_a = db_res + static_cast<uint32_t>(st) * (3 * kB16);  // kernel column 0 of this chunk
+          const uint64_t db_b = db_a + sc_stride, db_c = db_b + sc_stride;        // columns 1, 2
+          if (elect_one()) {
 #pragma unroll
             for (int sc = 0; sc < 3; ++sc) {
               // tile row g of tap (r, sc) = window rows (g + r) * (TW + 2) + sc ...: 8-row groups (TW + 2) * 128 B apart
-              const uint64_t da = umma_smem_desc_sbo(sa + sc * 128, tap_shift << 4);
+              const uint64_t db = sc == 0 ? db_a : (sc == 1 ? db_b : db_c);
 #pragma unroll
               for (int r = 0; r < 3; ++r) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_f16(tmem_acc, da + r * tap_shift + 2 * k,
-                           db0 + (((sc * nchunk + st) * 3 + r) * (Cfg::B_BYTES >> 4)) + 2 * k, idesc, (st | sc | r | k) != 0);
+                  umma_f16(tmem_acc, da0 + (sc * 8 + r * kTap + 2 * k), db + (r * kB16 + 2 * k), idesc, (st | sc | r | k) != 0);
               }
             }
-          } else {
-            const uint64_t da = umma_smem_desc<128>(sa);
-            const uint64_t db = umma_smem_desc<128>(sa + Cfg::A_BYTES);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (!(p.dbg & 8)) umma_f16(tmem_acc, da + r * tap_shift + 2 * k, db + r * (Cfg::B_BYTES >> 4) + 2 * k, idesc,
-                                           (st | r | k) != 0);
-            }
+            umma_commit(&empty[stage]);
           }
-          umma_commit(&empty[stage]);
+        } else {
+          const uint64_t da_0 = umma_smem_desc<128>(sa);
+          const uint64_t da_1 = da_0 + tap_shift, da_2 = da_1 + tap_shift;
+          const uint64_t db = da_0 + (Cfg::A_BYTES >> 4);
+          const bool skip = (p.dbg & 8) != 0;  // development probe: no MMAs
+          if (elect_one()) {
+            if (!skip) {
+#pragma unroll
+              for (int r = 0; r < 3; ++r) {
+                const uint64_t da = r == 0 ? da_0 : (r == 1 ? da_1 : da_2);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(tmem_acc, da + 2 * k, db + (r * (Cfg::B_BYTES >> 4) + 2 * k), idesc, (st | r | k) != 0);
+              }
+            }
+            umma_commit(&empty[stage]);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -231,6 +247,13 @@ __global__ void __launch_bounds__(STAGED ? 320 : 192, 1) conv_halo_kernel(const 
       const uint32_t aphase = (local >> 1) & 1;
       mbar_wait(&tfull[group], aphase);
       tc_fence_after();
+      if (p.dbg & 4) {  // development probe: skip the drain
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[group]);
+        cur = nxt;
+        continue;
+      }
       epilogue_tile_grouped<BN, false>(st, tmem_base + group * Cfg::ACC, quarter, lane, gtid, group, cur,
                                        tile + 2 < tw_.last ? &nxt : nullptr, &p.tmap_out, p.out_coff, tmap_res, p.res_coff,
                                        p.slope, [&]() {

@@ -24,6 +24,9 @@ SHAPES = [
     ("level4 3x3 s2 128->256", 8, 48, 160, 128, 256, 3, 2, False),
     ("root 1x1 256->128", 8, 48, 160, 256, 128, 1, 1, False),
     ("cls.l1 3x3 64->256", 8, 48, 160, 64, 256, 3, 1, False),
+    ("root 1x1 512->256 +res", 8, 24, 80, 512, 256, 1, 1, True),
+    ("root2 1x1 128->64", 8, 96, 320, 128, 64, 1, 1, False),
+    ("proj 1x1 64->128", 8, 48, 160, 64, 128, 1, 1, False),
 ]
 only = sys.argv[1:]
 SETS = 8
