@@ -153,60 +153,114 @@ __global__ void maxpool2x2_kernel(const T* __restrict__ in, T* __restrict__ out,
 // (oy, ox) gathers the <= ceil(k/f)^2 = 4 input pixels that reach it:
 //   oy = iy * f - pad + ky   <=>   iy = (oy + pad - ky) / f   when divisible.
 // ---------------------------------------------------------------------------
+// 16-byte vector load / store of V = 16 / sizeof(T) elements as floats, written so that the arrays stay in registers
+// (type-punning `*reinterpret_cast<uint4*>(array)` made ptxas keep them in local memory: ncu showed local loads / stores
+// and 60 % of the stall cycles on them).
+template <typename T>
+__device__ __forceinline__ void load_vec_f(const T* __restrict__ p, float (&v)[16 / sizeof(T)]);
+template <>
+__device__ __forceinline__ void load_vec_f<__nv_bfloat16>(const __nv_bfloat16* __restrict__ p, float (&v)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  v[0] = __uint_as_float(u.x << 16), v[1] = __uint_as_float(u.x & 0xffff0000u);
+  v[2] = __uint_as_float(u.y << 16), v[3] = __uint_as_float(u.y & 0xffff0000u);
+  v[4] = __uint_as_float(u.z << 16), v[5] = __uint_as_float(u.z & 0xffff0000u);
+  v[6] = __uint_as_float(u.w << 16), v[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+template <>
+__device__ __forceinline__ void load_vec_f<float>(const float* __restrict__ p, float (&v)[4]) {
+  const float4 u = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = u.x, v[1] = u.y, v[2] = u.z, v[3] = u.w;
+}
+__device__ __forceinline__ void store_vec_f(__nv_bfloat16* p, const float (&v)[8]) {
+  uint32_t o[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+    o[q] = static_cast<uint32_t>(__bfloat16_as_ushort(h.x)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h.y)) << 16);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+__device__ __forceinline__ void store_vec_f(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) upsample_add_kernel(const T* __restrict__ x, const float* __restrict__ wt,
                                                            const T* __restrict__ skip, T* __restrict__ out, int N, int H,
                                                            int W, int C, int f, int x_cstride, int skip_cstride,
                                                            int out_cstride) {
   grid_dep_sync();  // PDL: launched while the previous kernel drains
-  // grid = (segments of an output row, output row, image): 32-bit index math only
+  // grid = (segments of an output row, row parity class x slice, image): 32-bit index math only.  A thread owns one
+  // (output column, 8 channels) and walks the output rows oy = m * f + parity of its slice: the four taps that reach
+  // those pixels are the same for all of them, so their weights are loaded ONCE into registers (they were 8 of the 13
+  // 16-byte loads per output: the kernel was bound by L1 wavefronts, 2.0 TB/s of algorithmic traffic).
   constexpr int V = 16 / sizeof(T);
   const int k = 2 * f, pad = f / 2;
   const int Ho = H * f, Wo = W * f, cv = C / V;
-  const int n = blockIdx.z, oy = blockIdx.y;
+  const int n = blockIdx.z;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Wo * cv) return;
   const int ox = idx / cv;
   const int c = (idx - ox * cv) * V;
-  float acc[V];
-  const long opix = (static_cast<long>(n) * Ho + oy) * Wo + ox;
-  if (skip != nullptr) {
-    T s[V];
-    *reinterpret_cast<uint4*>(s) = __ldg(reinterpret_cast<const uint4*>(skip + opix * skip_cstride + c));
+  const int kx0 = (ox + pad) % f;
+  const int ix0 = (ox + pad - kx0) / f;
+  const int parity = blockIdx.y % f, slice = blockIdx.y / f, nslices = gridDim.y / f;
+  const int ky0 = (parity + pad) % f;
+  const int diy = (parity + pad - ky0) / f;  // iy0 = m + diy for output row m * f + parity
+  float wv[2][2][V];
 #pragma unroll
-    for (int q = 0; q < V; ++q) acc[q] = to_f(s[q]);
-  } else {
-#pragma unroll
-    for (int q = 0; q < V; ++q) acc[q] = 0.f;
-  }
-  float up[V];
-#pragma unroll
-  for (int q = 0; q < V; ++q) up[q] = 0.f;
-  const int ky0 = (oy + pad) % f, kx0 = (ox + pad) % f;
-  const int iy0 = (oy + pad - ky0) / f, ix0 = (ox + pad - kx0) / f;
-#pragma unroll
-  for (int a = 0; a < 2; ++a) {  // k = 2f: exactly two taps per axis reach an output pixel
-    const int ky = ky0 + a * f, iy = iy0 - a;
-    if (iy < 0 || iy >= H) continue;
+  for (int a = 0; a < 2; ++a) {
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
-      const int kx = kx0 + b * f, ix = ix0 - b;
-      if (ix < 0 || ix >= W) continue;
-      T v[V];
-      *reinterpret_cast<uint4*>(v) =
-          __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<long>(n) * H + iy) * W + ix) * x_cstride + c));
-      float wv[V];
+      const int ky = ky0 + a * f, kx = kx0 + b * f;
 #pragma unroll
-      for (int q = 0; q < V; q += 4)
-        *reinterpret_cast<float4*>(wv + q) = __ldg(reinterpret_cast<const float4*>(wt + (ky * k + kx) * C + c + q));
-#pragma unroll
-      for (int q = 0; q < V; ++q) up[q] = fmaf(to_f(v[q]), wv[q], up[q]);
+      for (int q = 0; q < V; q += 4) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(wt + (ky * k + kx) * C + c + q));
+        wv[a][b][q] = w4.x, wv[a][b][q + 1] = w4.y, wv[a][b][q + 2] = w4.z, wv[a][b][q + 3] = w4.w;
+      }
     }
   }
-  T o[V];
+  // every load of an output is issued before the first use (addresses clamped into the tensor; taps outside the input
+  // are dropped by predicate afterwards, as in the reference): one memory latency per output, not five
+  const bool x_ok[2] = {ix0 >= 0 && ix0 < W, ix0 - 1 >= 0 && ix0 - 1 < W};
+  const int ixc[2] = {min(max(ix0, 0), W - 1), min(max(ix0 - 1, 0), W - 1)};
+#pragma unroll 2
+  for (int m = slice; m < H; m += nslices) {
+    const int oy = m * f + parity;
+    const long opix = (static_cast<long>(n) * Ho + oy) * Wo + ox;
+    const int iy0 = m + diy;
+    float v[2][2][V];
 #pragma unroll
-  for (int q = 0; q < V; ++q) o[q] = from_f<T>(up[q] + acc[q]);
-  *reinterpret_cast<uint4*>(out + opix * out_cstride + c) = *reinterpret_cast<uint4*>(o);
+    for (int a = 0; a < 2; ++a) {  // k = 2f: exactly two taps per axis reach an output pixel
+      const int iyc = min(max(iy0 - a, 0), H - 1);
+#pragma unroll
+      for (int b = 0; b < 2; ++b) load_vec_f<T>(x + ((static_cast<long>(n) * H + iyc) * W + ixc[b]) * x_cstride + c, v[a][b]);
+    }
+    float acc[V];
+    if (skip != nullptr) {
+      load_vec_f<T>(skip + opix * skip_cstride + c, acc);
+    } else {
+#pragma unroll
+      for (int q = 0; q < V; ++q) acc[q] = 0.f;
+    }
+    float up[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) up[q] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const bool y_ok = iy0 - a >= 0 && iy0 - a < H;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const bool ok = y_ok && x_ok[b];
+#pragma unroll
+        for (int q = 0; q < V; ++q) up[q] = ok ? fmaf(v[a][b][q], wv[a][b][q], up[q]) : up[q];
+      }
+    }
+    float o[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) o[q] = up[q] + acc[q];
+    store_vec_f(out + opix * out_cstride + c, o);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -744,8 +798,13 @@ extern "C" int m3d_upsample_add_nhwc(const void* x, const float* weight, const v
   M3D_REQUIRE(C % V == 0 && x_cstride % V == 0 && out_cstride % V == 0 && (skip == nullptr || skip_cstride % V == 0),
               "channels must keep 16-byte vectors");
   M3D_REQUIRE(H * f <= 65535 && N <= 65535, "upsample: output too tall for the launch grid");
-  const dim3 grid(static_cast<unsigned>((static_cast<long>(W) * f * (C / V) + 255) / 256), static_cast<unsigned>(H * f),
-                  static_cast<unsigned>(N));
+  const unsigned gx = static_cast<unsigned>((static_cast<long>(W) * f * (C / V) + 255) / 256);
+  // ~8 blocks per SM in all; grid.y = f row-parity classes x slices of the input rows
+  long slices = (148L * 8 + static_cast<long>(gx) * N * f - 1) / (static_cast<long>(gx) * N * f);
+  if (slices < 1) slices = 1;
+  if (slices > H) slices = H;
+  const unsigned gy = static_cast<unsigned>(slices * f);
+  const dim3 grid(gx, gy, static_cast<unsigned>(N));
   if (dtype == M3D_BF16)
     M3D_CUDA_OK(launch_pdl(upsample_add_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, S(stream), 
         static_cast<const __nv_bfloat16*>(x), weight, static_cast<const __nv_bfloat16*>(skip),
