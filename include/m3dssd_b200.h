@@ -268,6 +268,22 @@ int m3d_flatten_heads(const float* heads, int heads_cstride, int N, int H, int W
 int m3d_refine_3d(const float* kept, const int* num_keep, int B, int max_out, int row_len, const double* p2,
                   const double* p2_inv, float score_thresh, int hill_climbing, double step_r_init, double r_lim,
                   double* out, int* valid, m3d_stream_t stream);
+/* Training targets on the device: compute_targets (lib/rpn_util.py:430-532) + the per-image
+ * post-processing of Dataset._targets (lib/dataloader.py:1014-1144) for a whole batch.  Ground truth per image, padded
+ * to max_gts / max_ign rows (device, float64 as numpy holds them): gts_val [B, max_gts, 4] (x1,y1,x2,y2), gts_3d
+ * [B, max_gts, 7] (cx, cy, z, w, h, l, rotY), box_lbls [B, max_gts] (class index >= 1), n_val [B]; ignore regions gts_ign
+ * [B, max_ign, 4], n_ign [B].  The anchors' boxes are rebuilt from (anchor, row, column) as locate_anchors does.
+ * Outputs in the reference's `imobjs` layout, M = A*H*W rows per image: labels_fg / labels_bg / labels_ign (0/1 bytes),
+ * labels (0 background, class, 3000 ignored), bbox_2d [B,M,4], bbox_3d [B,M,7] ((t - mean) / std, float32), any_val [B].
+ * means11 / stds11: host arrays (conf.bbox_means[0], conf.bbox_stds[0]). */
+size_t m3d_compute_targets_workspace(int batch, int max_gts);
+int m3d_compute_targets(const double* gts_val, const double* gts_3d, const int* box_lbls, const int* n_val, int max_gts,
+                        const double* gts_ign, const int* n_ign, int max_ign, const float* anchors /*[A,9] device*/,
+                        int batch, int A, int H, int W, float feat_stride, double fg_thresh, double ign_thresh,
+                        double bg_thresh_lo, double bg_thresh_hi, double best_thresh, const float* means11,
+                        const float* stds11, unsigned char* labels_fg, unsigned char* labels_bg, unsigned char* labels_ign,
+                        long long* labels, float* bbox_2d, float* bbox_3d, unsigned char* any_val, void* workspace,
+                        size_t workspace_bytes, m3d_stream_t stream);
 /* layout conversion for the NCHW-facing operators */
 int m3d_nchw_to_nhwc(const void* in, int in_dtype, void* out, int out_dtype, int N, int C, int H, int W,
                      int out_cstride, int out_coff, m3d_stream_t stream);

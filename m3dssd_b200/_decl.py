@@ -25,6 +25,8 @@ _SIGS = {
     "m3d_shape_align_om": [vp, vp, vp, i, f, f, vp, lg, vp],
     "m3d_center_align_om": [vp, vp, vp, i, i, i, vp, i, f, f, f, f, f, f, vp, i, lg, vp],
     "m3d_set_sm_limit": [i],
+    "m3d_compute_targets": [vp, vp, vp, vp, i, vp, vp, i, vp, i, i, i, i, f, db, db, db, db, db, vp, vp, vp, vp, vp, vp, vp, vp,
+                            vp, vp, sz, vp],
     "m3d_head_mlp": [vp, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, i, i, i, vp, i, i, f, vp],
     "m3d_refine_3d": [vp, vp, i, i, i, vp, vp, f, i, db, db, vp, vp, vp],
     "m3d_flatten_heads": [vp, i, i, i, i, i, vp, vp, vp, vp],
@@ -40,6 +42,7 @@ _SIZE_FNS = {
     "m3d_anab_pool_workspace": [i, i, i, vp, i, i],
     "m3d_anab_attention_workspace": [i, i],
     "m3d_decode_topk_workspace": [i],
+    "m3d_compute_targets_workspace": [i, i],
     "m3d_conv2d_wgrad_workspace": [i] * 7,
     "m3d_channel_sum_workspace": [i],
     "m3d_upsample_backward_workspace": [i, i],

@@ -21,3 +21,5 @@ ncu -i gpurun_out/${tag}_hot.ncu-rep --page raw --csv > gpurun_out/${tag}_hot_ra
 python tools/summarize_ncu.py hot gpurun_out/${tag}_hot_raw.csv > gpurun_out/${tag}_hot_kernels.md
 rm -f gpurun_out/${tag}_hot.ncu-rep
 ls -la gpurun_out/${tag}_*
+# BASELINE configs[3]: the training step (native kernels + the reference's loss in its static-shape form)
+timeout 900 python bench.py --mode train --steps 10 --warmup 3 > gpurun_out/${tag}_bench_train.json 2> gpurun_out/${tag}_bench_train.err; head -c 300 gpurun_out/${tag}_bench_train.json; echo
