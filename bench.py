@@ -295,8 +295,14 @@ def run_train(args):
         # on targets laid out as the reference's dataloader does (~300 foreground anchors per image)
         from m3dssd_b200.lib.loss.rpn_3d import RPN_3D_loss_smp
         synth.loss_conf(conf)
+        from m3dssd_b200.lib.targets import compute_targets_batch
         criterion = RPN_3D_loss_smp(conf).cuda()
-        targets = (train.targets_to(synth.make_targets(conf, B, seed=rank), "cuda"),)
+        feat_hw = (CROP[0] // conf.feat_stride, CROP[1] // conf.feat_stride)
+        # ground truth of NB batches (8 valid boxes + 2 ignore regions per image); the targets of a batch are built on
+        # the device (m3d_compute_targets = the reference's compute_targets + Dataset._targets): once here for the
+        # device-resident loop, every step inside the end-to-end loop
+        gts = [[synth.make_gts(conf, 8, 2, seed=1000 * rank + 10 * i + b) for b in range(B)] for i in range(4)]
+        targets = (compute_targets_batch(conf, gts[0], feat_hw),)
     else:
         criterion = None
         targets = train.surrogate_targets(conf, B, "cuda")
@@ -307,7 +313,10 @@ def run_train(args):
         e0.record()
         for i in range(n):
             x = host[i % NB].cuda(non_blocking=True) if from_host else dev[i % NB]
-            loss = step(x, *targets)
+            tg = targets
+            if from_host and criterion is not None:  # annotations in, targets built on the device, every step
+                tg = (compute_targets_batch(conf, gts[i % NB], feat_hw),)
+            loss = step(x, *tg)
             if from_host:
                 loss.item()  # the reference reads the loss every iteration (train_rpn_3d.py:208)
         e1.record()
@@ -388,7 +397,9 @@ def run_train(args):
                                "DLA-34 substituted for dla102 (BASELINE.json configs[3])",
                    "global_batch": world * B, "precision": "bf16 activations / fp32 master weights, statistics, optimizer",
                    "loss": ("RPN_3D_loss_smp (lib/loss/rpn_3d.py:659-1360, kitti_3d_base hyper-parameters: OHEM sampling, weighted "
-                            "cross-entropy, smooth-L1 3D, IoU loss) in its static-shape device form, m3dssd_b200.lib.loss.rpn_3d"
+                            "cross-entropy, smooth-L1 3D, IoU loss) in its static-shape device form, m3dssd_b200.lib.loss.rpn_3d; "
+                            "targets from 8 boxes + 2 ignore regions per image by m3d_compute_targets (compute_targets + "
+                            "Dataset._targets on the device; rebuilt every step in the e2e loop)"
                             if criterion is not None else
                             "surrogate (cross-entropy + smooth-L1, m3dssd_b200.train.surrogate_loss)"),
                    "optimizer": "SGD lr 0.004 momentum 0.9 weight_decay 5e-4",

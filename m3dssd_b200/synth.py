@@ -329,3 +329,22 @@ def condition_for_training(net, box_gain=0.05, center_gain=0.3):
         if last.bias is not None:
             last.bias.mul_(gain)
     return net
+
+
+def make_gts(conf, n_val=8, n_ign=2, seed=0, image_hw=None):
+    """Seeded KITTI-like annotations of one image in the form Dataset._targets hands to compute_targets
+    (lib/dataloader.py:1060-1084): gts_val / gts_ign [n, 4] boxes (x1, y1, x2, y2) whose sizes follow the anchors',
+    box_lbls (class index 1..len(lbls)), gts_3d [n, 7] = projected centre, depth, w3d, h3d, l3d, rotY."""
+    rng = np.random.default_rng(seed)
+    H, W = image_hw if image_hw is not None else conf.crop_size
+
+    def boxes(n):
+        h = np.exp(rng.uniform(np.log(20.0), np.log(0.7 * H), n))
+        w = h * rng.uniform(0.4, 1.8, n)
+        cx, cy = rng.uniform(0, W, n), rng.uniform(0.3 * H, 0.9 * H, n)
+        return np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], axis=1)
+    val = boxes(n_val)
+    g3d = np.stack([(val[:, 0] + val[:, 2]) / 2 + rng.normal(0, 3, n_val), (val[:, 1] + val[:, 3]) / 2 + rng.normal(0, 3, n_val),
+                    rng.uniform(4, 60, n_val), rng.uniform(0.5, 2.0, n_val), rng.uniform(1.2, 2.0, n_val),
+                    rng.uniform(0.8, 4.5, n_val), rng.uniform(-3.1, 3.1, n_val)], axis=1) if n_val else np.zeros((0, 7))
+    return {"gts_val": val, "gts_ign": boxes(n_ign), "box_lbls": rng.integers(1, len(conf.lbls) + 1, n_val), "gts_3d": g3d}

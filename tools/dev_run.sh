@@ -1,2 +1,3 @@
-timeout 200 python tools/probe_elementwise.py 2>&1 | head -2
-timeout 300 python -m pytest tests/test_ops_gpu.py -m gpu -x -q -k upsample 2>&1 | tail -2
+timeout 900 python bench.py --mode train --steps 10 --warmup 3 2>gpurun_out/r02_train.err | tail -1 > gpurun_out/r02_bench_train.json; python -c "
+import json; d=json.load(open('gpurun_out/r02_bench_train.json')); print(d['value'], d['ms_per_step'], d['e2e'], d['gpu_launches']); print(json.dumps(d['train']))"
+tail -3 gpurun_out/r02_train.err
