@@ -112,6 +112,10 @@ class ClockSampler:
             except OSError:
                 self._smi = None
 
+    def reset(self):
+        """Forget what was sampled so far (the sampler keeps running): call right before the timed region."""
+        self.samples, self.reasons = [], set()
+
     def stop(self):
         if self._thr is not None:
             self._stop.set()
@@ -525,13 +529,17 @@ def main():
         return e0.elapsed_time(e1)
 
     # ---------------------------------------------------------- device-resident throughput
+    # (NVML initialisation and the first, slow queries happen during the warm-up: started right before the timed loop
+    # they delayed rank 0 by tens of ms after the barrier, and the other ranks waited for it inside their all-gathers)
+    clocks = ClockSampler(local_rank) if rank == 0 else None  # one sampling thread per job, not per rank
+    if clocks:
+        clocks.start()
     for i in range(W):
         det.step_pipelined(dev[i % NB])
     drain()
     barrier()
-    clocks = ClockSampler(local_rank) if rank == 0 else None  # one sampling thread per job, not per rank
     if clocks:
-        clocks.start()
+        clocks.reset()
     ms_total = allmax(resident_loop(K))
     clk = clocks.stop() if clocks else None
     note("device-resident loop done: %.3f ms/step" % (ms_total / K))
