@@ -1,6 +1,2 @@
-for r in 1 2 3; do
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2951$r bench.py --gpus 2 --steps 30 --warmup 5 --no-cpu-baseline --no-extras 2>gpurun_out/r02_bench_2gpu.err | tail -1 > gpurun_out/r02_bench_2gpu_$r.json
-python -c "
-import json; d=json.load(open('gpurun_out/r02_bench_2gpu_$r.json')); print(d['n_gpus'], d['value'], d['e2e']['value'], d['ms_per_step'])"
-grep -i "note\|ms/step" gpurun_out/r02_bench_2gpu.err | tail -4
-done
+timeout 900 python -m pytest tests/test_conv_gpu.py tests/test_ops_gpu.py tests/test_model_gpu.py tests/test_teacher_forced_gpu.py -m gpu -x -q 2>&1 | tail -4
+timeout 300 python tools/gpu_profile.py > gpurun_out/r02z_ops.txt 2>&1; grep -E "^level1|^level0|^total|^stage" gpurun_out/r02z_ops.txt
