@@ -522,9 +522,83 @@ class Engine:
         alt = [self.detect_alt.get(i, op) for i, op in enumerate(self.ops[:self.n_detect_ops])]
         return [op for op in alt if op is not None]  # None: folded into a neighbour's kernel
 
+    def _side_tasks(self):
+        """Independent branches of the aggregation network that may run beside the small-grid layers of the trunk:
+        (after, [ops], before) = once op `after` has been issued the listed ops go to a side stream; the main stream
+        waits for them before op `before`.  dla_up.ida_1.proj_1 only reads level4's output, so its offset conv + DCN
+        (120 tiles, L1-bound) run under level5 + ida_0 (48..120 CTAs per launch, tensor-bound)."""
+        if os.environ.get("M3D_SIDE", "1") == "0":
+            return []
+        names = [m["name"] for m in self.meta]
+        tasks = []
+
+        want = os.environ.get("M3D_SIDE", "1")  # "0": none, "1": all, or a comma list of agg / pool / heads (development)
+
+        def add(tag, after, side, before):
+            if want != "1" and tag not in want.split(","):
+                return
+            try:
+                a = max(i for i, n in enumerate(names) if n == after or n.startswith(after + "."))
+                ops_ = [names.index(n) for n in side]
+                b = names.index(before)
+            except ValueError:
+                return
+            if all(a < i < b for i in ops_):
+                tasks.append(dict(after=a, ops=ops_, before=b))
+        # dla_up.ida_1.proj_1 reads level4 only: beside level5 + ida_0
+        add("agg", "level4", ["dla_up.ida_1.proj_1.offset", "dla_up.ida_1.proj_1"], "dla_up.ida_1.up_1")
+        # dla_up.ida_1.proj_2 and ida_up.proj_1 read ida_0's output only: beside ida_1's first up / node pair
+        add("agg", "dla_up.ida_0.node_1", ["dla_up.ida_1.proj_2.offset", "dla_up.ida_1.proj_2"], "dla_up.ida_1.up_2")
+        add("agg", "dla_up.ida_0.node_1", ["ida_up.proj_1.offset", "ida_up.proj_1"], "ida_up.up_1")
+        # Tree: max-pool + 1x1 project of the residual (model/pose_dla_dcn.py:303-309) beside the block's first conv
+        for lvl, prev in ((2, "level1"), (3, "level2"), (4, "level3"), (5, "level4")):
+            L = "level%d" % lvl
+            for proj, conv2 in ((L + ".project", L + ".tree1.conv2"), (L + ".tree1.project", L + ".tree1.tree1.conv2")):
+                add("pool", prev, [L + ".down", proj], conv2)
+        # the two centre alignments and their head groups are independent chains
+        add("heads", "center_align3d.om", ["center_align2d", "headsB.mlp"], "flatten_heads")
+        # ... and so is the depth head (input: the 3D-aligned features, or ANAB's output when the attention block is on)
+        add("heads", "anab.attention" if "anab.attention" in names else "center_align3d", ["headsZ.mlp"], "flatten_heads")
+        return tasks
+
+    def _exec(self, lo, hi, detect=False):
+        """Issue ops [lo, hi) of the plan (detect: the detection stages' variants), branches of _side_tasks on the side
+        stream (fork / join by stream events: captured into the CUDA graph as parallel branches)."""
+        if not hasattr(self, "_tasks"):
+            self._tasks = self._side_tasks()
+            self._side = torch.cuda.Stream() if self._tasks else None
+        tasks = [t for t in self._tasks if lo <= t["after"] and t["before"] <= hi]
+        on_side = {i for t in tasks for i in t["ops"]}
+        cur = torch.cuda.current_stream()
+        pending = set()
+
+        def pick(i):
+            return self.detect_alt.get(i, self.ops[i]) if detect else self.ops[i]
+
+        def join(i):
+            for k, t in enumerate(tasks):
+                if t["before"] == i and k in pending:
+                    cur.wait_event(t["done"])
+                    pending.discard(k)
+        for i in range(lo, hi):
+            join(i)
+            op = pick(i)
+            if op is not None and i not in on_side:
+                op()
+            for k, t in enumerate(tasks):
+                if t["after"] == i:
+                    self._side.wait_stream(cur)
+                    with torch.cuda.stream(self._side):
+                        for j in t["ops"]:
+                            if pick(j) is not None:
+                                pick(j)()
+                        t["done"] = torch.cuda.Event()
+                        t["done"].record(self._side)
+                    pending.add(k)
+        join(hi)  # branches that run to the end of the range
+
     def _run_forward(self, flatten=True):
-        for op in (self.ops if flatten else self._detect_ops()):
-            op()
+        self._exec(0, len(self.ops) if flatten else self.n_detect_ops, detect=not flatten)
 
     def _run_decode(self):
         ops.decode_topk_heads(self.score, self.cls_pred, self.heads, OUT_SLOTS, self.anchors, self.means_t, self.stds_t,
@@ -633,12 +707,10 @@ class Engine:
             return g
 
         def trunk():
-            for op in self.ops[:self.n_trunk_ops]:
-                op()
+            self._exec(0, self.n_trunk_ops, detect=True)
 
         def heads():
-            for op in self._detect_ops()[self.n_trunk_ops:]:
-                op()
+            self._exec(self.n_trunk_ops, self.n_detect_ops, detect=True)
 
         if self.use_graph:
             # the trunk of batch i+1 shares the device with the detection tail of batch i (one CTA per image on
