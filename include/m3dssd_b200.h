@@ -43,6 +43,10 @@ int m3d_version(void);
  * (one CTA per image, minutes of L2 latency each) runs under the trunk of the next: a persistent CTA needs a
  * whole SM's shared memory, so a grid of all SMs would otherwise run as two waves. */
 int m3d_set_sm_limit(int sms);
+/* Programmatic dependent launch for the kernels launched / captured from now on (default on).  Switch it off while two
+ * streams launch persistent kernels concurrently: a successor grid blocked in griddepcontrol.wait must never hold SMs
+ * that unscheduled CTAs of its predecessor need. */
+int m3d_set_pdl(int on);
 
 /* ------------------------------------------------------------------------
  * Engine-level convolution / DCNv2 on NHWC activations (tcgen05 implicit GEMM).

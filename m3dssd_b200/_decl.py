@@ -25,6 +25,7 @@ _SIGS = {
     "m3d_shape_align_om": [vp, vp, vp, i, f, f, vp, lg, vp],
     "m3d_center_align_om": [vp, vp, vp, i, i, i, vp, i, f, f, f, f, f, f, vp, i, lg, vp],
     "m3d_set_sm_limit": [i],
+    "m3d_set_pdl": [i],
     "m3d_compute_targets": [vp, vp, vp, vp, i, vp, vp, i, vp, i, i, i, i, f, db, db, db, db, db, vp, vp, vp, vp, vp, vp, vp, vp,
                             vp, vp, sz, vp],
     "m3d_head_mlp": [vp, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, i, i, i, vp, i, i, f, vp],

@@ -301,6 +301,16 @@ int persistent_sms() {
 int reserved_sms() { return sm_count() - persistent_sms(); }
 }  // namespace m3d
 
+namespace m3d {
+static bool g_pdl_on = true;
+bool pdl_switch() { return g_pdl_on; }
+}  // namespace m3d
+
+extern "C" int m3d_set_pdl(int on) {
+  m3d::g_pdl_on = on != 0;
+  return M3D_OK;
+}
+
 extern "C" int m3d_set_sm_limit(int sms) {
   M3D_REQUIRE(sms >= 0, "sm limit must be >= 0 (0 = the whole device)");
   m3d::g_sm_limit = sms;

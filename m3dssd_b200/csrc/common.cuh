@@ -56,13 +56,19 @@ int reserved_sms();
 #include <cstdlib>
 #include <utility>
 namespace m3d {
+// m3d_set_pdl(0 / 1): the engine switches programmatic dependent launch OFF for the launches it issues while a branch
+// of its plan runs on a second stream (api_conv.cu).  Two persistent grids then share the device and one of them has
+// unscheduled CTAs; a PDL successor whose CTAs sit blocked in griddepcontrol.wait on SMs those CTAs need can starve
+// them (observed as a hang with 148-CTA grids beside the 8 CTAs of the detection tail).  Without PDL nothing ever
+// occupies an SM while blocked, so progress is guaranteed whatever the hardware's CTA scheduling order.
+bool pdl_switch();
 inline bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {
     const char* e = getenv("M3D_PDL");
     on = (e == nullptr || atoi(e) != 0) ? 1 : 0;
   }
-  return on == 1;
+  return on == 1 && pdl_switch();
 }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

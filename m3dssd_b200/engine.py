@@ -580,21 +580,30 @@ class Engine:
                 if t["before"] == i and k in pending:
                     cur.wait_event(t["done"])
                     pending.discard(k)
-        for i in range(lo, hi):
-            join(i)
-            op = pick(i)
-            if op is not None and i not in on_side:
-                op()
-            for k, t in enumerate(tasks):
-                if t["after"] == i:
-                    self._side.wait_stream(cur)
-                    with torch.cuda.stream(self._side):
-                        for j in t["ops"]:
-                            if pick(j) is not None:
-                                pick(j)()
-                        t["done"] = torch.cuda.Event()
-                        t["done"].record(self._side)
-                    pending.add(k)
+        safe = os.environ.get("M3D_SIDE_PDL", "0") == "0"  # no PDL while a branch is in flight (see m3d_set_pdl)
+        try:
+            for i in range(lo, hi):
+                join(i)
+                op = pick(i)
+                if op is not None and i not in on_side:
+                    op()  # (the first op after a join is still launched without PDL: it waits for its predecessor,
+                    #        which may have had unscheduled CTAs, to complete)
+                if safe and not pending:
+                    ops.set_pdl(True)
+                for k, t in enumerate(tasks):
+                    if t["after"] == i:
+                        if safe:
+                            ops.set_pdl(False)
+                        self._side.wait_stream(cur)
+                        with torch.cuda.stream(self._side):
+                            for j in t["ops"]:
+                                if pick(j) is not None:
+                                    pick(j)()
+                            t["done"] = torch.cuda.Event()
+                            t["done"].record(self._side)
+                        pending.add(k)
+        finally:
+            ops.set_pdl(True)
         join(hi)  # branches that run to the end of the range
 
     def _run_forward(self, flatten=True):

@@ -305,6 +305,11 @@ def set_sm_limit(sms):
     check(lib().m3d_set_sm_limit(int(sms)))
 
 
+def set_pdl(on):
+    """Programmatic dependent launch for the kernels launched / captured from now on (see m3d_set_pdl)."""
+    check(lib().m3d_set_pdl(int(bool(on))))
+
+
 def head_mlp(x, x_coff, cx, w1, b1, w2, b2, w3, b3, G, A, rows3, out, out_coff, slope=0.01):
     """G fused three-layer 1x1 heads on x[..., x_coff:x_coff+cx] (bf16 NHWC) -> out[..., out_coff + g*A + a] (fp32 NHWC)."""
     N, H, W, cs = x.shape

@@ -1,6 +1,8 @@
-for v in 0 1; do echo "== M3D_SIDE=$v"; M3D_SIDE=$v timeout 300 python tools/gpu_profile.py 2>&1 | grep -E "^stage=(forward|detect) graph=True"; done
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-timeout 900 python bench.py --steps 30 --warmup 5 --no-cpu-baseline 2>gpurun_out/r02_bench_dev.err | tail -1 > gpurun_out/r02_bench_dev.json; python -c "
-import json; d=json.load(open('gpurun_out/r02_bench_dev.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches'], d['sustained']['value'])"
-timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-extras --attention ANAB 2>/dev/null | tail -1 | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('anab', d['value'], d['e2e']['value'])"
+for v in 0 1; do echo "== M3D_SIDE_PDL=$v (1 = PDL kept on beside branches)"; M3D_SIDE_PDL=$v timeout 90 python bench.py --steps 60 --warmup 5 --no-cpu-baseline --no-extras 2>/dev/null | tail -1 | python -c "
+import json,sys
+t=sys.stdin.read()
+try:
+    d=json.loads(t); print(d['value'], d['ms_per_step'], d['e2e']['value'])
+except Exception as e: print('FAILED/timeout', len(t))"; done
+echo "== M3D_SIDE=0"; M3D_SIDE=0 timeout 90 python bench.py --steps 60 --warmup 5 --no-cpu-baseline --no-extras 2>/dev/null | tail -1 | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'])"
