@@ -1,8 +1,4 @@
-for v in 0 1; do echo "== M3D_SIDE_PDL=$v (1 = PDL kept on beside branches)"; M3D_SIDE_PDL=$v timeout 90 python bench.py --steps 60 --warmup 5 --no-cpu-baseline --no-extras 2>/dev/null | tail -1 | python -c "
-import json,sys
-t=sys.stdin.read()
-try:
-    d=json.loads(t); print(d['value'], d['ms_per_step'], d['e2e']['value'])
-except Exception as e: print('FAILED/timeout', len(t))"; done
-echo "== M3D_SIDE=0"; M3D_SIDE=0 timeout 90 python bench.py --steps 60 --warmup 5 --no-cpu-baseline --no-extras 2>/dev/null | tail -1 | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'])"
+timeout 900 python -m pytest tests/test_multi_gpu.py -m gpu -x -q 2>&1 | tail -2
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 30 --warmup 5 --no-cpu-baseline 2>gpurun_out/r02_bench_2gpu.err | tail -1 > gpurun_out/r02_bench_2gpu.json
+python -c "
+import json; d=json.load(open('gpurun_out/r02_bench_2gpu.json')); print(d['n_gpus'], d['value'], d['e2e']['value'], d['ms_per_step'])"
