@@ -183,3 +183,34 @@ def test_dla102_runs_through_the_fused_engine():
             # bars were set on dla34 (Cin <= 512); dla102's 1x1 convs reduce over up to 2048 channels and its BatchNorm
             # cancels more of the sum, so one layer's bf16 rounding is a larger fraction of what is left: x1.5
             assert r["rms"] < 1.5 * BARS[r["kind"]][0] and r["max"] < 1.5 * BARS[r["kind"]][1], r
+
+
+@pytest.mark.parametrize("attention", [None, "ANAB"])
+def test_side_stream_branches_do_not_change_a_single_bit(attention, monkeypatch):
+    """Engine._side_tasks moves independent branches of the plan to a second stream (fork / join by events inside the
+    captured graphs).  A missing dependency would show up as a data race: the network outputs, the head buffer and the
+    kept detections must be bit-identical with the branches on (default) and off, graph-replayed and eager, and stay so
+    over repeated replays."""
+    conf, net, sd, x = _setup(attention, True, (96, 320), 2)
+    net = net.cuda().eval()
+    xc = x.cuda()
+    results = {}
+    for side in ("0", "1"):
+        for graph in (False, True):
+            monkeypatch.setenv("M3D_SIDE", side)
+            net.invalidate_engines()
+            eng = net.engine(2, 96, 320, precision="bf16", use_graph=graph, max_out=3000)
+            for rep in range(3):
+                kept, num = eng.detect(xc)
+                outs = eng.flatten_outputs()
+                torch.cuda.synchronize()
+                cur = [t.clone() for t in (kept, num, eng.heads, eng.score) + tuple(outs)]
+                key = (side, graph)
+                if key in results:
+                    assert all(torch.equal(a, b) for a, b in zip(cur, results[key])), "replay %d differs (%s)" % (rep, key)
+                results[key] = cur
+            if side == "1":
+                assert len(eng._tasks) >= 6, "no branches were scheduled"
+    ref = results[("0", False)]
+    for key, cur in results.items():
+        assert all(torch.equal(a, b) for a, b in zip(cur, ref)), key

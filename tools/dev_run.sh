@@ -1,4 +1,1 @@
-timeout 900 python -m pytest tests/test_multi_gpu.py -m gpu -x -q 2>&1 | tail -2
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 30 --warmup 5 --no-cpu-baseline 2>gpurun_out/r02_bench_2gpu.err | tail -1 > gpurun_out/r02_bench_2gpu.json
-python -c "
-import json; d=json.load(open('gpurun_out/r02_bench_2gpu.json')); print(d['n_gpus'], d['value'], d['e2e']['value'], d['ms_per_step'])"
+timeout 600 python -m pytest tests/test_model_gpu.py -m gpu -x -q -k side_stream 2>&1 | tail -8
