@@ -432,6 +432,9 @@ def main():
     ap.add_argument("--attention", default=None)
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer: BASELINE configs[1] / [2] (default); train: configs[3], the kitti_3d_base train step")
+    ap.add_argument("--backbone", default="dla34", choices=["dla34", "dla102"],
+                    help="dla34 = BASELINE.json's configs; dla102 = the backbone of the reference's shipped configs "
+                         "(scripts/config/kitti_3d_base.py:46), reported beside them")
     ap.add_argument("--train-loss", default="rpn3d", choices=["rpn3d", "surrogate"],
                     help="--mode train: the reference's RPN_3D_loss_smp (static-shape device form) or the round-2a surrogate")
     ap.add_argument("--input", default="u8", choices=["u8", "f32"],
@@ -487,7 +490,7 @@ def main():
             print("[bench rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
 
     conf = synth.make_conf(attention=args.attention, center_align=True, shape_align=True, crop_size=CROP,
-                           batch_size=LOCAL_BATCH)
+                           batch_size=LOCAL_BATCH, back_bone=args.backbone)
     conf.precision = "bf16"
     net = build(conf, "test")
     synth.randomize_weights(net)
@@ -673,8 +676,9 @@ def main():
             "metric": "images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD_ANAB if args.attention else WORKLOAD, "global_batch": world * LOCAL_BATCH,
-                       "image": "384x1280", "backbone": "dla34", "align": True, "attention": args.attention,
+            "config": {"workload": (WORKLOAD_ANAB if args.attention else WORKLOAD).replace("DLA-34", "DLA-102") if args.backbone == "dla102"
+                       else (WORKLOAD_ANAB if args.attention else WORKLOAD), "global_batch": world * LOCAL_BATCH,
+                       "image": "384x1280", "backbone": args.backbone, "align": True, "attention": args.attention,
                        "input": ("uint8 HWC images; Normalize + BGR->RGB + CHW (lib/augmentations.py:44-57) on the device, "
                                  "inside every step" if args.input == "u8" else "pre-normalised fp32 NCHW"),
                        "parallelism": "dp%d (images sharded; all-gather of detections before NMS)" % world,
