@@ -24,10 +24,16 @@ _MAP = {
 }
 
 
-def install(override_existing=True):
+# opt-in: `from lib.loss.rpn_3d import *` (scripts/train_rpn_3d.py:24) then yields the static-shape RPN_3D_loss_smp.  Not in
+# the default map because the reference's module also re-exports lib.rpn_util through its own star import.
+_LOSS_MAP = {"lib.loss.rpn_3d": "m3dssd_b200.lib.loss.rpn_3d"}
+
+
+def install(override_existing=True, loss=False):
     """Alias our modules under the reference's names.  Parent packages that are not importable
-    (running outside the reference checkout) are created as empty namespace modules."""
-    for ref_name, ours in _MAP.items():
+    (running outside the reference checkout) are created as empty namespace modules.  loss=True also aliases
+    lib.loss.rpn_3d (the device-side RPN_3D_loss_smp)."""
+    for ref_name, ours in list(_MAP.items()) + (list(_LOSS_MAP.items()) if loss else []):
         if not override_existing and ref_name in sys.modules:
             continue
         parts = ref_name.split(".")

@@ -18,7 +18,7 @@ _rois_cache = {}
 
 
 def _rois(conf, feat_size, device):
-    key = (id(conf.anchors), tuple(int(v) for v in feat_size), float(conf.feat_stride), str(device))
+    key = (hash(np.asarray(conf.anchors).tobytes()), tuple(int(v) for v in feat_size), float(conf.feat_stride), str(device))
     if key not in _rois_cache:
         r = torch.from_numpy(locate_anchors(conf.anchors, feat_size, conf.feat_stride).astype(np.float32))
         _rois_cache[key] = r.to(device)
