@@ -92,6 +92,12 @@ def test_dropin_aliases():
         from lib.nms.gpu_nms import gpu_nms  # noqa: F401
         import m3dssd_b200.model.M3d_inference_align as ours
         assert sys.modules["model.M3d_inference_align"] is ours
+        assert "lib.loss.rpn_3d" not in sys.modules  # opt-in only
+        dropin.install(loss=True)
+        ns = {}
+        exec("from lib.loss.rpn_3d import *", ns)  # scripts/train_rpn_3d.py:24
+        import m3dssd_b200.lib.loss.rpn_3d as our_loss
+        assert ns["RPN_3D_loss_smp"] is our_loss.RPN_3D_loss_smp
     finally:
         for k in [k for k in sys.modules if k.split(".")[0] in ("model", "lib")]:
             del sys.modules[k]
