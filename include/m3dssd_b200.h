@@ -104,19 +104,6 @@ typedef struct m3d_conv_desc {
   int om_cstride;
   int sigmoid_mask;
   int force_gather; /* testing: route a plain conv through the gather producer */
-  /* Class head, last layer (model/M3d_inference_align.py:223-234; bf16 1x1 conv with fp32 output, Cout = 4 * A logits with
-   * channel = class * A + anchor, one N tile): when cls_A > 0 the conv's epilogue also produces what m3d_cls_softmax and
-   * m3d_shape_align_om would compute from the logits -- bit for bit -- and writes the logits only if cls_write_logits. */
-  int cls_A;
-  int cls_write_logits;
-  float* cls_fg_max;            /* [N, P, Q] foreground probability of the top-1 anchor */
-  int* cls_fg_arg;              /* [N, P, Q] that anchor */
-  float* cls_score;             /* [N, A, P, Q] best foreground class probability */
-  unsigned char* cls_pred;      /* [N, A, P, Q] its class */
-  float* cls_shape_om;          /* [N*P*Q, 27] shape-align offsets / mask, or NULL */
-  const float* cls_anchors;     /* [A, cls_anchor_ld] (device) */
-  int cls_anchor_ld;
-  float cls_feat_stride, cls_thresh;
 } m3d_conv_desc;
 
 int m3d_conv2d_nhwc(const m3d_conv_desc* desc, m3d_stream_t stream);

@@ -35,10 +35,6 @@ class ConvDesc(C.Structure):
         ("slope", C.c_float),
         ("om", C.c_void_p), ("om_cstride", C.c_int), ("sigmoid_mask", C.c_int),
         ("force_gather", C.c_int),
-        ("cls_A", C.c_int), ("cls_write_logits", C.c_int),
-        ("cls_fg_max", C.c_void_p), ("cls_fg_arg", C.c_void_p), ("cls_score", C.c_void_p), ("cls_pred", C.c_void_p),
-        ("cls_shape_om", C.c_void_p), ("cls_anchors", C.c_void_p), ("cls_anchor_ld", C.c_int),
-        ("cls_feat_stride", C.c_float), ("cls_thresh", C.c_float),
     ]
 
 

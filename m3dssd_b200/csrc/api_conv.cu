@@ -474,16 +474,6 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
     p.res = d->res, p.res_cstride = d->res_cstride, p.res_coff = d->res_coff, p.res_goff = d->res_goff;
     p.slope = d->slope;
     p.total_tiles = static_cast<int>(total_tiles);
-    if (d->cls_A > 0) {
-      M3D_REQUIRE(staged_f32 && n_tiles == 1 && d->Cout == 4 * d->cls_A && d->cls_A <= 64 && d->slope == 1.0f,
-                  "class-head epilogue: bf16 1x1 conv, fp32 output, Cout = 4 * A <= 256 logits, no activation");
-      M3D_REQUIRE(d->cls_fg_max && d->cls_fg_arg && d->cls_score && d->cls_pred && (!d->cls_shape_om || d->cls_anchors),
-                  "class-head epilogue: NULL sink");
-      p.cls.A = d->cls_A, p.cls.write_logits = d->cls_write_logits;
-      p.cls.fg_max = d->cls_fg_max, p.cls.fg_arg = d->cls_fg_arg, p.cls.score = d->cls_score, p.cls.cls_pred = d->cls_pred;
-      p.cls.shape_om = d->cls_shape_om, p.cls.anchors = d->cls_anchors, p.cls.anchor_ld = d->cls_anchor_ld;
-      p.cls.feat_stride = d->cls_feat_stride, p.cls.thresh = d->cls_thresh;
-    }
     rc = launch_conv_tma(p, BN, bk, ksub, d->out_dtype, staged || staged_f32, stream);
     if (rc == M3D_ERR_UNSUPPORTED) set_last_error("no TMA conv kernel for BN=%d BK=%d", BN, bk);
     return rc;

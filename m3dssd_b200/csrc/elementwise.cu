@@ -7,7 +7,6 @@
 #include <algorithm>
 #include <cstdint>
 
-#include "align_om.cuh"
 #include "common.cuh"
 
 namespace m3d {
@@ -280,6 +279,8 @@ constexpr int SM_PIX = 32;
 // staged class-major in shared memory ([K*A][SM_PIX + 1]) so that the NHWC reads (144 contiguous floats per
 // pixel) and the anchor-major writes (16 bytes per (anchor, pixel), pixels contiguous) are both coalesced and
 // the column accesses are bank-conflict free.
+__device__ __forceinline__ void shape_align_om_pixel(float fg, int a, const float* __restrict__ anchors, int anchor_ld,
+                                                     float feat_stride, float thresh, float* __restrict__ om, long i);
 __global__ void __launch_bounds__(256) cls_softmax4_kernel(const float* __restrict__ logits, int lc_stride, int N, int H,
                                                            int W, int A, float* __restrict__ cls_out,
                                                            float* __restrict__ prob_out, float* __restrict__ fg_max,
@@ -417,6 +418,8 @@ __global__ void __launch_bounds__(256) cls_softmax_kernel(const float* __restric
 // for the top-1 anchor, zeroed where fg <= thresh; modulation mask = fg.
 // om layout: [N,H,W,27] = 18 offsets (dh, dw per tap) + 9 masks.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ void shape_align_om_pixel(float fg, int a, const float* __restrict__ anchors, int anchor_ld,
+                                                     float feat_stride, float thresh, float* __restrict__ om, long i);
 
 __global__ void shape_align_om_kernel(const float* __restrict__ fg_max, const int* __restrict__ fg_arg,
                                       const float* __restrict__ anchors, int anchor_ld, float feat_stride, float thresh,
@@ -425,6 +428,23 @@ __global__ void shape_align_om_kernel(const float* __restrict__ fg_max, const in
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (i >= npix) return;
   shape_align_om_pixel(fg_max[i], fg_arg[i], anchors, anchor_ld, feat_stride, thresh, om, i);
+}
+
+__device__ __forceinline__ void shape_align_om_pixel(float fg, int a, const float* __restrict__ anchors, int anchor_ld,
+                                                     float feat_stride, float thresh, float* __restrict__ om, long i) {
+  const float hard = fg > thresh ? 1.f : 0.f;
+  const float aw = anchors[a * anchor_ld + 2] - anchors[a * anchor_ld + 0];
+  const float ah = anchors[a * anchor_ld + 3] - anchors[a * anchor_ld + 1];
+  const float hstep = ah / feat_stride / 3.f - 1.f;
+  const float wstep = aw / feat_stride / 3.f - 1.f;
+  float* o = om + i * 27;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int ti = t / 3, tj = t % 3;
+    o[2 * t] = hstep * (static_cast<float>(ti) - 1.5f + 0.5f) * hard;
+    o[2 * t + 1] = wstep * (static_cast<float>(tj) - 1.5f + 0.5f) * hard;
+    o[18 + t] = fg;
+  }
 }
 
 // center_align offsets (feturealign_mgpu.py:58-77): the 1x1 DCNv2 samples at

@@ -10,7 +10,6 @@
 #pragma once
 #include <cuda_bf16.h>
 
-#include "align_om.cuh"
 #include "ptx.cuh"
 
 namespace m3d {
@@ -399,91 +398,6 @@ __device__ __forceinline__ void epilogue_tile_staged_f32(StagedEpilogue& st, uin
     }
     st.slab_count++;
   }
-}
-
-}  // namespace m3d
-
-namespace m3d {
-
-// ---------------------------------------------------------------- class head, last layer
-// The class logits of a pixel (4 classes x A anchors, channel = class * A + anchor; model/M3d_inference_align.py:
-// 223-234) are all in the thread's accumulator row: softmax over the classes, foreground probability, best foreground
-// class / score per anchor, top-1 foreground anchor per pixel and the shape-align offsets (feturealign_mgpu.py:119-172)
-// come straight out of TMEM.  Same expressions, in the same order, as cls_softmax4_kernel + shape_align_om_pixel
-// (elementwise.cu): the results are bit-identical to conv -> logits -> softmax kernel.  The two warps of a TMEM lane
-// quarter split the anchors; `s_comb` ([128][2] floats of shared memory) carries the second half's best foreground
-// anchor to the first.  NW = 8 epilogue warps, A <= 64 (a thread keeps 4 x 32 columns), bias_s: the layer's biases.
-struct ClsSinkArgs {
-  int A;
-  float* fg_max;
-  int* fg_arg;
-  float* score;
-  unsigned char* cls_pred;
-  float* shape_om;
-  const float* anchors;
-  int anchor_ld;
-  float feat_stride, thresh;
-};
-
-template <typename F>
-__device__ __forceinline__ void epilogue_tile_cls_softmax4(const ClsSinkArgs& c, uint32_t tmem_acc, int quarter, int lane,
-                                                           int ep_tid, int n, int p0, int q0, int TW, int P, int Q,
-                                                           const float* bias_s, float* s_comb, F on_tmem_drained) {
-  const int A = c.A;
-  const int half = ep_tid >> 7;
-  const int row = quarter * 32 + lane;
-  const int a_lo = half ? (A + 1) / 2 : 0, a_hi = half ? A : (A + 1) / 2;
-  const int p = p0 + row / TW, q = q0 + row % TW;
-  const bool ok = p < P && q < Q;
-  uint32_t v[4][32];
-  const uint32_t lane_base = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) tmem_ld32(lane_base + k * A + a_lo, v[k]);
-  tmem_ld_wait();
-  on_tmem_drained();
-  float best_fg = -1.f;
-  int best_a = 0;
-  const long HW = static_cast<long>(P) * Q;
-  const long pix = (static_cast<long>(n) * P + p) * Q + q;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const int a = a_lo + j;
-    if (a < a_hi) {
-      const float v0 = __uint_as_float(v[0][j]) + bias_s[a], v1 = __uint_as_float(v[1][j]) + bias_s[A + a];
-      const float v2 = __uint_as_float(v[2][j]) + bias_s[2 * A + a], v3 = __uint_as_float(v[3][j]) + bias_s[3 * A + a];
-      const float mx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
-      const float e0 = expf(v0 - mx), e1 = expf(v1 - mx), e2 = expf(v2 - mx), e3 = expf(v3 - mx);
-      const float sum = ((e0 + e1) + e2) + e3;
-      const float p0_ = e0 / sum, p1 = e1 / sum, p2 = e2 / sum, p3 = e3 / sum;
-      float best = p1;
-      int bestk = 1;
-      if (p2 > best) best = p2, bestk = 2;
-      if (p3 > best) best = p3, bestk = 3;
-      if (ok) {
-        const long r = (static_cast<long>(n) * A + a) * HW + static_cast<long>(p) * Q + q;
-        c.score[r] = best;
-        c.cls_pred[r] = static_cast<unsigned char>(bestk);
-      }
-      const float fg = 1.f - p0_;
-      if (fg > best_fg) best_fg = fg, best_a = a;  // first maximum wins, like torch.max
-    }
-  }
-  if (half == 1) {
-    s_comb[2 * row] = best_fg;
-    s_comb[2 * row + 1] = __int_as_float(best_a);
-  }
-  named_bar_sync(kEpiBarrier, 256);
-  if (half == 0) {
-    const float f1 = s_comb[2 * row];
-    if (f1 > best_fg) best_fg = f1, best_a = __float_as_int(s_comb[2 * row + 1]);
-    if (ok) {
-      c.fg_max[pix] = best_fg;
-      c.fg_arg[pix] = best_a;
-      if (c.shape_om != nullptr)
-        shape_align_om_pixel(best_fg, best_a, c.anchors, c.anchor_ld, c.feat_stride, c.thresh, c.shape_om, pix);
-    }
-  }
-  named_bar_sync(kEpiBarrier, 256);  // s_comb is free again
 }
 
 }  // namespace m3d

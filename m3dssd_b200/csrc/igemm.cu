@@ -228,34 +228,6 @@ __global__ void __launch_bounds__(64 + 32 * conv_epi_warps<STAGED>(), 1)
       const float* bias = p.bias ? p.bias + t.g * p.bias_goff : nullptr;
       if constexpr (STAGED && sizeof(OutT) == 4) {
         const int col0 = t.nt * BN;
-        if (p.cls.A > 0) {
-          // class head: score / class / top-1 foreground anchor / shape-align offsets straight from the accumulator
-          // (epilogue.cuh); the logits themselves only when asked for
-          float* bias_s = reinterpret_cast<float*>(stage_out + 2 * kSlabBytes);
-          if (p.cls.write_logits && ep_tid == 0) tma_store_wait_read<0>();  // the slabs double as s_comb below
-          named_bar_sync(kEpiBarrier, 32 * NW);  // previous tile no longer reads bias_s / the slabs
-          for (int i = ep_tid; i < BN; i += 32 * NW) bias_s[i] = (bias != nullptr && i < p.Cout) ? __ldg(bias + i) : 0.f;
-          named_bar_sync(kEpiBarrier, 32 * NW);
-          const ClsSinkArgs c{p.cls.A, p.cls.fg_max, p.cls.fg_arg, p.cls.score, p.cls.cls_pred, p.cls.shape_om,
-                              p.cls.anchors, p.cls.anchor_ld, p.cls.feat_stride, p.cls.thresh};
-          if (p.cls.write_logits) {
-            epilogue_tile_cls_softmax4(c, tmem_base + as * Cfg::ACC, quarter, lane, ep_tid, t.n, t.p0, t.q0, p.TW, p.P, p.Q,
-                                       bias_s, reinterpret_cast<float*>(stage_out), [] {});
-            // (the slab buffers double as s_comb above: the logits leave through them afterwards)
-            epilogue_tile_staged_f32<BN, NW>(st, tmem_base + as * Cfg::ACC, quarter, lane, ep_tid, t.n, t.p0, t.q0,
-                                             &p.tmap_out, p.out_coff + col0, bias, p.Cout - col0, p.slope, [&]() {
-                                               tc_fence_before();
-                                               mbar_arrive(&tempty[as]);
-                                             });
-          } else {
-            epilogue_tile_cls_softmax4(c, tmem_base + as * Cfg::ACC, quarter, lane, ep_tid, t.n, t.p0, t.q0, p.TW, p.P, p.Q,
-                                       bias_s, reinterpret_cast<float*>(stage_out), [&]() {
-                                         tc_fence_before();
-                                         mbar_arrive(&tempty[as]);
-                                       });
-          }
-          continue;
-        }
         epilogue_tile_staged_f32<BN, NW>(st, tmem_base + as * Cfg::ACC, quarter, lane, ep_tid, t.n, t.p0, t.q0,
                                          &p.tmap_out, p.out_coff + t.g * p.out_goff + col0, bias ? bias + col0 : nullptr,
                                          p.Cout - col0, p.slope, [&]() {

@@ -61,21 +61,6 @@ struct alignas(64) ConvTmaParams {
   int total_tiles;
   int dbg;     // development probe bits (M3D_DBG): 1 skip A loads, 4 skip the epilogue body, 8 skip MMAs, 16 skip the TMA store
   int a_wide;  // tmap_a are 5-D (BK, W, H, N, C/BK) maps whose box holds the stage's KSUB channel chunks
-  // Class head, last layer (fp32 staged variant only; cls_A > 0): the epilogue turns the tile's K = 4 x cls_A logits
-  // (channel = class * A + anchor) into what the detection stages read -- per anchor the best foreground score and
-  // class, per pixel the top-1 foreground anchor and the shape-align offsets -- and, unless cls_logits, skips the logits
-  struct ClsSink {
-    int A;
-    int write_logits;
-    float* fg_max;            // [N, P, Q]
-    int* fg_arg;              // [N, P, Q]
-    float* score;             // [N, A, P, Q]
-    unsigned char* cls_pred;  // [N, A, P, Q]
-    float* shape_om;          // [N*P*Q, 27] or null
-    const float* anchors;     // [A, anchor_ld]
-    int anchor_ld;
-    float feat_stride, thresh;
-  } cls;
 };
 
 struct alignas(64) ConvGatherParams {

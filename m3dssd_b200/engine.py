@@ -76,7 +76,6 @@ class Engine:
         self.named = {}  # name -> Act of notable intermediate activations (parity checks)
         self.n_launches = 0
         self.detect_alt = {}  # op index -> cheaper callable used by the detection stages
-        self._conv_args = {}
         self.use_graph = use_graph
         self.graph = None
         self.A = net.num_anchors
@@ -139,12 +138,10 @@ class Engine:
         res_coff = res.coff if res is not None else 0
         om_t = om
 
-        kwargs = dict(R=k, S=k, stride=stride, pad=pad, Cout=cout, bias=bias, res=res_t, res_coff=res_coff, slope=slope,
-                      weight_lo=lo, om=om_t, sigmoid_mask=sigmoid_mask, out_coff=out_coff, out_hw=out_hw)
-        self._conv_args[name] = (ins, hi, out, kwargs)  # (for variants of the same layer, e.g. the fused class head)
-
         def run():
-            ops.conv2d_nhwc(ins, hi, out, **kwargs)
+            ops.conv2d_nhwc(ins, hi, out, R=k, S=k, stride=stride, pad=pad, Cout=cout, bias=bias, res=res_t,
+                            res_coff=res_coff, slope=slope, weight_lo=lo, om=om_t, sigmoid_mask=sigmoid_mask,
+                            out_coff=out_coff, out_hw=out_hw)
 
         esz = 4 if self.fp32 else 2
         k_real = k * k * sum(a.c for a in inputs)
@@ -447,7 +444,6 @@ class Engine:
                   dict(op="softmax", logits=logits))
         # detection stages: same kernel without the flattened cls / prob copies (70 MB of stores nobody reads there)
         i_softmax = len(self.ops) - 1
-        i_cls3 = i_softmax - 1
         self.detect_alt[i_softmax] = lambda: ops.cls_softmax(logits, A, K, None, None, self.fg_max, self.fg_arg,
                                                              self.score, self.cls_pred)
         anchors = torch.tensor(np.asarray(conf.anchors), **f32).contiguous()
@@ -467,18 +463,6 @@ class Engine:
                                                                           self.score, self.cls_pred, anchors, stride, thr_s, om_s)
             self.detect_alt[len(self.ops) - 1] = None
             feats = self._align("shape_align", net.shape_align, feat, om_s)
-        else:
-            om_s, thr_s = None, 0.0
-        self._i_cls3, self._i_softmax = i_cls3, i_softmax
-        if (not self.fp32 and K == 4 and A <= 64 and self.meta[i_cls3]["name"] == "cls.l3"
-                and os.environ.get("M3D_FUSE_CLS", "0") != "0"):
-            # detection stages: the last class-head conv produces score / class / top-1 foreground anchor / shape-align
-            # offsets in its own epilogue (bit-identical to conv -> logits -> softmax kernel) and writes no logits
-            ins3, w3, out3, kw3 = self._conv_args["cls.l3"]
-            sink = dict(A=A, fg_max=self.fg_max, fg_arg=self.fg_arg, score=self.score, cls_pred=self.cls_pred,
-                        shape_om=om_s, anchors=anchors, feat_stride=stride, thresh=thr_s, write_logits=False)
-            self.detect_alt[i_cls3] = lambda: ops.conv2d_nhwc(ins3, w3, out3, cls=sink, **kw3)
-            self.detect_alt[i_softmax] = None
         # --- regression heads (slots follow HEAD_ORDER)
         heads = self._new("heads", B, Hf, Wf, 11 * A, torch.float32)
         self.heads = heads
@@ -695,8 +679,7 @@ class Engine:
     def flatten_outputs(self):
         """Refresh the reference's flattened network outputs (cls, prob, bbox_2d, bbox_3d) from the logits / head
         buffers after a "decode" / "detect" / pipelined step, which do not write them.  Returns the four tensors."""
-        self.ops[self._i_cls3]()     # the class logits (the detection stages may not write them) ...
-        self.ops[self._i_softmax]()  # ... and the full softmax (flattened cls / prob copies)
+        self.ops[min(self.detect_alt)]()  # the full softmax (flattened cls / prob copies)
         self.ops[self.n_detect_ops]()
         return self.cls_out, self.prob_out, self.bbox_2d, self.bbox_3d
 

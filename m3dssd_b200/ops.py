@@ -69,7 +69,7 @@ def pack_conv_weight(weight, in_splits=None, k_pad_to=None, fp32_mode=False, mod
 def conv2d_nhwc(inputs, weight, out, *, R, S, stride=1, pad=0, dil=1, Cout=None, bias=None, res=None,
                 slope=1.0, weight_lo=None, om=None, sigmoid_mask=False, groups=1, in_goff=None,
                 weight_goff=0, bias_goff=0, out_coff=0, out_goff=0, res_coff=0, res_goff=0,
-                force_gather=False, out_hw=None, cls=None):
+                force_gather=False, out_hw=None):
     """inputs: list of (tensor[N,H,W,Cbuf], coff, c) or bare tensors; out: tensor[N,P,Q,Cbuf_out]."""
     d = ConvDesc()
     ins = []
@@ -126,17 +126,6 @@ def conv2d_nhwc(inputs, weight, out, *, R, S, stride=1, pad=0, dil=1, Cout=None,
         d.om_cstride = om.shape[-1]
     d.sigmoid_mask = int(sigmoid_mask)
     d.force_gather = int(force_gather)
-    if cls is not None:
-        # class head, last layer: the epilogue also produces what cls_softmax (+ shape_align_om) compute from the logits
-        # (dict: A, fg_max, fg_arg, score, cls_pred[, shape_om, anchors, feat_stride, thresh][, write_logits])
-        d.cls_A = int(cls["A"])
-        d.cls_write_logits = int(bool(cls.get("write_logits", False)))
-        d.cls_fg_max, d.cls_fg_arg = cls["fg_max"].data_ptr(), cls["fg_arg"].data_ptr()
-        d.cls_score, d.cls_pred = cls["score"].data_ptr(), cls["cls_pred"].data_ptr()
-        if cls.get("shape_om") is not None:
-            d.cls_shape_om = cls["shape_om"].data_ptr()
-            d.cls_anchors, d.cls_anchor_ld = cls["anchors"].data_ptr(), cls["anchors"].shape[1]
-            d.cls_feat_stride, d.cls_thresh = float(cls["feat_stride"]), float(cls["thresh"])
     check(lib().m3d_conv2d_nhwc(C.byref(d), _stream()))
     _count(1)
     return out

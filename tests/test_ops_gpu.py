@@ -304,41 +304,3 @@ def test_preprocess_u8_bit_exact_vs_oracle(shape):
     ops.preprocess_u8(im.cuda(), out, mean, std, swap_rb=True)
     ref = O.preprocess_u8(im.numpy(), mean, std)
     assert np.array_equal(out.cpu().numpy(), ref)
-
-
-@pytest.mark.parametrize("hw", [(12, 40), (48, 160)])
-def test_class_head_epilogue_equals_conv_then_softmax(hw):
-    """The last class-head conv with the softmax / top-1 anchor / shape-align epilogue (the detection stages' variant)
-    writes the same bits as conv -> fp32 logits -> m3d_cls_softmax -> m3d_shape_align_om, partial tiles included, with
-    and without the logits."""
-    from m3dssd_b200 import ops, synth
-    g = _g(21)
-    H, W = hw
-    B, A, K, Cin = 2, 36, 4, 256
-    M = A * H * W
-    x = torch.randn(B, H, W, Cin, generator=g).bfloat16().cuda()
-    w = torch.randn(K * A, Cin, 1, 1, generator=g) / Cin ** 0.5
-    wp = ops.pack_conv_weight(w)[0].cuda()
-    bias = (torch.randn(K * A, generator=g) * 0.5).cuda()
-    anchors = torch.tensor(synth.make_conf().anchors).cuda()
-    f32 = dict(dtype=torch.float32, device="cuda")
-
-    def sinks():
-        return dict(fg_max=torch.zeros(B, H, W, **f32), fg_arg=torch.zeros(B, H, W, dtype=torch.int32, device="cuda"),
-                    score=torch.zeros(B, M, **f32), cls_pred=torch.zeros(B, M, dtype=torch.uint8, device="cuda"),
-                    shape_om=torch.zeros(B, H, W, 27, **f32))
-    # reference chain
-    logits = torch.zeros(B, H, W, K * A, **f32)
-    ops.conv2d_nhwc([x], wp, logits, R=1, S=1, stride=1, pad=0, Cout=K * A, bias=bias, slope=1.0)
-    assert "f32" in ops.last_kernel()
-    r = sinks()
-    ops.cls_softmax(logits, A, K, None, None, r["fg_max"], r["fg_arg"], r["score"], r["cls_pred"])
-    ops.shape_align_om(r["fg_max"], r["fg_arg"], anchors, 8.0, 0.5, r["shape_om"])
-    for write_logits in (False, True):
-        f = sinks()
-        out = torch.full_like(logits, 7.0)
-        ops.conv2d_nhwc([x], wp, out, R=1, S=1, stride=1, pad=0, Cout=K * A, bias=bias, slope=1.0,
-                        cls=dict(A=A, anchors=anchors, feat_stride=8.0, thresh=0.5, write_logits=write_logits, **f))
-        for k in r:
-            assert torch.equal(f[k], r[k]), (k, write_logits)
-        assert torch.equal(out, logits) if write_logits else bool((out == 7.0).all())
