@@ -210,6 +210,15 @@ int m3d_stem_conv7x7(const float* image_nchw, const float* weight /*[16,3,7,7]*/
  * numpy).  mean3 / std3 are host arrays indexed by the INPUT channel.  4x less host->device traffic than fp32. */
 int m3d_preprocess_u8(const unsigned char* image_hwc, float* out_nchw, int N, int H, int W, const float* mean3,
                       const float* std3, int swap_rb, m3d_stream_t stream);
+/* The reference's whole test-time transform for a RAGGED batch: Preprocess = ConvertToFloat + Padding(size) + Normalize
+ * (lib/augmentations.py:472-492; Padding :136-160 = cv2.copyMakeBorder bottom / right with 0) + BGR->RGB + HWC->CHW
+ * (lib/dataloader.py:904,942-950).  Image n is uint8 HWC [heights[n], widths[n], 3] at images + offsets[n] (device
+ * memory, any alignment); offsets / heights / widths are HOST arrays.  The 0 padding goes through Normalize like the
+ * reference's (padded value = -mean/std).  An image larger than H x W is an error, as in cv2 (M3D_ERR_INVALID).
+ * Bit-identical to numpy. */
+int m3d_preprocess_u8_pad(const unsigned char* images, const long long* offsets, const int* heights, const int* widths,
+                          float* out_nchw, int N, int H, int W, const float* mean3, const float* std3, int swap_rb,
+                          m3d_stream_t stream);
 /* The same layer on the tensor cores, written in 2x2 space-to-depth form: out [N, H/2, W/2, 64] bf16 with
  * channel (dy*2 + dx)*16 + c = stem output channel c at pixel (2Y+dy, 2X+dx).  The 7x7 conv becomes a
  * K = 3*8*8 implicit GEMM (stride-2 8x8 windows of the fp32 NCHW image gathered straight into the

@@ -15,6 +15,7 @@ _SIGS = {
     "m3d_conv2d_wgrad": [vp, i, i, vp, i, i, vp] + [i] * 12 + [vp, sz, vp],
     "m3d_channel_sum": [vp, lg, i, i, i, vp, vp, sz, vp],
     "m3d_preprocess_u8": [vp, vp, i, i, i, vp, vp, i, vp],
+    "m3d_preprocess_u8_pad": [vp, vp, vp, vp, vp, i, i, i, vp, vp, i, vp],
     "m3d_stem_conv7x7_s2d": [vp, vp, vp, vp, i, i, i, f, vp],
     "m3d_maxpool2x2_nhwc": [vp, vp, i, i, i, i, i, i, i, vp],
     "m3d_upsample_add_nhwc": [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp],

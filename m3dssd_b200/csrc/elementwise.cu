@@ -634,6 +634,50 @@ __global__ void __launch_bounds__(256) preprocess_u8_kernel(const unsigned char*
 }
 
 // ---------------------------------------------------------------------------
+// The reference's whole test-time transform, Preprocess = ConvertToFloat + Padding(size) + Normalize
+// (lib/augmentations.py:472-492, Padding :136-160), + BGR->RGB + HWC->CHW, for a RAGGED batch: image n is uint8 HWC
+// [h[n], w[n], 3] (KITTI frames are 370-376 x 1224-1242) and is padded on the bottom / right to H x W.  cv2's
+// copyMakeBorder pads with 0 BEFORE Normalize, so a padded pixel becomes (0/255 - mean[c]) / std[c], not 0 -- kept.
+// Same arithmetic as preprocess_u8_kernel (bit-identical to numpy).  4 output pixels per thread, byte loads (rows of
+// 3*w bytes have no alignment), one float4 store per plane.
+// ---------------------------------------------------------------------------
+constexpr int kPadBatch = 64;
+struct RaggedImages {
+  long long off[kPadBatch];
+  int h[kPadBatch], w[kPadBatch];
+};
+
+__global__ void __launch_bounds__(256) preprocess_u8_pad_kernel(const unsigned char* __restrict__ img, float* __restrict__ out,
+                                                                RaggedImages ri, int H, int W, Norm3 nm, int swap_rb) {
+  const int n = blockIdx.y;
+  const int W4 = W >> 2;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long>(H) * W4) return;
+  const int y = static_cast<int>(i / W4), x0 = static_cast<int>(i - static_cast<long>(y) * W4) * 4;
+  const int h = ri.h[n], w = ri.w[n];
+  const unsigned char* row = img + ri.off[n] + static_cast<long>(y) * w * 3;
+  float v[3][4];
+#pragma unroll
+  for (int px = 0; px < 4; ++px) {
+    const bool in = y < h && x0 + px < w;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const unsigned int byte = in ? __ldg(row + (x0 + px) * 3 + c) : 0u;
+      float x = __fdiv_rn(static_cast<float>(byte), 255.0f);
+      x = __fsub_rn(x, nm.mean[c]);
+      v[c][px] = __fdiv_rn(x, nm.stdv[c]);
+    }
+  }
+  const long HW = static_cast<long>(H) * W;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int oc = swap_rb ? 2 - c : c;
+    *reinterpret_cast<float4*>(out + (static_cast<long>(n) * 3 + oc) * HW + static_cast<long>(y) * W + x0) =
+        make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Backward of the depthwise ConvTranspose2d(2f, stride f, pad f/2) up-sampling (training path), bf16 NHWC:
 //   gx[n,iy,ix,c]   = sum_{ky,kx} gy[n, iy*f - pad + ky, ix*f - pad + kx, c] * w[ky,kx,c]
 //   gw[ky,kx,c]     = sum_{n,iy,ix} gy[n, iy*f - pad + ky, ix*f - pad + kx, c] * x[n,iy,ix,c]
@@ -753,6 +797,33 @@ extern "C" int m3d_preprocess_u8(const unsigned char* image_hwc, float* out_nchw
   const long npix4 = static_cast<long>(N) * HW / 4;
   preprocess_u8_kernel<<<cdiv(npix4, 256), 256, 0, S(stream)>>>(image_hwc, out_nchw, npix4, HW, nm, swap_rb);
   M3D_CUDA_OK(cudaGetLastError());
+  return M3D_OK;
+}
+
+extern "C" int m3d_preprocess_u8_pad(const unsigned char* images, const long long* offsets, const int* heights,
+                                     const int* widths, float* out_nchw, int N, int H, int W, const float* mean3,
+                                     const float* std3, int swap_rb, m3d_stream_t stream) {
+  M3D_REQUIRE(images && offsets && heights && widths && out_nchw && mean3 && std3, "NULL pointer");
+  M3D_REQUIRE(N >= 0 && H > 0 && W > 0 && W % 4 == 0, "W must be a multiple of 4 (got %dx%d)", H, W);
+  M3D_REQUIRE((reinterpret_cast<uintptr_t>(out_nchw) & 15) == 0, "output must be 16-byte aligned");
+  for (int n = 0; n < N; ++n)  // cv2.copyMakeBorder raises on a negative border: an image larger than the size is an error
+    M3D_REQUIRE(heights[n] >= 0 && widths[n] >= 0 && heights[n] <= H && widths[n] <= W && offsets[n] >= 0,
+                "image %d is %dx%d, larger than the padded size %dx%d", n, heights[n], widths[n], H, W);
+  Norm3 nm;
+  for (int c = 0; c < 3; ++c) nm.mean[c] = mean3[c], nm.stdv[c] = std3[c];
+  const long per_image = static_cast<long>(H) * (W / 4);
+  for (int n0 = 0; n0 < N; n0 += kPadBatch) {
+    const int nb = N - n0 < kPadBatch ? N - n0 : kPadBatch;
+    RaggedImages ri;
+    for (int k = 0; k < kPadBatch; ++k) {
+      ri.off[k] = k < nb ? offsets[n0 + k] : 0;
+      ri.h[k] = k < nb ? heights[n0 + k] : 0;
+      ri.w[k] = k < nb ? widths[n0 + k] : 0;
+    }
+    preprocess_u8_pad_kernel<<<dim3(static_cast<unsigned>(cdiv(per_image, 256)), nb), 256, 0, S(stream)>>>(
+        images, out_nchw + static_cast<long>(n0) * 3 * H * W, ri, H, W, nm, swap_rb);
+    M3D_CUDA_OK(cudaGetLastError());
+  }
   return M3D_OK;
 }
 

@@ -666,11 +666,19 @@ class Engine:
     def _set_input(self, images):
         """fp32 NCHW [B,3,H,W] (already normalised, as the reference's DataLoader yields) is copied into the input
         buffer; uint8 HWC [B,H,W,3] (what cv2.imread returns) goes through the device-side input pipeline:
-        Normalize + BGR->RGB + HWC->CHW of lib/augmentations.py:44-57 / lib/dataloader.py:942-950, bit-identical."""
+        Normalize + BGR->RGB + HWC->CHW of lib/augmentations.py:44-57 / lib/dataloader.py:942-950, bit-identical;
+        a list of B uint8 HWC frames of different sizes is zero-padded to H x W first (the reference's Preprocess)."""
+        mean = self.conf.get("image_means", (0.485, 0.456, 0.406))
+        std = self.conf.get("image_stds", (0.229, 0.224, 0.225))
+        if isinstance(images, (list, tuple)):
+            # ragged uint8 HWC frames (KITTI: 370-376 x 1224-1242): the reference's Preprocess = zero Padding on the
+            # bottom / right to the test size, then Normalize (lib/augmentations.py:472-492), on the device
+            assert len(images) == self.B, (len(images), self.B)
+            buf, off, hh, ww = ops.pack_ragged_u8([im.cpu() if torch.is_tensor(im) else im for im in images])
+            ops.preprocess_u8_pad(buf.to(self.dev, non_blocking=True), off, hh, ww, self.image, mean, std, swap_rb=True)
+            return
         if images.dtype == torch.uint8:
             assert tuple(images.shape) == (self.B, self.H, self.W, 3), (images.shape, self.image.shape)
-            mean = self.conf.get("image_means", (0.485, 0.456, 0.406))
-            std = self.conf.get("image_stds", (0.229, 0.224, 0.225))
             ops.preprocess_u8(images.contiguous(), self.image, mean, std, swap_rb=True)
             return
         assert tuple(images.shape) == tuple(self.image.shape), (images.shape, self.image.shape)

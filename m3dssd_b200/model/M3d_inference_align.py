@@ -125,6 +125,18 @@ class RPN(nn.Module):
         kept, num = eng.detect(x.float().contiguous(), scale_factor)
         return kept.clone(), num.clone()  # fresh tensors, like any nn.Module (the engine's buffers are reused per call)
 
+    def detect_images(self, images, size=None, scale_factor=1.0, max_out=None):
+        """detect() from the raw frames: a list of uint8 HWC (BGR, as cv2.imread returns) images of different sizes.
+        The reference's test loader applies Preprocess(conf.test_scale, means, stds) = zero Padding to `size` +
+        Normalize, then BGR->RGB + CHW (lib/dataloader.py:904,942-950; lib/augmentations.py:472-492) on the CPU, one
+        image at a time; here the packed bytes are copied once and transformed on the device (bit-identical)."""
+        size = size if size is not None else self.conf.get("test_scale", self.conf.get("crop_size"))
+        H, W = (int(size[0]), int(size[1]))
+        kw = {} if max_out is None else dict(max_out=int(max_out))
+        eng = self.engine(len(images), H, W, **kw)
+        kept, num = eng.detect(list(images), scale_factor)
+        return kept.clone(), num.clone()
+
     # --------------------------------------------------------------- forward
     def forward(self, x):
         if not self.training and x.is_cuda:

@@ -162,6 +162,47 @@ def preprocess_u8(image_hwc, out_nchw, mean=(0.485, 0.456, 0.406), std=(0.229, 0
     return out_nchw
 
 
+def pack_ragged_u8(images, pin=True):
+    """Host side of preprocess_u8_pad: uint8 HWC images of different sizes (numpy arrays or CPU tensors, as cv2.imread
+    returns them) -> one (pinned) byte buffer + (offsets, heights, widths) lists."""
+    arrs = [torch.as_tensor(a) for a in images]
+    for a in arrs:
+        if a.dtype != torch.uint8 or a.dim() != 3 or a.shape[-1] != 3:
+            raise ValueError("every image must be uint8 [h, w, 3], got %s %s" % (a.dtype, tuple(a.shape)))
+    sizes = [a.numel() for a in arrs]
+    offsets, total = [], 0
+    for n in sizes:
+        offsets.append(total)
+        total += n
+    buf = torch.empty(max(total, 1), dtype=torch.uint8)
+    if pin and torch.cuda.is_available():
+        buf = buf.pin_memory()
+    for a, o, n in zip(arrs, offsets, sizes):
+        buf[o:o + n] = a.contiguous().view(-1)
+    return buf, offsets, [int(a.shape[0]) for a in arrs], [int(a.shape[1]) for a in arrs]
+
+
+def preprocess_u8_pad(packed, offsets, heights, widths, out_nchw, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225),
+                      swap_rb=True):
+    """The reference's test-time transform Preprocess(size, mean, stds) (lib/augmentations.py:472-492: ConvertToFloat,
+    Padding = zero border on the bottom / right, Normalize) + BGR->RGB + CHW (lib/dataloader.py:942-950) for a ragged
+    batch on the device.  packed: 1-D uint8 CUDA tensor holding image n (HWC) at offsets[n]; out_nchw [N,3,H,W] fp32.
+    Raises M3DError for an image larger than H x W (cv2.copyMakeBorder raises there)."""
+    assert packed.dtype == torch.uint8 and packed.is_cuda and packed.is_contiguous() and packed.dim() == 1
+    N, _, H, W = out_nchw.shape
+    assert len(offsets) == len(heights) == len(widths) == N and out_nchw.shape[1] == 3
+    assert out_nchw.dtype == torch.float32 and out_nchw.is_contiguous() and out_nchw.is_cuda
+    for o, h, w in zip(offsets, heights, widths):
+        assert 0 <= o and o + h * w * 3 <= packed.numel(), "image outside the packed buffer"
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    s = (C.c_float * 3)(*[float(v) for v in std])
+    off = (C.c_longlong * max(N, 1))(*[int(v) for v in offsets])
+    hh = (C.c_int * max(N, 1))(*[int(v) for v in heights])
+    ww = (C.c_int * max(N, 1))(*[int(v) for v in widths])
+    check(lib().m3d_preprocess_u8_pad(_p(packed), off, hh, ww, _p(out_nchw), N, H, W, m, s, int(bool(swap_rb)), _stream()))
+    return out_nchw
+
+
 def pack_stem_s2d(w, b):
     """Stem weights [16,3,7,7] (BN folded) + bias [16] -> bf16 [64, 192] and bias [64] for m3d_stem_conv7x7_s2d:
     output channel (ey*2+ex)*16 + co, K index c*64 + r8*8 + s8 over the 8x8 stride-2 window."""

@@ -1,6 +1,3 @@
-for v in "" level3.tree2 level4 level5; do echo "== M3D_TAIL_SWITCH=$v"; M3D_TAIL_SWITCH=$v timeout 45 python bench.py --steps 60 --warmup 5 --no-cpu-baseline --no-extras 2>/dev/null | tail -1 | python -c "
-import json,sys
-t=sys.stdin.read()
-try:
-    d=json.loads(t); print(d['value'], d['ms_per_step'], d['e2e']['value'])
-except Exception as e: print('FAILED/timeout', len(t))"; done
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 400 python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; tail -c 600 gpurun_out/final_bench.json
