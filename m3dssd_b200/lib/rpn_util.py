@@ -1,7 +1,9 @@
 """The RPN helpers the model imports (mirror of the hot-path subset of lib/rpn_util.py):
 calc_output_size (:1401-1413), locate_anchors (:1329-1398), flatten_tensor (:892-901),
-bbox_transform_inv (:1137-1186) and im_detect_3d (:1416-1563).  The dataset /
-evaluation / plotting parts of that file are out of scope."""
+bbox_transform_inv (:1137-1186), im_detect_3d (:1416-1563) and the result-writing loop of test_kitti_3d (:1753-1852).
+The dataset / evaluation / plotting parts of that file are out of scope."""
+import os
+
 import numpy as np
 import torch
 
@@ -101,3 +103,79 @@ def kitti_result_lines(rows, valid, lbls):
                  + '{:.6f} {:.6f}\n').format(cls, r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[10], r[11],
                                              r[12], r[13])
     return text
+
+
+def _iter_test_items(dataset_test, rpn_conf):
+    """(image [3,H,W] or [1,3,H,W] tensor / uint8 HWC frame, imobj) pairs out of the reference's test loader items:
+    `(im, imobj)` tuples, or {'input', 'target': {'meta'}} dicts when conf.pre_compute_target
+    (lib/rpn_util.py:1776-1780)."""
+    for batch in dataset_test:
+        if isinstance(batch, dict):
+            im, imobj = batch["input"], batch["target"]["meta"]
+        else:
+            im, imobj = batch
+        yield im, imobj
+
+
+def _field(imobj, name, default=None):
+    v = imobj[name] if isinstance(imobj, dict) and name in imobj else getattr(imobj, name, default)
+    if isinstance(v, (list, tuple)) and len(v) == 1:  # DataLoader(batch_size=1) collation wraps ids in a list
+        v = v[0]
+    return v
+
+
+def test_kitti_3d(dataset_test, net, rpn_conf, results_path, test_path=None, use_log=True, writer=None,
+                  phase="validation", batch_size=8):
+    """The reference's evaluation driver (lib/rpn_util.py:1753-1860) up to and including the KITTI result files:
+    for every test image, detect -> first nms_topN_post kept boxes -> score cut 0.75 -> alpha -> rotation, hill_climb,
+    back-projection (:1801-1844) -> one `<id>.txt` per image (:1846-1850).  Same signature and file contents; the
+    images go through the network `batch_size` at a time, and decode / NMS / refinement stay on the device (one D2H
+    of <= 40 rows per image).  Images arrive as the reference's loader yields them (normalised [3,H,W] / [1,3,H,W]
+    tensors) or as raw uint8 HWC frames (then Preprocess runs on the device).  The devkit's compiled evaluation that
+    the reference shells out to afterwards (:1868-1900) is outside the path; returns the list of files written."""
+    os.makedirs(results_path, exist_ok=True)
+    net.eval()
+    written, pending = [], []
+
+    def flush():
+        if not pending:
+            return
+        ims = [p[0] for p in pending]
+        objs = [p[1] for p in pending]
+        n = len(ims)
+        while len(ims) < batch_size:  # a short last batch reuses the engine of the full ones
+            ims.append(ims[-1])
+        scale = float(_field(objs[0], "scale_factor", 1.0))
+        post = int(rpn_conf.nms_topN_post)
+        kw = {} if post == int(net.conf.nms_topN_post) else dict(max_out=post)  # (the engine's default: one engine, not two)
+        with torch.no_grad():
+            if torch.is_tensor(ims[0]) and ims[0].dtype != torch.uint8:
+                x = torch.stack([im.reshape(im.shape[-3:]) for im in ims]).cuda(non_blocking=True)
+                kept, num = net.detect(x, scale_factor=scale, **kw)
+            else:
+                kept, num = net.detect_images(ims, scale_factor=scale, **kw)
+            if rpn_conf.clip_boxes:  # im_detect_3d clips before the refinement (:1552-1556)
+                for b in range(n):
+                    imW, imH = float(_field(objs[b], "imW")), float(_field(objs[b], "imH"))
+                    kept[b, :, 0].clamp_(0, imW - 1), kept[b, :, 2].clamp_(0, imW - 1)
+                    kept[b, :, 1].clamp_(0, imH - 1), kept[b, :, 3].clamp_(0, imH - 1)
+            p2 = np.stack([np.asarray(_field(o, "p2"), dtype=np.float64).reshape(4, 4) for o in objs] +
+                          [np.asarray(_field(objs[-1], "p2"), dtype=np.float64).reshape(4, 4)] * (batch_size - n))
+            rows, valid = refine_detections(kept, num, p2, rpn_conf)
+        rows, valid = rows.cpu().numpy(), valid.cpu().numpy()
+        for b in range(n):
+            path = os.path.join(results_path, str(_field(objs[b], "id")) + ".txt")
+            with open(path, "w") as f:
+                f.write(kitti_result_lines(rows[b], valid[b], rpn_conf.lbls))
+            written.append(path)
+        pending.clear()
+
+    for im, imobj in _iter_test_items(dataset_test, rpn_conf):
+        if pending and (float(_field(imobj, "scale_factor", 1.0)) != float(_field(pending[0][1], "scale_factor", 1.0))):
+            flush()  # the decode takes one scale factor per launch
+        pending.append((im, imobj))
+        if len(pending) == batch_size:
+            flush()
+    flush()
+    return written
+

@@ -133,3 +133,27 @@ def preprocess_u8(im_hwc, mean, std):
     x /= np.asarray(std, dtype=np.float32)
     x = x[..., ::-1]  # cv2.COLOR_BGR2RGB
     return np.ascontiguousarray(np.moveaxis(x, -1, -3)).astype(np.float32)
+
+
+def preprocess_pad_u8(images, size, mean, std):
+    """The reference's test-time transform restated for a ragged batch: Preprocess(size, mean, stds)
+    (lib/augmentations.py:472-492) = ConvertToFloat (:36-41), Padding (:136-160: cv2.copyMakeBorder on the bottom /
+    right with the constant 0 -- BEFORE Normalize, so a padded pixel ends up at -mean/std), Normalize (:44-57); then
+    BGR->RGB and HWC->CHW (lib/dataloader.py:942-950).  images: list of uint8 [h_i, w_i, 3]; -> float32 [N,3,H,W].
+    An image larger than `size` is an error (copyMakeBorder raises on a negative border)."""
+    H, W = int(size[0]), int(size[1])
+    out = np.empty((len(images), 3, H, W), dtype=np.float32)
+    for n, im in enumerate(images):
+        im = np.asarray(im)
+        assert im.dtype == np.uint8 and im.ndim == 3 and im.shape[2] == 3
+        h, w = im.shape[:2]
+        if h > H or w > W:
+            raise ValueError("image %d is %dx%d, larger than %dx%d" % (n, h, w, H, W))
+        padded = np.zeros((H, W, 3), dtype=np.float32)
+        padded[:h, :w] = im.astype(np.float32)
+        padded /= 255.0
+        padded -= np.asarray(mean, dtype=np.float32)
+        padded /= np.asarray(std, dtype=np.float32)
+        out[n] = np.moveaxis(padded[..., ::-1], -1, 0)
+    return out
+

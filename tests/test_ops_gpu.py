@@ -304,3 +304,57 @@ def test_preprocess_u8_bit_exact_vs_oracle(shape):
     ops.preprocess_u8(im.cuda(), out, mean, std, swap_rb=True)
     ref = O.preprocess_u8(im.numpy(), mean, std)
     assert np.array_equal(out.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("size,n", [((48, 64), 6), ((384, 1280), 8), ((96, 320), 70)])
+def test_preprocess_u8_pad_ragged_bit_exact(size, n):
+    """Ragged frames -> zero Padding + Normalize + BGR->RGB + CHW on the device (m3d_preprocess_u8_pad) == the
+    reference's Preprocess: bit-exact against the committed golden (unmodified reference + cv2) and the oracle,
+    incl. full-size, 1x1 and empty frames, > 64 frames (two launches), and the error for an over-sized frame."""
+    import os
+    from m3dssd_b200 import ops
+    from m3dssd_b200._lib import M3DError
+    from oracle import oracle as O
+    H, W = size
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    if size == (48, 64):
+        g = np.load(os.path.join(os.path.dirname(__file__), "golden", "preprocess_pad_u8.npz"))
+        ims = [g["image_%d" % k] for k in range(int(g["n"]))]
+        ref = np.stack([g["expected_%d" % k] for k in range(int(g["n"]))])
+    else:
+        rng = np.random.default_rng(n)
+        hs = rng.integers(H - 14, H + 1, n)  # KITTI: 370-376 x 1224-1242 under 384 x 1280
+        ws = rng.integers(W - 56, W + 1, n)
+        hs[0], ws[0] = H, W
+        hs[1], ws[1] = 1, 1
+        hs[2], ws[2] = 0, 0
+        ims = [rng.integers(0, 256, (int(h), int(w), 3), dtype=np.uint8) for h, w in zip(hs, ws)]
+        ref = O.preprocess_pad_u8(ims, size, mean, std)
+    buf, off, hh, ww = ops.pack_ragged_u8(ims)
+    out = torch.full((len(ims), 3, H, W), float("nan"), dtype=torch.float32, device="cuda")
+    ops.preprocess_u8_pad(buf.cuda(), off, hh, ww, out, mean, std, swap_rb=True)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    with pytest.raises(M3DError):
+        ops.preprocess_u8_pad(buf.cuda(), off, [H + 1] + hh[1:], ww, out, mean, std)
+
+
+def test_detect_images_ragged_equals_padded_batch():
+    """RPN.detect_images(list of ragged uint8 frames) == RPN.engine.detect on the zero-padded uint8 batch... except the
+    padding: the reference pads BEFORE Normalize, so the padded uint8 batch (0 bytes) gives the same tensor."""
+    from m3dssd_b200 import synth
+    from m3dssd_b200.model.M3d_inference_align import build
+    conf = synth.make_conf(crop_size=(96, 320))
+    net = build(conf, "test")
+    synth.randomize_weights(net)
+    net = net.cuda().eval()
+    rng = np.random.default_rng(3)
+    full = synth.make_images_u8(2, (96, 320), seed=5).numpy()
+    ims = [full[0][:90, :301].copy(), full[1][:96, :316].copy()]
+    padded = np.zeros_like(full)
+    padded[0, :90, :301] = ims[0]
+    padded[1, :96, :316] = ims[1]
+    kept_a, num_a = net.detect_images(ims)
+    eng = net.engine(2, 96, 320)
+    kept_b, num_b = eng.detect(torch.from_numpy(padded).cuda())
+    assert torch.equal(num_a, num_b) and torch.equal(kept_a, kept_b)
+    assert int(num_a.sum()) > 0

@@ -154,3 +154,22 @@ def test_preprocess_oracle_vs_reference_normalize_golden():
     g = np.load(os.path.join(GOLD, "preprocess_u8.npz"))
     got = O.preprocess_u8(g["image"], g["mean"], g["std"])
     assert got.dtype == np.float32 and np.array_equal(got, g["expected_chw"])
+
+
+def test_preprocess_pad_oracle_vs_reference_preprocess_golden():
+    """oracle.preprocess_pad_u8 == the reference's Preprocess (ConvertToFloat + cv2 Padding + Normalize) + BGR->RGB +
+    CHW on ragged frames, bit for bit (fixture generated by tests/golden/make_golden_preprocess.py from the unmodified
+    lib/augmentations.py with the real cv2); an over-sized frame is an error like cv2's negative border."""
+    g = np.load(os.path.join(GOLD, "preprocess_pad_u8.npz"))
+    ims = [g["image_%d" % k] for k in range(int(g["n"]))]
+    got = O.preprocess_pad_u8(ims, g["size"], g["mean"], g["std"])
+    assert got.dtype == np.float32
+    for k in range(len(ims)):
+        assert np.array_equal(got[k], g["expected_%d" % k]), k
+    # a padded pixel is Normalize(0), not 0 (the reference pads before it normalises)
+    h, w = ims[1].shape[:2]
+    pad = got[1][:, h:, :]
+    assert pad.size and np.all(pad[0] == pad[0].flat[0]) and abs(float(pad[0].flat[0])) > 1.0
+    with pytest.raises(ValueError):
+        O.preprocess_pad_u8([np.zeros((49, 64, 3), np.uint8)], g["size"], g["mean"], g["std"])
+

@@ -1,3 +1,1 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 400 python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; tail -c 600 gpurun_out/final_bench.json
+timeout 600 python -m pytest tests/test_ops_gpu.py tests/test_writer_gpu.py -m gpu -x -q -k "preprocess or detect_images or kitti" 2>&1 | tail -30
