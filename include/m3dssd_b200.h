@@ -104,6 +104,10 @@ typedef struct m3d_conv_desc {
   int om_cstride;
   int sigmoid_mask;
   int force_gather; /* testing: route a plain conv through the gather producer */
+  /* Optional hint (0 = none): bit j set = the j-th 16-element slice of K (packed K index 16 j .. 16 j + 15) is zero in
+   * EVERY weight row, so its k-step may be skipped.  The 2x2 space-to-depth rewrite of a 3x3 conv (level0) has 20 such
+   * slices out of 36.  A kernel that cannot use the hint ignores it; a wrong hint gives wrong results. */
+  unsigned long long k16_zero[2];
 } m3d_conv_desc;
 
 int m3d_conv2d_nhwc(const m3d_conv_desc* desc, m3d_stream_t stream);

@@ -35,6 +35,7 @@ class ConvDesc(C.Structure):
         ("slope", C.c_float),
         ("om", C.c_void_p), ("om_cstride", C.c_int), ("sigmoid_mask", C.c_int),
         ("force_gather", C.c_int),
+        ("k16_zero", C.c_ulonglong * 2),
     ]
 
 

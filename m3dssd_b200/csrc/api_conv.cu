@@ -429,6 +429,11 @@ extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
       p.res = d->res, p.res_cstride = d->res_cstride, p.res_coff = d->res_coff;
       p.slope = d->slope;
       p.total_tiles = static_cast<int>(total_tiles);
+      if (uni && d->in_c[0] == 64 && getenv("M3D_NO_KSKIP") == nullptr) {  // K = 9 taps x 64 = 36 slices of 16
+        const unsigned long long all = (1ull << 36) - 1;
+        p.kzero = d->k16_zero[0] & all;
+        if (p.kzero == all) p.kzero = 0;  // nothing left to initialise the accumulator with: run it dense
+      }
       if (pair) return launch_conv_halo2(p, BN, stream);
       return launch_conv_halo(p, BN, d->out_dtype == M3D_F32 ? DT_F32 : DT_BF16, staged, stream);
     }

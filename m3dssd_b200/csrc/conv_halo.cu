@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(STAGED ? 320 : 192, 1) conv_halo_kernel(const 
     uint32_t phase = 0;
     int local = 0;
     if (BRES) mbar_wait(bres_bar, 0);
+    const unsigned long long kzero = BRES ? p.kzero : 0ull;
     const uint64_t db_res = umma_smem_desc<128>(smem_u32(b_res));                        // BRES: resident weights
     const uint32_t sc_stride = static_cast<uint32_t>(nchunk) * 3 * (Cfg::B_BYTES >> 4);  // one kernel column of them
     HALO_WALK_INIT;
@@ -177,7 +178,28 @@ __global__ void __launch_bounds__(STAGED ? 320 : 192, 1) conv_halo_kernel(const 
           const uint64_t da0 = umma_smem_desc_sbo(sa, kTap << 4);
           const uint64_t db_a = db_res + static_cast<uint32_t>(st) * (3 * kB16);  // kernel column 0 of this chunk
           const uint64_t db_b = db_a + sc_stride, db_c = db_b + sc_stride;        // columns 1, 2
-          if (elect_one()) {
+          if (kzero != 0) {
+            // structurally sparse weights (the space-to-depth rewrite of level0: 16 live k-steps of 36): a k-step
+            // whose 16 weight columns are zero in every row is not issued.  Host: one chunk, never all 36.
+            if (elect_one()) {
+              uint32_t acc = 0;
+#pragma unroll
+              for (int sc = 0; sc < 3; ++sc) {
+                const uint64_t db = sc == 0 ? db_a : (sc == 1 ? db_b : db_c);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    if (!((kzero >> ((r * 3 + sc) * 4 + k)) & 1ull)) {
+                      umma_f16(tmem_acc, da0 + (sc * 8 + r * kTap + 2 * k), db + (r * kB16 + 2 * k), idesc, acc);
+                      acc = 1;
+                    }
+                  }
+                }
+              }
+              umma_commit(&empty[stage]);
+            }
+          } else if (elect_one()) {
 #pragma unroll
             for (int sc = 0; sc < 3; ++sc) {
               // tile row g of tap (r, sc) = window rows (g + r) * (TW + 2) + sc ...: 8-row groups (TW + 2) * 128 B apart

@@ -61,6 +61,9 @@ struct alignas(64) ConvTmaParams {
   int total_tiles;
   int dbg;     // development probe bits (M3D_DBG): 1 skip A loads, 4 skip the epilogue body, 8 skip MMAs, 16 skip the TMA store
   int a_wide;  // tmap_a are 5-D (BK, W, H, N, C/BK) maps whose box holds the stage's KSUB channel chunks
+  // conv_halo resident-weight kernel, one chunk: bit (r * 3 + s) * 4 + k set = that k-step's weights are all zero
+  // (m3d_conv_desc::k16_zero) and its MMA is not issued
+  unsigned long long kzero;
 };
 
 struct alignas(64) ConvGatherParams {

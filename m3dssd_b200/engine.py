@@ -117,6 +117,7 @@ class Engine:
         cout = wf.shape[0]
         splits = [(a.c, self._cpad(a.c)) for a in inputs]
         hi, lo = ops.pack_conv_weight(wf.cpu(), in_splits=splits, mode=self.precision)
+        kz = ops.k16_zero_mask(hi) if (hi is not None and lo is None) else (0, 0)  # bf16 mode: zero k-steps may be skipped
         hi = hi.to(self.dev) if hi is not None else None
         if isinstance(lo, tuple):
             lo = tuple(t.to(self.dev) for t in lo)
@@ -141,7 +142,7 @@ class Engine:
         def run():
             ops.conv2d_nhwc(ins, hi, out, R=k, S=k, stride=stride, pad=pad, Cout=cout, bias=bias, res=res_t,
                             res_coff=res_coff, slope=slope, weight_lo=lo, om=om_t, sigmoid_mask=sigmoid_mask,
-                            out_coff=out_coff, out_hw=out_hw)
+                            out_coff=out_coff, out_hw=out_hw, k16_zero=kz)
 
         esz = 4 if self.fp32 else 2
         k_real = k * k * sum(a.c for a in inputs)

@@ -66,10 +66,21 @@ def pack_conv_weight(weight, in_splits=None, k_pad_to=None, fp32_mode=False, mod
     return w.to(torch.bfloat16).contiguous(), None
 
 
+def k16_zero_mask(packed):
+    """m3d_conv_desc.k16_zero for a packed bf16 weight matrix [rows, K]: bit j set = columns 16 j .. 16 j + 15 are zero
+    in every row (the kernel may skip that k-step).  (0, 0) when K has more than 128 such slices or none is zero."""
+    rows, K = packed.shape
+    if K % 16 or K // 16 > 128:
+        return 0, 0
+    dead = (packed.reshape(rows, K // 16, 16) == 0).all(dim=2).all(dim=0).cpu().tolist()
+    bits = sum(1 << j for j, z in enumerate(dead) if z)
+    return bits & ((1 << 64) - 1), bits >> 64
+
+
 def conv2d_nhwc(inputs, weight, out, *, R, S, stride=1, pad=0, dil=1, Cout=None, bias=None, res=None,
                 slope=1.0, weight_lo=None, om=None, sigmoid_mask=False, groups=1, in_goff=None,
                 weight_goff=0, bias_goff=0, out_coff=0, out_goff=0, res_coff=0, res_goff=0,
-                force_gather=False, out_hw=None):
+                force_gather=False, out_hw=None, k16_zero=(0, 0)):
     """inputs: list of (tensor[N,H,W,Cbuf], coff, c) or bare tensors; out: tensor[N,P,Q,Cbuf_out]."""
     d = ConvDesc()
     ins = []
@@ -126,6 +137,7 @@ def conv2d_nhwc(inputs, weight, out, *, R, S, stride=1, pad=0, dil=1, Cout=None,
         d.om_cstride = om.shape[-1]
     d.sigmoid_mask = int(sigmoid_mask)
     d.force_gather = int(force_gather)
+    d.k16_zero[0], d.k16_zero[1] = int(k16_zero[0]), int(k16_zero[1])
     check(lib().m3d_conv2d_nhwc(C.byref(d), _stream()))
     _count(1)
     return out
