@@ -111,20 +111,42 @@ __global__ void __launch_bounds__(320) anab_pool_region_kernel(const float* __re
   const int c = threadIdx.x;
   if (c >= C) return;
   float acc[kMaxLevels] = {0.f, 0.f, 0.f, 0.f};
-  for (int px = 0; px < npix; ++px) {
-    const int y = y0 + px / rw, x = x0 + px % rw;
-    const float v = __ldg(kvs + ((static_cast<long>(n) * H + y) * W + x) * cs + c);
+  // rows of rw pixels; within a row the pixel stride is constant, so five loads are issued before their first use
+  for (int ry = 0; ry < rh; ++ry) {
+    const float* row = kvs + ((static_cast<long>(n) * H + y0 + ry) * W + x0) * cs + c;
+    int rx = 0;
+    for (; rx + 5 <= rw; rx += 5) {
+      float v[5];
 #pragma unroll
-    for (int l = 0; l < kMaxLevels; ++l)
-      if (l < nlev) acc[l] = fmaf(v, s_sig[px * nlev + l], acc[l]);
+      for (int u = 0; u < 5; ++u) v[u] = __ldg(row + static_cast<long>(rx + u) * cs);
+#pragma unroll
+      for (int u = 0; u < 5; ++u)
+#pragma unroll
+        for (int l = 0; l < kMaxLevels; ++l)
+          if (l < nlev) acc[l] = fmaf(v[u], s_sig[(ry * rw + rx + u) * nlev + l], acc[l]);
+    }
+    for (; rx < rw; ++rx) {
+      const float v = __ldg(row + static_cast<long>(rx) * cs);
+#pragma unroll
+      for (int l = 0; l < kMaxLevels; ++l)
+        if (l < nlev) acc[l] = fmaf(v, s_sig[(ry * rw + rx) * nlev + l], acc[l]);
+    }
   }
   float* dst = part + ((static_cast<long>(n) * S * S + reg) * nlev) * C;
   for (int l = 0; l < nlev; ++l) dst[l * C + c] = acc[l];
 }
 
-__global__ void anab_pool_region_finish_kernel(const float* __restrict__ part, int H, int W, int ck, int cv,
-                                               const PoolGeom g, int S, int T, float* __restrict__ ktok,
-                                               float* __restrict__ vtok) {
+// Block (token, image), thread = (channel, slice): the f x f finest regions of the token's bin are dealt round-robin to
+// kFinSlices slices (the single token of a 1 x 1 level sums S * S = 256 regions: walked by one thread per channel, one
+// L2 round trip after the other, it was the straggler of the whole pooling, ~100 us), each slice keeps four loads in
+// flight, and the slices are combined through shared memory in a fixed order (deterministic).
+constexpr int kFinSlices = 3;
+constexpr int kFinThreads = 320;  // >= ck + cv (host check)
+
+__global__ void __launch_bounds__(kFinThreads* kFinSlices) anab_pool_region_finish_kernel(
+    const float* __restrict__ part, int H, int W, int ck, int cv, const PoolGeom g, int S, int T,
+    float* __restrict__ ktok, float* __restrict__ vtok) {
+  __shared__ float s_part[kFinSlices - 1][kFinThreads];
   const int tok = blockIdx.x, n = blockIdx.y;
   const int C = ck + cv;
   int lev = 0;
@@ -135,10 +157,25 @@ __global__ void anab_pool_region_finish_kernel(const float* __restrict__ part, i
   const int ry0 = (b / s) * f, rx0 = (b % s) * f;
   const float inv = 1.f / static_cast<float>((H / s) * (W / s));
   const float* src = part + (static_cast<long>(n) * S * S * g.nlev + lev) * C;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float acc = 0.f;
-    for (int ry = ry0; ry < ry0 + f; ++ry)
-      for (int rx = rx0; rx < rx0 + f; ++rx) acc += src[static_cast<long>(ry * S + rx) * g.nlev * C + c];
+  const long rstride = static_cast<long>(g.nlev) * C;
+  const int c = threadIdx.x % kFinThreads, slice = threadIdx.x / kFinThreads;
+  const int nreg = f * f;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c < C) {
+    auto at = [&](int i) { return __ldg(src + static_cast<long>((ry0 + i / f) * S + rx0 + i % f) * rstride + c); };
+    int i = slice;
+    for (; i + 3 * kFinSlices < nreg; i += 4 * kFinSlices) {
+      const float v0 = at(i), v1 = at(i + kFinSlices), v2 = at(i + 2 * kFinSlices), v3 = at(i + 3 * kFinSlices);
+      a0 += v0, a1 += v1, a2 += v2, a3 += v3;
+    }
+    for (; i < nreg; i += kFinSlices) a0 += at(i);
+  }
+  float acc = (a0 + a1) + (a2 + a3);
+  if (slice > 0) s_part[slice - 1][c] = acc;
+  __syncthreads();
+  if (slice == 0 && c < C) {
+#pragma unroll
+    for (int k = 0; k < kFinSlices - 1; ++k) acc += s_part[k][c];
     acc *= inv;
     if (c < ck)
       ktok[(static_cast<long>(n) * T + tok) * ck + c] = acc;
@@ -302,7 +339,7 @@ extern "C" int m3d_anab_pool(const float* kvs, int kvs_cstride, int N, int H, in
     if (exact && need <= workspace_bytes && getenv("M3D_ANAB_SIMT") == nullptr) {
       anab_pool_region_kernel<<<dim3(SS * SS, N), 320, 0, S(stream)>>>(kvs, kvs_cstride, H, W, ck + cv, nlev, SS, scratch);
       M3D_CUDA_OK(cudaGetLastError());
-      anab_pool_region_finish_kernel<<<dim3(T, N), 128, 0, S(stream)>>>(scratch, H, W, ck, cv, g, SS, T, ktok, vtok);
+      anab_pool_region_finish_kernel<<<dim3(T, N), kFinThreads * kFinSlices, 0, S(stream)>>>(scratch, H, W, ck, cv, g, SS, T, ktok, vtok);
       M3D_CUDA_OK(cudaGetLastError());
       return M3D_OK;
     }
