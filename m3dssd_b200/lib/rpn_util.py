@@ -125,14 +125,15 @@ def _field(imobj, name, default=None):
 
 
 def test_kitti_3d(dataset_test, net, rpn_conf, results_path, test_path=None, use_log=True, writer=None,
-                  phase="validation", batch_size=8):
+                  phase="validation", batch_size=8, **_unused):
     """The reference's evaluation driver (lib/rpn_util.py:1753-1860) up to and including the KITTI result files:
     for every test image, detect -> first nms_topN_post kept boxes -> score cut 0.75 -> alpha -> rotation, hill_climb,
     back-projection (:1801-1844) -> one `<id>.txt` per image (:1846-1850).  Same signature and file contents; the
     images go through the network `batch_size` at a time, and decode / NMS / refinement stay on the device (one D2H
     of <= 40 rows per image).  Images arrive as the reference's loader yields them (normalised [3,H,W] / [1,3,H,W]
-    tensors) or as raw uint8 HWC frames (then Preprocess runs on the device).  The devkit's compiled evaluation that
-    the reference shells out to afterwards (:1868-1900) is outside the path; returns the list of files written."""
+    tensors) or as raw uint8 HWC frames (then Preprocess runs on the device).  The KITTI AP evaluation the reference
+    runs on those files afterwards (lib/eval get_official_eval_result, :1866-1900) is outside the path; extra keyword
+    arguments (scripts/test_rpn_3d.py:59 passes val_train=) are accepted and ignored.  Returns the files written."""
     os.makedirs(results_path, exist_ok=True)
     net.eval()
     written, pending = [], []
