@@ -173,3 +173,37 @@ def test_preprocess_pad_oracle_vs_reference_preprocess_golden():
     with pytest.raises(ValueError):
         O.preprocess_pad_u8([np.zeros((49, 64, 3), np.uint8)], g["size"], g["mean"], g["std"])
 
+
+
+def test_kitti_writer_chain_vs_unmodified_reference_driver_golden():
+    """The evaluation loop around the path, pinned to the UNMODIFIED reference driver: lib/rpn_util.py test_kitti_3d
+    (:1753-1852) run on the reference network by tests/golden/make_golden_kitti_writer.py wrote two KITTI result files;
+    the oracle chain (ref_model forward + im_detect_3d restatement, hill_climb.refine_detections) formatted by the
+    product's kitti_result_lines must give the same files: same lines, same classes, numbers to float32 noise."""
+    from m3dssd_b200.lib import rpn_util as RU
+    from m3dssd_b200.model.M3d_inference_align import build
+    from oracle import hill_climb as HC
+    g = np.load(os.path.join(GOLD, "kitti_writer_align_96x320.npz"))
+    conf = synth.make_conf(crop_size=(96, 320), attention=None, center_align=True, shape_align=True)
+    sd = synth.randomize_weights(build(conf, "test"))
+    m = RM.RefModel(sd, conf, dcn="tv")
+    x = synth.make_images(2, (96, 320))
+    n_lines = 0
+    for i in range(2):
+        _, _, kept = m.detect(m.forward(x[i:i + 1]), 0)
+        rows = HC.refine_detections(kept.numpy(), g["p2"][i], hill_climbing=True, max_out=int(conf.nms_topN_post))
+        text = RU.kitti_result_lines(rows, np.ones(len(rows), dtype=bool), conf.lbls)
+        ref = str(g["text_%d" % i])
+        got_l, ref_l = text.splitlines(), ref.splitlines()
+        assert len(got_l) == len(ref_l) and len(ref_l) > 0, (i, len(got_l), len(ref_l))
+        assert text.endswith("\n") and ref.endswith("\n")
+        for a, b in zip(got_l, ref_l):
+            ta, tb = a.split(" "), b.split(" ")
+            assert len(ta) == len(tb) == 16 and ta[:3] == tb[:3], (a, b)  # class, "-1", "-1"
+            assert all(len(t.split(".")[1]) == 6 for t in ta[3:])  # '{:.6f}'
+            va, vb = np.array(ta[3:], dtype=np.float64), np.array(tb[3:], dtype=np.float64)
+            assert np.allclose(va, vb, rtol=2e-5, atol=2e-5), (a, b)
+        n_lines += len(ref_l)
+        exact = sum(a == b for a, b in zip(got_l, ref_l))
+        assert exact >= 0.5 * len(ref_l), (i, exact, len(ref_l))  # most lines agree to the last printed digit
+    assert n_lines == 50
