@@ -171,3 +171,44 @@ def test_pre_train_registers_fc_like_the_reference():
     plain = build(conf, "test")
     assert set(sd) - set(plain.state_dict()) == {"base.base.fc.weight", "base.base.fc.bias"}
     net.load_state_dict(sd, strict=True)
+
+
+def test_pack_ragged_u8_and_k16_zero_mask():
+    """Host helpers of the ragged input transform and of the k-step skipping hint (no GPU)."""
+    import numpy as np
+    import torch
+    from m3dssd_b200 import ops
+    ims = [np.full((3, 4, 3), 7, np.uint8), np.zeros((0, 0, 3), np.uint8), torch.full((2, 2, 3), 9, dtype=torch.uint8)]
+    buf, off, hh, ww = ops.pack_ragged_u8(ims, pin=False)
+    assert off == [0, 36, 36] and hh == [3, 0, 2] and ww == [4, 0, 2] and buf.numel() == 48
+    assert bool((buf[:36] == 7).all()) and bool((buf[36:] == 9).all())
+    with pytest.raises(ValueError):
+        ops.pack_ragged_u8([np.zeros((2, 2, 4), np.uint8)], pin=False)
+    with pytest.raises(ValueError):
+        ops.pack_ragged_u8([np.zeros((2, 2, 3), np.float32)], pin=False)
+    # level0's space-to-depth rewrite: 20 dead 16-channel k-steps of 36; a dense matrix: none; K > 2048: no hint
+    w0, _ = ops.s2d_conv3x3_weight(torch.randn(16, 16, 3, 3), torch.zeros(16))
+    hi, _ = ops.pack_conv_weight(w0, in_splits=[(64, 64)], mode="bf16")
+    lo, hi_word = ops.k16_zero_mask(hi)
+    assert bin(lo).count("1") == 20 and hi_word == 0
+    live = [[j for j in range(4) if not (lo >> (t * 4 + j)) & 1] for t in range(9)]  # per tap (r * 3 + s): live (dy, dx)
+    assert live[0] == [3] and live[4] == [0, 1, 2, 3] and live[8] == [0]  # corners see one sub-pixel, the centre all four
+    assert ops.k16_zero_mask(torch.ones(8, 64, dtype=torch.bfloat16)) == (0, 0)
+    assert ops.k16_zero_mask(torch.zeros(8, 4096, dtype=torch.bfloat16)) == (0, 0)
+    z = torch.ones(4, 16 * 70, dtype=torch.bfloat16)
+    z[:, 16 * 65:16 * 66] = 0
+    assert ops.k16_zero_mask(z) == (0, 1 << 1)
+
+
+def test_eval_driver_item_adapters():
+    """test_kitti_3d accepts the reference loader's two item forms and DataLoader-collated fields."""
+    import types
+    from m3dssd_b200.lib import rpn_util as RU
+    o = types.SimpleNamespace(id=["000007"], scale_factor=1.0)
+    assert RU._field(o, "id") == "000007" and RU._field(o, "missing", 3) == 3
+    assert RU._field({"id": "x"}, "id") == "x"
+    items = list(RU._iter_test_items([("im", "obj"), {"input": "im2", "target": {"meta": "obj2"}}], None))
+    assert items == [("im", "obj"), ("im2", "obj2")]
+    text = RU.kitti_result_lines([[0, 1.0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12.5, 0.9], [1] * 14], [True, False], ["Car", "Ped"])
+    assert text == "Car -1 -1 1.000000 2.000000 3.000000 4.000000 5.000000 6.000000 7.000000 8.000000 9.000000 " \
+                   "10.000000 11.000000 12.500000 0.900000\n"
