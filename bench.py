@@ -740,6 +740,15 @@ def time_surface(net, conf, torch, synth):
     out["rpn_forward_batch8"] = {"images_per_s": LOCAL_BATCH / t, "ms_per_call": 1e3 * t}
     t = timeit(lambda: net.detect(x8.cuda(non_blocking=True))[1].cpu(), 20)
     out["rpn_detect_batch8"] = {"images_per_s": LOCAL_BATCH / t, "ms_per_call": 1e3 * t}
+    try:  # raw frames in (ragged uint8 HWC, KITTI-sized), kept rows out: Preprocess on the device (RPN.detect_images)
+        import numpy as np
+        rng = np.random.default_rng(9)
+        frames = [rng.integers(0, 256, (int(rng.integers(CROP[0] - 14, CROP[0] - 7)), int(rng.integers(CROP[1] - 56, CROP[1] - 37)), 3),
+                               dtype=np.uint8) for _ in range(LOCAL_BATCH)]  # 370-376 x 1224-1242
+        t = timeit(lambda: net.detect_images(frames, size=CROP)[1].cpu(), 20)
+        out["rpn_detect_images_u8_ragged_batch8"] = {"images_per_s": LOCAL_BATCH / t, "ms_per_call": 1e3 * t}
+    except Exception as e:  # a sub-measurement must never cost the bench line
+        out["rpn_detect_images_u8_ragged_batch8"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:120])}
     out["note"] = "wall clock around host-tensor-in / host-result-out calls, synchronous (no pipelining across calls)"
     return out
 

@@ -186,9 +186,8 @@ def pack_ragged_u8(images, pin=True):
     for n in sizes:
         offsets.append(total)
         total += n
-    buf = torch.empty(max(total, 1), dtype=torch.uint8)
-    if pin and torch.cuda.is_available():
-        buf = buf.pin_memory()
+    # (torch's caching host allocator: after the first call a pinned block of this size is reused, no cudaHostAlloc)
+    buf = torch.empty(max(total, 1), dtype=torch.uint8, pin_memory=bool(pin and torch.cuda.is_available()))
     for a, o, n in zip(arrs, offsets, sizes):
         buf[o:o + n] = a.contiguous().view(-1)
     return buf, offsets, [int(a.shape[0]) for a in arrs], [int(a.shape[1]) for a in arrs]

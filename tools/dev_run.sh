@@ -1,4 +1,7 @@
-timeout 300 python -m pytest tests/test_multi_gpu.py -m gpu -x -q 2>&1 | tail -3
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 2 --steps 30 --warmup 20 --no-cpu-baseline --no-extras 2>gpurun_out/r02_bench_2gpu.err | tail -1 > gpurun_out/r02_bench_2gpu.json
+# final validation of a tree on one B200: the whole GPU suite, smoke(), the default bench line
+tag=${1:-r02f}
+timeout 900 python -m pytest tests -m gpu -x -q -rf > gpurun_out/${tag}_gpu_tests.log 2>&1; tail -2 gpurun_out/${tag}_gpu_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 400 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; head -c 200 gpurun_out/${tag}_bench.json; echo
 python -c "
-import json; d=json.load(open('gpurun_out/r02_bench_2gpu.json')); print(d['n_gpus'], d['value'], d['e2e']['value'], d['ms_per_step'])"
+import json; d=json.loads(open('gpurun_out/${tag}_bench.json').read().strip().splitlines()[-1]); print(d['value'], d['e2e']['value']); print(d['surface'])"
