@@ -111,6 +111,9 @@ typedef struct m3d_conv_desc {
 } m3d_conv_desc;
 
 int m3d_conv2d_nhwc(const m3d_conv_desc* desc, m3d_stream_t stream);
+/* sizeof(m3d_conv_desc) in the library: a binding written in another language compares it with the size of its own
+ * mirror of the struct before the first call (fields are only ever appended). */
+size_t m3d_conv_desc_size(void);
 
 /* ------------------------------------------------------------------------
  * DCNv2 operator, reference FFI shape (replaces dcn_v2_cuda_forward,

@@ -38,6 +38,7 @@ _SIGS = {
     "m3d_nhwc_to_nchw": [vp, i, vp, i, i, i, i, i, i, i, vp],
 }
 _SIZE_FNS = {
+    "m3d_conv_desc_size": [],
     "m3d_dcn_v2_forward_workspace": [i] * 12,
     "m3d_dcn_v2_backward_workspace": [i] * 11,
     "m3d_nms_workspace_bytes": [i, i],

@@ -64,6 +64,9 @@ def _declare(L):
     L.m3d_conv2d_nhwc.argtypes = [C.POINTER(ConvDesc), C.c_void_p]
     from . import _decl
     _decl.declare(L)
+    if L.m3d_conv_desc_size() != C.sizeof(ConvDesc):  # a stale .so next to newer Python (or the reverse)
+        raise M3DError("m3d_conv_desc is %d bytes in %s but %d in the Python mirror: rebuild with `python -m m3dssd_b200.build`"
+                       % (L.m3d_conv_desc_size(), LIB_PATH, C.sizeof(ConvDesc)))
 
 
 def check(rc):

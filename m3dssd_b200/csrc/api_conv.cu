@@ -320,6 +320,7 @@ extern "C" int m3d_set_sm_limit(int sms) {
 extern "C" const char* m3d_last_error(void) { return g_last_error; }
 extern "C" const char* m3d_last_kernel(void) { return g_last_kernel; }
 extern "C" int m3d_version(void) { return 100; }
+extern "C" size_t m3d_conv_desc_size(void) { return sizeof(m3d_conv_desc); }
 
 extern "C" int m3d_conv2d_nhwc(const m3d_conv_desc* d, m3d_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

@@ -212,3 +212,14 @@ def test_eval_driver_item_adapters():
     text = RU.kitti_result_lines([[0, 1.0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12.5, 0.9], [1] * 14], [True, False], ["Car", "Ped"])
     assert text == "Car -1 -1 1.000000 2.000000 3.000000 4.000000 5.000000 6.000000 7.000000 8.000000 9.000000 " \
                    "10.000000 11.000000 12.500000 0.900000\n"
+
+
+def test_conv_desc_mirror_matches_the_library():
+    """The ctypes mirror of m3d_conv_desc has the library's size and field order ends with the k16_zero hint (the
+    loader refuses a stale .so: _lib._declare)."""
+    import ctypes as C
+    from m3dssd_b200 import _lib
+    L = _lib.lib()
+    assert L.m3d_conv_desc_size() == C.sizeof(_lib.ConvDesc)
+    assert _lib.ConvDesc._fields_[-1][0] == "k16_zero" and _lib.ConvDesc.k16_zero.size == 16
+    assert _lib.ConvDesc.k16_zero.offset % 8 == 0
